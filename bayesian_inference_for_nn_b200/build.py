@@ -1,0 +1,66 @@
+"""In-tree build of libpyesian_b200.so (nvcc, sm_100a only).
+
+`python -m bayesian_inference_for_nn_b200.build` or `build()`; used by `__graft_entry__.build()`.
+Objects are cached by source mtime so that iterating on one kernel recompiles one file.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libpyesian_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _newest_header():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "pyesian_b200.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _compile(src):
+    obj = os.path.join(OBJ, src[:-3] + ".o")
+    sp = os.path.join(CSRC, src)
+    if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), _newest_header()):
+        return obj, ""
+    r = subprocess.run([NVCC] + FLAGS + ["-c", sp, "-o", obj], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    return obj, r.stderr
+
+
+def build(verbose=False, force=False):
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            os.unlink(os.path.join(OBJ, f))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        res = list(ex.map(_compile, _sources()))
+    objs = [o for o, _ in res]
+    log = "".join(l for _, l in res)
+    if log:
+        with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
+            f.write(log)
+    if verbose and log:
+        print(log)
+    if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcuda"] if False else
+                           [NVCC, "-shared", "-o", LIB] + objs, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

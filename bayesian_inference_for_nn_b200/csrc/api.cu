@@ -1,0 +1,460 @@
+// api.cu — the extern "C" boundary of libpyesian_b200.so (declared in include/pyesian_b200.h).
+// Exceptions stop here: every entry point returns a pyb_status and records pyb_last_error().
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+#include <new>
+
+namespace pyb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+// fused_small.cu / tc_path.cu
+bool fused_small_supported(pyb_handle* h);
+void fused_small_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss, float* grad);
+bool tc_supported(pyb_handle* h, int64_t S);
+void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss, float* grad);
+void tc_release(pyb_handle* h);
+void tc_invalidate_dataset(pyb_handle* h);
+
+void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
+  int path = h->opt_path;
+  if (path == PYB_PATH_AUTO) {
+    if (grad_out && tc_supported(h, S)) path = PYB_PATH_TENSOR;
+    else if (grad_out && fused_small_supported(h)) path = PYB_PATH_FUSED_SMALL;
+    else path = PYB_PATH_GENERIC;
+  }
+  if (path == PYB_PATH_TENSOR) {
+    PYB_REQUIRE(tc_supported(h, S), PYB_ERR_UNSUPPORTED, "tensor path does not support this model/dataset shape");
+    PYB_REQUIRE(grad_out != nullptr, PYB_ERR_UNSUPPORTED, "tensor path computes loss and gradient together");
+    tc_eval(h, theta, S, scale, loss_out, grad_out);
+  } else if (path == PYB_PATH_FUSED_SMALL) {
+    PYB_REQUIRE(fused_small_supported(h), PYB_ERR_UNSUPPORTED, "fused small path does not support this model shape");
+    PYB_REQUIRE(grad_out != nullptr, PYB_ERR_UNSUPPORTED, "fused small path computes loss and gradient together");
+    fused_small_eval(h, theta, S, scale, loss_out, grad_out);
+  } else {
+    generic_eval(h, theta, S, h->X.p, h->y_i.p, h->y_f.p, h->N, scale, loss_out, grad_out);
+  }
+  h->path_used = path;
+}
+}  // namespace pyb
+
+using namespace pyb;
+
+#define PYB_TRY try {
+#define PYB_CATCH                                      \
+  }                                                    \
+  catch (const pyb::Error& e) {                        \
+    pyb::set_last_error(e.what());                     \
+    return e.code;                                     \
+  }                                                    \
+  catch (const std::bad_alloc&) {                      \
+    pyb::set_last_error("host allocation failed");     \
+    return PYB_ERR_OOM;                                \
+  }                                                    \
+  catch (const std::exception& e) {                    \
+    pyb::set_last_error(e.what());                     \
+    return PYB_ERR_INVALID;                            \
+  }                                                    \
+  return PYB_OK;
+
+static void use_device(const pyb_handle* h) { PYB_CUDA(cudaSetDevice(h->device)); }
+
+extern "C" {
+
+int pyb_version(void) { return PYB_ABI_VERSION; }
+const char* pyb_last_error(void) { return pyb::g_last_error.c_str(); }
+
+int pyb_device_count(int32_t* n_out) {
+  PYB_TRY
+  PYB_REQUIRE(n_out, PYB_ERR_INVALID, "n_out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  *n_out = n;
+  PYB_CATCH
+}
+
+int pyb_create(const pyb_model_desc* d, int32_t device_id, uint64_t seed, pyb_handle** out) {
+  PYB_TRY
+  PYB_REQUIRE(d && out, PYB_ERR_INVALID, "NULL argument");
+  PYB_REQUIRE(d->n_layers >= 1 && d->n_layers <= kMaxLayers, PYB_ERR_INVALID, "n_layers must be in [1,16]");
+  PYB_REQUIRE(d->in_dim >= 1, PYB_ERR_INVALID, "in_dim must be >= 1");
+  PYB_REQUIRE(d->units && d->activation && d->use_bias, PYB_ERR_INVALID, "NULL layer arrays");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(PYB_ERR_CUDA, "no CUDA device: libpyesian_b200 has no CPU fallback");
+  }
+  PYB_REQUIRE(device_id >= 0 && device_id < ndev, PYB_ERR_INVALID, "device_id out of range");
+  cudaDeviceProp prop;
+  PYB_CUDA(cudaGetDeviceProperties(&prop, device_id));
+  PYB_REQUIRE(prop.major == 10, PYB_ERR_CUDA, "device is not sm_100-class (B200): this library is sm_100a only");
+  pyb_handle* h = new pyb_handle();
+  h->device = device_id;
+  h->sm_count = prop.multiProcessorCount;
+  h->seed = seed;
+  Model& m = h->model;
+  m.n_layers = d->n_layers;
+  m.in_dim = d->in_dim;
+  int fin = d->in_dim;
+  int64_t off = 0;
+  for (int l = 0; l < d->n_layers; ++l) {
+    LayerDesc& L = m.layer[l];
+    if (d->units[l] < 1) { delete h; throw Error(PYB_ERR_INVALID, "units must be >= 1"); }
+    int act = d->activation[l];
+    if (act < 0 || act > PYB_ACT_SIGMOID || (act == PYB_ACT_SOFTMAX && l != d->n_layers - 1)) {
+      delete h;
+      throw Error(PYB_ERR_UNSUPPORTED, "unsupported activation (softmax is only supported on the output layer)");
+    }
+    L.fan_in = fin; L.fan_out = d->units[l]; L.act = act; L.use_bias = d->use_bias[l] ? 1 : 0;
+    L.w_off = off; off += (int64_t)fin * L.fan_out;
+    L.b_off = -1;
+    if (L.use_bias) { L.b_off = off; off += L.fan_out; }
+    if (L.fan_out > m.max_width) m.max_width = L.fan_out;
+    fin = L.fan_out;
+  }
+  m.P = off;
+  m.out_dim = fin;
+  try {
+    PYB_CUDA(cudaSetDevice(device_id));
+    PYB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PYB_CUDA(cudaEventCreate(&h->ev0));
+    PYB_CUDA(cudaEventCreate(&h->ev1));
+  } catch (...) { delete h; throw; }
+  *out = h;
+  PYB_CATCH
+}
+
+int pyb_destroy(pyb_handle* h) {
+  PYB_TRY
+  if (!h) return PYB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  tc_release(h);
+  for (auto* b : h->ws.act) delete b;
+  h->ws.act.clear();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  PYB_CATCH
+}
+
+int pyb_param_count(const pyb_handle* h, int64_t* n) {
+  PYB_TRY
+  PYB_REQUIRE(h && n, PYB_ERR_INVALID, "NULL argument");
+  *n = h->model.P;
+  PYB_CATCH
+}
+
+int pyb_set_option(pyb_handle* h, const char* key, double v) {
+  PYB_TRY
+  PYB_REQUIRE(h && key, PYB_ERR_INVALID, "NULL argument");
+  if (!strcmp(key, "path")) {
+    PYB_REQUIRE(v >= 0 && v <= 3, PYB_ERR_INVALID, "path must be 0..3");
+    h->opt_path = (int)v;
+  } else if (!strcmp(key, "workspace_mb")) {
+    PYB_REQUIRE(v >= 1, PYB_ERR_INVALID, "workspace_mb must be >= 1");
+    h->opt_workspace_mb = v;
+  } else if (!strcmp(key, "chain_batch")) {
+    h->opt_chain_batch = (int64_t)v;
+  } else {
+    throw Error(PYB_ERR_INVALID, std::string("unknown option: ") + key);
+  }
+  PYB_CATCH
+}
+
+int pyb_get_info(const pyb_handle* h, const char* key, double* out) {
+  PYB_TRY
+  PYB_REQUIRE(h && key && out, PYB_ERR_INVALID, "NULL argument");
+  if (!strcmp(key, "path_used")) *out = h->path_used;
+  else if (!strcmp(key, "kernel_launches")) *out = (double)h->kernel_launches;
+  else if (!strcmp(key, "last_device_ms")) *out = h->last_device_ms;
+  else if (!strcmp(key, "sm_count")) *out = h->sm_count;
+  else if (!strcmp(key, "n_train")) *out = (double)h->n_train;
+  else throw Error(PYB_ERR_INVALID, std::string("unknown info key: ") + key);
+  PYB_CATCH
+}
+
+int pyb_set_dataset(pyb_handle* h, const float* X, int64_t N, const void* y, int32_t loss_kind, int32_t mem,
+                    int64_t n_train) {
+  PYB_TRY
+  PYB_REQUIRE(h && X && y, PYB_ERR_INVALID, "NULL argument");
+  PYB_REQUIRE(N >= 1 && N < (1ll << 31), PYB_ERR_INVALID, "N must be in [1, 2^31)");
+  PYB_REQUIRE(loss_kind == PYB_LOSS_SPARSE_CE || loss_kind == PYB_LOSS_MSE, PYB_ERR_INVALID, "bad loss_kind");
+  PYB_REQUIRE(mem == PYB_MEM_HOST || mem == PYB_MEM_DEVICE, PYB_ERR_INVALID, "bad mem");
+  const Model& m = h->model;
+  int last_act = m.layer[m.n_layers - 1].act;
+  if (loss_kind == PYB_LOSS_SPARSE_CE)
+    PYB_REQUIRE(last_act == PYB_ACT_SOFTMAX, PYB_ERR_UNSUPPORTED,
+                "SparseCategoricalCrossentropy needs a softmax output layer (logits path of Keras 2.15)");
+  else
+    PYB_REQUIRE(last_act != PYB_ACT_SOFTMAX, PYB_ERR_UNSUPPORTED, "MeanSquaredError on a softmax output is not supported");
+  use_device(h);
+  cudaMemcpyKind kind = mem == PYB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  h->X.alloc(N * m.in_dim);
+  PYB_CUDA(cudaMemcpyAsync(h->X.p, X, N * m.in_dim * sizeof(float), kind, h->stream));
+  if (loss_kind == PYB_LOSS_SPARSE_CE) {
+    h->y_i.alloc(N);
+    PYB_CUDA(cudaMemcpyAsync(h->y_i.p, y, N * sizeof(int32_t), kind, h->stream));
+    if (mem == PYB_MEM_HOST) {
+      const int32_t* yi = (const int32_t*)y;
+      for (int64_t i = 0; i < N; ++i)
+        if (yi[i] < 0 || yi[i] >= m.out_dim) throw Error(PYB_ERR_INVALID, "label out of range [0, out_dim)");
+    }
+  } else {
+    h->y_f.alloc(N * m.out_dim);
+    PYB_CUDA(cudaMemcpyAsync(h->y_f.p, y, N * m.out_dim * sizeof(float), kind, h->stream));
+  }
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  h->N = N;
+  h->n_train = n_train > 0 ? n_train : N;
+  h->loss_kind = loss_kind;
+  h->have_data = true;
+  tc_invalidate_dataset(h);
+  PYB_CATCH
+}
+
+int pyb_set_prior_gaussian(pyb_handle* h, const float* mean, const float* sigma, int32_t form) {
+  PYB_TRY
+  PYB_REQUIRE(h && mean && sigma, PYB_ERR_INVALID, "NULL argument");
+  const Model& m = h->model;
+  std::vector<float> mu(m.P), sg(m.P), iv(m.P);
+  if (form == PYB_PRIOR_SCALAR) {
+    for (int64_t i = 0; i < m.P; ++i) { mu[i] = mean[0]; sg[i] = sigma[0]; }
+  } else if (form == PYB_PRIOR_PER_VARIABLE) {
+    int v = 0;
+    for (int l = 0; l < m.n_layers; ++l) {
+      const LayerDesc& L = m.layer[l];
+      for (int64_t i = 0; i < (int64_t)L.fan_in * L.fan_out; ++i) { mu[L.w_off + i] = mean[v]; sg[L.w_off + i] = sigma[v]; }
+      ++v;
+      if (L.use_bias) {
+        for (int i = 0; i < L.fan_out; ++i) { mu[L.b_off + i] = mean[v]; sg[L.b_off + i] = sigma[v]; }
+        ++v;
+      }
+    }
+  } else if (form == PYB_PRIOR_PER_ELEMENT) {
+    for (int64_t i = 0; i < m.P; ++i) { mu[i] = mean[i]; sg[i] = sigma[i]; }
+  } else {
+    throw Error(PYB_ERR_INVALID, "bad prior form");
+  }
+  double c = 0.0;
+  for (int64_t i = 0; i < m.P; ++i) {
+    PYB_REQUIRE(sg[i] != 0.f, PYB_ERR_INVALID, "sigma must be non-zero");
+    iv[i] = 1.0f / (sg[i] * sg[i]);
+    c += (double)logf(sg[i]) + 0.9189385332046727;  // log sigma + 1/2 log 2pi; NaN for sigma<0 as tfp (SURVEY B-1)
+  }
+  use_device(h);
+  h->mu.alloc(m.P); h->sigma.alloc(m.P); h->inv_var.alloc(m.P);
+  PYB_CUDA(cudaMemcpy(h->mu.p, mu.data(), m.P * sizeof(float), cudaMemcpyHostToDevice));
+  PYB_CUDA(cudaMemcpy(h->sigma.p, sg.data(), m.P * sizeof(float), cudaMemcpyHostToDevice));
+  PYB_CUDA(cudaMemcpy(h->inv_var.p, iv.data(), m.P * sizeof(float), cudaMemcpyHostToDevice));
+  h->prior_const = c;
+  h->have_prior = true;
+  PYB_CATCH
+}
+
+int pyb_hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double m, int32_t L, int32_t sem,
+                 const float* q0) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  hmc_init(h, S, chain_offset, eps, m, L, sem, q0);
+  PYB_CATCH
+}
+
+int pyb_hmc_inject(pyb_handle* h, const float* p, const float* u) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  HmcState& st = h->hmc;
+  PYB_REQUIRE(st.inited, PYB_ERR_STATE, "pyb_hmc_init must be called first");
+  use_device(h);
+  const int64_t P = h->model.P;
+  if (p) {
+    st.inj_p.alloc(st.S * P);
+    PYB_CUDA(cudaMemcpy(st.inj_p.p, p, st.S * P * sizeof(float), cudaMemcpyHostToDevice));
+    st.have_inj_p = true;
+  }
+  if (u) {
+    st.inj_u.alloc(st.S);
+    PYB_CUDA(cudaMemcpy(st.inj_u.p, u, st.S * sizeof(float), cudaMemcpyHostToDevice));
+    st.have_inj_u = true;
+  }
+  PYB_CATCH
+}
+
+int pyb_hmc_run(pyb_handle* h, int32_t n_iters, int32_t burning, int32_t sampling, pyb_hmc_diag* out) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  hmc_run(h, n_iters, burning != 0, sampling != 0, out);
+  PYB_CATCH
+}
+
+int pyb_hmc_eval(pyb_handle* h, const float* q, int64_t S, float* U, float* loss, float* grad) {
+  PYB_TRY
+  PYB_REQUIRE(h && q, PYB_ERR_INVALID, "NULL argument");
+  use_device(h);
+  hmc_eval(h, q, S, U, loss, grad);
+  PYB_CATCH
+}
+
+int pyb_hmc_get_state(pyb_handle* h, float* q, float* p) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  HmcState& st = h->hmc;
+  PYB_REQUIRE(st.inited, PYB_ERR_STATE, "pyb_hmc_init must be called first");
+  use_device(h);
+  size_t n = (size_t)st.S * h->model.P * sizeof(float);
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  if (q) PYB_CUDA(cudaMemcpy(q, st.q.p, n, cudaMemcpyDeviceToHost));
+  if (p) PYB_CUDA(cudaMemcpy(p, st.p.p, n, cudaMemcpyDeviceToHost));
+  PYB_CATCH
+}
+
+int pyb_hmc_last(pyb_handle* h, float* U0, float* K0, float* U1, float* K1, float* log_alpha, int32_t* accepted,
+                 float* loss) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  HmcState& st = h->hmc;
+  PYB_REQUIRE(st.inited && st.iter > 0, PYB_ERR_STATE, "no iteration has run yet");
+  use_device(h);
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  size_t n = (size_t)st.S * sizeof(float);
+  if (U0) PYB_CUDA(cudaMemcpy(U0, st.U0.p, n, cudaMemcpyDeviceToHost));
+  if (K0) PYB_CUDA(cudaMemcpy(K0, st.K0.p, n, cudaMemcpyDeviceToHost));
+  if (U1) PYB_CUDA(cudaMemcpy(U1, st.U1.p, n, cudaMemcpyDeviceToHost));
+  if (K1) PYB_CUDA(cudaMemcpy(K1, st.K1.p, n, cudaMemcpyDeviceToHost));
+  if (log_alpha) PYB_CUDA(cudaMemcpy(log_alpha, st.log_alpha.p, n, cudaMemcpyDeviceToHost));
+  if (accepted) PYB_CUDA(cudaMemcpy(accepted, st.accepted.p, n, cudaMemcpyDeviceToHost));
+  if (loss) PYB_CUDA(cudaMemcpy(loss, st.ret_loss.p, n, cudaMemcpyDeviceToHost));
+  PYB_CATCH
+}
+
+int pyb_hmc_reset_samples(pyb_handle* h) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  HmcState& st = h->hmc;
+  PYB_REQUIRE(st.inited, PYB_ERR_STATE, "pyb_hmc_init must be called first");
+  use_device(h);
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaMemset(st.arena_count.p, 0, sizeof(int32_t)));
+  PYB_CUDA(cudaMemset(st.pending_freq.p, 0, st.S * sizeof(int32_t)));
+  PYB_CUDA(cudaMemset(st.last_idx.p, 0xff, st.S * sizeof(int32_t)));
+  st.arena_used_upper = 0;
+  st.host_samples.clear(); st.host_freq.clear(); st.host_chain.clear();
+  st.host_last_idx.assign(st.S, -1);
+  st.sampling_started = false;
+  PYB_CATCH
+}
+
+int pyb_hmc_sample_count(pyb_handle* h, int64_t* n) {
+  PYB_TRY
+  PYB_REQUIRE(h && n, PYB_ERR_INVALID, "NULL argument");
+  HmcState& st = h->hmc;
+  PYB_REQUIRE(st.inited, PYB_ERR_STATE, "pyb_hmc_init must be called first");
+  use_device(h);
+  hmc_flush_arena(h);
+  *n = (int64_t)st.host_freq.size();
+  PYB_CATCH
+}
+
+int pyb_hmc_samples(pyb_handle* h, float* samples, int32_t* freq, int32_t* chain) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  HmcState& st = h->hmc;
+  PYB_REQUIRE(st.inited, PYB_ERR_STATE, "pyb_hmc_init must be called first");
+  use_device(h);
+  hmc_flush_arena(h);
+  // chain-major, acceptance order within a chain (stable counting sort on the chain id)
+  const int64_t P = h->model.P, n = (int64_t)st.host_freq.size();
+  std::vector<int64_t> start(st.S + 1, 0);
+  for (int64_t i = 0; i < n; ++i) start[st.host_chain[i] - st.chain_offset + 1]++;
+  for (int64_t s = 0; s < st.S; ++s) start[s + 1] += start[s];
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t d = start[st.host_chain[i] - st.chain_offset]++;
+    if (samples) memcpy(samples + d * P, st.host_samples.data() + i * P, P * sizeof(float));
+    if (freq) freq[d] = st.host_freq[i];
+    if (chain) chain[d] = st.host_chain[i];
+  }
+  PYB_CATCH
+}
+
+int pyb_svgd_init(pyb_handle* h, int64_t S, int64_t offset, double lr, int32_t sem, const double* p0) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  svgd_init(h, S, offset, lr, sem, p0);
+  PYB_CATCH
+}
+
+int pyb_svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  if (idx)
+    for (int64_t i = 0; i < B; ++i)
+      PYB_REQUIRE(idx[i] >= 0 && idx[i] < h->N, PYB_ERR_INVALID, "batch index out of range");
+  svgd_step(h, idx, B, loss_out);
+  PYB_CATCH
+}
+
+int pyb_svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int32_t sem, float* phi, double* h_out) {
+  PYB_TRY
+  PYB_REQUIRE(h && X && G && phi, PYB_ERR_INVALID, "NULL argument");
+  PYB_REQUIRE(sem == PYB_SVGD_REFERENCE_LIVE || sem == PYB_SVGD_CANONICAL_MEDIAN, PYB_ERR_INVALID, "bad semantics");
+  use_device(h);
+  svgd_phi(h, X, G, S, sem, phi, h_out);
+  PYB_CATCH
+}
+
+__global__ void k_f32_to_f64(const float* a, double* b, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    b[i] = (double)a[i];
+}
+
+int pyb_svgd_get_particles(pyb_handle* h, double* out) {
+  PYB_TRY
+  PYB_REQUIRE(h && out, PYB_ERR_INVALID, "NULL argument");
+  SvgdState& sv = h->svgd;
+  PYB_REQUIRE(sv.inited, PYB_ERR_STATE, "pyb_svgd_init must be called first");
+  use_device(h);
+  int64_t n = sv.S * h->model.P;
+  DevBuf<double> tmp;
+  tmp.alloc(n);
+  k_f32_to_f64<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, h->stream>>>(sv.theta.p, tmp.p, n);
+  count_launch(h);
+  PYB_CUDA(cudaMemcpyAsync(out, tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CATCH
+}
+
+int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* id) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  (void)id;
+  PYB_REQUIRE(world >= 1 && rank >= 0 && rank < world, PYB_ERR_INVALID, "bad rank/world");
+  if (world > 1) throw Error(PYB_ERR_UNSUPPORTED, "sharded SVGD (NCCL all-gather) is not wired in this build");
+  h->svgd.rank = rank; h->svgd.world = world;
+  PYB_CATCH
+}
+
+int pyb_nccl_unique_id(void* out_128) {
+  PYB_TRY
+  PYB_REQUIRE(out_128, PYB_ERR_INVALID, "NULL argument");
+  throw Error(PYB_ERR_UNSUPPORTED, "NCCL plumbing is not wired in this build");
+  PYB_CATCH
+}
+
+int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt, float* mean,
+                float* var, float* all) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  predict(h, W, n, weight, x, Nt, mean, var, all);
+  PYB_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+// common.cuh — handle layout, error plumbing, Philox, small device helpers.
+// Part of libpyesian_b200.so (see include/pyesian_b200.h for the C ABI and reference citations).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/pyesian_b200.h"
+
+namespace pyb {
+
+// ------------------------------------------------------------------------------------------
+// errors: C++ exceptions are used internally and converted to status codes at the ABI boundary
+// ------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string& m);
+
+#define PYB_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      char _b[512];                                                                        \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+               __FILE__, __LINE__);                                                        \
+      throw pyb::Error(_e == cudaErrorMemoryAllocation ? PYB_ERR_OOM : PYB_ERR_CUDA, _b);  \
+    }                                                                                      \
+  } while (0)
+
+#define PYB_REQUIRE(cond, code, msg)                       \
+  do {                                                     \
+    if (!(cond)) throw pyb::Error((code), (msg));          \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device buffer (owning)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    release();
+    if (count == 0) return;
+    PYB_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    n = count;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// ------------------------------------------------------------------------------------------
+// model layout: the weight-layout packer's device-side view of the Keras Dense stack
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxLayers = 16;
+struct LayerDesc {
+  int fan_in, fan_out, act, use_bias;
+  int64_t w_off, b_off;  // offsets into the flat [P] parameter vector (b_off = -1: no bias)
+};
+struct Model {
+  int n_layers = 0;
+  int in_dim = 0;
+  int out_dim = 0;
+  int64_t P = 0;
+  int max_width = 0;
+  LayerDesc layer[kMaxLayers];
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  counter = (block, chain, iteration, stream), key = seed.
+// ------------------------------------------------------------------------------------------
+enum { STREAM_MOMENTUM = 0, STREAM_UNIFORM = 1, STREAM_INIT = 2 };
+
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#ifdef __CUDACC__
+// 4 standard normals from one Philox block (two Box-Muller pairs)
+__device__ inline void philox_normal4(uint32_t block, uint32_t chain, uint32_t iter, uint32_t stream,
+                                      uint64_t seed, float z[4]) {
+  uint32_t r[4];
+  philox4x32_10(block, chain, iter, stream, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const float k = 5.9604644775390625e-08f;  // 2^-24
+  float u1a = ((float)(r[0] >> 8) + 1.0f) * k, u2a = (float)(r[1] >> 8) * k;
+  float u1b = ((float)(r[2] >> 8) + 1.0f) * k, u2b = (float)(r[3] >> 8) * k;
+  float ra = sqrtf(-2.0f * logf(u1a)), rb = sqrtf(-2.0f * logf(u1b));
+  float sa, ca, sb, cb;
+  sincosf(6.283185307179586f * u2a, &sa, &ca);
+  sincosf(6.283185307179586f * u2b, &sb, &cb);
+  z[0] = ra * ca; z[1] = ra * sa; z[2] = rb * cb; z[3] = rb * sb;
+}
+__device__ inline float philox_uniform(uint32_t chain, uint32_t iter, uint32_t stream, uint64_t seed) {
+  uint32_t r[4];
+  philox4x32_10(0u, chain, iter, stream, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  return (float)(r[0] >> 8) * 5.9604644775390625e-08f;
+}
+
+__device__ inline float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum; result valid in thread 0 (all threads must call). scratch >= 32 entries.
+template <typename T>
+__device__ inline T block_sum(T v, T* scratch) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  T r = (threadIdx.x < nw) ? scratch[threadIdx.x] : T(0);
+  if (w == 0) r = warp_sum(r);
+  return r;
+}
+
+__device__ inline float act_apply(float z, int act) {
+  switch (act) {
+    case PYB_ACT_RELU: return fmaxf(z, 0.0f);
+    case PYB_ACT_TANH: return tanhf(z);
+    case PYB_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+    default: return z;
+  }
+}
+// derivative through the activation OUTPUT (relu'(z) = 1[z>0] <=> 1[a>0])
+__device__ inline float act_grad_from_output(float a, int act) {
+  switch (act) {
+    case PYB_ACT_RELU: return a > 0.0f ? 1.0f : 0.0f;
+    case PYB_ACT_TANH: return 1.0f - a * a;
+    case PYB_ACT_SIGMOID: return a * (1.0f - a);
+    default: return 1.0f;
+  }
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct HmcState {
+  bool inited = false;
+  int64_t S = 0, chain_offset = 0;
+  double eps = 0, m = 1;
+  int L = 0, semantics = 0;
+  uint64_t iter = 0;  // global iteration counter (RNG counter word)
+  DevBuf<float> q, p, g, q0;
+  DevBuf<float> inj_p, inj_u;
+  bool have_inj_p = false, have_inj_u = false;
+  // per-chain scalars
+  DevBuf<float> loss, loss0, Up0, Up1, K0, K1, U0, U1, log_alpha, ret_loss;
+  DevBuf<int32_t> accepted;
+  DevBuf<double> partial_e, partial_k;  // [S, nblk] reduction scratch
+  DevBuf<int32_t> pending_freq, slot_first, slot_acc;
+  DevBuf<unsigned long long> counters;  // [0]=n_accepted [1]=n_total [2]=n_nan ; double sums after
+  DevBuf<double> loss_sum;      // [1]
+  // sample arena
+  DevBuf<float> arena;          // [cap, P]
+  DevBuf<int32_t> arena_freq, arena_chain, last_idx, arena_count;
+  int64_t arena_cap = 0;
+  int64_t arena_used_upper = 0;  // host-side upper bound of arena_count
+  std::vector<float> host_samples;
+  std::vector<int32_t> host_freq, host_chain;
+  std::vector<int64_t> host_last_idx;   // per chain: index into host arrays of its last sample (-1: none)
+  bool sampling_started = false;
+};
+
+struct SvgdState {
+  bool inited = false;
+  int64_t S = 0, offset = 0;
+  double lr = 0;
+  int semantics = 0;
+  int64_t t = 0;
+  DevBuf<float> theta, g, adam_m, adam_v, phi, loss;
+  DevBuf<double> d2, K, rowsum;
+  DevBuf<unsigned long long> sel, hist;   // radix-select state (2 x {prefix,mask,k}) and 256-bin histogram
+  DevBuf<double> h2, mean_loss, Krow;
+  DevBuf<float> Xb;
+  DevBuf<int32_t> yb_i, idx;
+  DevBuf<float> yb_f;
+  // comm
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  DevBuf<float> theta_all, g_all;
+};
+
+struct Workspace {
+  // generic-path activations for a chain batch: act[l] = [Bc, N, width_l], dz ping-pong
+  std::vector<DevBuf<float>*> act;
+  DevBuf<float> dz_a, dz_b;
+  DevBuf<float> partial;  // split-K partials
+  DevBuf<double> loss_partial;
+  int64_t Bc = 0, N = 0;
+};
+
+}  // namespace pyb
+
+struct pyb_handle {
+  int device = 0;
+  int sm_count = 148;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  pyb::Model model;
+  // dataset
+  int64_t N = 0, n_train = 0;
+  int loss_kind = 0;
+  pyb::DevBuf<float> X, y_f;
+  pyb::DevBuf<int32_t> y_i;
+  bool have_data = false;
+  // prior (per element) + derived
+  pyb::DevBuf<float> mu, sigma, inv_var;
+  bool have_prior = false;
+  double prior_const = 0;  // sum_i log sigma_i + P/2 log 2pi (NaN when any sigma<0, as tfp's log_prob)
+  // options
+  int opt_path = PYB_PATH_AUTO;
+  double opt_workspace_mb = 4096;
+  int64_t opt_chain_batch = 0;
+  int path_used = PYB_PATH_GENERIC;
+  int64_t kernel_launches = 0;
+  double last_device_ms = 0;
+  pyb::Workspace ws;
+  pyb::HmcState hmc;
+  pyb::SvgdState svgd;
+  void* tc = nullptr;     // tensor-core path state (tc_path.cu)
+  void* fused = nullptr;  // fused small path state
+};
+
+namespace pyb {
+inline void count_launch(pyb_handle* h, int n = 1) { h->kernel_launches += n; }
+
+// generic_mlp.cu
+// loss[S] (mean loss over the batch), grad[S,P] = scale * d(mean loss)/d(theta)  (grad may be null)
+void generic_eval(pyb_handle* h, const float* theta, int64_t S, const float* X, const int32_t* y_i,
+                  const float* y_f, int64_t N, float scale, float* loss_out, float* grad_out);
+// forward only: out [S, N, out_dim] (softmax applied when the last activation is softmax)
+void generic_forward(pyb_handle* h, const float* theta, int64_t S, const float* X, int64_t N, float* out);
+int64_t generic_chain_batch(pyb_handle* h, int64_t S, int64_t N, bool backward);
+
+// dispatcher (api.cu): picks generic / fused-small / tensor path
+void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out);
+
+// sampler.cu
+void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double m, int L, int sem, const float* q0);
+void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_diag* out);
+void hmc_eval(pyb_handle* h, const float* q, int64_t S, float* U, float* loss, float* grad);
+void hmc_flush_arena(pyb_handle* h);
+
+// svgd.cu
+void svgd_init(pyb_handle* h, int64_t S, int64_t offset, double lr, int sem, const double* p0);
+void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out);
+void svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int sem, float* phi, double* h_out);
+
+// predict.cu
+void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
+             float* mean, float* var, float* all);
+}  // namespace pyb

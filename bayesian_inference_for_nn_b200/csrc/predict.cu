@@ -1,0 +1,93 @@
+// predict.cu — posterior predictive for n weight samples at once.
+// Replaces BayesianModel.predict's Python loop (BayesianModel.py:106-129: n x {assign weights,
+// forward, NaN->0, accumulate}) and the np.var the Plotter takes over the per-draw outputs
+// (Plotter.py:244).  Weighted form = frequency-weighted exact expectation over the stored samples.
+#include "common.cuh"
+#include <algorithm>
+
+namespace pyb {
+
+// s1 += w*o ; s2 += w*o*o over the chunk's samples (NaN -> 0), optional copy to all_out
+__global__ void k_pred_accum(const float* out, int64_t n_chunk, int64_t elems, const float* w, double* s1, double* s2) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= elems) return;
+  double a = 0.0, b = 0.0;
+  for (int64_t k = 0; k < n_chunk; ++k) {
+    float o = out[k * elems + e];
+    if (o != o) o = 0.f;
+    double ww = w ? (double)w[k] : 1.0;
+    a += ww * (double)o;
+    b += ww * (double)o * (double)o;
+  }
+  s1[e] += a;
+  s2[e] += b;
+}
+__global__ void k_nan_to_zero(float* v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (v[i] != v[i]) v[i] = 0.f;
+}
+__global__ void k_pred_finish(const double* s1, const double* s2, double wsum, int64_t elems, float* mean, float* var) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= elems) return;
+  double m = s1[e] / wsum;
+  double v = s2[e] / wsum - m * m;
+  mean[e] = (float)m;
+  var[e] = (float)(v > 0.0 ? v : 0.0);
+}
+
+void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
+             float* mean, float* var, float* all) {
+  PYB_REQUIRE(n > 0 && Nt > 0, PYB_ERR_INVALID, "n and Nt must be > 0");
+  PYB_REQUIRE(W && x && mean && var, PYB_ERR_INVALID, "null pointer");
+  const Model& m = h->model;
+  const int64_t P = m.P, C = m.out_dim, elems = Nt * C;
+  DevBuf<float> dW, dx, dw, dout, dmean, dvar;
+  DevBuf<double> s1, s2;
+  dx.alloc(Nt * m.in_dim);
+  PYB_CUDA(cudaMemcpyAsync(dx.p, x, Nt * m.in_dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  double wsum = 0.0;
+  if (weight) {
+    for (int64_t i = 0; i < n; ++i) wsum += weight[i];
+    dw.alloc(n);
+    PYB_CUDA(cudaMemcpyAsync(dw.p, weight, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    wsum = (double)n;
+  }
+  PYB_REQUIRE(wsum > 0.0, PYB_ERR_INVALID, "weights must sum to a positive value");
+  // chunk of samples per pass: bounded by the generic workspace and a 512 MiB output buffer
+  int64_t chunk = generic_chain_batch(h, n, Nt, false);
+  int64_t out_cap = (int64_t)((512ull << 20) / (sizeof(float) * (size_t)elems));
+  if (out_cap < 1) out_cap = 1;
+  chunk = std::min(chunk, out_cap);
+  dW.alloc(chunk * P);
+  dout.alloc(chunk * elems);
+  s1.alloc(elems); s2.alloc(elems); dmean.alloc(elems); dvar.alloc(elems);
+  PYB_CUDA(cudaMemsetAsync(s1.p, 0, elems * sizeof(double), h->stream));
+  PYB_CUDA(cudaMemsetAsync(s2.p, 0, elems * sizeof(double), h->stream));
+  PYB_CUDA(cudaEventRecord(h->ev0, h->stream));
+  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+    int64_t nb = std::min(chunk, n - i0);
+    PYB_CUDA(cudaMemcpyAsync(dW.p, W + i0 * P, nb * P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    generic_forward(h, dW.p, nb, dx.p, Nt, dout.p);
+    k_pred_accum<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(dout.p, nb, elems, weight ? dw.p + i0 : nullptr,
+                                                                         s1.p, s2.p);
+    count_launch(h);
+    if (all) {
+      k_nan_to_zero<<<(unsigned)std::min<int64_t>((nb * elems + 255) / 256, 4096), 256, 0, h->stream>>>(dout.p, nb * elems);
+      count_launch(h);
+      PYB_CUDA(cudaMemcpyAsync(all + i0 * elems, dout.p, nb * elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  k_pred_finish<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(s1.p, s2.p, wsum, elems, dmean.p, dvar.p);
+  count_launch(h);
+  PYB_CUDA(cudaEventRecord(h->ev1, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(mean, dmean.p, elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(var, dvar.p, elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+  float ms = 0.f;
+  PYB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_device_ms = ms;
+}
+
+}  // namespace pyb

@@ -1,0 +1,423 @@
+// svgd.cu — SVGD for S particles at once.
+//
+// REFERENCE_LIVE  (SVGD.step SVGD.py:84-141 + _svgd_gradients :54-68 + rbf_kernel :183-202):
+//   sequential Gauss-Seidel sweep; for particle i: g_i = grad of the minibatch MEAN loss (no prior,
+//   no N scaling, :110-112), K_ik = exp(-||x_i-x_k||^2) in float64 with gamma = 1,
+//   phi_i = ((sum_k K_ik) g_i + 2 sum_k K_ik (x_i - x_k)) / M in float32, legacy-Adam DESCENT on phi.
+//   g_i only depends on theta_i, which nobody else modifies before its turn, so all S gradients
+//   come from ONE batched evaluation; only the kernel row + Adam are sequential.
+// CANONICAL_MEDIAN (SVGD.baseline__kernel SVGD.py:165-181; north_star's formula): Jacobi update,
+//   d2 over all pairs, h^2 = 0.5 median(d2)/log(M+1) with the median over all M*M entries (exact
+//   radix select, mean of the two middle order statistics), K = exp(-d2/2h^2),
+//   phi = (K grad_logp + (-K X + X rowsum K)/h^2)/M, Adam ascent.
+//
+// Sharding: the kernels take the global particle matrix [S_tot, P] and a local row range, so the
+// same code serves one GPU (row range = everything) and the all-gathered multi-GPU layout.
+#include "common.cuh"
+#include <math.h>
+#include <algorithm>
+
+namespace pyb {
+
+__global__ void k_svgd_init(float* theta, const double* p0, const float* mu, const float* sigma, int64_t P,
+                            uint64_t seed, int64_t offset) {
+  int64_t s = blockIdx.y;
+  int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (base >= P) return;
+  float z[4];
+  if (p0) {
+    for (int j = 0; j < 4; ++j) z[j] = (base + j < P) ? (float)p0[s * P + base + j] : 0.f;
+  } else {
+    philox_normal4((uint32_t)(base >> 2), (uint32_t)(offset + s), 0u, STREAM_INIT, seed, z);
+    for (int j = 0; j < 4; ++j)
+      if (base + j < P) z[j] = mu[base + j] + sigma[base + j] * z[j];  // one prior draw per element (SVGD.py:150-155)
+  }
+  for (int j = 0; j < 4; ++j)
+    if (base + j < P) theta[s * P + base + j] = z[j];
+}
+
+__global__ void k_gather_rows(const float* X, const int32_t* y_i, const float* y_f, const int32_t* idx, int64_t B,
+                              int D, int C, float* Xb, int32_t* yb_i, float* yb_f) {
+  int64_t b = blockIdx.x;
+  int64_t r = idx[b];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) Xb[b * D + d] = X[r * D + d];
+  if (y_i && threadIdx.x == 0) yb_i[b] = y_i[r];
+  if (y_f)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) yb_f[b * C + c] = y_f[r * C + c];
+}
+
+// ---- live sweep ---------------------------------------------------------------------------
+// Krow[k] = exp(-gamma * ||x_i - x_k||^2), float64; one block per k
+__global__ void k_live_row(const float* theta, int64_t P, int i, double gamma, double* Krow) {
+  __shared__ double scratch[32];
+  int k = blockIdx.x;
+  const float* xi = theta + (int64_t)i * P;
+  const float* xk = theta + (int64_t)k * P;
+  double a = 0.0;
+  for (int64_t e = threadIdx.x; e < P; e += blockDim.x) {
+    double d = (double)xi[e] - (double)xk[e];
+    a += d * d;
+  }
+  double t = block_sum<double>(a, scratch);
+  if (threadIdx.x == 0) Krow[k] = exp(-gamma * t);
+}
+
+__device__ inline float adam_update(float th, float g, float& m, float& v, float lr_t, float b1, float b2, float eh) {
+  m = b1 * m + (1.0f - b1) * g;
+  v = b2 * v + (1.0f - b2) * g * g;
+  return th - lr_t * m / (sqrtf(v) + eh);
+}
+
+// phi_i[e] = (wsum*g_i[e] + 2 gamma sum_k K_ik (x_i[e]-x_k[e])) / M ; Adam descent on particle i
+__global__ void k_live_update(float* theta, const float* g, float* am, float* av, float* phi_out, int64_t P,
+                              int S, int i, double gamma, const double* Krow, float lr_t) {
+  __shared__ double Ks[1024];
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double xi = (e < P) ? (double)theta[(int64_t)i * P + e] : 0.0;
+  double acc = 0.0;
+  float wsum = 0.f;
+  for (int k0 = 0; k0 < S; k0 += 1024) {
+    int n = min(1024, S - k0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) Ks[k] = Krow[k0 + k];
+    __syncthreads();
+    if (e < P)
+      for (int k = 0; k < n; ++k) acc += Ks[k] * (xi - (double)theta[(int64_t)(k0 + k) * P + e]);
+    for (int k = 0; k < n; ++k) wsum += (float)Ks[k];
+  }
+  if (e < P) {
+    int64_t o = (int64_t)i * P + e;
+    float gk = (float)(2.0 * gamma * acc);
+    float phi = (wsum * g[o] + gk) / (float)S;
+    if (phi_out) phi_out[o] = phi;
+    theta[o] = adam_update(theta[o], phi, am[o], av[o], lr_t, 0.9f, 0.999f, 1e-7f);
+  }
+}
+
+// ---- canonical (Jacobi) -------------------------------------------------------------------
+// d2[i][j] for local rows i in [r0, r0+Sl), all j in [0, St): direct difference form in float64
+// (what scipy pdist computes), 16x16 output tile per block, P streamed through shared memory.
+__global__ void __launch_bounds__(256) k_gram_d2(const float* X, int64_t P, int r0, int Sl, int St, double* d2) {
+  __shared__ float xi[16][65], xj[16][65];
+  int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  int i = blockIdx.y * 16 + ti, j = blockIdx.x * 16 + tj;
+  double acc = 0.0;
+  for (int64_t e0 = 0; e0 < P; e0 += 64) {
+    for (int t = threadIdx.x; t < 16 * 64; t += 256) {
+      int r = t >> 6, c = t & 63;
+      int gi = blockIdx.y * 16 + r, gj = blockIdx.x * 16 + r;
+      xi[r][c] = (gi < Sl && e0 + c < P) ? X[(int64_t)(r0 + gi) * P + e0 + c] : 0.f;
+      xj[r][c] = (gj < St && e0 + c < P) ? X[(int64_t)gj * P + e0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      double d = (double)xi[ti][c] - (double)xj[tj][c];
+      acc += d * d;
+    }
+    __syncthreads();
+  }
+  if (i < Sl && j < St) d2[(int64_t)i * St + j] = acc;
+}
+
+// radix select over the bit patterns of non-negative doubles (monotone as uint64)
+struct SelectState { unsigned long long prefix, mask, k; };
+__global__ void k_select_hist(const double* v, int64_t n, const SelectState* st, int shift, unsigned long long* hist) {
+  __shared__ unsigned int h[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) h[t] = 0;
+  __syncthreads();
+  unsigned long long prefix = st->prefix, mask = st->mask;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+    if ((b & mask) == prefix) atomicAdd(&h[(b >> shift) & 0xff], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 256; t += blockDim.x)
+    if (h[t]) atomicAdd(&hist[t], (unsigned long long)h[t]);
+}
+__global__ void k_select_pick(SelectState* st, int shift, unsigned long long* hist) {
+  if (threadIdx.x == 0) {
+    unsigned long long k = st->k, c = 0;
+    int b = 0;
+    for (; b < 256; ++b) {
+      if (c + hist[b] > k) break;
+      c += hist[b];
+    }
+    if (b > 255) b = 255;
+    st->k = k - c;
+    st->prefix |= ((unsigned long long)b) << shift;
+    st->mask |= 0xffull << shift;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) hist[t] = 0;
+}
+// bandwidth from the two middle order statistics: h2 = 0.5*median/log(St+1)
+__global__ void k_bandwidth(const SelectState* a, const SelectState* b, int St, double* h2_out) {
+  double lo = __longlong_as_double((long long)a->prefix), hi = __longlong_as_double((long long)b->prefix);
+  double med = 0.5 * (lo + hi);
+  h2_out[0] = 0.5 * med / log((double)St + 1.0);
+  h2_out[1] = med;
+}
+
+// K = exp(-d2/(2 h2)) in place; rowsum per local row (one block per row)
+__global__ void k_kernel_rowsum(double* d2, int St, const double* h2, double* rowsum) {
+  __shared__ double scratch[32];
+  int i = blockIdx.x;
+  double inv = 1.0 / (2.0 * h2[0]);
+  double a = 0.0;
+  for (int j = threadIdx.x; j < St; j += blockDim.x) {
+    double k = exp(-d2[(int64_t)i * St + j] * inv);
+    d2[(int64_t)i * St + j] = k;
+    a += k;
+  }
+  double t = block_sum<double>(a, scratch);
+  if (threadIdx.x == 0) rowsum[i] = t;
+}
+
+// phi[i][e] = ( sum_j K[i][j] (G[j][e] - X[j][e]/h2) + X[i][e] rowsum[i]/h2 ) / St     (float64 accumulate)
+__global__ void __launch_bounds__(256) k_phi_canonical(const double* K, const float* X, const float* G, int64_t P,
+                                                        int r0, int Sl, int St, const double* h2,
+                                                        const double* rowsum, float* phi) {
+  __shared__ double Ks[8][128];
+  int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  int i0 = blockIdx.y * 8;
+  double inv_h2 = 1.0 / h2[0];
+  double acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+  for (int j0 = 0; j0 < St; j0 += 128) {
+    int n = min(128, St - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 8 * 128; t += 256) {
+      int r = t >> 7, c = t & 127;
+      Ks[r][c] = (i0 + r < Sl && c < n) ? K[(int64_t)(i0 + r) * St + j0 + c] : 0.0;
+    }
+    __syncthreads();
+    if (e < P)
+      for (int c = 0; c < n; ++c) {
+        int64_t o = (int64_t)(j0 + c) * P + e;
+        double y = (double)G[o] - (double)X[o] * inv_h2;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] += Ks[r][c] * y;
+      }
+  }
+  if (e < P)
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (i0 + r < Sl) {
+        double xi = (double)X[(int64_t)(r0 + i0 + r) * P + e];
+        phi[(int64_t)(i0 + r) * P + e] = (float)((acc[r] + xi * rowsum[i0 + r] * inv_h2) / (double)St);
+      }
+}
+
+// live-formula phi evaluated Jacobi-style for every row (parity hook): gamma fixed, float64 kernel
+__global__ void k_kernel_fixed_rowsum(double* d2, int St, double gamma, double* rowsum) {
+  __shared__ double scratch[32];
+  int i = blockIdx.x;
+  double a = 0.0;
+  for (int j = threadIdx.x; j < St; j += blockDim.x) {
+    double k = exp(-gamma * d2[(int64_t)i * St + j]);
+    d2[(int64_t)i * St + j] = k;
+    a += (double)(float)k;
+  }
+  double t = block_sum<double>(a, scratch);
+  if (threadIdx.x == 0) rowsum[i] = t;
+}
+__global__ void __launch_bounds__(256) k_phi_live_all(const double* K, const float* X, const float* G, int64_t P,
+                                                       int S, double gamma, const double* rowsum, float* phi) {
+  int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  int i = blockIdx.y;
+  if (e >= P) return;
+  double xi = (double)X[(int64_t)i * P + e], acc = 0.0;
+  for (int k = 0; k < S; ++k) acc += K[(int64_t)i * S + k] * (xi - (double)X[(int64_t)k * P + e]);
+  float gk = (float)(2.0 * gamma * acc);
+  phi[(int64_t)i * P + e] = ((float)rowsum[i] * G[(int64_t)i * P + e] + gk) / (float)S;
+}
+
+// glogp = -(g + (theta-mu)/sigma^2)   (g already scaled by n_train)
+__global__ void k_glogp(float* g, const float* theta, const float* mu, const float* inv_var, int64_t P) {
+  int64_t s = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t o = s * P + i;
+    g[o] = -(g[o] + (theta[o] - mu[i]) * inv_var[i]);
+  }
+}
+
+__global__ void k_adam_all(float* theta, const float* phi, float* am, float* av, int64_t n, float sign, float lr_t) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
+    theta[o] = adam_update(theta[o], sign * phi[o], am[o], av[o], lr_t, 0.9f, 0.999f, 1e-7f);
+}
+
+__global__ void k_mean_float(const float* v, int64_t n, double* out) {
+  __shared__ double scratch[32];
+  double a = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += (double)v[i];
+  double t = block_sum<double>(a, scratch);
+  if (threadIdx.x == 0) out[0] = t / (double)n;
+}
+
+// ------------------------------------------------------------------------------------------
+static double adam_lr_t(double lr, int64_t t) {
+  return lr * sqrt(1.0 - pow(0.999, (double)t)) / (1.0 - pow(0.9, (double)t));
+}
+
+// exact median bandwidth of d2 [n] (device, float64) -> h2 (device double[2] = {h2, median})
+static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int St, double* h2_dev) {
+  SvgdState& sc = h->svgd;
+  sc.sel.alloc(6);
+  sc.hist.alloc(256);
+  SelectState init[2];
+  init[0].prefix = 0; init[0].mask = 0; init[0].k = (unsigned long long)((n - 1) / 2);
+  init[1].prefix = 0; init[1].mask = 0; init[1].k = (unsigned long long)(n / 2);
+  PYB_CUDA(cudaMemcpyAsync(sc.sel.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemsetAsync(sc.hist.p, 0, 256 * sizeof(unsigned long long), h->stream));
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)h->sm_count);
+  for (int w = 0; w < 2; ++w)
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      k_select_hist<<<blocks, 256, 0, h->stream>>>(d2, n, reinterpret_cast<SelectState*>(sc.sel.p) + w, shift, sc.hist.p);
+      k_select_pick<<<1, 256, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p) + w, shift, sc.hist.p);
+      count_launch(h, 2);
+    }
+  k_bandwidth<<<1, 1, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p), reinterpret_cast<SelectState*>(sc.sel.p) + 1, St, h2_dev);
+  count_launch(h);
+}
+
+// phi for local rows [r0, r0+Sl) of the global particle matrix X_all [St,P] with gradients G_all
+static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all, int r0, int Sl, int St,
+                          float* phi_local, double* h_host_out) {
+  SvgdState& sv = h->svgd;
+  SvgdState& sc = h->svgd;
+  const int64_t P = h->model.P;
+  PYB_REQUIRE(Sl == St, PYB_ERR_UNSUPPORTED, "sharded median bandwidth needs the comm path (not wired in this build)");
+  sv.d2.alloc((size_t)Sl * St);
+  sv.rowsum.alloc(Sl);
+  sc.h2.alloc(2);
+  dim3 g1((St + 15) / 16, (Sl + 15) / 16);
+  k_gram_d2<<<g1, 256, 0, h->stream>>>(X_all, P, r0, Sl, St, sv.d2.p);
+  count_launch(h);
+  median_bandwidth(h, sv.d2.p, (int64_t)Sl * St, St, sc.h2.p);
+  k_kernel_rowsum<<<Sl, 256, 0, h->stream>>>(sv.d2.p, St, sc.h2.p, sv.rowsum.p);
+  dim3 g2((unsigned)((P + 255) / 256), (Sl + 7) / 8);
+  k_phi_canonical<<<g2, 256, 0, h->stream>>>(sv.d2.p, X_all, G_all, P, r0, Sl, St, sc.h2.p, sv.rowsum.p, phi_local);
+  count_launch(h, 2);
+  if (h_host_out) {
+    double v[2];
+    PYB_CUDA(cudaMemcpyAsync(v, sc.h2.p, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    PYB_CUDA(cudaStreamSynchronize(h->stream));
+    *h_host_out = sqrt(v[0]);
+  }
+}
+
+void svgd_init(pyb_handle* h, int64_t S, int64_t offset, double lr, int sem, const double* p0) {
+  PYB_REQUIRE(h->have_data && h->have_prior, PYB_ERR_STATE, "dataset and prior must be set first");
+  PYB_REQUIRE(S > 0 && S <= 65535, PYB_ERR_INVALID, "S must be in [1, 65535]");
+  PYB_REQUIRE(sem == PYB_SVGD_REFERENCE_LIVE || sem == PYB_SVGD_CANONICAL_MEDIAN, PYB_ERR_INVALID, "bad semantics");
+  SvgdState& sv = h->svgd;
+  const int64_t P = h->model.P;
+  sv.S = S; sv.offset = offset; sv.lr = lr; sv.semantics = sem; sv.t = 0;
+  sv.theta.alloc(S * P); sv.g.alloc(S * P); sv.adam_m.alloc(S * P); sv.adam_v.alloc(S * P); sv.phi.alloc(S * P);
+  sv.loss.alloc(S);
+  PYB_CUDA(cudaMemsetAsync(sv.adam_m.p, 0, S * P * sizeof(float), h->stream));
+  PYB_CUDA(cudaMemsetAsync(sv.adam_v.p, 0, S * P * sizeof(float), h->stream));
+  DevBuf<double> tmp;
+  if (p0) {
+    tmp.alloc(S * P);
+    PYB_CUDA(cudaMemcpyAsync(tmp.p, p0, S * P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  dim3 grid((unsigned)((P + 1023) / 1024), (unsigned)S);
+  k_svgd_init<<<grid, 256, 0, h->stream>>>(sv.theta.p, p0 ? tmp.p : nullptr, h->mu.p, h->sigma.p, P, h->seed, offset);
+  count_launch(h);
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+  sv.inited = true;
+}
+
+void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
+  SvgdState& sv = h->svgd;
+  PYB_REQUIRE(sv.inited, PYB_ERR_STATE, "pyb_svgd_init must be called first");
+  SvgdState& sc = h->svgd;
+  const Model& m = h->model;
+  const int64_t P = m.P, S = sv.S;
+  const float* Xb = h->X.p;
+  const int32_t* yb_i = h->y_i.p;
+  const float* yb_f = h->y_f.p;
+  int64_t Nb = h->N;
+  PYB_CUDA(cudaEventRecord(h->ev0, h->stream));
+  if (idx) {
+    PYB_REQUIRE(B > 0, PYB_ERR_INVALID, "B must be > 0 with batch_idx");
+    sv.idx.alloc(B);
+    sv.Xb.alloc(B * m.in_dim);
+    if (h->loss_kind == PYB_LOSS_SPARSE_CE) sv.yb_i.alloc(B); else sv.yb_f.alloc(B * m.out_dim);
+    PYB_CUDA(cudaMemcpyAsync(sv.idx.p, idx, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    k_gather_rows<<<(unsigned)B, 128, 0, h->stream>>>(h->X.p, h->loss_kind == PYB_LOSS_SPARSE_CE ? h->y_i.p : nullptr,
+                                                      h->loss_kind == PYB_LOSS_MSE ? h->y_f.p : nullptr, sv.idx.p, B,
+                                                      m.in_dim, m.out_dim, sv.Xb.p, sv.yb_i.p, sv.yb_f.p);
+    count_launch(h);
+    Xb = sv.Xb.p; yb_i = sv.yb_i.p; yb_f = sv.yb_f.p; Nb = B;
+  }
+  sv.t += 1;
+  const float lr_t = (float)adam_lr_t(sv.lr, sv.t);
+  const float scale = (sv.semantics == PYB_SVGD_REFERENCE_LIVE) ? 1.0f : (float)h->n_train;
+  generic_eval(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
+  if (sv.semantics == PYB_SVGD_REFERENCE_LIVE) {
+    sc.Krow.alloc(S);
+    for (int i = 0; i < (int)S; ++i) {
+      k_live_row<<<(unsigned)S, 256, 0, h->stream>>>(sv.theta.p, P, i, 1.0, sc.Krow.p);
+      k_live_update<<<(unsigned)((P + 255) / 256), 256, 0, h->stream>>>(sv.theta.p, sv.g.p, sv.adam_m.p, sv.adam_v.p,
+                                                                        sv.phi.p, P, (int)S, i, 1.0, sc.Krow.p, lr_t);
+      count_launch(h, 2);
+    }
+  } else {
+    dim3 gg((unsigned)std::min<int64_t>((P + 255) / 256, 1024), (unsigned)S);
+    k_glogp<<<gg, 256, 0, h->stream>>>(sv.g.p, sv.theta.p, h->mu.p, h->inv_var.p, P);
+    count_launch(h);
+    phi_canonical(h, sv.theta.p, sv.g.p, 0, (int)S, (int)S, sv.phi.p, nullptr);
+    int blocks = (int)std::min<int64_t>((S * P + 255) / 256, 8 * (int64_t)h->sm_count);
+    k_adam_all<<<blocks, 256, 0, h->stream>>>(sv.theta.p, sv.phi.p, sv.adam_m.p, sv.adam_v.p, S * P, -1.0f, lr_t);
+    count_launch(h);
+  }
+  sc.mean_loss.alloc(1);
+  k_mean_float<<<1, 256, 0, h->stream>>>(sv.loss.p, S, sc.mean_loss.p);
+  count_launch(h);
+  PYB_CUDA(cudaEventRecord(h->ev1, h->stream));
+  double ml = 0.0;
+  PYB_CUDA(cudaMemcpyAsync(&ml, sc.mean_loss.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+  float ms = 0.f;
+  PYB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_device_ms = ms;
+  if (loss_out) *loss_out = ml;
+}
+
+void svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int sem, float* phi, double* h_out) {
+  PYB_REQUIRE(S > 0 && S <= 65535, PYB_ERR_INVALID, "S must be in [1, 65535]");
+  const int64_t P = h->model.P;
+  SvgdState& sv = h->svgd;
+  DevBuf<double> dX64;
+  DevBuf<float> dX, dG, dphi;
+  dX64.alloc(S * P); dX.alloc(S * P); dG.alloc(S * P); dphi.alloc(S * P);
+  PYB_CUDA(cudaMemcpyAsync(dX64.p, X, S * P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(dG.p, G, S * P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((unsigned)((P + 1023) / 1024), (unsigned)S);
+  k_svgd_init<<<grid, 256, 0, h->stream>>>(dX.p, dX64.p, nullptr, nullptr, P, 0, 0);  // f64 -> f32 (SVGD.py:62-63,101)
+  count_launch(h);
+  if (sem == PYB_SVGD_CANONICAL_MEDIAN) {
+    phi_canonical(h, dX.p, dG.p, 0, (int)S, (int)S, dphi.p, h_out);
+  } else {
+    sv.d2.alloc((size_t)S * S);
+    sv.rowsum.alloc(S);
+    dim3 g1((unsigned)((S + 15) / 16), (unsigned)((S + 15) / 16));
+    k_gram_d2<<<g1, 256, 0, h->stream>>>(dX.p, P, 0, (int)S, (int)S, sv.d2.p);
+    k_kernel_fixed_rowsum<<<(unsigned)S, 256, 0, h->stream>>>(sv.d2.p, (int)S, 1.0, sv.rowsum.p);
+    dim3 g2((unsigned)((P + 255) / 256), (unsigned)S);
+    k_phi_live_all<<<g2, 256, 0, h->stream>>>(sv.d2.p, dX.p, dG.p, P, (int)S, 1.0, sv.rowsum.p, dphi.p);
+    count_launch(h, 3);
+    if (h_out) *h_out = 1.0;
+  }
+  PYB_CUDA(cudaMemcpyAsync(phi, dphi.p, S * P * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+}
+
+}  // namespace pyb

@@ -1,0 +1,190 @@
+"""Thin Python wrapper over one libpyesian_b200 handle (one GPU).
+
+Host arrays are NumPy; device-resident inputs arrive through DLPack (see ``tensors.py``).  Every
+method is a single C-ABI call plus argument marshalling — no arithmetic happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .keras_json import ModelSpec
+from .tensors import ingest
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(a.shape)))
+    return a
+
+
+class Engine:
+    def __init__(self, spec: ModelSpec, device: int = 0, seed: int = 0):
+        self.lib = _lib.load()
+        self.spec = spec
+        n = len(spec.dense)
+        self._units = (C.c_int32 * n)(*[d.units for d in spec.dense])
+        self._acts = (C.c_int32 * n)(*[d.activation for d in spec.dense])
+        self._bias = (C.c_int32 * n)(*[1 if d.use_bias else 0 for d in spec.dense])
+        desc = _lib.ModelDesc(n, spec.in_dim, self._units, self._acts, self._bias)
+        h = C.c_void_p()
+        check(self.lib.pyb_create(C.byref(desc), int(device), C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(h)))
+        self.h = h
+        p = C.c_int64()
+        check(self.lib.pyb_param_count(self.h, C.byref(p)))
+        self.P = p.value
+        assert self.P == spec.n_params, (self.P, spec.n_params)
+        self.S = 0
+        self.N = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.pyb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- options / info
+    def set_option(self, key: str, value: float):
+        check(self.lib.pyb_set_option(self.h, key.encode(), float(value)))
+
+    def info(self, key: str) -> float:
+        v = C.c_double()
+        check(self.lib.pyb_get_info(self.h, key.encode(), C.byref(v)))
+        return v.value
+
+    # ---- inputs
+    def set_dataset(self, X, y, loss_kind: int, n_train: int = 0):
+        """X [N, in_dim] (NumPy / DLPack / tf.Tensor), y int labels [N] or float [N, out_dim]."""
+        Xa, xmem, xptr = ingest(X, np.float32)
+        ydt = np.int32 if loss_kind == _lib.LOSS_SPARSE_CE else np.float32
+        ya, ymem, yptr = ingest(y, ydt)
+        N = int(Xa.shape[0])
+        if int(np.prod(Xa.shape[1:])) != self.spec.in_dim:
+            raise ValueError("X has %d features per row, the model expects %d" % (int(np.prod(Xa.shape[1:])), self.spec.in_dim))
+        if int(ya.shape[0]) != N:
+            raise ValueError("X and y disagree on the number of rows")
+        if xmem != ymem:   # mixed residency: bring y to where X is by staging through the host
+            raise ValueError("X and y must both be host or both be device tensors")
+        check(self.lib.pyb_set_dataset(self.h, xptr, N, yptr, int(loss_kind), int(xmem), int(n_train)))
+        self.N = N
+
+    def set_prior(self, mean, sigma, form: int):
+        m = _f32(np.atleast_1d(mean).reshape(-1))
+        s = _f32(np.atleast_1d(sigma).reshape(-1))
+        check(self.lib.pyb_set_prior_gaussian(self.h, _ptr(m), _ptr(s), int(form)))
+
+    # ---- HMC
+    def hmc_init(self, S, eps, m, L, semantics=_lib.HMC_REFERENCE, q0=None, chain_offset=0):
+        q0a = None if q0 is None else _f32(q0, (S, self.P))
+        check(self.lib.pyb_hmc_init(self.h, int(S), int(chain_offset), float(eps), float(m), int(L), int(semantics),
+                                    _ptr(q0a)))
+        self.S = int(S)
+
+    def hmc_inject(self, p=None, u=None):
+        pa = None if p is None else _f32(p, (self.S, self.P))
+        ua = None if u is None else _f32(u, (self.S,))
+        check(self.lib.pyb_hmc_inject(self.h, _ptr(pa), _ptr(ua)))
+
+    def hmc_run(self, n_iters, burning=False, sampling=True):
+        d = _lib.HmcDiag()
+        check(self.lib.pyb_hmc_run(self.h, int(n_iters), int(bool(burning)), int(bool(sampling)), C.byref(d)))
+        return {k: getattr(d, k) for k, _ in _lib.HmcDiag._fields_}
+
+    def hmc_eval(self, q, want_grad=True):
+        q = _f32(q)
+        S = q.shape[0]
+        U = np.empty(S, np.float32)
+        loss = np.empty(S, np.float32)
+        g = np.empty((S, self.P), np.float32) if want_grad else None
+        check(self.lib.pyb_hmc_eval(self.h, _ptr(q), S, _ptr(U), _ptr(loss), _ptr(g)))
+        return U, loss, g
+
+    def hmc_state(self):
+        q = np.empty((self.S, self.P), np.float32)
+        p = np.empty((self.S, self.P), np.float32)
+        check(self.lib.pyb_hmc_get_state(self.h, _ptr(q), _ptr(p)))
+        return q, p
+
+    def hmc_last(self):
+        S = self.S
+        f = lambda: np.empty(S, np.float32)
+        U0, K0, U1, K1, la, loss = f(), f(), f(), f(), f(), f()
+        acc = np.empty(S, np.int32)
+        check(self.lib.pyb_hmc_last(self.h, _ptr(U0), _ptr(K0), _ptr(U1), _ptr(K1), _ptr(la), _ptr(acc), _ptr(loss)))
+        return dict(U0=U0, K0=K0, U1=U1, K1=K1, log_alpha=la, accept=acc.astype(bool), loss=loss)
+
+    def hmc_reset_samples(self):
+        check(self.lib.pyb_hmc_reset_samples(self.h))
+
+    def hmc_samples(self):
+        n = C.c_int64()
+        check(self.lib.pyb_hmc_sample_count(self.h, C.byref(n)))
+        n = n.value
+        s = np.empty((n, self.P), np.float32)
+        f = np.empty(n, np.int32)
+        c = np.empty(n, np.int32)
+        if n:
+            check(self.lib.pyb_hmc_samples(self.h, _ptr(s), _ptr(f), _ptr(c)))
+        return s, f, c
+
+    # ---- SVGD
+    def svgd_init(self, S, lr, semantics=_lib.SVGD_REFERENCE_LIVE, particles0=None, offset=0):
+        p0 = None if particles0 is None else np.ascontiguousarray(particles0, dtype=np.float64)
+        if p0 is not None and p0.shape != (S, self.P):
+            raise ValueError("particles0 must be [S, P]")
+        check(self.lib.pyb_svgd_init(self.h, int(S), int(offset), float(lr), int(semantics), _ptr(p0)))
+        self.S = int(S)
+
+    def svgd_step(self, batch_idx=None):
+        loss = C.c_double()
+        if batch_idx is None:
+            check(self.lib.pyb_svgd_step(self.h, None, 0, C.byref(loss)))
+        else:
+            idx = np.ascontiguousarray(batch_idx, dtype=np.int32)
+            check(self.lib.pyb_svgd_step(self.h, _ptr(idx), int(idx.shape[0]), C.byref(loss)))
+        return loss.value
+
+    def svgd_phi(self, X, G, semantics):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        G = _f32(G, X.shape)
+        phi = np.empty(X.shape, np.float32)
+        h = C.c_double()
+        check(self.lib.pyb_svgd_phi(self.h, _ptr(X), _ptr(G), int(X.shape[0]), int(semantics), _ptr(phi), C.byref(h)))
+        return phi, h.value
+
+    def svgd_particles(self):
+        out = np.empty((self.S, self.P), np.float64)
+        check(self.lib.pyb_svgd_get_particles(self.h, _ptr(out)))
+        return out
+
+    # ---- predictive
+    def predict(self, W, x, weights=None, want_all=False):
+        W = _f32(W)
+        if W.ndim != 2 or W.shape[1] != self.P:
+            raise ValueError("W must be [n, P]")
+        x = _f32(x)
+        x = x.reshape(x.shape[0], -1)
+        if x.shape[1] != self.spec.in_dim:
+            raise ValueError("x has %d features per row, the model expects %d" % (x.shape[1], self.spec.in_dim))
+        n, Nt, Cc = W.shape[0], x.shape[0], self.spec.out_dim
+        w = None if weights is None else _f32(weights, (n,))
+        mean = np.empty((Nt, Cc), np.float32)
+        var = np.empty((Nt, Cc), np.float32)
+        allo = np.empty((n, Nt, Cc), np.float32) if want_all else None
+        check(self.lib.pyb_predict(self.h, _ptr(W), n, _ptr(w), _ptr(x), Nt, _ptr(mean), _ptr(var), _ptr(allo)))
+        return mean, var, allo

@@ -1,0 +1,176 @@
+"""BayesianModel — posterior container whose ``predict`` runs on the device.
+
+Mirrors Pyesian/nn/BayesianModel.py:10-203: ``apply_distribution`` with the same bounds errors and
+interval insertion (:25-48), ``predict(x, nb_samples)`` returning ``(list_of_per_draw_outputs, mean)``
+(:106-129), ``sample_model`` (:79-89), and the ``store``/``load`` folder format (:132-203:
+``config.json``, ``layers_config.txt``, ``distribution{i}/``).
+
+What changed underneath: the reference loops ``nb_samples`` times {draw a weight vector, assign it
+variable by variable, eager forward, NaN->0}.  Here the draws are made first (same ``Sampled.sample``
+semantics), duplicates are collapsed into integer weights, and ONE ``pyb_predict`` call evaluates all
+distinct weight vectors on the GPU and reduces mean/variance there.  ``mode="exact"`` replaces the
+Monte-Carlo draw by the frequency-weighted expectation over every stored sample.
+"""
+import os
+import shutil
+
+import numpy as np
+
+from ..distributions import Distribution, Sampled
+from ..engine import Engine
+from ..keras_json import parse_model_json
+from ..tensors import to_numpy
+
+
+class ParticleModel:
+    """One weight vector of the model: what ``sample_model()`` / ``SVGD.result()`` hand out in place
+    of a Keras model.  ``predict``/``__call__`` run the forward pass on the GPU."""
+
+    def __init__(self, owner: "BayesianModel", weights: np.ndarray):
+        self._owner = owner
+        self._w = np.ascontiguousarray(weights, dtype=np.float32).reshape(1, -1)
+
+    def get_weights(self):
+        spec = self._owner._spec
+        return [self._w[0, off:off + int(np.prod(shape))].reshape(shape).copy() for (_, _, off, shape) in spec.variables()]
+
+    def flat_weights(self):
+        return self._w[0].copy()
+
+    def predict(self, x, **_):
+        mean, _, _ = self._owner._engine_for_predict().predict(self._w, to_numpy(x, np.float32))
+        return mean
+
+    __call__ = predict
+
+
+class BayesianModel:
+    def __init__(self, model_config: str, device: int = 0):
+        self._model_config = model_config
+        self._spec = parse_model_json(model_config)
+        self._n_layers = self._spec.n_keras_layers
+        self._layers_dtbn_intervals = []
+        self._distributions = []
+        self._device = device
+        self._engine = None
+        self.last_variance = None
+
+    # ---- distributions (BayesianModel.py:25-61) -------------------------------------------
+    def apply_distribution(self, distribution: Distribution, start_layer: int, end_layer: int):
+        if start_layer > end_layer:
+            raise ValueError("starting_layer must be less than end_layer")
+        elif start_layer < 0 or end_layer >= self._n_layers:
+            raise ValueError("out of bounds")
+        interval = [start_layer, end_layer]
+        if len(self._layers_dtbn_intervals) == 0:
+            self._layers_dtbn_intervals.append(interval)
+            self._distributions.append(distribution)
+            return
+        for i in range(len(self._layers_dtbn_intervals)):
+            if start_layer > self._layers_dtbn_intervals[i][0]:
+                self._layers_dtbn_intervals = (self._layers_dtbn_intervals[:i + 1] + [interval]
+                                               + self._layers_dtbn_intervals[i + 1:])
+                self._distributions = self._distributions[:i + 1] + [distribution] + self._distributions[i + 1:]
+                break
+
+    def apply_distributions_layers(self, layer_list, dtbn_list):
+        self._layers_dtbn_intervals = layer_list
+        self._distributions = dtbn_list
+
+    # ---- weight draws ---------------------------------------------------------------------
+    def _engine_for_predict(self) -> Engine:
+        if self._engine is None:
+            self._engine = Engine(self._spec, device=self._device)
+        return self._engine
+
+    def _draw_flat(self):
+        """One flat [P] weight vector assembled from every interval's distribution
+        (``_sample_weights`` BayesianModel.py:63-77)."""
+        w = np.zeros(self._spec.n_params, np.float32)
+        for (start, end), dist in zip(self._layers_dtbn_intervals, self._distributions):
+            lo, hi = self._spec.layer_param_range(start, end)
+            v = to_numpy(dist.sample(), np.float32).reshape(-1)
+            w[lo:hi] = v[:hi - lo]
+        return w
+
+    def sample_model(self) -> ParticleModel:
+        return ParticleModel(self, self._draw_flat())
+
+    def sample_n_models(self, n):
+        return [self.sample_model() for _ in range(n)]
+
+    # ---- predictive -----------------------------------------------------------------------
+    def predict(self, x, nb_samples: int, y_true=None, loss_func=None, mode: str = "reference"):
+        """-> (list of nb_samples arrays [N,C], mean [N,C]).  ``self.last_variance`` holds the
+        population variance over the draws (what Plotter.regression_uncertainty takes with np.var)."""
+        x = to_numpy(x, np.float32)
+        x = x.reshape(x.shape[0], -1)
+        eng = self._engine_for_predict()
+        single = (len(self._distributions) == 1 and isinstance(self._distributions[0], Sampled)
+                  and self._spec.layer_param_range(*self._layers_dtbn_intervals[0]) == (0, self._spec.n_params))
+        if single and mode == "exact":
+            d = self._distributions[0]
+            mean, var, _ = eng.predict(d.samples, x, weights=np.asarray(d.frequencies, np.float32))
+            self.last_variance = var
+            return [mean], mean
+        if single:
+            d = self._distributions[0]
+            draws = np.fromiter((d.sample_index() for _ in range(nb_samples)), dtype=np.int64, count=nb_samples)
+            uniq, inverse, counts = np.unique(draws, return_inverse=True, return_counts=True)
+            mean, var, allo = eng.predict(d.samples[uniq], x, weights=counts.astype(np.float32), want_all=True)
+            self.last_variance = var
+            return [allo[i] for i in inverse], mean
+        W = np.stack([self._draw_flat() for _ in range(nb_samples)])
+        mean, var, allo = eng.predict(W, x, want_all=True)
+        self.last_variance = var
+        return [allo[i] for i in range(nb_samples)], mean
+
+    def uncertainty_mask(self, x, nb_samples, threshold, mode="reference"):
+        """max_c mean_c < threshold — the 'uncertainty area' of Plotter.py:71-72."""
+        _, mean = self.predict(x, nb_samples, mode=mode)
+        return mean.max(axis=-1) < threshold
+
+    # ---- persistence (BayesianModel.py:132-203) ---------------------------------------------
+    _REGISTRY = {"Sampled": Sampled}
+
+    @classmethod
+    def load(cls, model_path: str, custom_distribution_register=None) -> "BayesianModel":
+        reg = dict(cls._REGISTRY)
+        reg.update(custom_distribution_register or {})
+        with open(os.path.join(model_path, "config.json"), "r") as f:
+            bm = BayesianModel(f.read())
+        intervals = []
+        with open(os.path.join(model_path, "layers_config.txt"), "r") as f:
+            n = int(f.readline())
+            for _ in range(n):
+                intervals.append((f.readline()[:-1], int(f.readline()), int(f.readline())))
+        for i, (name, start, end) in enumerate(intervals):
+            if name not in reg:
+                raise ValueError("no loader registered for distribution %r" % name)
+            bm.apply_distribution(reg[name].load(os.path.join(model_path, "distribution%d" % i)), start, end)
+        return bm
+
+    def _empty_folder(self, path):
+        for name in os.listdir(path):
+            p = os.path.join(path, name)
+            try:
+                if os.path.isfile(p) or os.path.islink(p):
+                    os.unlink(p)
+                elif os.path.isdir(p):
+                    shutil.rmtree(p)
+            except Exception as e:
+                print("Failed to delete %s. Reason: %s" % (p, e))
+
+    def store(self, model_path: str):
+        if not os.path.exists(model_path):
+            os.makedirs(model_path)
+        self._empty_folder(model_path)
+        with open(os.path.join(model_path, "config.json"), "w") as f:
+            f.write(self._model_config)
+        with open(os.path.join(model_path, "layers_config.txt"), "w") as f:
+            f.write(str(len(self._layers_dtbn_intervals)) + "\n")
+            for (start, end), d in zip(self._layers_dtbn_intervals, self._distributions):
+                f.write(d.__class__.__name__ + "\n" + str(start) + "\n" + str(end) + "\n")
+        for i, d in enumerate(self._distributions):
+            os.mkdir(os.path.join(model_path, "distribution%d" % i))
+            d.store(os.path.join(model_path, "distribution%d" % i))

@@ -1,0 +1,112 @@
+"""SVGD — Stein variational gradient descent, all particles in one device batch.
+
+Drop-in for Pyesian/optimizers/SVGD.py:45-251.  Same surface: hyper-parameters ``batch_size, M, lr``
+(:220-225), ``compile(..., prior=...)`` (:223), generic ``train`` loop (Optimizer.py:94-137),
+``step()`` returning the mean minibatch loss over particles (:125,141), train/valid loss histories
+appended every 10 steps (:137-139), ``result()`` unpacking as ``(models, train_losses, valid_losses)``
+(:244-249) — the returned object is also usable as the ``BayesianModel`` north_star asks for
+(``result().predict(...)``, ``result().bayesian_model``).
+
+``semantics="reference"`` (default) is the live code path: sequential sweep, gamma = 1, one
+particle's gradient broadcast, legacy-Adam descent (:100-123).  ``semantics="canonical"`` is the
+median-heuristic Stein update of ``baseline__kernel`` (:165-181) applied Jacobi-style with the prior
+gradient included.  Minibatches: one shuffled pass per epoch without replacement, last
+batch partial (Optimizer.py:35-41, SVGD.py:91-95).
+"""
+import numpy as np
+
+from .. import _lib
+from ..distributions import Sampled
+from ..engine import Engine
+from ..keras_json import parse_model_json
+from ..nn import BayesianModel, ParticleModel
+from .Optimizer import Optimizer
+
+
+class SVGDResult(tuple):
+    """``(models, train_losses, valid_losses)`` that also answers as a BayesianModel."""
+
+    def __new__(cls, models, train_losses, valid_losses, bayesian_model):
+        obj = super().__new__(cls, (models, train_losses, valid_losses))
+        obj.bayesian_model = bayesian_model
+        return obj
+
+    def predict(self, x, nb_samples=None, **kw):
+        n = nb_samples if nb_samples is not None else len(self[0])
+        return self.bayesian_model.predict(x, n, **kw)
+
+    def store(self, path):
+        return self.bayesian_model.store(path)
+
+    def sample_model(self):
+        return self.bayesian_model.sample_model()
+
+
+class SVGD(Optimizer):
+    def __init__(self):
+        super().__init__()
+        self._step = 0
+        self._M = None
+        self.train_losses = []
+        self.valid_losses = []
+        self._engine = None
+        self._valid_engine = None
+
+    def compile_extra_components(self, **kwargs):
+        self._batch_size = int(self._hyperparameters.batch_size)
+        self._spec = parse_model_json(self._model_config)
+        self._prior = kwargs["prior"]
+        self._M = int(self._hyperparameters.M)
+        self._lr = self._hyperparameters.lr
+        sem = self._hp("semantics", "reference")
+        self._semantics = (_lib.SVGD_CANONICAL_MEDIAN if sem in ("canonical", _lib.SVGD_CANONICAL_MEDIAN)
+                           else _lib.SVGD_REFERENCE_LIVE)
+        self._rng = np.random.default_rng(self._hp("seed", None))
+        self._engine = Engine(self._spec, device=int(self._hp("device", 0)), seed=int(self._hp("seed", 0)))
+        x, y = self._dataset.training_arrays()
+        self._n_train = x.shape[0]
+        self._engine.set_dataset(x, y, self._dataset.loss_kind, n_train=self._n_train)
+        self._engine.set_prior(*self._prior.lower(self._spec))
+        self._engine.svgd_init(self._M, self._lr, self._semantics, particles0=kwargs.get("particles0"))
+        self._num_particles = self._spec.n_params
+        self._epoch_batches = iter(())
+
+    def _next_batch(self):
+        """shuffle(cardinality).batch(batch_size): restart the pass when exhausted (SVGD.py:91-95)."""
+        b = next(self._epoch_batches, None)
+        if b is None:
+            perm = self._rng.permutation(self._n_train).astype(np.int32)
+            self._epoch_batches = iter([perm[i:i + self._batch_size] for i in range(0, self._n_train, self._batch_size)])
+            b = next(self._epoch_batches)
+        return b
+
+    def _validation_loss(self):
+        """mean over particles of the loss on the whole validation split (SVGD.py:126-129)."""
+        if self._dataset.valid_size == 0:
+            return 0.0
+        if self._valid_engine is None:
+            self._valid_engine = Engine(self._spec, device=int(self._hp("device", 0)))
+            xv, yv = self._dataset.split_arrays("valid")
+            self._valid_engine.set_dataset(xv, yv, self._dataset.loss_kind)
+            self._valid_engine.set_prior(np.float32([0.0]), np.float32([1.0]), _lib.PRIOR_SCALAR)
+        _, loss, _ = self._valid_engine.hmc_eval(self._engine.svgd_particles().astype(np.float32), want_grad=False)
+        return float(loss.mean())
+
+    def step(self, save_document_path=None):
+        self._step += 1
+        total_loss = self._engine.svgd_step(self._next_batch())
+        if self._step % 10 == 0:
+            self.train_losses.append(total_loss)
+            self.valid_losses.append(self._validation_loss())
+        return total_loss
+
+    @property
+    def particles(self):
+        return self._engine.svgd_particles()
+
+    def result(self):
+        parts = self._engine.svgd_particles().astype(np.float32)
+        bm = BayesianModel(self._model_config, device=int(self._hp("device", 0)))
+        bm.apply_distribution(Sampled(parts, [1] * parts.shape[0]), 0, self._spec.n_keras_layers - 1)
+        models = [ParticleModel(bm, parts[i]) for i in range(parts.shape[0])]
+        return SVGDResult(models, self.train_losses, self.valid_losses, bm)

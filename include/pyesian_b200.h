@@ -1,0 +1,156 @@
+/* pyesian_b200.h — C ABI of libpyesian_b200.so
+ *
+ * B200-native (sm_100a) implementation of ONE hot path of leoelm/Bayesian_inference_for_NN
+ * ("Pyesian"): the particle-batched log-posterior forward/backward of a Keras Dense MLP over the
+ * whole dataset for S weight samples at once, fused with the HMC leapfrog / Hamiltonian /
+ * Metropolis update and the SVGD Stein step, plus the BayesianModel posterior predictive.
+ *
+ * The reference has no FFI layer of its own (it is pure Python on TensorFlow eager); the entry
+ * points below are what a ctypes binding inside the reference's optimizer classes would bind.
+ * Each one cites the reference code (path:line under the reference checkout) it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types, no exceptions across the boundary.
+ *   - every call returns 0 (PYB_OK) or a negative pyb_status; pyb_last_error() gives the message
+ *     (thread-local).
+ *   - the library owns all device memory behind the handle; caller-owned buffers are only read
+ *     or written for the duration of the call.  `mem` says whether a caller buffer is host or
+ *     device memory (device pointers come from DLPack capsules on the Python side).
+ *   - one handle = one GPU; a handle is not thread-safe; there is NO CPU fallback: without a
+ *     usable sm_100 device pyb_create fails with PYB_ERR_CUDA.
+ *   - flat parameter order everywhere = model.layers order -> (kernel [in,out] C-order, bias)
+ *     (HMC.py:178-183, SVGD.py:159-160,230-239, BayesianModel.py:73-77).
+ */
+#ifndef PYESIAN_B200_H
+#define PYESIAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYB_ABI_VERSION 1
+
+typedef enum {
+  PYB_OK = 0,
+  PYB_ERR_INVALID = -1,     /* bad argument */
+  PYB_ERR_CUDA = -2,        /* CUDA runtime/driver failure, or no sm_100 device */
+  PYB_ERR_STATE = -3,       /* call made in the wrong state (e.g. run before init) */
+  PYB_ERR_UNSUPPORTED = -4, /* model/loss combination outside the hot path */
+  PYB_ERR_OOM = -5          /* device memory */
+} pyb_status;
+
+typedef enum { PYB_ACT_LINEAR = 0, PYB_ACT_RELU = 1, PYB_ACT_SOFTMAX = 2, PYB_ACT_TANH = 3,
+               PYB_ACT_SIGMOID = 4 } pyb_activation;
+typedef enum { PYB_LOSS_SPARSE_CE = 0, PYB_LOSS_MSE = 1 } pyb_loss;
+typedef enum { PYB_MEM_HOST = 0, PYB_MEM_DEVICE = 1 } pyb_mem;
+typedef enum { PYB_PRIOR_SCALAR = 0, PYB_PRIOR_PER_VARIABLE = 1, PYB_PRIOR_PER_ELEMENT = 2 } pyb_prior_form;
+typedef enum { PYB_HMC_REFERENCE = 0, PYB_HMC_CANONICAL = 1 } pyb_hmc_semantics;
+typedef enum { PYB_SVGD_REFERENCE_LIVE = 0, PYB_SVGD_CANONICAL_MEDIAN = 1 } pyb_svgd_semantics;
+/* which device path evaluates the MLP; AUTO picks by shape */
+typedef enum { PYB_PATH_AUTO = 0, PYB_PATH_GENERIC = 1, PYB_PATH_FUSED_SMALL = 2, PYB_PATH_TENSOR = 3 } pyb_path;
+
+typedef struct pyb_handle pyb_handle;
+
+/* Dense stack parsed from the Keras model JSON (model.to_json(); consumed at HMC.py:56,
+ * SVGD.py:222, BayesianModel.py:18).  The JSON parse itself is host logic on the Python side. */
+typedef struct {
+  int32_t n_layers;
+  int32_t in_dim;
+  const int32_t* units;      /* [n_layers] */
+  const int32_t* activation; /* [n_layers] pyb_activation */
+  const int32_t* use_bias;   /* [n_layers] 0/1 */
+} pyb_model_desc;
+
+typedef struct {
+  double mean_loss;      /* mean over chains of the loss step() would return (HMC.py:96,104) */
+  double accept_rate;    /* accepted / total since the phase started (HMC.py:112,122) */
+  int64_t n_accepted;    /* over all local chains and iterations of this call */
+  int64_t n_total;
+  int64_t n_nan;         /* proposals whose Hamiltonian difference was NaN (rejected) */
+  int64_t grad_evals;    /* chain x position evaluations actually executed in this call */
+  double device_ms;      /* CUDA-event time of the call's kernels on the handle's stream */
+  int64_t kernel_launches;
+} pyb_hmc_diag;
+
+/* ---- library ---- */
+int pyb_version(void);
+const char* pyb_last_error(void);
+int pyb_device_count(int32_t* n_out);
+
+/* ---- handle / model (replaces tf.keras.models.model_from_json + variable creation,
+ *      HMC.py:56, SVGD.py:222, BayesianModel.py:18) ---- */
+int pyb_create(const pyb_model_desc* desc, int32_t device_id, uint64_t seed, pyb_handle** out);
+int pyb_destroy(pyb_handle* h);
+int pyb_param_count(const pyb_handle* h, int64_t* n_params_out);
+/* knobs: "path" (pyb_path), "workspace_mb", "chain_batch", "sync_each_iter" ... */
+int pyb_set_option(pyb_handle* h, const char* key, double value);
+/* read-outs: "path_used", "kernel_launches", "last_device_ms", "workspace_bytes", "tensor_path_ok" */
+int pyb_get_info(const pyb_handle* h, const char* key, double* value_out);
+
+/* ---- inputs ---- */
+/* Full training batch kept resident in HBM (HMC.py:63-65: ONE full-dataset batch frozen for the
+ * run; SVGD.py:220-221 draws minibatches from the same pool).  X [N, in_dim] float32 row-major;
+ * y int32 [N] (SPARSE_CE) or float32 [N, out_dim] (MSE).  n_train multiplies the mean loss in the
+ * potential (HMC.py:158); pass N (or <=0) for the reference behaviour. */
+int pyb_set_dataset(pyb_handle* h, const float* X, int64_t N, const void* y, int32_t loss_kind,
+                    int32_t mem, int64_t n_train);
+/* GaussianPrior.get_model_priors (GaussianPrior.py:100-121, :28-47): sigma = rho used RAW.
+ * SCALAR: 1 value each; PER_VARIABLE: one per trainable variable (kernel, bias, kernel, ...);
+ * PER_ELEMENT: n_params values.  Host pointers. */
+int pyb_set_prior_gaussian(pyb_handle* h, const float* mean, const float* sigma, int32_t form);
+
+/* ---- HMC (HMC.py:45-72 compile, :74-104 step, :106-126 train, :128-171 helpers) ---- */
+/* S local chains whose global ids are chain_offset .. chain_offset+S-1 (RNG counters use the
+ * global id, so a sharded run reproduces the unsharded one).  q0 NULL => every chain starts at
+ * the prior mean (HMC.py:69-72); else host float32 [S, P]. */
+int pyb_hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double epsilon, double m, int32_t L,
+                 int32_t semantics, const float* q0);
+/* test hook: momenta [S,P] and/or uniforms [S] (host) for the NEXT iteration only. */
+int pyb_hmc_inject(pyb_handle* h, const float* p, const float* u);
+/* n_iters iterations of HMC.step(sampling, burning) for all chains, no host sync inside. */
+int pyb_hmc_run(pyb_handle* h, int32_t n_iters, int32_t burning, int32_t sampling, pyb_hmc_diag* diag_out);
+/* parity hook: U = -log prior + n_train*mean_loss, the mean loss, and dU/dq for S given
+ * positions (HMC._potential_energy HMC.py:149-159 and the gradient _step_p takes :128-136).
+ * All host pointers; U/loss/grad may be NULL. */
+int pyb_hmc_eval(pyb_handle* h, const float* q, int64_t S, float* U_out, float* loss_out, float* grad_out);
+int pyb_hmc_get_state(pyb_handle* h, float* q_out, float* p_out);
+/* per-chain values of the LAST iteration (any may be NULL). */
+int pyb_hmc_last(pyb_handle* h, float* U0, float* K0, float* U1, float* K1, float* log_alpha,
+                 int32_t* accepted, float* loss);
+/* samples + frequencies of every chain (HMC.py:75-77,92-104; HMC.result :176-184), chain-major,
+ * within a chain in acceptance order. */
+int pyb_hmc_reset_samples(pyb_handle* h);
+int pyb_hmc_sample_count(pyb_handle* h, int64_t* n_out);
+int pyb_hmc_samples(pyb_handle* h, float* samples_out, int32_t* freq_out, int32_t* chain_out);
+
+/* ---- SVGD (SVGD.py:219-228 compile, :143-157 init, :84-141 step, :54-68 + :183-202 live kernel,
+ *      :165-181 median-heuristic kernel, legacy Adam created :226 applied :120) ---- */
+/* particles0 NULL => one prior sample per element (Philox); else host float64 [S, P]. */
+int pyb_svgd_init(pyb_handle* h, int64_t S, int64_t particle_offset, double lr, int32_t semantics,
+                  const double* particles0);
+/* One step on the minibatch given by row indices into the resident dataset (host int32 [B]);
+ * batch_idx NULL => the full dataset.  loss_out = mean over particles of the minibatch loss. */
+int pyb_svgd_step(pyb_handle* h, const int32_t* batch_idx, int64_t B, double* loss_out);
+/* parity hook: phi for given particles X [S,P] (float64) and gradients G [S,P] (float32):
+ * CANONICAL_MEDIAN: phi=(K G + dxkxy)/S with the median bandwidth, h_out = h.
+ * REFERENCE_LIVE : row i = ((sum_k K_ik) G_i + 2 sum_k K_ik (x_i-x_k))/S with gamma=1 (Jacobi
+ * evaluation of the formula the live sweep applies row by row). */
+int pyb_svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int32_t semantics,
+                 float* phi_out, double* h_out);
+int pyb_svgd_get_particles(pyb_handle* h, double* particles_out);
+/* NCCL plumbing for sharded particles: all ranks pass the same 128-byte ncclUniqueId. */
+int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id_128);
+int pyb_nccl_unique_id(void* out_128);
+
+/* ---- posterior predictive (BayesianModel.predict BayesianModel.py:106-129; Plotter.py:244) ----
+ * W [n,P] weight samples, weight [n] or NULL (=1), x [Nt,in_dim]; mean/var [Nt,out_dim] with
+ * NaN->0 per element and population variance; all_out [n,Nt,out_dim] or NULL.  Host pointers. */
+int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x,
+                int64_t Nt, float* mean_out, float* var_out, float* all_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYESIAN_B200_H */
