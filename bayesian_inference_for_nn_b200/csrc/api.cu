@@ -134,6 +134,7 @@ int pyb_destroy(pyb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   tc_release(h);
   for (auto* b : h->ws.act) delete b;
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   h->ws.act.clear();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -160,6 +161,9 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_workspace_mb = v;
   } else if (!strcmp(key, "chain_batch")) {
     h->opt_chain_batch = (int64_t)v;
+  } else if (!strcmp(key, "profile")) {
+    h->prof_enabled = v != 0;
+    h->prof_ms = h->prof_flops = 0; h->prof_launches = 0; h->prof_used = 0;
   } else {
     throw Error(PYB_ERR_INVALID, std::string("unknown option: ") + key);
   }
@@ -173,6 +177,9 @@ int pyb_get_info(const pyb_handle* h, const char* key, double* out) {
   else if (!strcmp(key, "kernel_launches")) *out = (double)h->kernel_launches;
   else if (!strcmp(key, "last_device_ms")) *out = h->last_device_ms;
   else if (!strcmp(key, "sm_count")) *out = h->sm_count;
+  else if (!strcmp(key, "prof_ms")) *out = h->prof_ms;
+  else if (!strcmp(key, "prof_flops")) *out = h->prof_flops;
+  else if (!strcmp(key, "prof_launches")) *out = (double)h->prof_launches;
   else if (!strcmp(key, "n_train")) *out = (double)h->n_train;
   else throw Error(PYB_ERR_INVALID, std::string("unknown info key: ") + key);
   PYB_CATCH

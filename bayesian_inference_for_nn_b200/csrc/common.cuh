@@ -252,12 +252,43 @@ struct pyb_handle {
   pyb::Workspace ws;
   pyb::HmcState hmc;
   pyb::SvgdState svgd;
+  // live per-kernel timing of the dominant (GEMM) kernels: CUDA events on the launching stream
+  bool prof_enabled = false;
+  std::vector<cudaEvent_t> prof_events;   // begin/end pairs, resolved by prof_resolve()
+  size_t prof_used = 0;
+  double prof_ms = 0, prof_flops = 0;
+  int64_t prof_launches = 0;
   void* tc = nullptr;     // tensor-core path state (tc_path.cu)
   void* fused = nullptr;  // fused small path state
 };
 
 namespace pyb {
 inline void count_launch(pyb_handle* h, int n = 1) { h->kernel_launches += n; }
+// bracket ONE dominant-kernel launch with events (no-ops unless the "profile" option is on)
+inline void prof_begin(pyb_handle* h) {
+  if (!h->prof_enabled) return;
+  if (h->prof_used + 2 > h->prof_events.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    h->prof_events.push_back(a); h->prof_events.push_back(b);
+  }
+  cudaEventRecord(h->prof_events[h->prof_used], h->stream);
+}
+inline void prof_end(pyb_handle* h, double flops) {
+  if (!h->prof_enabled) return;
+  cudaEventRecord(h->prof_events[h->prof_used + 1], h->stream);
+  h->prof_used += 2;
+  h->prof_flops += flops;
+  h->prof_launches += 1;
+}
+// call after a stream sync: fold the recorded pairs into prof_ms
+inline void prof_resolve(pyb_handle* h) {
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]) == cudaSuccess) h->prof_ms += ms;
+  }
+  h->prof_used = 0;
+}
 
 // generic_mlp.cu
 // loss[S] (mean loss over the batch), grad[S,P] = scale * d(mean loss)/d(theta)  (grad may be null)

@@ -194,7 +194,9 @@ __global__ void k_softmax_rows(float* z, int64_t total_rows, int C) {
 template <bool TA, bool TB>
 static void launch_gemm(pyb_handle* h, const GemmArgs& g, int batch) {
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch * g.splits);
+  prof_begin(h);
   k_sgemm<TA, TB><<<grid, 256, 0, h->stream>>>(g);
+  prof_end(h, 2.0 * g.M * g.N * (double)g.K * batch);
   count_launch(h);
 }
 

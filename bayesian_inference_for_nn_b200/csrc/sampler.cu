@@ -429,6 +429,7 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
   float ms = 0.f;
   PYB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_device_ms = ms;
+  prof_resolve(h);
   if (out) {
     unsigned long long c[4];
     double ls = 0.0;

@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — posterior grad-evals/s (chains x leapfrog steps) of the HMC hot path on B200.
+
+Workload (BASELINE.json configs[2], the config the metric and the >=1024-chain target are quoted
+on; it fits one GPU): HMC, 1024 chains per GPU, synthetic MNIST-shaped data 60000x784 (U[0,1),
+labels U{0..9}), 784-256-10 MLP, L=20, Gaussian prior N(0,1), reference leapfrog semantics.
+One "step" = one HMC sampling iteration of every local chain: momentum draw, L+1 full-dataset
+log-posterior forward/backward evaluations, Hamiltonian, Metropolis accept, sample bookkeeping.
+The metric counts S*L grad-evals per step (the endpoint evaluation is overhead).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N>1 is launched by torchrun (one rank per GPU).  Chains shard across ranks with no data-path
+collective (weak scaling: 1024 chains per GPU); torch.distributed is used only for the barrier and
+the max-over-ranks of the device time.  `--impl reference` times the reference's own loop shape on
+the host cores (oracle port: ONE chain, eager per-position evaluation, HMC.py:74-104).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_IN, HIDDEN, N_CLS = 784, 256, 10
+FLOPS_PER_GRADEVAL = 2.0 * (D_IN * HIDDEN + HIDDEN * N_CLS) + 2.0 * (D_IN * HIDDEN + 2 * HIDDEN * N_CLS)  # per row
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    # development overrides (the defaults ARE the named config; a line with overrides says so)
+    ap.add_argument("--chains", type=int, default=int(os.environ.get("PYB_BENCH_CHAINS", 1024)))
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("PYB_BENCH_ROWS", 60000)))
+    ap.add_argument("--leapfrog", type=int, default=int(os.environ.get("PYB_BENCH_L", 20)))
+    ap.add_argument("--eps", type=float, default=2e-5)
+    ap.add_argument("--path", default=os.environ.get("PYB_BENCH_PATH", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def synth(rows, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.random((rows, D_IN), dtype=np.float32)
+    y = rng.integers(0, N_CLS, rows).astype(np.int32)
+    return X, y
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return {"bf16_sustained": float(j["bf16_tflops_sustained"]), "bf16_burst": float(j["bf16_tflops"]),
+                    "hbm": float(j["hbm_gbs"]), "source": "measured"}
+        except Exception:
+            pass
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [v.strip() for v in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(args, steps, warmup, rows):
+    """The reference's loop shape on the host cores: one chain, L+2 gradient + 2 potential
+    evaluations per iteration (oracle.reference_style_hmc_iteration follows HMC.py:74-104)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyesian_oracle as O
+    X, y = synth(rows)
+    spec = O.MLPSpec(D_IN, [HIDDEN, N_CLS], ["relu", "softmax"])
+    mu, sg = O.expand_prior(spec, 0.0, 1.0)
+    prob = O.Problem(spec, X, y, O.LOSS_SPARSE_CE, mu, sg)
+    rng = np.random.default_rng(0)
+    q = np.zeros((1, spec.n_params), np.float32)
+    for _ in range(warmup):
+        q, _, _ = O.reference_style_hmc_iteration(prob, q, rng, args.eps, 1.0, args.leapfrog)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        q, _, _ = O.reference_style_hmc_iteration(prob, q, rng, args.eps, 1.0, args.leapfrog)
+    dt = time.perf_counter() - t0
+    return args.leapfrog * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    # bounded sample: each step is ONE reference-style iteration of ONE chain on the full dataset
+    val, dt = cpu_reference_run(args, args.steps, min(args.warmup, 1), args.rows)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "posterior_grad_evals_per_s", "value": val, "unit": "grad-evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "grad-evals/s", "cores": cores, "kind": "port",
+                         "sample": "1 chain x %d iterations (L=%d, %d rows x 784, 784-256-10), numpy fp32 BLAS on all "
+                                   "host cores; reference loop shape HMC.py:74-104 (TensorFlow is not installable here)"
+                                   % (args.steps, args.leapfrog, args.rows)},
+        "e2e": {"value": val, "unit": "grad-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "C3 HMC 784-256-10 MLP, %d chains/GPU, %d rows x 784 synthetic MNIST-shaped, L=%d, "
+                        "reference leapfrog semantics, Gaussian prior N(0,1)" % (args.chains, args.rows, args.leapfrog),
+            "chains_per_gpu": args.chains, "chains_total": args.chains * world, "rows": args.rows, "L": args.leapfrog,
+            "epsilon": args.eps, "evals_executed_per_step_per_chain": args.leapfrog + 1,
+            "parallelism": "chains sharded x%d, no data-path collective" % world,
+            "l2_policy": "inputs exceed L2 (X hi/lo 188 MB + per-chain operands >> 126 MB)",
+            "named_config": bool(args.chains == 1024 and args.rows == 60000 and args.leapfrog == 20)}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from bayesian_inference_for_nn_b200 import _lib, keras_json
+    from bayesian_inference_for_nn_b200.engine import Engine
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    S, L = args.chains, args.leapfrog
+    X, y = synth(args.rows)
+    spec = keras_json.parse_model_json(keras_json.make_sequential_json(D_IN, [HIDDEN, N_CLS], ["relu", "softmax"]))
+    eng = Engine(spec, device=local_rank, seed=1234)
+    paths = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "fused": _lib.PATH_FUSED_SMALL,
+             "tensor": _lib.PATH_TENSOR}
+    eng.set_option("path", paths[args.path])
+    eng.set_dataset(X, y, _lib.LOSS_SPARSE_CE)          # inputs resident in HBM before the timed region
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.hmc_init(S, args.eps, 1.0, L, _lib.HMC_REFERENCE, chain_offset=rank * S)
+    eng.hmc_run(2, burning=True, sampling=False)         # leave the all-zero start (relu'(0)=0 there)
+
+    for _ in range(args.warmup):
+        eng.hmc_run(1, burning=False, sampling=True)
+    eng.set_option("profile", 1)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    d = eng.hmc_run(args.steps, burning=False, sampling=True)   # EXACTLY K steps, device-timed inside
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = max_over_ranks(d["device_ms"])
+    wall_s = max_over_ranks(wall)
+    launches = d["kernel_launches"]
+    prof_ms, prof_flops, prof_n = eng.info("prof_ms"), eng.info("prof_flops"), eng.info("prof_launches")
+    eng.set_option("profile", 0)
+    path_used = int(eng.info("path_used"))
+    total_evals = sum_over_ranks(S * L * args.steps)
+    value = total_evals / (dev_ms / 1e3)
+    accept_rate = d["accept_rate"]
+
+    # ---- e2e: same steps through the public C ABI with HOST buffers (H2D of the step's inputs from
+    # pinned memory + D2H of the step's result inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        try:
+            import torch
+            Xp = torch.from_numpy(X).pin_memory().numpy()
+            yp = torch.from_numpy(y).pin_memory().numpy()
+        except Exception:
+            Xp, yp = X, y
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            eng.set_dataset(Xp, yp, _lib.LOSS_SPARSE_CE)
+            eng.hmc_run(1, burning=False, sampling=True)
+            last = eng.hmc_last()
+            d2h = sum(v.nbytes for v in last.values())
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": total_evals / e2e_s, "unit": "grad-evals/s", "h2d_bytes_per_step": int(Xp.nbytes + yp.nbytes),
+               "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    algo_flops_per_eval = FLOPS_PER_GRADEVAL * args.rows
+    # roofline for the dominant kernel family (the fwd/bwd GEMMs): algorithmic flops they cover /
+    # their summed CUDA-event time on the launching stream
+    roof = None
+    if prof_ms > 0:
+        achieved = prof_flops / (prof_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                "peak_source": "%s bf16 dense sustained (cuBLAS)" % peaks["source"],
+                "kernel": {1: "k_sgemm (fp32 SIMT)", 2: "fused small", 3: "tc_gemm bf16x3 (tcgen05)"}.get(path_used, "?"),
+                "launches": int(prof_n), "avg_launch_ms": prof_ms / max(1, prof_n),
+                "kernel_share_of_step": prof_ms / d["device_ms"],
+                "whole_step_algorithmic_tflops": value / max(1, world) * algo_flops_per_eval / 1e12}
+    cpu = None
+    if not args.no_cpu_baseline:
+        # bounded sample: 1 chain, 2 iterations on a 6000-row slice scaled to the full row count
+        rows_s = min(args.rows, 6000)
+        v, dt = cpu_reference_run(args, 2, 1, rows_s)
+        cpu = {"value": v * rows_s / args.rows, "unit": "grad-evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "1 chain x 2 iterations (L=%d) on %d of %d rows, scaled by rows; numpy fp32 BLAS, reference "
+                         "loop shape (HMC.py:74-104); %.1f s" % (L, rows_s, args.rows, dt)}
+    line = {
+        "metric": "posterior_grad_evals_per_s", "value": value, "unit": "grad-evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core products, fp32 accumulate)"
+        if path_used == 3 else "f32", "data": "synthetic", "config": workload_config(args, world),
+        "wall_ms_per_step": 1e3 * wall_s / args.steps, "accept_rate": accept_rate, "path_used": path_used,
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
