@@ -1,10 +1,774 @@
-// tc_path.cu — placeholder until the tcgen05 path lands.
+// tc_path.cu — tensor-core path for the MNIST-width case (BASELINE config C3/C4/C5 shapes):
+// two-layer Dense MLP whose first layer is a real dense contraction (D x H with H <= 256).
+//
+// What runs where, per chain batch (Bc chains), per log-posterior evaluation:
+//   k_pack_w1     theta -> W1^T split into bf16 hi/lo, K-major [Bc*H, D]            (SIMT, tiny)
+//   tc_gemm<G1>   Z1 = X W1 (+b1, act) -> A1^T fp32 [Bc, H, Npad]                    (tcgen05 + TMA)
+//   k_layer2      per row: z2, softmax-CE / MSE, dZ2, dZ1 = (dZ2 W2^T) act'(a1)
+//                 -> dZ1^T split bf16 hi/lo [Bc*H, Npad]; loss, dW2, db2 partials    (SIMT)
+//   tc_gemm<G2>   [dW1; db1] = [X^T; 1] dZ1 -> grad[:, 0 : D*H + H]                  (tcgen05 + TMA)
+// fp32-grade products on bf16 tensor cores: every operand is split x = hi + lo (bf16 each) and the
+// MMA issues hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator (relative error ~2^-16 per
+// product, far inside the 1e-4 parity budget; single-pass BF16/TF32 would not be).
+//
+// The GEMM kernel is ONE persistent, warp-specialised kernel used for both contractions:
+//   D[M, H] = A[M, K] * B[H, K]^T,  A shared by all chains, B per chain.
+//   G1: A = X [N, D],  B = W1^T[b] [H, D],     M = rows,     K = D   (784)
+//   G2: A = [X^T;1] [D+1, N], B = dZ1^T[b] [H, N], M = D+1,  K = rows (60000)
+// CTA tile = 2 x (128 x H) accumulators in TMEM (2*256 = 512 columns) sharing each B stage, K
+// streamed in 32-element (64 B, SWIZZLE_64B) chunks through a 3-stage TMA/mbarrier ring:
+// 64 KB/stage for 2*3*128*256*32*2 flop => ~42 B/clk/SM of L2->SM traffic at full MMA rate.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warp 2 TMEM allocator,
+// warps 4-7 epilogue (TMEM lane == output row).
 #include "common.cuh"
+#include <cuda_bf16.h>
+#include <algorithm>
+
 namespace pyb {
-bool tc_supported(pyb_handle*, int64_t) { return false; }
-void tc_eval(pyb_handle*, const float*, int64_t, float, float*, float*) {
-  throw Error(PYB_ERR_UNSUPPORTED, "tensor path not built");
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers (sm_100a)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-void tc_release(pyb_handle*) {}
-void tc_invalidate_dataset(pyb_handle*) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile with 64-byte rows, SWIZZLE_64B: 8-row atoms of 512 B (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address, bits [0,14)
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;                            // layout type SWIZZLE_64B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM kernel
+// ------------------------------------------------------------------------------------------
+constexpr int TC_BK = 32;                       // K elements per stage
+constexpr int TC_STAGES = 3;
+constexpr int TC_A_TILE_BYTES = 128 * TC_BK * 2;    // 8 KB
+constexpr int TC_B_TILE_BYTES = 256 * TC_BK * 2;    // 16 KB (H <= 256)
+constexpr int TC_STAGE_BYTES = 4 * TC_A_TILE_BYTES + 2 * TC_B_TILE_BYTES;   // 64 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers + bias*/ + 1024;
+constexpr int TC_THREADS = 256;
+
+enum { EPI_BIAS_ACT_T = 0, EPI_STORE = 1 };
+
+struct TcGemmParams {
+  int K, n_mtiles, n_pairs, n_batch, H;
+  int order, sub_batch, total_items;
+  int epi;
+  // EPI_BIAS_ACT_T: out_t[b][col][row] = act(D[row][col] + bias[b][col])   (row < M_valid)
+  const float* bias; int64_t bias_stride; int act;
+  float* out_t; int64_t out_t_chain_stride; int64_t out_t_ld;
+  // EPI_STORE: out[b*out_stride + row*out_ld + col] = D[row][col]           (row < M_valid)
+  float* out; int64_t out_stride; int out_ld;
+  int M_valid;
+};
+
+__device__ __forceinline__ void tc_decode(const TcGemmParams& p, int item, int& b, int& mp) {
+  if (p.order == 0) {            // chain-major: the pairs of one chain run side by side (G2)
+    b = item / p.n_pairs;
+    mp = item - b * p.n_pairs;
+  } else {                       // sub-batched: [sub-batch][pair][chain in sub-batch] (G1)
+    int per_sb = p.n_pairs * p.sub_batch;
+    int sb = item / per_sb;
+    int rem = item - sb * per_sb;
+    int first = sb * p.sub_batch;
+    int size = min(p.sub_batch, p.n_batch - first);
+    mp = rem / size;
+    b = first + (rem - mp * size);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [TC_STAGES]
+  uint64_t* empty_bar = bars + TC_STAGES;       // [TC_STAGES]
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;
+  uint64_t* tmem_empty = bars + 2 * TC_STAGES + 1;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * TC_STAGES + 2);
+  float* bias_s = (float*)(smem + TC_STAGES * TC_STAGE_BYTES + 1024);   // [256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  const uint32_t b_bytes = (uint32_t)p.H * TC_BK * 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int b, mp;
+        tc_decode(p, item, b, mp);
+        const int mt0 = mp * 2;
+        const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
+        const uint32_t bytes = (uint32_t)n_mt * 2 * TC_A_TILE_BYTES + 2 * b_bytes;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = stage_base + stage * TC_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], bytes);
+          const int k0 = kc * TC_BK;
+          for (int mt = 0; mt < n_mt; ++mt) {
+            tma_load_2d(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], k0, (mt0 + mt) * 128);
+            tma_load_2d(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, (mt0 + mt) * 128);
+          }
+          tma_load_2d(st + 4 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], k0, b * p.H);
+          tma_load_2d(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &tmB_lo, &full_bar[stage], k0, b * p.H);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=BF16, both K-major, N = H, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.H >> 3) << 17) | ((128u >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const int k_tail = p.K - (nk - 1) * TC_BK;                 // valid K elements of the last chunk
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int b, mp;
+        tc_decode(p, item, b, mp);
+        const int mt0 = mp * 2;
+        const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
+        mbar_wait(tmem_empty, acc_phase ^ 1);                    // epilogue has drained the accumulators
+        tc_fence_after();
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + stage * TC_STAGE_BYTES);
+          const int nks = (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t koff = ks * 32;                       // 16 bf16 = 32 bytes along K inside the atom
+            const uint64_t bh = make_smem_desc_sw64(st + 4 * TC_A_TILE_BYTES + koff);
+            const uint64_t bl = make_smem_desc_sw64(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES + koff);
+            for (int mt = 0; mt < n_mt; ++mt) {
+              const uint64_t ah = make_smem_desc_sw64(st + mt * TC_A_TILE_BYTES + koff);
+              const uint64_t al = make_smem_desc_sw64(st + (2 + mt) * TC_A_TILE_BYTES + koff);
+              const uint32_t d = tmem_base + (uint32_t)mt * 256;
+              tc_mma_bf16(d, ah, bh, idesc, (kc | ks) != 0);
+              tc_mma_bf16(d, al, bh, idesc, 1);
+              tc_mma_bf16(d, ah, bl, idesc, 1);
+            }
+          }
+          tc_commit(&empty_bar[stage]);                          // smem slot reusable once these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tmem_full);                                    // accumulators complete
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM lane == row of the 128-row tile =====
+    const int et = threadIdx.x - 128;                            // 0..127
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int b, mp;
+      tc_decode(p, item, b, mp);
+      const int mt0 = mp * 2;
+      const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
+      if (p.epi == EPI_BIAS_ACT_T) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");           // previous item's readers are done
+        for (int c = et; c < p.H; c += 128) bias_s[c] = p.bias ? p.bias[(int64_t)b * p.bias_stride + c] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(tmem_full, acc_phase);
+      tc_fence_after();
+      for (int mt = 0; mt < n_mt; ++mt) {
+        const int row = (mt0 + mt) * 128 + et;
+        const bool valid = row < p.M_valid;
+        for (int c0 = 0; c0 < p.H; c0 += 32) {
+          float v[32];
+          tc_ld32(tmem_base + lane_base + (uint32_t)(mt * 256 + c0), v);
+          if (p.epi == EPI_BIAS_ACT_T) {
+            if (valid) {
+              float* o = p.out_t + (int64_t)b * p.out_t_chain_stride + (int64_t)c0 * p.out_t_ld + row;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.H) o[(int64_t)j * p.out_t_ld] = act_apply(v[j] + bias_s[c0 + j], p.act);
+            }
+          } else {
+            if (valid) {
+              float* o = p.out + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.H) o[j] = v[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty);
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SIMT helpers around the GEMMs
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// src [R, C] fp32 (row stride lds) -> hi/lo [R, C] bf16 (row stride ldd), same orientation
+__global__ void k_split_rows(const float* src, int64_t R, int C, int64_t lds, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                             int64_t ldd) {
+  const int64_t total = R * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C;
+    int c = (int)(i - r * C);
+    __nv_bfloat16 h, l;
+    split_bf16(src[r * lds + c], h, l);
+    hi[r * ldd + c] = h;
+    lo[r * ldd + c] = l;
+  }
+}
+
+// src [R, C] fp32 (batch stride sb) -> transposed hi/lo [C(+ones row), Rpad] bf16 per batch element.
+// grid (ceil(C/32), ceil(R/32), batch), block (32, 8)
+__global__ void k_split_transpose(const float* src, int64_t sb, int R, int C, int64_t lds, __nv_bfloat16* hi,
+                                  __nv_bfloat16* lo, int64_t db, int64_t ldd) {
+  __shared__ float t[32][33];
+  const float* s = src + (int64_t)blockIdx.z * sb;
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < R && c < C) ? s[(int64_t)r * lds + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) {
+      __nv_bfloat16 h, l;
+      split_bf16(t[threadIdx.x][i], h, l);
+      int64_t o = (int64_t)blockIdx.z * db + (int64_t)c * ldd + r;
+      hi[o] = h;
+      lo[o] = l;
+    }
+  }
+}
+
+__global__ void k_fill_bf16(__nv_bfloat16* p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = __float2bfloat16_rn(v);
+}
+
+// Layer 2 forward/backward for one chain and a group of 128-row tiles.  thread == row in phases
+// A/A2, thread == hidden unit in phase B (dW2 accumulation).
+constexpr int L2_CMAX = 16;
+constexpr int L2_TILES = 8;     // 128-row tiles per block
+struct Layer2Params {
+  const float* a1t; int64_t a1t_chain_stride; int64_t ld;   // [Bc][H][Npad]
+  __nv_bfloat16* zt_hi; __nv_bfloat16* zt_lo;              // [Bc*H][Npad]
+  const float* theta; int64_t P; int64_t w2_off, b2_off;
+  int H, C, N, act1, out_act, loss_kind;
+  const int32_t* y_i; const float* y_f;
+  float scale;                 // n_train (or 1): dZ = scale * d(mean loss)/dz
+  double* loss_partial;        // [Bc][n_groups]
+  float* w2_partial;           // [Bc][n_groups][H*C + C]
+  int n_groups;
+};
+__global__ void __launch_bounds__(128) k_layer2(Layer2Params p) {
+  __shared__ float W2s[256 * L2_CMAX];
+  __shared__ float dz2s[128 * L2_CMAX];
+  __shared__ float b2s[L2_CMAX];
+  __shared__ double scratch[32];
+  const int t = threadIdx.x, b = blockIdx.y, g = blockIdx.x;
+  const int H = p.H, C = p.C;
+  const float* th = p.theta + (int64_t)b * p.P;
+  for (int i = t; i < H * L2_CMAX; i += 128) {
+    int h = i / L2_CMAX, c = i % L2_CMAX;
+    W2s[i] = (c < C) ? th[p.w2_off + (int64_t)h * C + c] : 0.f;
+  }
+  if (t < L2_CMAX) b2s[t] = (t < C) ? th[p.b2_off + t] : 0.f;
+  __syncthreads();
+  const float* a1 = p.a1t + (int64_t)b * p.a1t_chain_stride;
+  __nv_bfloat16* zh = p.zt_hi + (int64_t)b * H * p.ld;
+  __nv_bfloat16* zl = p.zt_lo + (int64_t)b * H * p.ld;
+  float accw[2][L2_CMAX];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int c = 0; c < L2_CMAX; ++c) accw[i][c] = 0.f;
+  float accb = 0.f;
+  double loss_acc = 0.0;
+  const float invN = p.scale / (float)p.N;
+  for (int tile = 0; tile < L2_TILES; ++tile) {
+    const int row0 = (g * L2_TILES + tile) * 128;
+    if (row0 >= p.N) break;
+    const int r = row0 + t;
+    const bool valid = r < p.N;
+    // ---- phase A: z2 = a1 W2 + b2
+    float z[L2_CMAX];
+#pragma unroll
+    for (int c = 0; c < L2_CMAX; ++c) z[c] = b2s[c];
+    if (valid) {
+      for (int h = 0; h < H; ++h) {
+        float a = a1[(int64_t)h * p.ld + r];
+        const float4* w = reinterpret_cast<const float4*>(&W2s[h * L2_CMAX]);
+#pragma unroll
+        for (int q4 = 0; q4 < L2_CMAX / 4; ++q4) {
+          float4 wv = w[q4];
+          z[q4 * 4 + 0] = fmaf(a, wv.x, z[q4 * 4 + 0]);
+          z[q4 * 4 + 1] = fmaf(a, wv.y, z[q4 * 4 + 1]);
+          z[q4 * 4 + 2] = fmaf(a, wv.z, z[q4 * 4 + 2]);
+          z[q4 * 4 + 3] = fmaf(a, wv.w, z[q4 * 4 + 3]);
+        }
+      }
+    }
+    // ---- loss and dZ2
+    float dz[L2_CMAX];
+#pragma unroll
+    for (int c = 0; c < L2_CMAX; ++c) dz[c] = 0.f;
+    if (valid) {
+      if (p.loss_kind == PYB_LOSS_SPARSE_CE) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c) if (c < C) mx = fmaxf(mx, z[c]);
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c) if (c < C) se += expf(z[c] - mx);
+        const int yi = p.y_i[r];
+        float zy = 0.f;
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c) if (c == yi) zy = z[c];
+        loss_acc += (double)(logf(se) - (zy - mx));
+        const float inv = 1.0f / se;
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c)
+          if (c < C) dz[c] = (expf(z[c] - mx) * inv - (c == yi ? 1.f : 0.f)) * invN;
+      } else {
+        float acc = 0.f;
+        const float sc = 2.0f * invN / (float)C;
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c)
+          if (c < C) {
+            float a = act_apply(z[c], p.out_act);
+            float df = a - p.y_f[(int64_t)r * C + c];
+            acc += df * df;
+            dz[c] = sc * df * act_grad_from_output(a, p.out_act);
+          }
+        loss_acc += (double)(acc / (float)C);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < L2_CMAX; ++c) dz2s[t * L2_CMAX + c] = dz[c];
+    // ---- phase A2: dZ1 = (dZ2 W2^T) * act'(a1) -> split bf16, transposed store (coalesced over rows)
+    if (valid) {
+      for (int h = 0; h < H; ++h) {
+        float a = a1[(int64_t)h * p.ld + r];
+        const float4* w = reinterpret_cast<const float4*>(&W2s[h * L2_CMAX]);
+        float da = 0.f;
+#pragma unroll
+        for (int q4 = 0; q4 < L2_CMAX / 4; ++q4) {
+          float4 wv = w[q4];
+          da = fmaf(dz[q4 * 4 + 0], wv.x, da);
+          da = fmaf(dz[q4 * 4 + 1], wv.y, da);
+          da = fmaf(dz[q4 * 4 + 2], wv.z, da);
+          da = fmaf(dz[q4 * 4 + 3], wv.w, da);
+        }
+        float d1 = da * act_grad_from_output(a, p.act1);
+        __nv_bfloat16 hi, lo;
+        split_bf16(d1, hi, lo);
+        zh[(int64_t)h * p.ld + r] = hi;
+        zl[(int64_t)h * p.ld + r] = lo;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: dW2[h][c] += sum_r a1[h][r] dZ2[r][c]; thread == hidden unit (two per thread)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int h = t + hh * 128;
+      if (h < H) {
+        const float4* arow = reinterpret_cast<const float4*>(a1 + (int64_t)h * p.ld + row0);
+        for (int r4 = 0; r4 < 32; ++r4) {
+          float4 av = arow[r4];
+          float aj[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4* dzr = reinterpret_cast<const float4*>(&dz2s[(r4 * 4 + j) * L2_CMAX]);
+#pragma unroll
+            for (int q4 = 0; q4 < L2_CMAX / 4; ++q4) {
+              float4 dv = dzr[q4];
+              accw[hh][q4 * 4 + 0] = fmaf(aj[j], dv.x, accw[hh][q4 * 4 + 0]);
+              accw[hh][q4 * 4 + 1] = fmaf(aj[j], dv.y, accw[hh][q4 * 4 + 1]);
+              accw[hh][q4 * 4 + 2] = fmaf(aj[j], dv.z, accw[hh][q4 * 4 + 2]);
+              accw[hh][q4 * 4 + 3] = fmaf(aj[j], dv.w, accw[hh][q4 * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+    if (t < C) {
+      float s = 0.f;
+      for (int rr = 0; rr < 128; ++rr) s += dz2s[rr * L2_CMAX + t];
+      accb += s;
+    }
+    __syncthreads();
+  }
+  float* wp = p.w2_partial + ((int64_t)b * p.n_groups + g) * (H * C + C);
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int h = t + hh * 128;
+    if (h < H)
+#pragma unroll
+      for (int c = 0; c < L2_CMAX; ++c)
+        if (c < C) wp[h * C + c] = accw[hh][c];
+  }
+  if (t < C) wp[H * C + t] = accb;
+  double tot = block_sum<double>(loss_acc, scratch);
+  if (t == 0) p.loss_partial[(int64_t)b * p.n_groups + g] = tot;
+}
+
+// grad[b][w2_off + i] = sum_g partial[b][g][i] (fixed order); loss[b] = sum_g loss_partial / N
+__global__ void k_layer2_reduce(const float* w2_partial, const double* loss_partial, int n_groups, int count,
+                                float* grad, int64_t P, int64_t w2_off, float* loss_out, int N) {
+  int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < n_groups; ++g) s += w2_partial[((int64_t)b * n_groups + g) * count + i];
+    grad[(int64_t)b * P + w2_off + i] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) {
+    double s = 0.0;
+    for (int g = 0; g < n_groups; ++g) s += loss_partial[(int64_t)b * n_groups + g];
+    loss_out[b] = (float)(s / (double)N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PYB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    PYB_REQUIRE(f != nullptr && q == cudaDriverEntryPointSuccess, PYB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    fn = (PFN_encodeTiled)f;
+  }
+  return fn;
+}
+// 2-D bf16 tensor [rows, k] with row pitch ld_elems, box [TC_BK, box_rows], SWIZZLE_64B, zero OOB fill
+static CUtensorMap make_map(const void* base, int64_t k, int64_t rows, int64_t ld_elems, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  PYB_REQUIRE((ld_elems * 2) % 16 == 0, PYB_ERR_INVALID, "tensor map pitch must be a multiple of 16 bytes");
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PYB_REQUIRE(r == CUDA_SUCCESS, PYB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return m;
+}
+
+struct TcState {
+  bool data_ready = false, bufs_ready = false;
+  int64_t N = 0, Npad = 0, Bc = 0;
+  int D = 0, H = 0, C = 0;
+  DevBuf<__nv_bfloat16> x_hi, x_lo, xt_hi, xt_lo;       // [N][D], [D+1][Npad]
+  DevBuf<__nv_bfloat16> w_hi, w_lo;                     // [Bc*H][D]
+  DevBuf<__nv_bfloat16> z_hi, z_lo;                     // [Bc*H][Npad]
+  DevBuf<float> a1t;                                    // [Bc][H][Npad]
+  DevBuf<float> w2_partial;
+  DevBuf<double> loss_partial;
+  CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo, mW_hi, mW_lo, mZ_hi, mZ_lo;
+  int n_groups = 0;
+  bool attr_set = false;
+};
+static TcState* tc_state(pyb_handle* h) {
+  if (!h->tc) h->tc = new TcState();
+  return (TcState*)h->tc;
+}
+void tc_release(pyb_handle* h) {
+  if (h->tc) delete (TcState*)h->tc;
+  h->tc = nullptr;
+}
+void tc_invalidate_dataset(pyb_handle* h) {
+  if (h->tc) { ((TcState*)h->tc)->data_ready = false; ((TcState*)h->tc)->bufs_ready = false; }
+}
+
+bool tc_supported(pyb_handle* h, int64_t S) {
+  const Model& m = h->model;
+  (void)S;
+  if (m.n_layers != 2 || !h->have_data) return false;
+  const LayerDesc& L1 = m.layer[0];
+  const LayerDesc& L2 = m.layer[1];
+  if (!L1.use_bias || !L2.use_bias) return false;
+  if (L1.fan_out % 16 != 0 || L1.fan_out < 16 || L1.fan_out > 256) return false;
+  if (L1.fan_in % 8 != 0 || L1.fan_in < 64) return false;
+  if (L2.fan_out > L2_CMAX) return false;
+  if (L1.act == PYB_ACT_SOFTMAX) return false;
+  if (h->N < 128) return false;
+  return true;
+}
+
+static void launch_gemm_tc(pyb_handle* h, TcState* st, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                           const CUtensorMap& b_hi, const CUtensorMap& b_lo, TcGemmParams p, double flops) {
+  if (!st->attr_set) {
+    PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    st->attr_set = true;
+  }
+  int grid = std::min(p.total_items, h->sm_count);
+  prof_begin(h);
+  tc_gemm_bf16x3<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  prof_end(h, flops);
+  count_launch(h);
+}
+
+static void tc_prepare_data(pyb_handle* h, TcState* st) {
+  const Model& m = h->model;
+  st->N = h->N; st->D = m.layer[0].fan_in; st->H = m.layer[0].fan_out; st->C = m.layer[1].fan_out;
+  st->Npad = ((st->N + 127) / 128) * 128;
+  const int64_t N = st->N, Npad = st->Npad;
+  const int D = st->D;
+  st->x_hi.alloc(N * D); st->x_lo.alloc(N * D);
+  st->xt_hi.alloc((int64_t)(D + 1) * Npad); st->xt_lo.alloc((int64_t)(D + 1) * Npad);
+  PYB_CUDA(cudaMemsetAsync(st->xt_hi.p, 0, st->xt_hi.bytes(), h->stream));
+  PYB_CUDA(cudaMemsetAsync(st->xt_lo.p, 0, st->xt_lo.bytes(), h->stream));
+  k_split_rows<<<(unsigned)std::min<int64_t>((N * D + 255) / 256, 65535), 256, 0, h->stream>>>(h->X.p, N, D, D, st->x_hi.p,
+                                                                                             st->x_lo.p, D);
+  dim3 g2((D + 31) / 32, (unsigned)((N + 31) / 32), 1), blk(32, 8);
+  k_split_transpose<<<g2, blk, 0, h->stream>>>(h->X.p, 0, (int)N, D, D, st->xt_hi.p, st->xt_lo.p, 0, Npad);
+  k_fill_bf16<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(st->xt_hi.p + (int64_t)D * Npad, N, 1.0f);  // ones row -> db1
+  count_launch(h, 3);
+  st->mX_hi = make_map(st->x_hi.p, D, N, D, 128);
+  st->mX_lo = make_map(st->x_lo.p, D, N, D, 128);
+  st->mXT_hi = make_map(st->xt_hi.p, N, D + 1, Npad, 128);
+  st->mXT_lo = make_map(st->xt_lo.p, N, D + 1, Npad, 128);
+  st->data_ready = true;
+  st->bufs_ready = false;
+}
+
+static void tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S) {
+  // chain batch: intermediates are A1^T fp32 + dZ1^T hi/lo = 8 bytes per (chain, hidden, row)
+  int64_t per_chain = (int64_t)st->H * st->Npad * 8;
+  int64_t budget = (int64_t)(std::max(h->opt_workspace_mb, 20000.0) * 1024.0 * 1024.0);
+  int64_t bc = std::max<int64_t>(1, budget / per_chain);
+  if (h->opt_chain_batch > 0) bc = std::min<int64_t>(bc, h->opt_chain_batch);
+  bc = std::min<int64_t>(bc, S);
+  if (bc >= h->sm_count) bc = (bc / h->sm_count) * h->sm_count;      // whole waves of G2 work
+  if (st->bufs_ready && st->Bc >= bc) return;
+  st->Bc = bc;
+  const int H = st->H, D = st->D;
+  st->w_hi.alloc(bc * H * D); st->w_lo.alloc(bc * H * D);
+  st->z_hi.alloc(bc * H * st->Npad); st->z_lo.alloc(bc * H * st->Npad);
+  st->a1t.alloc(bc * H * st->Npad);
+  PYB_CUDA(cudaMemsetAsync(st->a1t.p, 0, st->a1t.bytes(), h->stream));   // padded rows stay finite (phase B reads them)
+  st->n_groups = (int)((st->N + 128 * L2_TILES - 1) / (128 * L2_TILES));
+  st->w2_partial.alloc((size_t)bc * st->n_groups * (H * st->C + st->C));
+  st->loss_partial.alloc((size_t)bc * st->n_groups);
+  st->mW_hi = make_map(st->w_hi.p, D, bc * H, D, H);
+  st->mW_lo = make_map(st->w_lo.p, D, bc * H, D, H);
+  st->mZ_hi = make_map(st->z_hi.p, st->N, bc * H, st->Npad, H);
+  st->mZ_lo = make_map(st->z_lo.p, st->N, bc * H, st->Npad, H);
+  st->bufs_ready = true;
+}
+
+void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
+  TcState* st = tc_state(h);
+  const Model& m = h->model;
+  if (!st->data_ready) tc_prepare_data(h, st);
+  tc_prepare_bufs(h, st, S);
+  const LayerDesc& L1 = m.layer[0];
+  const LayerDesc& L2 = m.layer[1];
+  const int D = st->D, H = st->H, C = st->C;
+  const int64_t N = st->N, Npad = st->Npad, P = m.P;
+  for (int64_t b0 = 0; b0 < S; b0 += st->Bc) {
+    const int nb = (int)std::min<int64_t>(st->Bc, S - b0);
+    const float* th = theta + b0 * P;
+    float* gr = grad_out + b0 * P;
+    // 1. W1 [D,H] per chain -> W1^T hi/lo [H, D]
+    {
+      dim3 g((H + 31) / 32, (D + 31) / 32, nb), blk(32, 8);
+      k_split_transpose<<<g, blk, 0, h->stream>>>(th + L1.w_off, P, D, H, H, st->w_hi.p, st->w_lo.p, (int64_t)H * D, D);
+      count_launch(h);
+    }
+    // 2. G1: A1^T = act(X W1 + b1)^T
+    {
+      TcGemmParams p = {};
+      p.K = D; p.n_mtiles = (int)((N + 127) / 128); p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
+      p.order = 1; p.sub_batch = 32; p.total_items = p.n_pairs * nb;
+      p.epi = EPI_BIAS_ACT_T;
+      p.bias = th + L1.b_off; p.bias_stride = P; p.act = L1.act;
+      p.out_t = st->a1t.p; p.out_t_chain_stride = (int64_t)H * Npad; p.out_t_ld = Npad;
+      p.M_valid = (int)N;
+      launch_gemm_tc(h, st, st->mX_hi, st->mX_lo, st->mW_hi, st->mW_lo, p, 2.0 * N * D * (double)H * nb);
+    }
+    // 3. layer 2 + loss + dZ1^T
+    {
+      Layer2Params p = {};
+      p.a1t = st->a1t.p; p.a1t_chain_stride = (int64_t)H * Npad; p.ld = Npad;
+      p.zt_hi = st->z_hi.p; p.zt_lo = st->z_lo.p;
+      p.theta = th; p.P = P; p.w2_off = L2.w_off; p.b2_off = L2.b_off;
+      p.H = H; p.C = C; p.N = (int)N; p.act1 = L1.act; p.out_act = L2.act; p.loss_kind = h->loss_kind;
+      p.y_i = h->y_i.p; p.y_f = h->y_f.p; p.scale = scale;
+      p.loss_partial = st->loss_partial.p; p.w2_partial = st->w2_partial.p; p.n_groups = st->n_groups;
+      dim3 g(st->n_groups, nb);
+      k_layer2<<<g, 128, 0, h->stream>>>(p);
+      dim3 rg((H * C + C + 255) / 256, nb);
+      k_layer2_reduce<<<rg, 256, 0, h->stream>>>(st->w2_partial.p, st->loss_partial.p, st->n_groups, H * C + C, gr, P,
+                                                 L2.w_off, loss_out ? loss_out + b0 : nullptr, (int)N);
+      count_launch(h, 2);
+    }
+    // 4. G2: [dW1; db1] = [X^T; 1] dZ1
+    {
+      TcGemmParams p = {};
+      p.K = (int)N; p.n_mtiles = (D + 1 + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
+      p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
+      p.epi = EPI_STORE;
+      p.out = gr; p.out_stride = P; p.out_ld = H; p.M_valid = D + 1;
+      launch_gemm_tc(h, st, st->mXT_hi, st->mXT_lo, st->mZ_hi, st->mZ_lo, p, 2.0 * N * (double)(D + 1) * H * nb);
+    }
+  }
+  PYB_CUDA(cudaGetLastError());
+}
+
+// debug / unit-test entry: D[M,Nn] = A[M,K] B[Nn,K]^T through the tcgen05 kernel (host pointers)
+void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn, int K, float* Dout) {
+  PYB_REQUIRE(Nn % 16 == 0 && Nn >= 16 && Nn <= 256 && K % 8 == 0, PYB_ERR_INVALID, "Nn%16, Nn<=256, K%8 required");
+  TcState* st = tc_state(h);
+  DevBuf<float> dA, dB, dD;
+  DevBuf<__nv_bfloat16> ah, al, bh, bl;
+  dA.alloc((size_t)M * K); dB.alloc((size_t)Nn * K); dD.alloc((size_t)M * Nn);
+  ah.alloc((size_t)M * K); al.alloc((size_t)M * K); bh.alloc((size_t)Nn * K); bl.alloc((size_t)Nn * K);
+  PYB_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)M * K * 4, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(dB.p, B, (size_t)Nn * K * 4, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemsetAsync(dD.p, 0xff, (size_t)M * Nn * 4, h->stream));
+  k_split_rows<<<1024, 256, 0, h->stream>>>(dA.p, M, K, K, ah.p, al.p, K);
+  k_split_rows<<<1024, 256, 0, h->stream>>>(dB.p, Nn, K, K, bh.p, bl.p, K);
+  CUtensorMap ma_h = make_map(ah.p, K, M, K, 128), ma_l = make_map(al.p, K, M, K, 128);
+  CUtensorMap mb_h = make_map(bh.p, K, Nn, K, Nn), mb_l = make_map(bl.p, K, Nn, K, Nn);
+  TcGemmParams p = {};
+  p.K = K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = 1; p.H = Nn;
+  p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
+  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M;
+  launch_gemm_tc(h, st, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K);
+  PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+}
+
 }  // namespace pyb
+
+extern "C" int pyb_debug_tc_gemm(pyb_handle* h, const float* A, const float* B, int32_t M, int32_t Nn, int32_t K,
+                                 float* D) {
+  try {
+    if (!h || !A || !B || !D) throw pyb::Error(PYB_ERR_INVALID, "NULL argument");
+    PYB_CUDA(cudaSetDevice(h->device));
+    pyb::tc_debug_gemm(h, A, B, M, Nn, K, D);
+  } catch (const pyb::Error& e) {
+    pyb::set_last_error(e.what());
+    return e.code;
+  }
+  return PYB_OK;
+}

@@ -1,0 +1,175 @@
+"""GPU tests of the tcgen05/TMA path (bf16x3 split products): the raw GEMM kernel against float64
+NumPy, then log-prob/gradient/trajectory parity of the MNIST-width HMC path against the oracle and
+against the generic fp32 SIMT path on the same inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+from bayesian_inference_for_nn_b200 import _lib, keras_json  # noqa: E402
+from bayesian_inference_for_nn_b200.engine import Engine  # noqa: E402
+
+
+def engine(D, H, Cc, act="relu", out_act="softmax", seed=0):
+    js = keras_json.make_sequential_json(D, [H, Cc], [act, out_act])
+    return Engine(keras_json.parse_model_json(js), seed=seed)
+
+
+def debug_gemm(eng, A, B):
+    lib = _lib.load()
+    fn = lib.pyb_debug_tc_gemm
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    fn.restype = C.c_int
+    A = np.ascontiguousarray(A, np.float32)
+    B = np.ascontiguousarray(B, np.float32)
+    D = np.empty((A.shape[0], B.shape[0]), np.float32)
+    _lib.check(fn(eng.h, A.ctypes.data, B.ctypes.data, A.shape[0], B.shape[0], A.shape[1], D.ctypes.data))
+    return D
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 256, 32), (128, 256, 784), (300, 64, 96), (785, 256, 1000), (1000, 128, 40),
+                                     (2500, 16, 2048)])
+def test_split_bf16_gemm_matches_float64(M, Nn, K):
+    rng = np.random.default_rng(M + Nn + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((Nn, K)) * 0.3).astype(np.float32)
+    eng = engine(64, 32, 4)
+    D = debug_gemm(eng, A, B)
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.sqrt((A.astype(np.float64) ** 2).sum(1))[:, None] * np.sqrt((B.astype(np.float64) ** 2).sum(1))[None]
+    err = np.abs(D - want) / scale
+    assert np.isfinite(D).all()
+    assert err.max() < 3e-5, err.max()        # ~2^-16 per product, error relative to |a||b|
+    assert rel_err(D, want) < 2e-5
+
+
+def problem(oracle, D, H, Cc, N, S, seed, act="relu", loss="ce", q_scale=0.05):
+    O = oracle
+    rng = np.random.default_rng(seed)
+    out_act = "softmax" if loss == "ce" else "linear"
+    spec = O.MLPSpec(D, [H, Cc], [act, out_act])
+    X = rng.random((N, D)).astype(np.float32)
+    if loss == "ce":
+        y, kind = rng.integers(0, Cc, N).astype(np.int32), O.LOSS_SPARSE_CE
+    else:
+        y, kind = rng.standard_normal((N, Cc)).astype(np.float32), O.LOSS_MSE
+    q = (rng.standard_normal((S, spec.n_params)) * q_scale).astype(np.float32)
+    if act == "relu":
+        q = move_off_relu_kinks(q, X, D, H)
+    mu, sg = O.expand_prior(spec, 0.0, 1.0)
+    return spec, O.Problem(spec, X, y, kind, mu, sg), q, out_act, rng
+
+
+def move_off_relu_kinks(q, X, D, H, margin=1e-3):
+    """relu'(z) = 1[z>0] is discontinuous: a pre-activation within rounding distance of 0 flips the
+    mask between ANY two fp32 implementations (and a single flipped unit moves a random-label
+    gradient by ~1e-3 relative), so the 1e-4 gradient tolerance is only meaningful away from the
+    kinks.  Shift each hidden unit's bias into the middle of a gap of its pre-activations so that
+    min |z1| >= margin for every (row, unit)."""
+    q = q.copy()
+    X64 = X.astype(np.float64)
+    for s in range(q.shape[0]):
+        W = q[s, :D * H].astype(np.float64).reshape(D, H)
+        b = q[s, D * H:D * H + H].astype(np.float64)
+        Z = np.sort(X64 @ W + b, axis=0)                       # [N, H]
+        for h in range(H):
+            z = Z[:, h]
+            edges = np.concatenate([[z[0] - 1.0], z, [z[-1] + 1.0]])
+            gaps = edges[1:] - edges[:-1]
+            mids = 0.5 * (edges[1:] + edges[:-1])
+            ok = np.where(gaps > 4 * margin)[0]
+            m = mids[ok[np.argmin(np.abs(mids[ok]))]]          # admissible gap centre closest to zero
+            b[h] -= m
+        q[s, D * H:D * H + H] = b.astype(np.float32)
+        Zc = X64 @ W + q[s, D * H:D * H + H].astype(np.float64)
+        assert np.abs(Zc).min() > 0.5 * margin
+    return q
+
+
+CASES = [(784, 256, 10, 512, 3, "relu", "ce"), (784, 128, 10, 300, 2, "relu", "ce"), (64, 32, 4, 1000, 5, "tanh", "ce"),
+         (128, 64, 3, 257, 2, "sigmoid", "mse"), (784, 256, 10, 128, 1, "relu", "ce")]
+
+
+@pytest.mark.parametrize("D,H,Cc,N,S,act,loss", CASES)
+def test_tensor_path_logprob_and_gradient(oracle, D, H, Cc, N, S, act, loss):
+    O = oracle
+    spec, prob, q, out_act, _ = problem(O, D, H, Cc, N, S, seed=D + H + N, act=act, loss=loss)
+    U64, loss64, g64 = O.potential(prob, q, np.float64)
+    eng = engine(D, H, Cc, act, out_act)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.set_option("path", _lib.PATH_TENSOR)
+    U, ls, g = eng.hmc_eval(q)
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    np.testing.assert_allclose(U, U64, rtol=1e-4)
+    np.testing.assert_allclose(ls, loss64, rtol=1e-4)
+    for s in range(S):
+        assert rel_err(g[s], g64[s]) < 1e-4, (s, rel_err(g[s], g64[s]))
+    # and against the fp32 SIMT path on the same device
+    eng.set_option("path", _lib.PATH_GENERIC)
+    Ug, lg, gg = eng.hmc_eval(q)
+    np.testing.assert_allclose(U, Ug, rtol=1e-4)
+    for s in range(S):
+        assert rel_err(g[s], gg[s]) < 1e-4
+    # chain batching inside the tensor path must not change anything
+    eng.set_option("path", _lib.PATH_TENSOR)
+    eng.set_option("chain_batch", 1)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)     # re-upload also re-derives the split operands
+    U1, _, g1 = eng.hmc_eval(q)
+    np.testing.assert_array_equal(U, U1)
+    np.testing.assert_array_equal(g, g1)
+
+
+def test_tensor_path_hmc_iteration_matches_oracle(oracle):
+    O = oracle
+    D, H, Cc, N, S, L, eps = 784, 256, 10, 640, 3, 4, 1e-3
+    spec, prob, q, out_act, rng = problem(O, D, H, Cc, N, S, seed=11)
+    p = rng.standard_normal((S, spec.n_params)).astype(np.float32)
+    u = np.float32([0.0, 0.999, 0.5])
+    want = O.hmc_iteration(prob, q, p, u, eps, 1.0, L, False, O.HMC_REFERENCE, np.float64)
+    eng = engine(D, H, Cc)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.hmc_init(S, eps, 1.0, L, _lib.HMC_REFERENCE, q0=q)        # path AUTO must pick the tensor path
+    eng.hmc_inject(p=p, u=u)
+    d = eng.hmc_run(1, burning=False, sampling=True)
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    last = eng.hmc_last()
+    for k in ("U0", "K0", "U1", "K1"):
+        np.testing.assert_allclose(last[k], want[k], rtol=1e-4, err_msg=k)
+    lu = np.log(np.maximum(u.astype(np.float64), 1e-300))
+    decisive = np.abs(want["log_alpha"] - lu) > 1e-5 * np.maximum(1.0, np.abs(want["U0"]))
+    np.testing.assert_array_equal(last["accept"][decisive], want["accept"][decisive])
+    qd, pd = eng.hmc_state()
+    for s in range(S):
+        if last["accept"][s] == want["accept"][s]:
+            assert rel_err(qd[s], want["q"][s]) < 1e-3
+            assert rel_err(pd[s], want["pL"][s]) < 1e-3
+    assert d["grad_evals"] == S * (L + 1)
+
+
+def test_tensor_path_reversibility_canonical(oracle):
+    """Size-independent property: the textbook leapfrog is time-reversible.  Integrate L steps,
+    negate the momentum, integrate L more: the chain returns to its start (to fp32 rounding)."""
+    O = oracle
+    D, H, Cc, N, S, L, eps = 784, 256, 10, 2048, 4, 5, 5e-4
+    spec, prob, q, out_act, rng = problem(O, D, H, Cc, N, S, seed=3)
+    p = rng.standard_normal((S, spec.n_params)).astype(np.float32)
+    eng = engine(D, H, Cc)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.hmc_init(S, eps, 1.0, L, _lib.HMC_CANONICAL, q0=q)
+    eng.hmc_inject(p=p)
+    eng.hmc_run(1, burning=True, sampling=False)
+    q1, p1 = eng.hmc_state()
+    e0 = eng.hmc_last()
+    assert np.all(np.abs(e0["log_alpha"]) < 0.5)                    # energy nearly conserved
+    eng.hmc_inject(p=-p1)
+    eng.hmc_run(1, burning=True, sampling=False)
+    q2, p2 = eng.hmc_state()
+    assert rel_err(q2, q) < 1e-5 and rel_err(-p2, p) < 1e-4
+    assert np.abs(q1 - q).max() > 0
