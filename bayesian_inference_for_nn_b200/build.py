@@ -50,7 +50,7 @@ def build(verbose=False, force=False):
     objs = [o for o, _ in res]
     log = "".join(l for _, l in res)
     if log:
-        with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
+        with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
             f.write(log)
     if verbose and log:
         print(log)

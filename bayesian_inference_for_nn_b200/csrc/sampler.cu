@@ -279,8 +279,13 @@ void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double
   st.counters.alloc(4);
   st.loss_sum.alloc(1);
   st.arena_count.alloc(1);
-  // arena: at least 2S rows (first sampling iteration), about 1 GiB otherwise
-  int64_t cap = (int64_t)((1ull << 30) / (sizeof(float) * (size_t)P));
+  // sample arena: at least 2S rows (the first sampling iteration records two states per chain);
+  // otherwise a quarter of the free HBM (<= 32 GiB) so that flushes to the host are rare
+  size_t free_b = 0, total_b = 0;
+  PYB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = std::min<size_t>(free_b / 4, (size_t)32 << 30);
+  budget = std::max<size_t>(budget, (size_t)1 << 28);
+  int64_t cap = (int64_t)(budget / (sizeof(float) * (size_t)P));
   if (cap < 2 * S) cap = 2 * S;
   if (cap > (1ll << 30)) cap = 1ll << 30;
   st.arena_cap = cap;

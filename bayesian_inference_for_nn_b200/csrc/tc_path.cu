@@ -2,10 +2,11 @@
 // two-layer Dense MLP whose first layer is a real dense contraction (D x H with H <= 256).
 //
 // What runs where, per chain batch (Bc chains), per log-posterior evaluation:
-//   k_pack_w1     theta -> W1^T split into bf16 hi/lo, K-major [Bc*H, D]            (SIMT, tiny)
-//   tc_gemm<G1>   Z1 = X W1 (+b1, act) -> A1^T fp32 [Bc, H, Npad]                    (tcgen05 + TMA)
-//   k_layer2      per row: z2, softmax-CE / MSE, dZ2, dZ1 = (dZ2 W2^T) act'(a1)
-//                 -> dZ1^T split bf16 hi/lo [Bc*H, Npad]; loss, dW2, db2 partials    (SIMT)
+//   k_split_transpose  theta -> W1^T split into bf16 hi/lo, K-major [Bc*H, D]       (SIMT, tiny)
+//   tc_gemm<G1>   Z1 = X W1 (+b1, act) -> A1^T split bf16 hi/lo [Bc*H, Npad]         (tcgen05 + TMA)
+//   k_layer2      per row: z2 = a1 W2 + b2, softmax-CE / MSE, dZ2,
+//                 dZ1 = (dZ2 W2^T) act'(a1) -> dZ1^T, dZ2^T split bf16 hi/lo; loss, db2  (SIMT, HBM-bound)
+//   tc_gemm<G3>   dW2 = A1^T dZ2 -> grad[:, w2_off : w2_off + H*C]                   (tcgen05 + TMA, HBM-bound)
 //   tc_gemm<G2>   [dW1; db1] = [X^T; 1] dZ1 -> grad[:, 0 : D*H + H]                  (tcgen05 + TMA)
 // fp32-grade products on bf16 tensor cores: every operand is split x = hi + lo (bf16 each) and the
 // MMA issues hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator (relative error ~2^-16 per
@@ -19,7 +20,7 @@
 // streamed in 32-element (64 B, SWIZZLE_64B) chunks through a 3-stage TMA/mbarrier ring:
 // 64 KB/stage for 2*3*128*256*32*2 flop => ~42 B/clk/SM of L2->SM traffic at full MMA rate.
 // Roles: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warp 2 TMEM allocator,
-// warps 4-7 epilogue (TMEM lane == output row).
+// warps 4-7 epilogue of accumulator 0 and warps 8-11 of accumulator 1 (TMEM lane == output row).
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -114,20 +115,21 @@ constexpr int TC_A_TILE_BYTES = 128 * TC_BK * 2;    // 8 KB
 constexpr int TC_B_TILE_BYTES = 256 * TC_BK * 2;    // 16 KB (H <= 256)
 constexpr int TC_STAGE_BYTES = 4 * TC_A_TILE_BYTES + 2 * TC_B_TILE_BYTES;   // 64 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers + bias*/ + 1024;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;
 
-enum { EPI_BIAS_ACT_T = 0, EPI_STORE = 1 };
+enum { EPI_BIAS_ACT_T_SPLIT = 0, EPI_STORE = 1 };
 
 struct TcGemmParams {
   int K, n_mtiles, n_pairs, n_batch, H;
+  int a_batch_rows;            // A row offset per chain (0: A shared by all chains)
   int order, sub_batch, total_items;
   int epi;
-  // EPI_BIAS_ACT_T: out_t[b][col][row] = act(D[row][col] + bias[b][col])   (row < M_valid)
+  // EPI_BIAS_ACT_T_SPLIT: a = act(D[row][col] + bias[b][col]) -> bf16 hi/lo at [b*H + col][row]  (row < M_valid)
   const float* bias; int64_t bias_stride; int act;
-  float* out_t; int64_t out_t_chain_stride; int64_t out_t_ld;
-  // EPI_STORE: out[b*out_stride + row*out_ld + col] = D[row][col]           (row < M_valid)
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int64_t out_t_ld;
+  // EPI_STORE: out[b*out_stride + row*out_ld + col] = D[row][col]   (row < M_valid, col < N_valid)
   float* out; int64_t out_stride; int out_ld;
-  int M_valid;
+  int M_valid, N_valid;
 };
 
 __device__ __forceinline__ void tc_decode(const TcGemmParams& p, int item, int& b, int& mp) {
@@ -173,7 +175,7 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 128);
+    mbar_init(tmem_empty, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -203,8 +205,8 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_expect_tx(&full_bar[stage], bytes);
           const int k0 = kc * TC_BK;
           for (int mt = 0; mt < n_mt; ++mt) {
-            tma_load_2d(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], k0, (mt0 + mt) * 128);
-            tma_load_2d(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, (mt0 + mt) * 128);
+            tma_load_2d(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], k0, b * p.a_batch_rows + (mt0 + mt) * 128);
+            tma_load_2d(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, b * p.a_batch_rows + (mt0 + mt) * 128);
           }
           tma_load_2d(st + 4 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], k0, b * p.H);
           tma_load_2d(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &tmB_lo, &full_bar[stage], k0, b * p.H);
@@ -253,8 +255,10 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM lane == row of the 128-row tile =====
-    const int et = threadIdx.x - 128;                            // 0..127
+    // ===== epilogue: warps 4-7 drain accumulator 0, warps 8-11 accumulator 1; TMEM lane == tile row =====
+    const int grp = (warp - 4) >> 2;                             // which accumulator / m-tile of the pair
+    const int et = (threadIdx.x - 128) & 127;                    // row inside the 128-row tile
+    const int eall = threadIdx.x - 128;                          // 0..255
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -262,32 +266,51 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tc_decode(p, item, b, mp);
       const int mt0 = mp * 2;
       const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
-      if (p.epi == EPI_BIAS_ACT_T) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");           // previous item's readers are done
-        for (int c = et; c < p.H; c += 128) bias_s[c] = p.bias ? p.bias[(int64_t)b * p.bias_stride + c] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.epi == EPI_BIAS_ACT_T_SPLIT) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // previous item's readers are done
+        for (int c = eall; c < p.H; c += 256) bias_s[c] = p.bias ? p.bias[(int64_t)b * p.bias_stride + c] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(tmem_full, acc_phase);
       tc_fence_after();
-      for (int mt = 0; mt < n_mt; ++mt) {
-        const int row = (mt0 + mt) * 128 + et;
+      if (grp < n_mt) {
+        const int row = (mt0 + grp) * 128 + et;
         const bool valid = row < p.M_valid;
         for (int c0 = 0; c0 < p.H; c0 += 32) {
           float v[32];
-          tc_ld32(tmem_base + lane_base + (uint32_t)(mt * 256 + c0), v);
-          if (p.epi == EPI_BIAS_ACT_T) {
-            if (valid) {
-              float* o = p.out_t + (int64_t)b * p.out_t_chain_stride + (int64_t)c0 * p.out_t_ld + row;
+          tc_ld32(tmem_base + lane_base + (uint32_t)(grp * 256 + c0), v);
+          if (p.epi == EPI_BIAS_ACT_T_SPLIT) {
+            // even lanes own even columns, odd lanes odd columns; the partner lane's value arrives by
+            // shuffle so that (row, row+1) leave as one 32-bit bf16x2 word: half the store instructions,
+            // 64 B contiguous per half-warp.  All lanes take part in the shuffles (rows >= M_valid too).
+            const int odd = lane & 1;
+            const bool pair_valid = (row & ~1) < p.M_valid;
+            const int64_t o = ((int64_t)b * p.H + c0) * p.out_t_ld + (row & ~1);
+            uint32_t* ohi = reinterpret_cast<uint32_t*>(p.out_hi);
+            uint32_t* olo = reinterpret_cast<uint32_t*>(p.out_lo);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < p.H) o[(int64_t)j * p.out_t_ld] = act_apply(v[j] + bias_s[c0 + j], p.act);
+            for (int j = 0; j < 32; j += 2) {
+              const float a_e = act_apply(v[j] + bias_s[min(c0 + j, p.H - 1)], p.act);
+              const float a_o = act_apply(v[j + 1] + bias_s[min(c0 + j + 1, p.H - 1)], p.act);
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? a_e : a_o, 1);
+              const float x0 = odd ? recv : a_e;       // row & ~1
+              const float x1 = odd ? a_o : recv;       // (row & ~1) + 1
+              const int cj = j + odd;
+              if (pair_valid && c0 + cj < p.H) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                const int64_t w = (o + (int64_t)cj * p.out_t_ld) >> 1;
+                ohi[w] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                olo[w] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
             }
           } else {
             if (valid) {
               float* o = p.out + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (c0 + j < p.H) o[j] = v[j];
+                if (c0 + j < p.N_valid) o[j] = v[j];
             }
           }
         }
@@ -356,187 +379,209 @@ __global__ void k_fill_bf16(__nv_bfloat16* p, int64_t n, float v) {
     p[i] = __float2bfloat16_rn(v);
 }
 
-// Layer 2 forward/backward for one chain and a group of 128-row tiles.  thread == row in phases
-// A/A2, thread == hidden unit in phase B (dW2 accumulation).
+// Layer 2 forward/backward.  One thread owns TWO adjacent data rows (packed bf16x2 loads/stores are
+// then 128 B per warp); a block walks 256-row tiles of one chain.  a1 = hi + lo is read ONCE: for
+// relu the derivative mask is kept as 2 x 256 bits in registers; other activations re-read a1.
 constexpr int L2_CMAX = 16;
-constexpr int L2_TILES = 8;     // 128-row tiles per block
+constexpr int L2_ROWS = 256;    // rows per tile (128 threads x 2)
 struct Layer2Params {
-  const float* a1t; int64_t a1t_chain_stride; int64_t ld;   // [Bc][H][Npad]
-  __nv_bfloat16* zt_hi; __nv_bfloat16* zt_lo;              // [Bc*H][Npad]
+  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;     // A1^T [Bc*H][ld]
+  __nv_bfloat16* zt_hi; __nv_bfloat16* zt_lo;               // dZ1^T [Bc*H][ld]
+  __nv_bfloat16* z2_hi; __nv_bfloat16* z2_lo;               // dZ2^T [Bc*16][ld]
+  int64_t ld;
   const float* theta; int64_t P; int64_t w2_off, b2_off;
   int H, C, N, act1, out_act, loss_kind;
   const int32_t* y_i; const float* y_f;
   float scale;                 // n_train (or 1): dZ = scale * d(mean loss)/dz
   double* loss_partial;        // [Bc][n_groups]
-  float* w2_partial;           // [Bc][n_groups][H*C + C]
-  int n_groups;
+  float* b2_partial;           // [Bc][n_groups][16]
+  int n_groups, n_tiles;
 };
-__global__ void __launch_bounds__(128) k_layer2(Layer2Params p) {
-  __shared__ float W2s[256 * L2_CMAX];
-  __shared__ float dz2s[128 * L2_CMAX];
-  __shared__ float b2s[L2_CMAX];
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+template <int CP>
+__device__ __forceinline__ void l2_loss_dz(const Layer2Params& p, int r, bool valid, const float* z, float* dz,
+                                           double& loss_acc, float invN) {
+  const int C = p.C;
+#pragma unroll
+  for (int c = 0; c < CP; ++c) dz[c] = 0.f;
+  if (!valid) return;
+  if (p.loss_kind == PYB_LOSS_SPARSE_CE) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) if (c < C) mx = fmaxf(mx, z[c]);
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) if (c < C) se += expf(z[c] - mx);
+    const int yi = p.y_i[r];
+    float zy = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) if (c == yi) zy = z[c];
+    loss_acc += (double)(logf(se) - (zy - mx));
+    const float inv = 1.0f / se;
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < C) dz[c] = (expf(z[c] - mx) * inv - (c == yi ? 1.f : 0.f)) * invN;
+  } else {
+    float acc = 0.f;
+    const float sc = 2.0f * invN / (float)C;
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < C) {
+        float a = act_apply(z[c], p.out_act);
+        float df = a - p.y_f[(int64_t)r * C + c];
+        acc += df * df;
+        dz[c] = sc * df * act_grad_from_output(a, p.out_act);
+      }
+    loss_acc += (double)(acc / (float)C);
+  }
+}
+// CP = class count padded to a multiple of 4 (register tile of the per-row logits)
+template <int CP>
+__global__ void __launch_bounds__(128, 4) k_layer2(Layer2Params p) {
+  __shared__ __align__(16) float W2s[256 * CP];
+  __shared__ float b2s[CP];
+  __shared__ uint32_t mask_s[2][8][128];
+  __shared__ float redf[4][CP];
   __shared__ double scratch[32];
-  const int t = threadIdx.x, b = blockIdx.y, g = blockIdx.x;
+  const int t = threadIdx.x, b = blockIdx.y;
   const int H = p.H, C = p.C;
   const float* th = p.theta + (int64_t)b * p.P;
-  for (int i = t; i < H * L2_CMAX; i += 128) {
-    int h = i / L2_CMAX, c = i % L2_CMAX;
+  for (int i = t; i < H * CP; i += 128) {
+    int h = i / CP, c = i % CP;
     W2s[i] = (c < C) ? th[p.w2_off + (int64_t)h * C + c] : 0.f;
   }
-  if (t < L2_CMAX) b2s[t] = (t < C) ? th[p.b2_off + t] : 0.f;
+  if (t < CP) b2s[t] = (t < C) ? th[p.b2_off + t] : 0.f;
   __syncthreads();
-  const float* a1 = p.a1t + (int64_t)b * p.a1t_chain_stride;
-  __nv_bfloat16* zh = p.zt_hi + (int64_t)b * H * p.ld;
-  __nv_bfloat16* zl = p.zt_lo + (int64_t)b * H * p.ld;
-  float accw[2][L2_CMAX];
+  const uint32_t* ah = reinterpret_cast<const uint32_t*>(p.a_hi + (int64_t)b * H * p.ld);
+  const uint32_t* al = reinterpret_cast<const uint32_t*>(p.a_lo + (int64_t)b * H * p.ld);
+  uint32_t* zh = reinterpret_cast<uint32_t*>(p.zt_hi + (int64_t)b * H * p.ld);
+  uint32_t* zl = reinterpret_cast<uint32_t*>(p.zt_lo + (int64_t)b * H * p.ld);
+  uint32_t* z2h = reinterpret_cast<uint32_t*>(p.z2_hi + (int64_t)b * L2_CMAX * p.ld);
+  uint32_t* z2l = reinterpret_cast<uint32_t*>(p.z2_lo + (int64_t)b * L2_CMAX * p.ld);
+  const int64_t ld2 = p.ld >> 1;           // row pitch in packed pairs
+  float accb[CP];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int c = 0; c < L2_CMAX; ++c) accw[i][c] = 0.f;
-  float accb = 0.f;
+  for (int c = 0; c < CP; ++c) accb[c] = 0.f;
   double loss_acc = 0.0;
   const float invN = p.scale / (float)p.N;
-  for (int tile = 0; tile < L2_TILES; ++tile) {
-    const int row0 = (g * L2_TILES + tile) * 128;
-    if (row0 >= p.N) break;
-    const int r = row0 + t;
-    const bool valid = r < p.N;
-    // ---- phase A: z2 = a1 W2 + b2
-    float z[L2_CMAX];
+  const bool relu = p.act1 == PYB_ACT_RELU;
+  const int nhb = (H + 31) >> 5;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int r0 = tile * L2_ROWS + 2 * t;
+    const int64_t col = (int64_t)(tile * (L2_ROWS / 2) + t);     // packed-pair column index
+    const bool v0 = r0 < p.N, v1 = r0 + 1 < p.N;
+    // ---- phase A: z2 = a1 W2 + b2 for both rows; relu mask bits go to shared memory
+    float z0[CP], z1[CP];
 #pragma unroll
-    for (int c = 0; c < L2_CMAX; ++c) z[c] = b2s[c];
-    if (valid) {
-      for (int h = 0; h < H; ++h) {
-        float a = a1[(int64_t)h * p.ld + r];
-        const float4* w = reinterpret_cast<const float4*>(&W2s[h * L2_CMAX]);
+    for (int c = 0; c < CP; ++c) { z0[c] = b2s[c]; z1[c] = b2s[c]; }
+    for (int hb = 0; hb < nhb; ++hb) {
+      uint32_t m0 = 0u, m1 = 0u;
+      const uint32_t* ahp = ah + (int64_t)(hb * 32) * ld2 + col;
+      const uint32_t* alp = al + (int64_t)(hb * 32) * ld2 + col;
+      const int jn = min(32, H - hb * 32);
+#pragma unroll 4
+      for (int j = 0; j < jn; ++j) {
+        const float2 hi = unpack_bf16x2(ahp[(int64_t)j * ld2]);
+        const float2 lo = unpack_bf16x2(alp[(int64_t)j * ld2]);
+        const float a0 = hi.x + lo.x, a1v = hi.y + lo.y;
+        m0 |= (a0 > 0.f ? 1u : 0u) << j;
+        m1 |= (a1v > 0.f ? 1u : 0u) << j;
+        const float4* w = reinterpret_cast<const float4*>(&W2s[(hb * 32 + j) * CP]);
 #pragma unroll
-        for (int q4 = 0; q4 < L2_CMAX / 4; ++q4) {
-          float4 wv = w[q4];
-          z[q4 * 4 + 0] = fmaf(a, wv.x, z[q4 * 4 + 0]);
-          z[q4 * 4 + 1] = fmaf(a, wv.y, z[q4 * 4 + 1]);
-          z[q4 * 4 + 2] = fmaf(a, wv.z, z[q4 * 4 + 2]);
-          z[q4 * 4 + 3] = fmaf(a, wv.w, z[q4 * 4 + 3]);
+        for (int q4 = 0; q4 < CP / 4; ++q4) {
+          const float4 wv = w[q4];
+          z0[q4 * 4 + 0] = fmaf(a0, wv.x, z0[q4 * 4 + 0]); z1[q4 * 4 + 0] = fmaf(a1v, wv.x, z1[q4 * 4 + 0]);
+          z0[q4 * 4 + 1] = fmaf(a0, wv.y, z0[q4 * 4 + 1]); z1[q4 * 4 + 1] = fmaf(a1v, wv.y, z1[q4 * 4 + 1]);
+          z0[q4 * 4 + 2] = fmaf(a0, wv.z, z0[q4 * 4 + 2]); z1[q4 * 4 + 2] = fmaf(a1v, wv.z, z1[q4 * 4 + 2]);
+          z0[q4 * 4 + 3] = fmaf(a0, wv.w, z0[q4 * 4 + 3]); z1[q4 * 4 + 3] = fmaf(a1v, wv.w, z1[q4 * 4 + 3]);
         }
       }
+      mask_s[0][hb][t] = m0;
+      mask_s[1][hb][t] = m1;
     }
-    // ---- loss and dZ2
-    float dz[L2_CMAX];
+    // ---- loss and dZ2 (scaled); dZ2^T stored split for the dW2 GEMM
+    float dz0[CP], dz1[CP];
+    l2_loss_dz<CP>(p, r0, v0, z0, dz0, loss_acc, invN);
+    l2_loss_dz<CP>(p, r0 + 1, v1, z1, dz1, loss_acc, invN);
 #pragma unroll
-    for (int c = 0; c < L2_CMAX; ++c) dz[c] = 0.f;
-    if (valid) {
-      if (p.loss_kind == PYB_LOSS_SPARSE_CE) {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < L2_CMAX; ++c) if (c < C) mx = fmaxf(mx, z[c]);
-        float se = 0.f;
-#pragma unroll
-        for (int c = 0; c < L2_CMAX; ++c) if (c < C) se += expf(z[c] - mx);
-        const int yi = p.y_i[r];
-        float zy = 0.f;
-#pragma unroll
-        for (int c = 0; c < L2_CMAX; ++c) if (c == yi) zy = z[c];
-        loss_acc += (double)(logf(se) - (zy - mx));
-        const float inv = 1.0f / se;
-#pragma unroll
-        for (int c = 0; c < L2_CMAX; ++c)
-          if (c < C) dz[c] = (expf(z[c] - mx) * inv - (c == yi ? 1.f : 0.f)) * invN;
-      } else {
-        float acc = 0.f;
-        const float sc = 2.0f * invN / (float)C;
-#pragma unroll
-        for (int c = 0; c < L2_CMAX; ++c)
-          if (c < C) {
-            float a = act_apply(z[c], p.out_act);
-            float df = a - p.y_f[(int64_t)r * C + c];
-            acc += df * df;
-            dz[c] = sc * df * act_grad_from_output(a, p.out_act);
-          }
-        loss_acc += (double)(acc / (float)C);
-      }
+    for (int c = 0; c < CP; ++c) {
+      accb[c] += dz0[c] + dz1[c];
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(dz0[c], h0, l0);
+      split_bf16(dz1[c], h1, l1);
+      z2h[(int64_t)c * ld2 + col] = pack_bf16x2(h0, h1);
+      z2l[(int64_t)c * ld2 + col] = pack_bf16x2(l0, l1);
     }
+    // ---- phase A2: dZ1 = (dZ2 W2^T) * act'(a1) -> split bf16, transposed packed store
+    for (int hb = 0; hb < nhb; ++hb) {
+      const uint32_t m0 = mask_s[0][hb][t], m1 = mask_s[1][hb][t];   // own writes: no barrier needed
+      uint32_t* zhp = zh + (int64_t)(hb * 32) * ld2 + col;
+      uint32_t* zlp = zl + (int64_t)(hb * 32) * ld2 + col;
+      const int jn = min(32, H - hb * 32);
+#pragma unroll 4
+      for (int j = 0; j < jn; ++j) {
+        const int h = hb * 32 + j;
+        const float4* w = reinterpret_cast<const float4*>(&W2s[h * CP]);
+        float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < L2_CMAX; ++c) dz2s[t * L2_CMAX + c] = dz[c];
-    // ---- phase A2: dZ1 = (dZ2 W2^T) * act'(a1) -> split bf16, transposed store (coalesced over rows)
-    if (valid) {
-      for (int h = 0; h < H; ++h) {
-        float a = a1[(int64_t)h * p.ld + r];
-        const float4* w = reinterpret_cast<const float4*>(&W2s[h * L2_CMAX]);
-        float da = 0.f;
-#pragma unroll
-        for (int q4 = 0; q4 < L2_CMAX / 4; ++q4) {
-          float4 wv = w[q4];
-          da = fmaf(dz[q4 * 4 + 0], wv.x, da);
-          da = fmaf(dz[q4 * 4 + 1], wv.y, da);
-          da = fmaf(dz[q4 * 4 + 2], wv.z, da);
-          da = fmaf(dz[q4 * 4 + 3], wv.w, da);
+        for (int q4 = 0; q4 < CP / 4; ++q4) {
+          const float4 wv = w[q4];
+          d0 = fmaf(dz0[q4 * 4 + 0], wv.x, d0); d1 = fmaf(dz1[q4 * 4 + 0], wv.x, d1);
+          d0 = fmaf(dz0[q4 * 4 + 1], wv.y, d0); d1 = fmaf(dz1[q4 * 4 + 1], wv.y, d1);
+          d0 = fmaf(dz0[q4 * 4 + 2], wv.z, d0); d1 = fmaf(dz1[q4 * 4 + 2], wv.z, d1);
+          d0 = fmaf(dz0[q4 * 4 + 3], wv.w, d0); d1 = fmaf(dz1[q4 * 4 + 3], wv.w, d1);
         }
-        float d1 = da * act_grad_from_output(a, p.act1);
-        __nv_bfloat16 hi, lo;
-        split_bf16(d1, hi, lo);
-        zh[(int64_t)h * p.ld + r] = hi;
-        zl[(int64_t)h * p.ld + r] = lo;
-      }
-    }
-    __syncthreads();
-    // ---- phase B: dW2[h][c] += sum_r a1[h][r] dZ2[r][c]; thread == hidden unit (two per thread)
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int h = t + hh * 128;
-      if (h < H) {
-        const float4* arow = reinterpret_cast<const float4*>(a1 + (int64_t)h * p.ld + row0);
-        for (int r4 = 0; r4 < 32; ++r4) {
-          float4 av = arow[r4];
-          float aj[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4* dzr = reinterpret_cast<const float4*>(&dz2s[(r4 * 4 + j) * L2_CMAX]);
-#pragma unroll
-            for (int q4 = 0; q4 < L2_CMAX / 4; ++q4) {
-              float4 dv = dzr[q4];
-              accw[hh][q4 * 4 + 0] = fmaf(aj[j], dv.x, accw[hh][q4 * 4 + 0]);
-              accw[hh][q4 * 4 + 1] = fmaf(aj[j], dv.y, accw[hh][q4 * 4 + 1]);
-              accw[hh][q4 * 4 + 2] = fmaf(aj[j], dv.z, accw[hh][q4 * 4 + 2]);
-              accw[hh][q4 * 4 + 3] = fmaf(aj[j], dv.w, accw[hh][q4 * 4 + 3]);
-            }
-          }
+        if (relu) {
+          d0 = ((m0 >> j) & 1u) ? d0 : 0.f;
+          d1 = ((m1 >> j) & 1u) ? d1 : 0.f;
+        } else {
+          const float2 hi = unpack_bf16x2(ah[(int64_t)h * ld2 + col]);
+          const float2 lo = unpack_bf16x2(al[(int64_t)h * ld2 + col]);
+          d0 *= act_grad_from_output(hi.x + lo.x, p.act1);
+          d1 *= act_grad_from_output(hi.y + lo.y, p.act1);
         }
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(d0, h0, l0);
+        split_bf16(d1, h1, l1);
+        zhp[(int64_t)j * ld2] = pack_bf16x2(h0, h1);
+        zlp[(int64_t)j * ld2] = pack_bf16x2(l0, l1);
       }
     }
-    if (t < C) {
-      float s = 0.f;
-      for (int rr = 0; rr < 128; ++rr) s += dz2s[rr * L2_CMAX + t];
-      accb += s;
-    }
-    __syncthreads();
   }
-  float* wp = p.w2_partial + ((int64_t)b * p.n_groups + g) * (H * C + C);
+  // ---- per-block partials: db2 (sum of dZ2 over the block's rows) and the loss
+  const int lane = t & 31, w = t >> 5;
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    const int h = t + hh * 128;
-    if (h < H)
-#pragma unroll
-      for (int c = 0; c < L2_CMAX; ++c)
-        if (c < C) wp[h * C + c] = accw[hh][c];
+  for (int c = 0; c < CP; ++c) {
+    float sum = warp_sum(accb[c]);
+    if (lane == 0) redf[w][c] = sum;
   }
-  if (t < C) wp[H * C + t] = accb;
+  __syncthreads();
+  if (t < L2_CMAX)
+    p.b2_partial[((int64_t)b * p.n_groups + blockIdx.x) * L2_CMAX + t] =
+        (t < CP) ? redf[0][t] + redf[1][t] + redf[2][t] + redf[3][t] : 0.f;
   double tot = block_sum<double>(loss_acc, scratch);
-  if (t == 0) p.loss_partial[(int64_t)b * p.n_groups + g] = tot;
+  if (t == 0) p.loss_partial[(int64_t)b * p.n_groups + blockIdx.x] = tot;
 }
 
-// grad[b][w2_off + i] = sum_g partial[b][g][i] (fixed order); loss[b] = sum_g loss_partial / N
-__global__ void k_layer2_reduce(const float* w2_partial, const double* loss_partial, int n_groups, int count,
-                                float* grad, int64_t P, int64_t w2_off, float* loss_out, int N) {
-  int b = blockIdx.y;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+// grad[b][b2_off + c] = sum_g b2_partial[b][g][c] (fixed order); loss[b] = sum_g loss_partial / N
+__global__ void k_layer2_reduce(const float* b2_partial, const double* loss_partial, int n_groups, int C, float* grad,
+                                int64_t P, int64_t b2_off, float* loss_out, int N) {
+  __shared__ double scratch[32];
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (t < C) {
     float s = 0.f;
-    for (int g = 0; g < n_groups; ++g) s += w2_partial[((int64_t)b * n_groups + g) * count + i];
-    grad[(int64_t)b * P + w2_off + i] = s;
+    for (int g = 0; g < n_groups; ++g) s += b2_partial[((int64_t)b * n_groups + g) * L2_CMAX + t];
+    grad[(int64_t)b * P + b2_off + t] = s;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) {
-    double s = 0.0;
-    for (int g = 0; g < n_groups; ++g) s += loss_partial[(int64_t)b * n_groups + g];
-    loss_out[b] = (float)(s / (double)N);
-  }
+  double a = 0.0;
+  for (int g = t; g < n_groups; g += blockDim.x) a += loss_partial[(int64_t)b * n_groups + g];
+  double tot = block_sum<double>(a, scratch);
+  if (t == 0 && loss_out) loss_out[b] = (float)(tot / (double)N);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -577,11 +622,13 @@ struct TcState {
   int D = 0, H = 0, C = 0;
   DevBuf<__nv_bfloat16> x_hi, x_lo, xt_hi, xt_lo;       // [N][D], [D+1][Npad]
   DevBuf<__nv_bfloat16> w_hi, w_lo;                     // [Bc*H][D]
-  DevBuf<__nv_bfloat16> z_hi, z_lo;                     // [Bc*H][Npad]
-  DevBuf<float> a1t;                                    // [Bc][H][Npad]
-  DevBuf<float> w2_partial;
+  DevBuf<__nv_bfloat16> z_hi, z_lo;                     // dZ1^T [Bc*H][Npad]
+  DevBuf<__nv_bfloat16> a_hi, a_lo;                     // A1^T  [Bc*H][Npad]
+  DevBuf<__nv_bfloat16> z2_hi, z2_lo;                   // dZ2^T [Bc*16][Npad]
+  DevBuf<float> b2_partial;
   DevBuf<double> loss_partial;
-  CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo, mW_hi, mW_lo, mZ_hi, mZ_lo;
+  CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo, mW_hi, mW_lo, mZ_hi, mZ_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
+  int n_tiles = 0;
   int n_groups = 0;
   bool attr_set = false;
 };
@@ -628,7 +675,7 @@ static void launch_gemm_tc(pyb_handle* h, TcState* st, const CUtensorMap& a_hi, 
 static void tc_prepare_data(pyb_handle* h, TcState* st) {
   const Model& m = h->model;
   st->N = h->N; st->D = m.layer[0].fan_in; st->H = m.layer[0].fan_out; st->C = m.layer[1].fan_out;
-  st->Npad = ((st->N + 127) / 128) * 128;
+  st->Npad = ((st->N + L2_ROWS - 1) / L2_ROWS) * L2_ROWS;
   const int64_t N = st->N, Npad = st->Npad;
   const int D = st->D;
   st->x_hi.alloc(N * D); st->x_lo.alloc(N * D);
@@ -650,7 +697,7 @@ static void tc_prepare_data(pyb_handle* h, TcState* st) {
 }
 
 static void tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S) {
-  // chain batch: intermediates are A1^T fp32 + dZ1^T hi/lo = 8 bytes per (chain, hidden, row)
+  // chain batch: intermediates are A1^T hi/lo + dZ1^T hi/lo = 8 bytes per (chain, hidden, row)
   int64_t per_chain = (int64_t)st->H * st->Npad * 8;
   int64_t budget = (int64_t)(std::max(h->opt_workspace_mb, 20000.0) * 1024.0 * 1024.0);
   int64_t bc = std::max<int64_t>(1, budget / per_chain);
@@ -662,15 +709,25 @@ static void tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S) {
   const int H = st->H, D = st->D;
   st->w_hi.alloc(bc * H * D); st->w_lo.alloc(bc * H * D);
   st->z_hi.alloc(bc * H * st->Npad); st->z_lo.alloc(bc * H * st->Npad);
-  st->a1t.alloc(bc * H * st->Npad);
-  PYB_CUDA(cudaMemsetAsync(st->a1t.p, 0, st->a1t.bytes(), h->stream));   // padded rows stay finite (phase B reads them)
-  st->n_groups = (int)((st->N + 128 * L2_TILES - 1) / (128 * L2_TILES));
-  st->w2_partial.alloc((size_t)bc * st->n_groups * (H * st->C + st->C));
+  st->a_hi.alloc(bc * H * st->Npad); st->a_lo.alloc(bc * H * st->Npad);
+  st->z2_hi.alloc(bc * L2_CMAX * st->Npad); st->z2_lo.alloc(bc * L2_CMAX * st->Npad);
+  // rows >= N of the transposed buffers are never written; keep them finite (they are read as packed pairs)
+  PYB_CUDA(cudaMemsetAsync(st->z2_hi.p, 0, st->z2_hi.bytes(), h->stream));
+  PYB_CUDA(cudaMemsetAsync(st->z2_lo.p, 0, st->z2_lo.bytes(), h->stream));
+  PYB_CUDA(cudaMemsetAsync(st->a_hi.p, 0, st->a_hi.bytes(), h->stream));
+  PYB_CUDA(cudaMemsetAsync(st->a_lo.p, 0, st->a_lo.bytes(), h->stream));
+  st->n_tiles = (int)(st->Npad / L2_ROWS);
+  st->n_groups = std::min(st->n_tiles, std::max(1, (int)((8 * (int64_t)h->sm_count + bc - 1) / bc)));
+  st->b2_partial.alloc((size_t)bc * st->n_groups * L2_CMAX);
   st->loss_partial.alloc((size_t)bc * st->n_groups);
   st->mW_hi = make_map(st->w_hi.p, D, bc * H, D, H);
   st->mW_lo = make_map(st->w_lo.p, D, bc * H, D, H);
   st->mZ_hi = make_map(st->z_hi.p, st->N, bc * H, st->Npad, H);
   st->mZ_lo = make_map(st->z_lo.p, st->N, bc * H, st->Npad, H);
+  st->mA_hi = make_map(st->a_hi.p, st->N, bc * H, st->Npad, 128);
+  st->mA_lo = make_map(st->a_lo.p, st->N, bc * H, st->Npad, 128);
+  st->mZ2_hi = make_map(st->z2_hi.p, st->N, bc * L2_CMAX, st->Npad, L2_CMAX);
+  st->mZ2_lo = make_map(st->z2_lo.p, st->N, bc * L2_CMAX, st->Npad, L2_CMAX);
   st->bufs_ready = true;
 }
 
@@ -693,40 +750,52 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
       k_split_transpose<<<g, blk, 0, h->stream>>>(th + L1.w_off, P, D, H, H, st->w_hi.p, st->w_lo.p, (int64_t)H * D, D);
       count_launch(h);
     }
-    // 2. G1: A1^T = act(X W1 + b1)^T
+    // 2. G1: A1^T = act(X W1 + b1)^T, split bf16
     {
       TcGemmParams p = {};
       p.K = D; p.n_mtiles = (int)((N + 127) / 128); p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
-      p.order = 1; p.sub_batch = 32; p.total_items = p.n_pairs * nb;
-      p.epi = EPI_BIAS_ACT_T;
+      p.a_batch_rows = 0; p.order = 1; p.sub_batch = 32; p.total_items = p.n_pairs * nb;
+      p.epi = EPI_BIAS_ACT_T_SPLIT;
       p.bias = th + L1.b_off; p.bias_stride = P; p.act = L1.act;
-      p.out_t = st->a1t.p; p.out_t_chain_stride = (int64_t)H * Npad; p.out_t_ld = Npad;
-      p.M_valid = (int)N;
+      p.out_hi = st->a_hi.p; p.out_lo = st->a_lo.p; p.out_t_ld = Npad;
+      p.M_valid = (int)N; p.N_valid = H;
       launch_gemm_tc(h, st, st->mX_hi, st->mX_lo, st->mW_hi, st->mW_lo, p, 2.0 * N * D * (double)H * nb);
     }
-    // 3. layer 2 + loss + dZ1^T
+    // 3. layer 2 + loss + dZ1^T, dZ2^T
     {
       Layer2Params p = {};
-      p.a1t = st->a1t.p; p.a1t_chain_stride = (int64_t)H * Npad; p.ld = Npad;
-      p.zt_hi = st->z_hi.p; p.zt_lo = st->z_lo.p;
+      p.a_hi = st->a_hi.p; p.a_lo = st->a_lo.p; p.zt_hi = st->z_hi.p; p.zt_lo = st->z_lo.p;
+      p.z2_hi = st->z2_hi.p; p.z2_lo = st->z2_lo.p; p.ld = Npad;
       p.theta = th; p.P = P; p.w2_off = L2.w_off; p.b2_off = L2.b_off;
       p.H = H; p.C = C; p.N = (int)N; p.act1 = L1.act; p.out_act = L2.act; p.loss_kind = h->loss_kind;
       p.y_i = h->y_i.p; p.y_f = h->y_f.p; p.scale = scale;
-      p.loss_partial = st->loss_partial.p; p.w2_partial = st->w2_partial.p; p.n_groups = st->n_groups;
+      p.loss_partial = st->loss_partial.p; p.b2_partial = st->b2_partial.p; p.n_groups = st->n_groups;
+      p.n_tiles = st->n_tiles;
       dim3 g(st->n_groups, nb);
-      k_layer2<<<g, 128, 0, h->stream>>>(p);
-      dim3 rg((H * C + C + 255) / 256, nb);
-      k_layer2_reduce<<<rg, 256, 0, h->stream>>>(st->w2_partial.p, st->loss_partial.p, st->n_groups, H * C + C, gr, P,
-                                                 L2.w_off, loss_out ? loss_out + b0 : nullptr, (int)N);
+      if (C <= 4) k_layer2<4><<<g, 128, 0, h->stream>>>(p);
+      else if (C <= 8) k_layer2<8><<<g, 128, 0, h->stream>>>(p);
+      else if (C <= 12) k_layer2<12><<<g, 128, 0, h->stream>>>(p);
+      else k_layer2<16><<<g, 128, 0, h->stream>>>(p);
+      k_layer2_reduce<<<nb, 64, 0, h->stream>>>(st->b2_partial.p, st->loss_partial.p, st->n_groups, C, gr, P, L2.b_off,
+                                                loss_out ? loss_out + b0 : nullptr, (int)N);
       count_launch(h, 2);
     }
-    // 4. G2: [dW1; db1] = [X^T; 1] dZ1
+    // 4. G3: dW2[h][c] = sum_r a1[r][h] dZ2[r][c]   (A = A1^T per chain, B = dZ2^T per chain, N = 16)
+    {
+      TcGemmParams p = {};
+      p.K = (int)N; p.n_mtiles = (H + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = L2_CMAX;
+      p.a_batch_rows = H; p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
+      p.epi = EPI_STORE;
+      p.out = gr + L2.w_off; p.out_stride = P; p.out_ld = C; p.M_valid = H; p.N_valid = C;
+      launch_gemm_tc(h, st, st->mA_hi, st->mA_lo, st->mZ2_hi, st->mZ2_lo, p, 2.0 * N * (double)H * C * nb);
+    }
+    // 5. G2: [dW1; db1] = [X^T; 1] dZ1
     {
       TcGemmParams p = {};
       p.K = (int)N; p.n_mtiles = (D + 1 + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
-      p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
+      p.a_batch_rows = 0; p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
       p.epi = EPI_STORE;
-      p.out = gr; p.out_stride = P; p.out_ld = H; p.M_valid = D + 1;
+      p.out = gr; p.out_stride = P; p.out_ld = H; p.M_valid = D + 1; p.N_valid = H;
       launch_gemm_tc(h, st, st->mXT_hi, st->mXT_lo, st->mZ_hi, st->mZ_lo, p, 2.0 * N * (double)(D + 1) * H * nb);
     }
   }
@@ -751,7 +820,7 @@ void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn,
   TcGemmParams p = {};
   p.K = K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = 1; p.H = Nn;
   p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
-  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M;
+  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0;
   launch_gemm_tc(h, st, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K);
   PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
   PYB_CUDA(cudaStreamSynchronize(h->stream));
