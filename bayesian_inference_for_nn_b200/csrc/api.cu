@@ -17,13 +17,18 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
 void tc_release(pyb_handle* h);
 void tc_invalidate_dataset(pyb_handle* h);
 
-void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
+int resolve_path(pyb_handle* h, int64_t S, bool with_grad) {
   int path = h->opt_path;
   if (path == PYB_PATH_AUTO) {
-    if (grad_out && tc_supported(h, S)) path = PYB_PATH_TENSOR;
-    else if (grad_out && fused_small_supported(h)) path = PYB_PATH_FUSED_SMALL;
+    if (with_grad && tc_supported(h, S)) path = PYB_PATH_TENSOR;
+    else if (with_grad && fused_small_supported(h)) path = PYB_PATH_FUSED_SMALL;
     else path = PYB_PATH_GENERIC;
   }
+  return path;
+}
+
+void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
+  int path = resolve_path(h, S, grad_out != nullptr);
   if (path == PYB_PATH_TENSOR) {
     PYB_REQUIRE(tc_supported(h, S), PYB_ERR_UNSUPPORTED, "tensor path does not support this model/dataset shape");
     PYB_REQUIRE(grad_out != nullptr, PYB_ERR_UNSUPPORTED, "tensor path computes loss and gradient together");

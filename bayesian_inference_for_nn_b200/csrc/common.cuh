@@ -300,6 +300,9 @@ int64_t generic_chain_batch(pyb_handle* h, int64_t S, int64_t N, bool backward);
 
 // dispatcher (api.cu): picks generic / fused-small / tensor path
 void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out);
+int resolve_path(pyb_handle* h, int64_t S, bool with_grad);
+bool fused_small_supported(pyb_handle* h);
+void fused_small_hmc_iteration(pyb_handle* h, bool burning);
 
 // sampler.cu
 void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double m, int L, int sem, const float* q0);

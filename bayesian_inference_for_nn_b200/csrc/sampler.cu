@@ -16,9 +16,16 @@ constexpr int EW_PER_THREAD = 4;
 constexpr int EW_CHUNK = EW_THREADS * EW_PER_THREAD;  // elements of one chain handled by one block
 
 static inline int ew_blocks(int64_t P) { return (int)((P + EW_CHUNK - 1) / EW_CHUNK); }
+// chains ride on grid.y/grid.z (grid.y alone stops at 65535)
+constexpr int CHAIN_Y = 32768;
+static inline dim3 chain_grid(int nblk, int64_t S) {
+  return dim3((unsigned)nblk, (unsigned)std::min<int64_t>(S, CHAIN_Y), (unsigned)((S + CHAIN_Y - 1) / CHAIN_Y));
+}
+__device__ __forceinline__ int64_t chain_index() { return (int64_t)blockIdx.z * gridDim.y + blockIdx.y; }
 
-__global__ void k_init_q(float* q, const float* q0, const float* mu, int64_t P) {
-  int64_t s = blockIdx.y;
+__global__ void k_init_q(float* q, const float* q0, const float* mu, int64_t P, int64_t S) {
+  int64_t s = chain_index();
+  if (s >= S) return;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x)
     q[s * P + i] = q0 ? q0[s * P + i] : mu[i];
 }
@@ -26,9 +33,10 @@ __global__ void k_init_q(float* q, const float* q0, const float* mu, int64_t P) 
 // p = std * N(0,1) (or injected); partial[s][blk] = sum p^2 over the block's chunk
 __global__ void __launch_bounds__(EW_THREADS) k_momentum(float* p, const float* inj, int64_t P, float stdv,
                                                           uint64_t seed, uint32_t iter, int64_t chain_offset,
-                                                          double* partial) {
+                                                          double* partial, int64_t S) {
   __shared__ double scratch[32];
-  int64_t s = blockIdx.y;
+  int64_t s = chain_index();
+  if (s >= S) return;
   int64_t base = (int64_t)blockIdx.x * EW_CHUNK + (int64_t)threadIdx.x * EW_PER_THREAD;
   double acc = 0.0;
   if (base < P) {
@@ -73,14 +81,15 @@ __global__ void k_finish(const double* partial, int nblk, double scale, float* o
 struct KickArgs {
   float* q; float* p; const float* g; float* q0;
   const float* mu; const float* inv_var;
-  int64_t P;
+  int64_t P, S;
   float kick1, kick2, drift;
   int snapshot, energy, kinetic;
   double* partial_e; double* partial_k;
 };
 __global__ void __launch_bounds__(EW_THREADS) k_kick_drift(KickArgs a) {
   __shared__ double scratch[32];
-  int64_t s = blockIdx.y;
+  int64_t s = chain_index();
+  if (s >= a.S) return;
   int64_t base = (int64_t)blockIdx.x * EW_CHUNK + threadIdx.x;
   double e = 0.0, k = 0.0;
 #pragma unroll
@@ -113,9 +122,10 @@ __global__ void __launch_bounds__(EW_THREADS) k_kick_drift(KickArgs a) {
 
 // prior energy partial + total gradient (parity hook pyb_hmc_eval)
 __global__ void __launch_bounds__(EW_THREADS) k_prior(const float* q, float* g, const float* mu,
-                                                       const float* inv_var, int64_t P, double* partial_e) {
+                                                       const float* inv_var, int64_t P, double* partial_e, int64_t S) {
   __shared__ double scratch[32];
-  int64_t s = blockIdx.y;
+  int64_t s = chain_index();
+  if (s >= S) return;
   int64_t base = (int64_t)blockIdx.x * EW_CHUNK + threadIdx.x;
   double e = 0.0;
 #pragma unroll
@@ -229,8 +239,9 @@ __global__ void __launch_bounds__(1024) k_record_slots(const int32_t* accepted, 
 // q = accepted ? q : q0 (HMC.py:97-101) and copy recorded samples into the arena
 __global__ void __launch_bounds__(EW_THREADS) k_select_record(float* q, const float* q0, const int32_t* accepted,
                                                                const int32_t* slot_first, const int32_t* slot_acc,
-                                                               float* arena, int64_t P, int sampling) {
-  int64_t s = blockIdx.y;
+                                                               float* arena, int64_t P, int sampling, int64_t S) {
+  int64_t s = chain_index();
+  if (s >= S) return;
   int acc = accepted[s];
   int sf = sampling ? slot_first[s] : -1, sa = sampling ? slot_acc[s] : -1;
   int64_t base = (int64_t)blockIdx.x * EW_CHUNK + threadIdx.x;
@@ -306,8 +317,7 @@ void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double
     PYB_CUDA(cudaMemcpyAsync(tmp.p, q0, S * P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     q0d = tmp.p;
   }
-  dim3 grid((unsigned)std::min<int64_t>((P + 255) / 256, 1024), (unsigned)S);
-  k_init_q<<<grid, 256, 0, h->stream>>>(st.q.p, q0d, h->mu.p, P);
+  k_init_q<<<chain_grid((int)std::min<int64_t>((P + 255) / 256, 1024), S), 256, 0, h->stream>>>(st.q.p, q0d, h->mu.p, P, S);
   count_launch(h);
   PYB_CUDA(cudaStreamSynchronize(h->stream));
   st.inited = true;
@@ -348,12 +358,11 @@ static void launch_kick(pyb_handle* h, float kick1, float kick2, float drift, bo
   const int64_t P = h->model.P;
   int nblk = ew_blocks(P);
   KickArgs a;
-  a.q = st.q.p; a.p = st.p.p; a.g = st.g.p; a.q0 = st.q0.p; a.mu = h->mu.p; a.inv_var = h->inv_var.p; a.P = P;
+  a.q = st.q.p; a.p = st.p.p; a.g = st.g.p; a.q0 = st.q0.p; a.mu = h->mu.p; a.inv_var = h->inv_var.p; a.P = P; a.S = st.S;
   a.kick1 = kick1; a.kick2 = kick2; a.drift = drift;
   a.snapshot = snapshot; a.energy = energy; a.kinetic = kinetic;
   a.partial_e = st.partial_e.p; a.partial_k = st.partial_k.p;
-  dim3 grid(nblk, (unsigned)st.S);
-  k_kick_drift<<<grid, EW_THREADS, 0, h->stream>>>(a);
+  k_kick_drift<<<chain_grid(nblk, st.S), EW_THREADS, 0, h->stream>>>(a);
   count_launch(h);
   if (energy) { k_finish<<<(unsigned)st.S, 128, 0, h->stream>>>(st.partial_e.p, nblk, 1.0, Up_out); count_launch(h); }
   if (kinetic) {
@@ -376,6 +385,7 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
   PYB_CUDA(cudaMemsetAsync(st.counters.p, 0, 4 * sizeof(unsigned long long), h->stream));
   PYB_CUDA(cudaMemsetAsync(st.loss_sum.p, 0, sizeof(double), h->stream));
   PYB_CUDA(cudaEventRecord(h->ev0, h->stream));
+  const int path = resolve_path(h, S, true);
   for (int it = 0; it < n_iters; ++it) {
     bool first = sampling && !st.sampling_started;
     if (sampling) {
@@ -384,10 +394,15 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
       if (!st.arena.p) st.arena.alloc((size_t)st.arena_cap * P);
       st.arena_used_upper += need;
     }
+    dim3 gridp = chain_grid(nblk, S);
+    if (path == PYB_PATH_FUSED_SMALL) {
+      PYB_REQUIRE(fused_small_supported(h), PYB_ERR_UNSUPPORTED, "fused small path does not support this model shape");
+      fused_small_hmc_iteration(h, burning);     // whole iteration (momentum .. Metropolis test) in ONE launch
+      h->path_used = path;
+    } else {
     // momentum + K0  (HMC.py:78-79)
-    dim3 gridp(nblk, (unsigned)S);
     k_momentum<<<gridp, EW_THREADS, 0, h->stream>>>(st.p.p, st.have_inj_p ? st.inj_p.p : nullptr, P, stdv, h->seed,
-                                                    (uint32_t)st.iter, st.chain_offset, st.partial_k.p);
+                                                    (uint32_t)st.iter, st.chain_offset, st.partial_k.p, S);
     count_launch(h);
     k_finish<<<(unsigned)S, 128, 0, h->stream>>>(st.partial_k.p, nblk, 1.0 / (2.0 * st.m), st.K0.p);
     count_launch(h);
@@ -415,6 +430,7 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
     a.ret_loss = st.ret_loss.p; a.counters = st.counters.p; a.loss_sum = st.loss_sum.p;
     k_accept<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(a);
     count_launch(h);
+    }
     if (sampling) {
       k_record_slots<<<1, 1024, 0, h->stream>>>(st.accepted.p, S, first ? 1 : 0, st.arena_count.p, st.arena_freq.p,
                                                 st.arena_chain.p, st.last_idx.p, st.pending_freq.p,
@@ -423,7 +439,7 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
       st.sampling_started = true;
     }
     k_select_record<<<gridp, EW_THREADS, 0, h->stream>>>(st.q.p, st.q0.p, st.accepted.p, st.slot_first.p,
-                                                         st.slot_acc.p, st.arena.p, P, sampling ? 1 : 0);
+                                                         st.slot_acc.p, st.arena.p, P, sampling ? 1 : 0, S);
     count_launch(h);
     st.have_inj_p = st.have_inj_u = false;
     st.iter++;
@@ -463,8 +479,7 @@ void hmc_eval(pyb_handle* h, const float* q, int64_t S, float* U, float* loss, f
   part.alloc((size_t)S * nblk);
   PYB_CUDA(cudaMemcpyAsync(dq.p, q, S * P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   eval_loss_grad(h, dq.p, S, (float)h->n_train, dloss.p, grad ? dg.p : nullptr);
-  dim3 grid(nblk, (unsigned)S);
-  k_prior<<<grid, EW_THREADS, 0, h->stream>>>(dq.p, grad ? dg.p : nullptr, h->mu.p, h->inv_var.p, P, part.p);
+  k_prior<<<chain_grid(nblk, S), EW_THREADS, 0, h->stream>>>(dq.p, grad ? dg.p : nullptr, h->mu.p, h->inv_var.p, P, part.p, S);
   k_finish<<<(unsigned)S, 128, 0, h->stream>>>(part.p, nblk, 1.0, dUp.p);
   k_potential<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(dUp.p, dloss.p, (float)h->prior_const,
                                                                   (float)h->n_train, dU.p, S);

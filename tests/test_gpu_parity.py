@@ -86,10 +86,11 @@ def test_hmc_iteration_with_injected_randomness(oracle, name, path):
             k += 1
 
 
-def test_trajectory_endpoints_before_accept(oracle):
+@pytest.mark.parametrize("path", ["generic", "auto"])
+def test_trajectory_endpoints_before_accept(oracle, path):
     """q_L itself (not only the post-accept state): force acceptance by burning."""
     g = load_golden("hmc_c1_mini")
-    eng, _ = make_engine(g, oracle)
+    eng, _ = make_engine(g, oracle, path)
     eng.hmc_init(int(g["S"]), float(g["eps"]), float(g["m"]), int(g["L"]), int(g["semantics"]), q0=g["q"])
     eng.hmc_inject(p=g["p"], u=g["u"])
     d = eng.hmc_run(1, burning=True, sampling=False)
@@ -98,36 +99,38 @@ def test_trajectory_endpoints_before_accept(oracle):
     assert rel_err(q, g["qL"]) < TOL_TRAJ and rel_err(p, g["pL"]) < TOL_TRAJ
 
 
-def test_device_rng_matches_philox_restatement(oracle):
+@pytest.mark.parametrize("path", ["generic", "auto"])
+def test_device_rng_matches_philox_restatement(oracle, path):
     O = oracle
     g = load_golden("hmc_c1_mini")
     seed, S, m = 0x1234ABCD5678, 3, 0.5
-    eng, spec = make_engine(g, O, seed=seed)
+    eng, spec = make_engine(g, O, path, seed=seed)
     eng.hmc_init(S, 1e-3, m, 1, _lib.HMC_REFERENCE, chain_offset=5)
     eng.hmc_run(2, burning=True, sampling=False)       # iteration counters 0 and 1
     # momenta of the third iteration, read back after a zero-step-size iteration (p unchanged by kicks)
-    eng2, _ = make_engine(g, O, seed=seed)
+    eng2, _ = make_engine(g, O, path, seed=seed)
     eng2.hmc_init(S, 0.0, m, 1, _lib.HMC_REFERENCE, chain_offset=5)
     eng2.hmc_run(1, burning=True, sampling=False)
     _, p = eng2.hmc_state()
     want = O.philox_normals(seed, np.arange(5, 5 + S), 0, O.STREAM_MOMENTUM, spec.n_params) * np.float32(m)
     np.testing.assert_allclose(p, want, rtol=2e-5, atol=2e-6)
     # canonical semantics draws with std sqrt(m)
-    eng3, _ = make_engine(g, O, seed=seed)
+    eng3, _ = make_engine(g, O, path, seed=seed)
     eng3.hmc_init(S, 0.0, m, 1, _lib.HMC_CANONICAL, chain_offset=5)
     eng3.hmc_run(1, burning=True, sampling=False)
     _, p3 = eng3.hmc_state()
     np.testing.assert_allclose(p3, want / np.float32(m) * np.float32(np.sqrt(m)), rtol=2e-5, atol=2e-6)
 
 
-def test_multi_iteration_run_matches_oracle_with_device_rng(oracle):
+@pytest.mark.parametrize("path", ["generic", "auto"])
+def test_multi_iteration_run_matches_oracle_with_device_rng(oracle, path):
     """Whole phase (several iterations, device Philox momenta and uniforms) against the oracle fed
     the restated streams: states, accept decisions and the Sampled bookkeeping."""
     O = oracle
     g = load_golden("hmc_c1_mini")
     seed, S, n_it = 77, 5, 4
     eps, m, L = 2e-3, 1.0, 4
-    eng, spec = make_engine(g, O, seed=seed)
+    eng, spec = make_engine(g, O, path, seed=seed)
     eng.hmc_init(S, eps, m, L, _lib.HMC_REFERENCE)
     mu, sg = O.expand_prior(spec, 0.0, float(g["sigma"]))
     prob = O.Problem(spec, g["X"], g["y"], int(g["loss_kind"]), mu, sg)
@@ -160,10 +163,11 @@ def test_multi_iteration_run_matches_oracle_with_device_rng(oracle):
     assert k == samples.shape[0]
 
 
-def test_negative_sigma_rejects_everything_after_burn_in(oracle):
+@pytest.mark.parametrize("path", ["generic", "auto"])
+def test_negative_sigma_rejects_everything_after_burn_in(oracle, path):
     """SURVEY B-1 / HMC_classification.py:50: GaussianPrior(0,-1) => NaN Hamiltonian."""
     g = load_golden("hmc_c1_mini")
-    eng, _ = make_engine(g, oracle)
+    eng, _ = make_engine(g, oracle, path)
     eng.set_prior([0.0], [-1.0], _lib.PRIOR_SCALAR)
     eng.hmc_init(4, 0.005, 0.5, 5, _lib.HMC_REFERENCE)
     d = eng.hmc_run(3, burning=True, sampling=False)
@@ -178,17 +182,18 @@ def test_negative_sigma_rejects_everything_after_burn_in(oracle):
     assert samples.shape[0] == 4 and freq.tolist() == [6, 6, 6, 6]
 
 
-def test_sharded_chains_reproduce_the_unsharded_run(oracle):
+@pytest.mark.parametrize("path", ["generic", "auto"])
+def test_sharded_chains_reproduce_the_unsharded_run(oracle, path):
     """Chains never interact and RNG counters use the global chain id: running chains [0,6) in one
     handle or as [0,3)+[3,6) in two handles gives the same states."""
     g = load_golden("hmc_c1_mini")
-    full, _ = make_engine(g, oracle, seed=9)
+    full, _ = make_engine(g, oracle, path, seed=9)
     full.hmc_init(6, 2e-3, 1.0, 3, _lib.HMC_REFERENCE)
     full.hmc_run(3, burning=False, sampling=True)
     qf, _ = full.hmc_state()
     parts = []
     for off in (0, 3):
-        e, _ = make_engine(g, oracle, seed=9)
+        e, _ = make_engine(g, oracle, path, seed=9)
         e.hmc_init(3, 2e-3, 1.0, 3, _lib.HMC_REFERENCE, chain_offset=off)
         e.hmc_run(3, burning=False, sampling=True)
         parts.append(e.hmc_state()[0])
@@ -311,3 +316,17 @@ def test_errors_cross_the_boundary_as_status_codes():
         eng.hmc_run(1)
     with pytest.raises(_lib.PyesianB200Error):
         eng.hmc_init(2, 0.1, 1.0, 0)
+
+
+def test_auto_path_selection(oracle):
+    """AUTO picks the fused one-launch kernel for small-width nets and the generic path otherwise."""
+    g = load_golden("hmc_c1_mini")
+    eng, _ = make_engine(g, oracle, "auto")
+    eng.hmc_init(4, 1e-3, 1.0, 3)
+    d = eng.hmc_run(2, burning=False, sampling=True)
+    assert int(eng.info("path_used")) == _lib.PATH_FUSED_SMALL
+    assert d["kernel_launches"] == 2 * 3          # trajectory kernel + slot scan + select/record per iteration
+    g3 = load_golden("hmc_c3_mini")                # 96 rows: below the tensor path's minimum tile
+    eng3, _ = make_engine(g3, oracle, "auto")
+    eng3.hmc_eval(g3["q"])
+    assert int(eng3.info("path_used")) == _lib.PATH_GENERIC
