@@ -61,6 +61,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// operand tile load: plain 2-D [rows, K] tensor, or row-tile-blocked 3-D [chain*k_tiles][rows][128] tensor
+// (K = data rows, blocked in tiles of 128 so that one (chain, tile) block is contiguous in HBM)
+__device__ __forceinline__ void tma_load_operand(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int blocked,
+                                                 int k0, int row0, int b, int k_tiles) {
+  if (blocked) tma_load_3d(smem_dst, map, bar, k0 & 127, row0, b * k_tiles + (k0 >> 7));
+  else tma_load_2d(smem_dst, map, bar, k0, row0);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -121,12 +135,14 @@ enum { EPI_BIAS_ACT_T_SPLIT = 0, EPI_STORE = 1 };
 
 struct TcGemmParams {
   int K, n_mtiles, n_pairs, n_batch, H;
-  int a_batch_rows;            // A row offset per chain (0: A shared by all chains)
+  int a_batch_rows;            // A row offset per chain (0: A shared by all chains); unused when A is blocked
+  int a_blocked, b_blocked, k_tiles;   // operand addressing (see tma_load_operand); k_tiles = K/128
+  int a_box_rows;              // rows of one A TMA box (128, or H when a per-chain A has fewer rows)
   int order, sub_batch, total_items;
   int epi;
   // EPI_BIAS_ACT_T_SPLIT: a = act(D[row][col] + bias[b][col]) -> bf16 hi/lo at [b*H + col][row]  (row < M_valid)
   const float* bias; int64_t bias_stride; int act;
-  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int64_t out_t_ld;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_tiles;   // blocked [b][tile][col][128] output
   // EPI_STORE: out[b*out_stride + row*out_ld + col] = D[row][col]   (row < M_valid, col < N_valid)
   float* out; int64_t out_stride; int out_ld;
   int M_valid, N_valid;
@@ -147,6 +163,15 @@ __device__ __forceinline__ void tc_decode(const TcGemmParams& p, int item, int& 
   }
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_apply_t(float z) {
+  if (ACT == PYB_ACT_RELU) return fmaxf(z, 0.0f);
+  if (ACT == PYB_ACT_TANH) return tanhf(z);
+  if (ACT == PYB_ACT_SIGMOID) return 1.0f / (1.0f + expf(-z));
+  return z;
+}
+
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -198,18 +223,21 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc_decode(p, item, b, mp);
         const int mt0 = mp * 2;
         const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
-        const uint32_t bytes = (uint32_t)n_mt * 2 * TC_A_TILE_BYTES + 2 * b_bytes;
+        const uint32_t bytes = (uint32_t)n_mt * 2 * (uint32_t)p.a_box_rows * TC_BK * 2 + 2 * b_bytes;
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], bytes);
           const int k0 = kc * TC_BK;
           for (int mt = 0; mt < n_mt; ++mt) {
-            tma_load_2d(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], k0, b * p.a_batch_rows + (mt0 + mt) * 128);
-            tma_load_2d(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, b * p.a_batch_rows + (mt0 + mt) * 128);
+            const int arow = (p.a_blocked ? 0 : b * p.a_batch_rows) + (mt0 + mt) * 128;
+            tma_load_operand(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], p.a_blocked, k0, arow, b, p.k_tiles);
+            tma_load_operand(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], p.a_blocked, k0, arow, b, p.k_tiles);
           }
-          tma_load_2d(st + 4 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], k0, b * p.H);
-          tma_load_2d(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &tmB_lo, &full_bar[stage], k0, b * p.H);
+          const int brow = p.b_blocked ? 0 : b * p.H;
+          tma_load_operand(st + 4 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], p.b_blocked, k0, brow, b, p.k_tiles);
+          tma_load_operand(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &tmB_lo, &full_bar[stage], p.b_blocked, k0, brow, b,
+                           p.k_tiles);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -266,7 +294,7 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tc_decode(p, item, b, mp);
       const int mt0 = mp * 2;
       const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
-      if (p.epi == EPI_BIAS_ACT_T_SPLIT) {
+      if (EPI == EPI_BIAS_ACT_T_SPLIT) {
         asm volatile("bar.sync 1, 256;" ::: "memory");           // previous item's readers are done
         for (int c = eall; c < p.H; c += 256) bias_s[c] = p.bias ? p.bias[(int64_t)b * p.bias_stride + c] : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -279,30 +307,31 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int c0 = 0; c0 < p.H; c0 += 32) {
           float v[32];
           tc_ld32(tmem_base + lane_base + (uint32_t)(grp * 256 + c0), v);
-          if (p.epi == EPI_BIAS_ACT_T_SPLIT) {
+          if (EPI == EPI_BIAS_ACT_T_SPLIT) {
             // even lanes own even columns, odd lanes odd columns; the partner lane's value arrives by
             // shuffle so that (row, row+1) leave as one 32-bit bf16x2 word: half the store instructions,
             // 64 B contiguous per half-warp.  All lanes take part in the shuffles (rows >= M_valid too).
             const int odd = lane & 1;
             const bool pair_valid = (row & ~1) < p.M_valid;
-            const int64_t o = ((int64_t)b * p.H + c0) * p.out_t_ld + (row & ~1);
-            uint32_t* ohi = reinterpret_cast<uint32_t*>(p.out_hi);
-            uint32_t* olo = reinterpret_cast<uint32_t*>(p.out_lo);
+            const int64_t w0 = ((((int64_t)b * p.out_tiles + (mt0 + grp)) * p.H + c0 + odd) * 128 + (et & ~1)) >> 1;
+            uint32_t* ohi = reinterpret_cast<uint32_t*>(p.out_hi) + w0;
+            uint32_t* olo = reinterpret_cast<uint32_t*>(p.out_lo) + w0;
+            const bool full = (c0 + 32 <= p.H);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float a_e = act_apply(v[j] + bias_s[min(c0 + j, p.H - 1)], p.act);
-              const float a_o = act_apply(v[j + 1] + bias_s[min(c0 + j + 1, p.H - 1)], p.act);
+              const float a_e = act_apply_t<ACT>(v[j] + bias_s[c0 + j]);
+              const float a_o = act_apply_t<ACT>(v[j + 1] + bias_s[c0 + j + 1]);
               const float recv = __shfl_xor_sync(0xffffffffu, odd ? a_e : a_o, 1);
               const float x0 = odd ? recv : a_e;       // row & ~1
               const float x1 = odd ? a_o : recv;       // (row & ~1) + 1
-              const int cj = j + odd;
-              if (pair_valid && c0 + cj < p.H) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                const int64_t w = (o + (int64_t)cj * p.out_t_ld) >> 1;
-                ohi[w] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                olo[w] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              if (pair_valid && (full || c0 + j + odd < p.H)) {
+                const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);           // one cvt.rn.bf16x2.f32
+                const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hp);
+                const float r0 = x0 - __uint_as_float(hw << 16);
+                const float r1 = x1 - __uint_as_float(hw & 0xffff0000u);
+                const __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
+                ohi[j * 64] = hw;                                                  // column c0+j+odd is j*64 words on
+                olo[j * 64] = *reinterpret_cast<const uint32_t*>(&lp);
               }
             }
           } else {
@@ -388,7 +417,7 @@ struct Layer2Params {
   const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;     // A1^T [Bc*H][ld]
   __nv_bfloat16* zt_hi; __nv_bfloat16* zt_lo;               // dZ1^T [Bc*H][ld]
   __nv_bfloat16* z2_hi; __nv_bfloat16* z2_lo;               // dZ2^T [Bc*16][ld]
-  int64_t ld;
+  int k_tiles;                 // 128-row tiles per chain; arrays are blocked [chain][tile][unit][128]
   const float* theta; int64_t P; int64_t w2_off, b2_off;
   int H, C, N, act1, out_act, loss_kind;
   const int32_t* y_i; const float* y_f;
@@ -457,13 +486,14 @@ __global__ void __launch_bounds__(128, 4) k_layer2(Layer2Params p) {
   }
   if (t < CP) b2s[t] = (t < C) ? th[p.b2_off + t] : 0.f;
   __syncthreads();
-  const uint32_t* ah = reinterpret_cast<const uint32_t*>(p.a_hi + (int64_t)b * H * p.ld);
-  const uint32_t* al = reinterpret_cast<const uint32_t*>(p.a_lo + (int64_t)b * H * p.ld);
-  uint32_t* zh = reinterpret_cast<uint32_t*>(p.zt_hi + (int64_t)b * H * p.ld);
-  uint32_t* zl = reinterpret_cast<uint32_t*>(p.zt_lo + (int64_t)b * H * p.ld);
-  uint32_t* z2h = reinterpret_cast<uint32_t*>(p.z2_hi + (int64_t)b * L2_CMAX * p.ld);
-  uint32_t* z2l = reinterpret_cast<uint32_t*>(p.z2_lo + (int64_t)b * L2_CMAX * p.ld);
-  const int64_t ld2 = p.ld >> 1;           // row pitch in packed pairs
+  // blocked layout, in packed bf16x2 words: ((chain*k_tiles + tile128)*rows_per_block + unit)*64 + pair
+  const uint32_t* ah = reinterpret_cast<const uint32_t*>(p.a_hi);
+  const uint32_t* al = reinterpret_cast<const uint32_t*>(p.a_lo);
+  uint32_t* zh = reinterpret_cast<uint32_t*>(p.zt_hi);
+  uint32_t* zl = reinterpret_cast<uint32_t*>(p.zt_lo);
+  uint32_t* z2h = reinterpret_cast<uint32_t*>(p.z2_hi);
+  uint32_t* z2l = reinterpret_cast<uint32_t*>(p.z2_lo);
+  const int64_t ld2 = 64;                  // pitch between hidden units inside a block, in packed pairs
   float accb[CP];
 #pragma unroll
   for (int c = 0; c < CP; ++c) accb[c] = 0.f;
@@ -473,7 +503,9 @@ __global__ void __launch_bounds__(128, 4) k_layer2(Layer2Params p) {
   const int nhb = (H + 31) >> 5;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int r0 = tile * L2_ROWS + 2 * t;
-    const int64_t col = (int64_t)(tile * (L2_ROWS / 2) + t);     // packed-pair column index
+    const int64_t tile128 = (int64_t)b * p.k_tiles + tile * 2 + (t >> 6);   // this thread's 128-row block
+    const int64_t col = tile128 * H * 64 + (t & 63);                        // word offset of (unit 0, this row pair)
+    const int64_t col2 = tile128 * L2_CMAX * 64 + (t & 63);                 // same for the dZ2^T blocks
     const bool v0 = r0 < p.N, v1 = r0 + 1 < p.N;
     // ---- phase A: z2 = a1 W2 + b2 for both rows; relu mask bits go to shared memory
     float z0[CP], z1[CP];
@@ -514,8 +546,8 @@ __global__ void __launch_bounds__(128, 4) k_layer2(Layer2Params p) {
       __nv_bfloat16 h0, l0, h1, l1;
       split_bf16(dz0[c], h0, l0);
       split_bf16(dz1[c], h1, l1);
-      z2h[(int64_t)c * ld2 + col] = pack_bf16x2(h0, h1);
-      z2l[(int64_t)c * ld2 + col] = pack_bf16x2(l0, l1);
+      z2h[(int64_t)c * ld2 + col2] = pack_bf16x2(h0, h1);
+      z2l[(int64_t)c * ld2 + col2] = pack_bf16x2(l0, l1);
     }
     // ---- phase A2: dZ1 = (dZ2 W2^T) * act'(a1) -> split bf16, transposed packed store
     for (int hb = 0; hb < nhb; ++hb) {
@@ -602,6 +634,19 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 // 2-D bf16 tensor [rows, k] with row pitch ld_elems, box [TC_BK, box_rows], SWIZZLE_64B, zero OOB fill
+// row-tile-blocked bf16 tensor [blocks][rows_per_block][128]: box [TC_BK, box_rows, 1], SWIZZLE_64B
+static CUtensorMap make_map_blocked(const void* base, int64_t blocks, int rows_per_block, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {128, (cuuint64_t)rows_per_block, (cuuint64_t)blocks};
+  cuuint64_t strides[2] = {256, (cuuint64_t)rows_per_block * 256};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PYB_REQUIRE(r == CUDA_SUCCESS, PYB_ERR_CUDA, "cuTensorMapEncodeTiled (blocked) failed");
+  return m;
+}
 static CUtensorMap make_map(const void* base, int64_t k, int64_t rows, int64_t ld_elems, int box_rows) {
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
@@ -659,15 +704,26 @@ bool tc_supported(pyb_handle* h, int64_t S) {
   return true;
 }
 
+template <int EPI, int ACT>
+static void launch_gemm_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                             const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p) {
+  static bool attr_set = false;    // per instantiation
+  if (!attr_set) {
+    PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3<EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  tc_gemm_bf16x3<EPI, ACT><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+}
 static void launch_gemm_tc(pyb_handle* h, TcState* st, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                            const CUtensorMap& b_hi, const CUtensorMap& b_lo, TcGemmParams p, double flops) {
-  if (!st->attr_set) {
-    PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    st->attr_set = true;
-  }
+  (void)st;
   int grid = std::min(p.total_items, h->sm_count);
   prof_begin(h);
-  tc_gemm_bf16x3<<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  if (p.epi == EPI_STORE) launch_gemm_inst<EPI_STORE, 0>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
+  else if (p.act == PYB_ACT_RELU) launch_gemm_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_RELU>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
+  else if (p.act == PYB_ACT_TANH) launch_gemm_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_TANH>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
+  else if (p.act == PYB_ACT_SIGMOID) launch_gemm_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_SIGMOID>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
+  else launch_gemm_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_LINEAR>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
   prof_end(h, flops);
   count_launch(h);
 }
@@ -690,8 +746,8 @@ static void tc_prepare_data(pyb_handle* h, TcState* st) {
   count_launch(h, 3);
   st->mX_hi = make_map(st->x_hi.p, D, N, D, 128);
   st->mX_lo = make_map(st->x_lo.p, D, N, D, 128);
-  st->mXT_hi = make_map(st->xt_hi.p, N, D + 1, Npad, 128);
-  st->mXT_lo = make_map(st->xt_lo.p, N, D + 1, Npad, 128);
+  st->mXT_hi = make_map(st->xt_hi.p, Npad, D + 1, Npad, 128);
+  st->mXT_lo = make_map(st->xt_lo.p, Npad, D + 1, Npad, 128);
   st->data_ready = true;
   st->bufs_ready = false;
 }
@@ -712,6 +768,9 @@ static void tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S) {
   st->a_hi.alloc(bc * H * st->Npad); st->a_lo.alloc(bc * H * st->Npad);
   st->z2_hi.alloc(bc * L2_CMAX * st->Npad); st->z2_lo.alloc(bc * L2_CMAX * st->Npad);
   // rows >= N of the transposed buffers are never written; keep them finite (they are read as packed pairs)
+  // the blocked buffers are read over whole 128-row tiles: rows >= N must hold zeros, not garbage
+  PYB_CUDA(cudaMemsetAsync(st->z_hi.p, 0, st->z_hi.bytes(), h->stream));
+  PYB_CUDA(cudaMemsetAsync(st->z_lo.p, 0, st->z_lo.bytes(), h->stream));
   PYB_CUDA(cudaMemsetAsync(st->z2_hi.p, 0, st->z2_hi.bytes(), h->stream));
   PYB_CUDA(cudaMemsetAsync(st->z2_lo.p, 0, st->z2_lo.bytes(), h->stream));
   PYB_CUDA(cudaMemsetAsync(st->a_hi.p, 0, st->a_hi.bytes(), h->stream));
@@ -722,12 +781,13 @@ static void tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S) {
   st->loss_partial.alloc((size_t)bc * st->n_groups);
   st->mW_hi = make_map(st->w_hi.p, D, bc * H, D, H);
   st->mW_lo = make_map(st->w_lo.p, D, bc * H, D, H);
-  st->mZ_hi = make_map(st->z_hi.p, st->N, bc * H, st->Npad, H);
-  st->mZ_lo = make_map(st->z_lo.p, st->N, bc * H, st->Npad, H);
-  st->mA_hi = make_map(st->a_hi.p, st->N, bc * H, st->Npad, 128);
-  st->mA_lo = make_map(st->a_lo.p, st->N, bc * H, st->Npad, 128);
-  st->mZ2_hi = make_map(st->z2_hi.p, st->N, bc * L2_CMAX, st->Npad, L2_CMAX);
-  st->mZ2_lo = make_map(st->z2_lo.p, st->N, bc * L2_CMAX, st->Npad, L2_CMAX);
+  const int64_t blocks = bc * (st->Npad / 128);
+  st->mZ_hi = make_map_blocked(st->z_hi.p, blocks, H, H);
+  st->mZ_lo = make_map_blocked(st->z_lo.p, blocks, H, H);
+  st->mA_hi = make_map_blocked(st->a_hi.p, blocks, H, std::min(H, 128));
+  st->mA_lo = make_map_blocked(st->a_lo.p, blocks, H, std::min(H, 128));
+  st->mZ2_hi = make_map_blocked(st->z2_hi.p, blocks, L2_CMAX, L2_CMAX);
+  st->mZ2_lo = make_map_blocked(st->z2_lo.p, blocks, L2_CMAX, L2_CMAX);
   st->bufs_ready = true;
 }
 
@@ -754,10 +814,10 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
     {
       TcGemmParams p = {};
       p.K = D; p.n_mtiles = (int)((N + 127) / 128); p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
-      p.a_batch_rows = 0; p.order = 1; p.sub_batch = 32; p.total_items = p.n_pairs * nb;
+      p.a_batch_rows = 0; p.a_box_rows = 128; p.order = 1; p.sub_batch = 32; p.total_items = p.n_pairs * nb;
       p.epi = EPI_BIAS_ACT_T_SPLIT;
       p.bias = th + L1.b_off; p.bias_stride = P; p.act = L1.act;
-      p.out_hi = st->a_hi.p; p.out_lo = st->a_lo.p; p.out_t_ld = Npad;
+      p.out_hi = st->a_hi.p; p.out_lo = st->a_lo.p; p.out_tiles = (int)(Npad / 128);
       p.M_valid = (int)N; p.N_valid = H;
       launch_gemm_tc(h, st, st->mX_hi, st->mX_lo, st->mW_hi, st->mW_lo, p, 2.0 * N * D * (double)H * nb);
     }
@@ -765,7 +825,7 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
     {
       Layer2Params p = {};
       p.a_hi = st->a_hi.p; p.a_lo = st->a_lo.p; p.zt_hi = st->z_hi.p; p.zt_lo = st->z_lo.p;
-      p.z2_hi = st->z2_hi.p; p.z2_lo = st->z2_lo.p; p.ld = Npad;
+      p.z2_hi = st->z2_hi.p; p.z2_lo = st->z2_lo.p; p.k_tiles = (int)(Npad / 128);
       p.theta = th; p.P = P; p.w2_off = L2.w_off; p.b2_off = L2.b_off;
       p.H = H; p.C = C; p.N = (int)N; p.act1 = L1.act; p.out_act = L2.act; p.loss_kind = h->loss_kind;
       p.y_i = h->y_i.p; p.y_f = h->y_f.p; p.scale = scale;
@@ -783,7 +843,8 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
     // 4. G3: dW2[h][c] = sum_r a1[r][h] dZ2[r][c]   (A = A1^T per chain, B = dZ2^T per chain, N = 16)
     {
       TcGemmParams p = {};
-      p.K = (int)N; p.n_mtiles = (H + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = L2_CMAX;
+      p.K = (int)Npad; p.n_mtiles = (H + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = L2_CMAX;
+      p.a_blocked = 1; p.b_blocked = 1; p.k_tiles = (int)(Npad / 128); p.a_box_rows = std::min(H, 128);
       p.a_batch_rows = H; p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
       p.epi = EPI_STORE;
       p.out = gr + L2.w_off; p.out_stride = P; p.out_ld = C; p.M_valid = H; p.N_valid = C;
@@ -792,7 +853,8 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
     // 5. G2: [dW1; db1] = [X^T; 1] dZ1
     {
       TcGemmParams p = {};
-      p.K = (int)N; p.n_mtiles = (D + 1 + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
+      p.K = (int)Npad; p.n_mtiles = (D + 1 + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
+      p.a_blocked = 0; p.b_blocked = 1; p.k_tiles = (int)(Npad / 128); p.a_box_rows = 128;
       p.a_batch_rows = 0; p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
       p.epi = EPI_STORE;
       p.out = gr; p.out_stride = P; p.out_ld = H; p.M_valid = D + 1; p.N_valid = H;
@@ -820,7 +882,7 @@ void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn,
   TcGemmParams p = {};
   p.K = K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = 1; p.H = Nn;
   p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
-  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0;
+  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0; p.a_box_rows = 128;
   launch_gemm_tc(h, st, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K);
   PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
   PYB_CUDA(cudaStreamSynchronize(h->stream));
