@@ -20,7 +20,7 @@
 // streamed in 32-element (64 B, SWIZZLE_64B) chunks through a 3-stage TMA/mbarrier ring:
 // 64 KB/stage for 2*3*128*256*32*2 flop => ~42 B/clk/SM of L2->SM traffic at full MMA rate.
 // Roles: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warp 2 TMEM allocator,
-// warps 4-7 epilogue of accumulator 0 and warps 8-11 of accumulator 1 (TMEM lane == output row).
+// warps 4-19 epilogue: (accumulator, column half) x 4 lane quadrants (TMEM lane == output row).
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -129,7 +129,7 @@ constexpr int TC_A_TILE_BYTES = 128 * TC_BK * 2;    // 8 KB
 constexpr int TC_B_TILE_BYTES = 256 * TC_BK * 2;    // 16 KB (H <= 256)
 constexpr int TC_STAGE_BYTES = 4 * TC_A_TILE_BYTES + 2 * TC_B_TILE_BYTES;   // 64 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers + bias*/ + 1024;
-constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS = 640;
 
 enum { EPI_BIAS_ACT_T_SPLIT = 0, EPI_STORE = 1 };
 
@@ -200,7 +200,7 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 256);
+    mbar_init(tmem_empty, 512);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -283,10 +283,11 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warps 4-7 drain accumulator 0, warps 8-11 accumulator 1; TMEM lane == tile row =====
-    const int grp = (warp - 4) >> 2;                             // which accumulator / m-tile of the pair
+    // ===== epilogue: 16 warps = (accumulator, column half) x 4 lane quadrants; TMEM lane == tile row =====
+    const int grp = ((warp - 4) >> 2) & 1;                       // which accumulator / m-tile of the pair
+    const int half = (warp - 4) >> 3;                            // which half of the accumulator's columns
     const int et = (threadIdx.x - 128) & 127;                    // row inside the 128-row tile
-    const int eall = threadIdx.x - 128;                          // 0..255
+    const int eall = threadIdx.x - 128;                          // 0..511
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -295,16 +296,17 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int mt0 = mp * 2;
       const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
       if (EPI == EPI_BIAS_ACT_T_SPLIT) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");           // previous item's readers are done
-        for (int c = eall; c < p.H; c += 256) bias_s[c] = p.bias ? p.bias[(int64_t)b * p.bias_stride + c] : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");           // previous item's readers are done
+        for (int c = eall; c < p.H; c += 512) bias_s[c] = p.bias ? p.bias[(int64_t)b * p.bias_stride + c] : 0.f;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
       }
       mbar_wait(tmem_full, acc_phase);
       tc_fence_after();
       if (grp < n_mt) {
         const int row = (mt0 + grp) * 128 + et;
         const bool valid = row < p.M_valid;
-        for (int c0 = 0; c0 < p.H; c0 += 32) {
+        const int c_split = ((p.H + 63) >> 6) << 5;              // first half: [0, c_split), second: [c_split, H)
+        for (int c0 = half ? c_split : 0; c0 < (half ? p.H : min(c_split, p.H)); c0 += 32) {
           float v[32];
           tc_ld32(tmem_base + lane_base + (uint32_t)(grp * 256 + c0), v);
           if (EPI == EPI_BIAS_ACT_T_SPLIT) {
