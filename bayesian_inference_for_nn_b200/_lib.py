@@ -99,6 +99,31 @@ def check(status):
         raise PyesianB200Error(status, msg.decode("utf-8", "replace") if msg else "")
 
 
+def preload_nccl():
+    """Map libnccl.so.2 into the process (RTLD_GLOBAL) so the library's dlopen-by-soname finds it.
+    torch already does this when it is imported; otherwise use the copy bundled with the CUDA wheels."""
+    import glob
+    import sys
+    if "torch" in sys.modules:
+        return True
+    for base in sys.path:
+        for cand in glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                os.environ.setdefault("PYB_NCCL_LIB", cand)
+                return True
+            except OSError:
+                pass
+    return False
+
+
+def nccl_unique_id() -> bytes:
+    preload_nccl()
+    buf = C.create_string_buffer(128)
+    check(load().pyb_nccl_unique_id(buf))
+    return buf.raw
+
+
 def device_count():
     n = C.c_int32(0)
     check(load().pyb_device_count(C.byref(n)))

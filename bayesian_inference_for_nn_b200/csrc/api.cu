@@ -138,6 +138,7 @@ int pyb_destroy(pyb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   tc_release(h);
+  if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }
   for (auto* b : h->ws.act) delete b;
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   h->ws.act.clear();
@@ -446,9 +447,13 @@ int pyb_svgd_get_particles(pyb_handle* h, double* out) {
 int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* id) {
   PYB_TRY
   PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
-  (void)id;
   PYB_REQUIRE(world >= 1 && rank >= 0 && rank < world, PYB_ERR_INVALID, "bad rank/world");
-  if (world > 1) throw Error(PYB_ERR_UNSUPPORTED, "sharded SVGD (NCCL all-gather) is not wired in this build");
+  use_device(h);
+  if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }
+  if (world > 1) {
+    PYB_REQUIRE(id != nullptr, PYB_ERR_INVALID, "nccl unique id is NULL");
+    h->svgd.nccl_comm = nccl_comm_init(rank, world, id);
+  }
   h->svgd.rank = rank; h->svgd.world = world;
   PYB_CATCH
 }
@@ -456,7 +461,7 @@ int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* id
 int pyb_nccl_unique_id(void* out_128) {
   PYB_TRY
   PYB_REQUIRE(out_128, PYB_ERR_INVALID, "NULL argument");
-  throw Error(PYB_ERR_UNSUPPORTED, "NCCL plumbing is not wired in this build");
+  nccl_unique_id(out_128);
   PYB_CATCH
 }
 

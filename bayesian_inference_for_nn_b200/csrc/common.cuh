@@ -5,6 +5,8 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <stdexcept>
@@ -314,6 +316,15 @@ void hmc_flush_arena(pyb_handle* h);
 void svgd_init(pyb_handle* h, int64_t S, int64_t offset, double lr, int sem, const double* p0);
 void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out);
 void svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int sem, float* phi, double* h_out);
+
+// nccl_shim.cu (NCCL resolved with dlopen; only sharded SVGD uses it)
+void nccl_unique_id(void* out_128);
+void* nccl_comm_init(int rank, int world, const void* id_128);
+void nccl_comm_destroy(void* comm);
+void nccl_all_gather_f32(void* comm, const float* send, float* recv, size_t count_per_rank, cudaStream_t s);
+void nccl_all_reduce_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t s);
+void nccl_all_reduce_f64(void* comm, double* buf, size_t count, cudaStream_t s);
+void nccl_broadcast_f32(void* comm, float* buf, size_t count, int root, cudaStream_t s);
 
 // predict.cu
 void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,

@@ -1,0 +1,85 @@
+// nccl_shim.cu — NCCL is resolved at run time with dlopen/dlsym, so libpyesian_b200.so carries no link
+// dependency on it: only sharded SVGD (particle/gradient all-gather, histogram all-reduce) needs it.
+// The Python side preloads the libnccl.so.2 that ships with the CUDA stack (torch's bundled copy) so the
+// soname lookup below finds the already-mapped library.
+#include "common.cuh"
+#include <dlfcn.h>
+
+namespace pyb {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { NCCL_UINT64 = 5, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };
+enum { NCCL_SUM = 0 };
+
+struct NcclApi {
+  int (*GetUniqueId)(ncclUniqueId*);
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  int (*CommDestroy)(ncclComm_t);
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(int);
+  bool ok = false;
+};
+
+static NcclApi& api() {
+  static NcclApi a;
+  if (a.ok) return a;
+  void* lib = nullptr;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  const char* env = getenv("PYB_NCCL_LIB");
+  if (!lib && env) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  PYB_REQUIRE(lib != nullptr, PYB_ERR_UNSUPPORTED, "libnccl.so.2 not found (preload it or set PYB_NCCL_LIB)");
+#define PYB_SYM(field, name)                                                               \
+  a.field = (decltype(a.field))dlsym(lib, name);                                           \
+  PYB_REQUIRE(a.field != nullptr, PYB_ERR_UNSUPPORTED, "NCCL symbol missing: " name);
+  PYB_SYM(GetUniqueId, "ncclGetUniqueId")
+  PYB_SYM(CommInitRank, "ncclCommInitRank")
+  PYB_SYM(CommDestroy, "ncclCommDestroy")
+  PYB_SYM(AllGather, "ncclAllGather")
+  PYB_SYM(AllReduce, "ncclAllReduce")
+  PYB_SYM(Broadcast, "ncclBroadcast")
+  PYB_SYM(GetErrorString, "ncclGetErrorString")
+#undef PYB_SYM
+  a.ok = true;
+  return a;
+}
+
+static void nccl_check(int rc, const char* what) {
+  if (rc != 0) throw Error(PYB_ERR_CUDA, std::string(what) + " failed: " + api().GetErrorString(rc));
+}
+
+void nccl_unique_id(void* out_128) {
+  ncclUniqueId id;
+  nccl_check(api().GetUniqueId(&id), "ncclGetUniqueId");
+  memcpy(out_128, id.internal, 128);
+}
+void* nccl_comm_init(int rank, int world, const void* id_128) {
+  ncclUniqueId id;
+  memcpy(id.internal, id_128, 128);
+  ncclComm_t c = nullptr;
+  nccl_check(api().CommInitRank(&c, world, id, rank), "ncclCommInitRank");
+  return (void*)c;
+}
+void nccl_comm_destroy(void* comm) {
+  if (comm) api().CommDestroy((ncclComm_t)comm);
+}
+void nccl_all_gather_f32(void* comm, const float* send, float* recv, size_t count_per_rank, cudaStream_t s) {
+  nccl_check(api().AllGather(send, recv, count_per_rank, NCCL_FLOAT32, (ncclComm_t)comm, s), "ncclAllGather");
+}
+void nccl_all_reduce_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t s) {
+  nccl_check(api().AllReduce(buf, buf, count, NCCL_UINT64, NCCL_SUM, (ncclComm_t)comm, s), "ncclAllReduce");
+}
+void nccl_all_reduce_f64(void* comm, double* buf, size_t count, cudaStream_t s) {
+  nccl_check(api().AllReduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t)comm, s), "ncclAllReduce");
+}
+void nccl_broadcast_f32(void* comm, float* buf, size_t count, int root, cudaStream_t s) {
+  nccl_check(api().Broadcast(buf, buf, count, NCCL_FLOAT32, root, (ncclComm_t)comm, s), "ncclBroadcast");
+}
+
+}  // namespace pyb

@@ -262,19 +262,22 @@ static double adam_lr_t(double lr, int64_t t) {
 }
 
 // exact median bandwidth of d2 [n] (device, float64) -> h2 (device double[2] = {h2, median})
-static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int St, double* h2_dev) {
+// exact median over the GLOBAL set of St*St distances; each rank histograms its own rows and the 256-bin
+// histograms are all-reduced (2 KB per pass), so every rank picks the same bins
+static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t n_global, int St, double* h2_dev) {
   SvgdState& sc = h->svgd;
   sc.sel.alloc(6);
   sc.hist.alloc(256);
   SelectState init[2];
-  init[0].prefix = 0; init[0].mask = 0; init[0].k = (unsigned long long)((n - 1) / 2);
-  init[1].prefix = 0; init[1].mask = 0; init[1].k = (unsigned long long)(n / 2);
+  init[0].prefix = 0; init[0].mask = 0; init[0].k = (unsigned long long)((n_global - 1) / 2);
+  init[1].prefix = 0; init[1].mask = 0; init[1].k = (unsigned long long)(n_global / 2);
   PYB_CUDA(cudaMemcpyAsync(sc.sel.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   PYB_CUDA(cudaMemsetAsync(sc.hist.p, 0, 256 * sizeof(unsigned long long), h->stream));
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)h->sm_count);
   for (int w = 0; w < 2; ++w)
     for (int shift = 56; shift >= 0; shift -= 8) {
       k_select_hist<<<blocks, 256, 0, h->stream>>>(d2, n, reinterpret_cast<SelectState*>(sc.sel.p) + w, shift, sc.hist.p);
+      if (sc.world > 1) nccl_all_reduce_u64(sc.nccl_comm, sc.hist.p, 256, h->stream);
       k_select_pick<<<1, 256, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p) + w, shift, sc.hist.p);
       count_launch(h, 2);
     }
@@ -288,14 +291,14 @@ static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all,
   SvgdState& sv = h->svgd;
   SvgdState& sc = h->svgd;
   const int64_t P = h->model.P;
-  PYB_REQUIRE(Sl == St, PYB_ERR_UNSUPPORTED, "sharded median bandwidth needs the comm path (not wired in this build)");
+  PYB_REQUIRE(Sl == St || sv.world > 1, PYB_ERR_STATE, "row-sharded phi needs pyb_svgd_set_comm");
   sv.d2.alloc((size_t)Sl * St);
   sv.rowsum.alloc(Sl);
   sc.h2.alloc(2);
   dim3 g1((St + 15) / 16, (Sl + 15) / 16);
   k_gram_d2<<<g1, 256, 0, h->stream>>>(X_all, P, r0, Sl, St, sv.d2.p);
   count_launch(h);
-  median_bandwidth(h, sv.d2.p, (int64_t)Sl * St, St, sc.h2.p);
+  median_bandwidth(h, sv.d2.p, (int64_t)Sl * St, (int64_t)St * St, St, sc.h2.p);
   k_kernel_rowsum<<<Sl, 256, 0, h->stream>>>(sv.d2.p, St, sc.h2.p, sv.rowsum.p);
   dim3 g2((unsigned)((P + 255) / 256), (Sl + 7) / 8);
   k_phi_canonical<<<g2, 256, 0, h->stream>>>(sv.d2.p, X_all, G_all, P, r0, Sl, St, sc.h2.p, sv.rowsum.p, phi_local);
@@ -358,20 +361,50 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
   sv.t += 1;
   const float lr_t = (float)adam_lr_t(sv.lr, sv.t);
   const float scale = (sv.semantics == PYB_SVGD_REFERENCE_LIVE) ? 1.0f : (float)h->n_train;
-  generic_eval(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
-  if (sv.semantics == PYB_SVGD_REFERENCE_LIVE) {
-    sc.Krow.alloc(S);
-    for (int i = 0; i < (int)S; ++i) {
-      k_live_row<<<(unsigned)S, 256, 0, h->stream>>>(sv.theta.p, P, i, 1.0, sc.Krow.p);
-      k_live_update<<<(unsigned)((P + 255) / 256), 256, 0, h->stream>>>(sv.theta.p, sv.g.p, sv.adam_m.p, sv.adam_v.p,
-                                                                        sv.phi.p, P, (int)S, i, 1.0, sc.Krow.p, lr_t);
-      count_launch(h, 2);
-    }
-  } else {
+  const int R = sv.world, St = (int)(S * R), r0 = (int)(S * sv.rank);
+  if (resolve_path(h, S, true) == PYB_PATH_FUSED_SMALL && !idx)
+    eval_loss_grad(h, sv.theta.p, S, scale, sv.loss.p, sv.g.p);
+  else
+    generic_eval(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
+  // particles / gradients of every rank (the one exchange step of the path)
+  const float* theta_all = sv.theta.p;
+  const float* g_all = sv.g.p;
+  if (sv.semantics != PYB_SVGD_REFERENCE_LIVE) {
     dim3 gg((unsigned)std::min<int64_t>((P + 255) / 256, 1024), (unsigned)S);
     k_glogp<<<gg, 256, 0, h->stream>>>(sv.g.p, sv.theta.p, h->mu.p, h->inv_var.p, P);
     count_launch(h);
-    phi_canonical(h, sv.theta.p, sv.g.p, 0, (int)S, (int)S, sv.phi.p, nullptr);
+  }
+  if (R > 1) {
+    sv.theta_all.alloc((size_t)St * P);
+    sv.g_all.alloc((size_t)St * P);
+    nccl_all_gather_f32(sv.nccl_comm, sv.theta.p, sv.theta_all.p, (size_t)S * P, h->stream);
+    nccl_all_gather_f32(sv.nccl_comm, sv.g.p, sv.g_all.p, (size_t)S * P, h->stream);
+    theta_all = sv.theta_all.p;
+    g_all = sv.g_all.p;
+  }
+  if (sv.semantics == PYB_SVGD_REFERENCE_LIVE) {
+    // sequential sweep over ALL particles in global order: rank rr updates its rows (against the current
+    // global state) and broadcasts them before the next rank starts
+    sc.Krow.alloc(St);
+    float* th_all = (R > 1) ? sv.theta_all.p : sv.theta.p;
+    for (int rr = 0; rr < R; ++rr) {
+      if (rr == sv.rank) {
+        for (int i = 0; i < (int)S; ++i) {
+          const int gi = r0 + i;
+          k_live_row<<<(unsigned)St, 256, 0, h->stream>>>(th_all, P, gi, 1.0, sc.Krow.p);
+          k_live_update<<<(unsigned)((P + 255) / 256), 256, 0, h->stream>>>(
+              th_all, sv.g.p - (int64_t)r0 * P, sv.adam_m.p - (int64_t)r0 * P, sv.adam_v.p - (int64_t)r0 * P,
+              sv.phi.p - (int64_t)r0 * P, P, St, gi, 1.0, sc.Krow.p, lr_t);
+          count_launch(h, 2);
+        }
+      }
+      if (R > 1) nccl_broadcast_f32(sv.nccl_comm, th_all + (int64_t)rr * S * P, (size_t)S * P, rr, h->stream);
+    }
+    if (R > 1)
+      PYB_CUDA(cudaMemcpyAsync(sv.theta.p, th_all + (int64_t)r0 * P, (size_t)S * P * sizeof(float), cudaMemcpyDeviceToDevice,
+                               h->stream));
+  } else {
+    phi_canonical(h, theta_all, g_all, r0, (int)S, St, sv.phi.p, nullptr);
     int blocks = (int)std::min<int64_t>((S * P + 255) / 256, 8 * (int64_t)h->sm_count);
     k_adam_all<<<blocks, 256, 0, h->stream>>>(sv.theta.p, sv.phi.p, sv.adam_m.p, sv.adam_v.p, S * P, -1.0f, lr_t);
     count_launch(h);
@@ -379,6 +412,7 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
   sc.mean_loss.alloc(1);
   k_mean_float<<<1, 256, 0, h->stream>>>(sv.loss.p, S, sc.mean_loss.p);
   count_launch(h);
+  if (R > 1) nccl_all_reduce_f64(sv.nccl_comm, sc.mean_loss.p, 1, h->stream);
   PYB_CUDA(cudaEventRecord(h->ev1, h->stream));
   double ml = 0.0;
   PYB_CUDA(cudaMemcpyAsync(&ml, sc.mean_loss.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -387,7 +421,7 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
   float ms = 0.f;
   PYB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_device_ms = ms;
-  if (loss_out) *loss_out = ml;
+  if (loss_out) *loss_out = ml / (double)R;
 }
 
 void svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int sem, float* phi, double* h_out) {

@@ -150,6 +150,13 @@ class Engine:
         check(self.lib.pyb_svgd_init(self.h, int(S), int(offset), float(lr), int(semantics), _ptr(p0)))
         self.S = int(S)
 
+    def svgd_set_comm(self, rank: int, world: int, unique_id: bytes = None):
+        """Shard particles over `world` ranks (one process per GPU); all ranks pass the same 128-byte id
+        obtained once from `_lib.nccl_unique_id()`."""
+        _lib.preload_nccl()
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        check(self.lib.pyb_svgd_set_comm(self.h, int(rank), int(world), buf))
+
     def svgd_step(self, batch_idx=None):
         loss = C.c_double()
         if batch_idx is None:

@@ -1,0 +1,53 @@
+"""Multi-GPU tests (need >= 2 B200s on the box; skipped otherwise): SVGD particles sharded over two
+ranks with NCCL (particle/gradient all-gather, all-reduced median histograms, sequential live sweep)
+must reproduce the single-GPU golden run."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, uid, sem, out):
+    import numpy as np
+    from bayesian_inference_for_nn_b200 import _lib, keras_json
+    from bayesian_inference_for_nn_b200.engine import Engine
+    from conftest import load_golden as lg
+    g = lg("svgd_mini")
+    S = g["particles0"].shape[0]
+    Sl = S // world
+    eng = Engine(keras_json.parse_model_json(keras_json.make_sequential_json(2, [50, 2], ["relu", "softmax"])), device=rank)
+    eng.set_dataset(g["X"], g["y"], _lib.LOSS_SPARSE_CE)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.svgd_set_comm(rank, world, uid)
+    eng.svgd_init(Sl, float(g["lr"]), sem, particles0=g["particles0"][rank * Sl:(rank + 1) * Sl], offset=rank * Sl)
+    losses = [eng.svgd_step(ix) for ix in g["idx"]]
+    out.put((rank, eng.svgd_particles(), losses))
+    eng.close()
+
+
+@pytest.mark.parametrize("sem,key", [(1, "can"), (0, "live")])
+def test_svgd_sharded_over_two_gpus_matches_golden(sem, key):
+    from bayesian_inference_for_nn_b200 import _lib
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    uid = _lib.nccl_unique_id()
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, uid, sem, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = load_golden("svgd_mini")
+    parts = np.concatenate([r[1] for r in res])
+    np.testing.assert_allclose(res[0][2], g[key + "_losses"], rtol=1e-4)       # all-reduced mean loss
+    np.testing.assert_allclose(res[1][2], g[key + "_losses"], rtol=1e-4)
+    lr, n = float(g["lr"]), len(g["idx"])
+    assert np.abs(parts - g[key + "_particles"]).max() < 2e-3 * lr * n + 1e-6
