@@ -42,6 +42,13 @@ void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, f
   }
   h->path_used = path;
 }
+void eval_on_batch(pyb_handle* h, const float* theta, int64_t S, const float* Xb, const int32_t* yb_i, const float* yb_f,
+                   int64_t Nb, float scale, float* loss_out, float* grad_out) {
+  if (Xb == h->X.p && Nb == h->N) { eval_loss_grad(h, theta, S, scale, loss_out, grad_out); return; }
+  const bool tensor_ok = grad_out && tc_supported_rows(h, Nb) && (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_TENSOR);
+  if (tensor_ok) { tc_eval_batch(h, Xb, yb_i, yb_f, Nb, theta, S, scale, loss_out, grad_out); h->path_used = PYB_PATH_TENSOR; }
+  else { generic_eval(h, theta, S, Xb, yb_i, yb_f, Nb, scale, loss_out, grad_out); h->path_used = PYB_PATH_GENERIC; }
+}
 }  // namespace pyb
 
 using namespace pyb;

@@ -207,6 +207,9 @@ struct SvgdState {
   DevBuf<double> d2, K, rowsum;
   DevBuf<unsigned long long> sel, hist;   // radix-select state (2 x {prefix,mask,k}) and 256-bin histogram
   DevBuf<double> h2, mean_loss, Krow;
+  // tensor-core Gram / Stein contraction operands (bf16 hi/lo kept as raw 16-bit words)
+  DevBuf<uint16_t> xh, xl, yth, ytl, kh, kl;
+  DevBuf<float> gram, ybuf, kf, norms;
   DevBuf<float> Xb;
   DevBuf<int32_t> yb_i, idx;
   DevBuf<float> yb_f;
@@ -305,6 +308,19 @@ void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, f
 int resolve_path(pyb_handle* h, int64_t S, bool with_grad);
 bool fused_small_supported(pyb_handle* h);
 void fused_small_hmc_iteration(pyb_handle* h, bool burning);
+
+// tc_path.cu
+bool tc_supported_rows(pyb_handle* h, int64_t n_rows);
+void tc_eval_batch(pyb_handle* h, const float* Xb, const int32_t* yb_i, const float* yb_f, int64_t Nb, const float* theta,
+                   int64_t S, float scale, float* loss_out, float* grad_out);
+void tc_forward(pyb_handle* h, const float* theta, int64_t S, const float* x, int64_t N, float* out);
+void tc_split_rows(pyb_handle* h, const float* src, int64_t R, int C, int64_t lds, void* hi, void* lo, int64_t ldd);
+void tc_split_transpose(pyb_handle* h, const float* src, int R, int C, int64_t lds, void* hi, void* lo, int64_t ldd);
+void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t lda, int64_t a_rows_total, int a_row0, int M,
+                   const void* b_hi, const void* b_lo, int64_t ldb, int Nn, int64_t K, float* out, int64_t ldc);
+// loss + gradient on an arbitrary device-resident batch (api.cu): tensor path when the shape allows, else generic
+void eval_on_batch(pyb_handle* h, const float* theta, int64_t S, const float* Xb, const int32_t* yb_i, const float* yb_f,
+                   int64_t Nb, float scale, float* loss_out, float* grad_out);
 
 // sampler.cu
 void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double m, int L, int sem, const float* q0);

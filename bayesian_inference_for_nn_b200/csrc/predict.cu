@@ -64,11 +64,14 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
   s1.alloc(elems); s2.alloc(elems); dmean.alloc(elems); dvar.alloc(elems);
   PYB_CUDA(cudaMemsetAsync(s1.p, 0, elems * sizeof(double), h->stream));
   PYB_CUDA(cudaMemsetAsync(s2.p, 0, elems * sizeof(double), h->stream));
+  const bool use_tensor = tc_supported_rows(h, Nt) && (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_TENSOR);
+  h->path_used = use_tensor ? PYB_PATH_TENSOR : PYB_PATH_GENERIC;
   PYB_CUDA(cudaEventRecord(h->ev0, h->stream));
   for (int64_t i0 = 0; i0 < n; i0 += chunk) {
     int64_t nb = std::min(chunk, n - i0);
     PYB_CUDA(cudaMemcpyAsync(dW.p, W + i0 * P, nb * P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    generic_forward(h, dW.p, nb, dx.p, Nt, dout.p);
+    if (use_tensor) tc_forward(h, dW.p, nb, dx.p, Nt, dout.p);
+    else generic_forward(h, dW.p, nb, dx.p, Nt, dout.p);
     k_pred_accum<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(dout.p, nb, elems, weight ? dw.p + i0 : nullptr,
                                                                          s1.p, s2.p);
     count_launch(h);

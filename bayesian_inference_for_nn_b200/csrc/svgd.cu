@@ -234,6 +234,43 @@ __global__ void __launch_bounds__(256) k_phi_live_all(const double* K, const flo
   phi[(int64_t)i * P + e] = ((float)rowsum[i] * G[(int64_t)i * P + e] + gk) / (float)S;
 }
 
+// ---- tensor-core variant of the canonical update (large S): Gram and K*Y as bf16x3 GEMMs ---------
+__global__ void k_row_norms(const float* X, int64_t P, double* norms) {
+  __shared__ double scratch[32];
+  const float* x = X + (int64_t)blockIdx.x * P;
+  double a = 0.0;
+  for (int64_t e = threadIdx.x; e < P; e += blockDim.x) a += (double)x[e] * (double)x[e];
+  double t = block_sum<double>(a, scratch);
+  if (threadIdx.x == 0) norms[blockIdx.x] = t;
+}
+// d2[i][j] = max(n_{r0+i} + n_j - 2 G[i][j], 0); exact zero on the diagonal (pdist has d(x,x) = 0)
+__global__ void k_d2_from_gram(const float* G, const double* norms, int r0, int Sl, int St, double* d2) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Sl * St) return;
+  int i = (int)(idx / St), j = (int)(idx - (int64_t)i * St);
+  double v = norms[r0 + i] + norms[j] - 2.0 * (double)G[idx];
+  d2[idx] = (j == r0 + i || v < 0.0) ? 0.0 : v;
+}
+__global__ void k_double_to_float(const double* a, float* b, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    b[i] = (float)a[i];
+}
+// Y = G - X / h2   (row-major [St, P])
+__global__ void k_stein_rhs(const float* X, const float* G, const double* h2, int64_t n, float* Y) {
+  const float inv = (float)(1.0 / h2[0]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    Y[i] = G[i] - X[i] * inv;
+}
+// phi = (KY + X_i rowsum_i / h2) / St   in place on the GEMM output
+__global__ void k_phi_finish(float* phi, const float* X, int64_t P, int r0, int St, const double* h2, const double* rowsum) {
+  const int i = blockIdx.y;
+  const double c = rowsum[i] / h2[0];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t o = (int64_t)i * P + e;
+    phi[o] = (float)(((double)phi[o] + (double)X[(int64_t)(r0 + i) * P + e] * c) / (double)St);
+  }
+}
+
 // glogp = -(g + (theta-mu)/sigma^2)   (g already scaled by n_train)
 __global__ void k_glogp(float* g, const float* theta, const float* mu, const float* inv_var, int64_t P) {
   int64_t s = blockIdx.y;
@@ -295,14 +332,45 @@ static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all,
   sv.d2.alloc((size_t)Sl * St);
   sv.rowsum.alloc(Sl);
   sc.h2.alloc(2);
-  dim3 g1((St + 15) / 16, (Sl + 15) / 16);
-  k_gram_d2<<<g1, 256, 0, h->stream>>>(X_all, P, r0, Sl, St, sv.d2.p);
-  count_launch(h);
+  // large particle sets: Gram matrix and the K*Y contraction run on the tensor cores (bf16x3 split);
+  // small ones keep the direct float64 kernels (bit-for-bit the formulation scipy's pdist uses)
+  const bool tensor = St >= 256 && P >= 64 && (St % 8) == 0 &&
+                      (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_TENSOR);
+  const int64_t Ppad = (P + 7) / 8 * 8;
+  if (tensor) {
+    sv.xh.alloc((size_t)St * Ppad); sv.xl.alloc((size_t)St * Ppad);
+    sv.gram.alloc((size_t)Sl * St); sv.norms.alloc(0); sc.Krow.alloc(St);
+    tc_split_rows(h, X_all, St, (int)P, P, sv.xh.p, sv.xl.p, Ppad);
+    tc_gemm_split(h, sv.xh.p, sv.xl.p, Ppad, St, r0, Sl, sv.xh.p, sv.xl.p, Ppad, St, P, sv.gram.p, St);
+    k_row_norms<<<St, 256, 0, h->stream>>>(X_all, P, sc.Krow.p);
+    k_d2_from_gram<<<(unsigned)(((int64_t)Sl * St + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sc.Krow.p, r0, Sl, St, sv.d2.p);
+    count_launch(h, 2);
+  } else {
+    dim3 g1((St + 15) / 16, (Sl + 15) / 16);
+    k_gram_d2<<<g1, 256, 0, h->stream>>>(X_all, P, r0, Sl, St, sv.d2.p);
+    count_launch(h);
+  }
   median_bandwidth(h, sv.d2.p, (int64_t)Sl * St, (int64_t)St * St, St, sc.h2.p);
   k_kernel_rowsum<<<Sl, 256, 0, h->stream>>>(sv.d2.p, St, sc.h2.p, sv.rowsum.p);
-  dim3 g2((unsigned)((P + 255) / 256), (Sl + 7) / 8);
-  k_phi_canonical<<<g2, 256, 0, h->stream>>>(sv.d2.p, X_all, G_all, P, r0, Sl, St, sc.h2.p, sv.rowsum.p, phi_local);
-  count_launch(h, 2);
+  count_launch(h);
+  if (tensor) {
+    // phi = (K Y + X rowsum/h2)/St with Y = G - X/h2: A = K [Sl, St] (K-major), B = Y^T [P, St]
+    const int blocks = (int)std::min<int64_t>(((int64_t)St * P + 255) / 256, 16 * (int64_t)h->sm_count);
+    sv.kf.alloc((size_t)Sl * St); sv.kh.alloc((size_t)Sl * St); sv.kl.alloc((size_t)Sl * St);
+    sv.ybuf.alloc((size_t)St * P); sv.yth.alloc((size_t)P * St); sv.ytl.alloc((size_t)P * St);
+    k_double_to_float<<<blocks, 256, 0, h->stream>>>(sv.d2.p, sv.kf.p, (int64_t)Sl * St);
+    tc_split_rows(h, sv.kf.p, Sl, St, St, sv.kh.p, sv.kl.p, St);
+    k_stein_rhs<<<blocks, 256, 0, h->stream>>>(X_all, G_all, sc.h2.p, (int64_t)St * P, sv.ybuf.p);
+    tc_split_transpose(h, sv.ybuf.p, St, (int)P, P, sv.yth.p, sv.ytl.p, St);
+    tc_gemm_split(h, sv.kh.p, sv.kl.p, St, Sl, 0, Sl, sv.yth.p, sv.ytl.p, St, (int)P, St, phi_local, P);
+    dim3 gf((unsigned)std::min<int64_t>((P + 255) / 256, 1024), (unsigned)Sl);
+    k_phi_finish<<<gf, 256, 0, h->stream>>>(phi_local, X_all, P, r0, St, sc.h2.p, sv.rowsum.p);
+    count_launch(h, 3);
+  } else {
+    dim3 g2((unsigned)((P + 255) / 256), (Sl + 7) / 8);
+    k_phi_canonical<<<g2, 256, 0, h->stream>>>(sv.d2.p, X_all, G_all, P, r0, Sl, St, sc.h2.p, sv.rowsum.p, phi_local);
+    count_launch(h);
+  }
   if (h_host_out) {
     double v[2];
     PYB_CUDA(cudaMemcpyAsync(v, sc.h2.p, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
@@ -362,10 +430,7 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
   const float lr_t = (float)adam_lr_t(sv.lr, sv.t);
   const float scale = (sv.semantics == PYB_SVGD_REFERENCE_LIVE) ? 1.0f : (float)h->n_train;
   const int R = sv.world, St = (int)(S * R), r0 = (int)(S * sv.rank);
-  if (resolve_path(h, S, true) == PYB_PATH_FUSED_SMALL && !idx)
-    eval_loss_grad(h, sv.theta.p, S, scale, sv.loss.p, sv.g.p);
-  else
-    generic_eval(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
+  eval_on_batch(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
   // particles / gradients of every rank (the one exchange step of the path)
   const float* theta_all = sv.theta.p;
   const float* g_all = sv.g.p;

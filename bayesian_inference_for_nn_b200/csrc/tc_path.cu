@@ -146,6 +146,8 @@ struct TcGemmParams {
   // EPI_STORE: out[b*out_stride + row*out_ld + col] = D[row][col]   (row < M_valid, col < N_valid)
   float* out; int64_t out_stride; int out_ld;
   int M_valid, N_valid;
+  int a_row0;                  // first A row of this launch (row-sharded callers)
+  int n_cols_total;            // >0: chain b owns columns [b*H, min((b+1)*H, n_cols_total)) of one wide output
 };
 
 __device__ __forceinline__ void tc_decode(const TcGemmParams& p, int item, int& b, int& mp) {
@@ -230,7 +232,7 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_expect_tx(&full_bar[stage], bytes);
           const int k0 = kc * TC_BK;
           for (int mt = 0; mt < n_mt; ++mt) {
-            const int arow = (p.a_blocked ? 0 : b * p.a_batch_rows) + (mt0 + mt) * 128;
+            const int arow = (p.a_blocked ? 0 : p.a_row0 + b * p.a_batch_rows) + (mt0 + mt) * 128;
             tma_load_operand(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], p.a_blocked, k0, arow, b, p.k_tiles);
             tma_load_operand(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], p.a_blocked, k0, arow, b, p.k_tiles);
           }
@@ -314,7 +316,7 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             // shuffle so that (row, row+1) leave as one 32-bit bf16x2 word: half the store instructions,
             // 64 B contiguous per half-warp.  All lanes take part in the shuffles (rows >= M_valid too).
             const int odd = lane & 1;
-            const bool pair_valid = (row & ~1) < p.M_valid;
+            const bool v_even = (row & ~1) < p.M_valid, v_odd = (row | 1) < p.M_valid;   // rows >= M_valid store zeros
             const int64_t w0 = ((((int64_t)b * p.out_tiles + (mt0 + grp)) * p.H + c0 + odd) * 128 + (et & ~1)) >> 1;
             uint32_t* ohi = reinterpret_cast<uint32_t*>(p.out_hi) + w0;
             uint32_t* olo = reinterpret_cast<uint32_t*>(p.out_lo) + w0;
@@ -324,9 +326,9 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const float a_e = act_apply_t<ACT>(v[j] + bias_s[c0 + j]);
               const float a_o = act_apply_t<ACT>(v[j + 1] + bias_s[c0 + j + 1]);
               const float recv = __shfl_xor_sync(0xffffffffu, odd ? a_e : a_o, 1);
-              const float x0 = odd ? recv : a_e;       // row & ~1
-              const float x1 = odd ? a_o : recv;       // (row & ~1) + 1
-              if (pair_valid && (full || c0 + j + odd < p.H)) {
+              const float x0 = v_even ? (odd ? recv : a_e) : 0.f;       // row & ~1
+              const float x1 = v_odd ? (odd ? a_o : recv) : 0.f;        // (row & ~1) + 1
+              if (full || c0 + j + odd < p.H) {
                 const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);           // one cvt.rn.bf16x2.f32
                 const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hp);
                 const float r0 = x0 - __uint_as_float(hw << 16);
@@ -339,9 +341,10 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           } else {
             if (valid) {
               float* o = p.out + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
+              const int nvalid = p.n_cols_total > 0 ? min(p.N_valid, p.n_cols_total - b * p.H) : p.N_valid;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (c0 + j < p.N_valid) o[j] = v[j];
+                if (c0 + j < nvalid) o[j] = v[j];
             }
           }
         }
@@ -602,6 +605,72 @@ __global__ void __launch_bounds__(128, 4) k_layer2(Layer2Params p) {
   if (t == 0) p.loss_partial[(int64_t)b * p.n_groups + blockIdx.x] = tot;
 }
 
+// forward-only layer 2 (posterior predictive): out[b][row][c] = softmax(a1 W2 + b2) or act(.)
+struct Layer2FwdParams {
+  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo; int k_tiles;
+  const float* theta; int64_t P; int64_t w2_off, b2_off;
+  int H, C, N, out_act, n_tiles;
+  float* out;
+};
+__global__ void __launch_bounds__(128) k_layer2_fwd(Layer2FwdParams p) {
+  __shared__ __align__(16) float W2s[256 * L2_CMAX];
+  __shared__ float b2s[L2_CMAX];
+  const int t = threadIdx.x, b = blockIdx.y, H = p.H, C = p.C;
+  const float* th = p.theta + (int64_t)b * p.P;
+  for (int i = t; i < H * L2_CMAX; i += 128) {
+    int h = i / L2_CMAX, c = i % L2_CMAX;
+    W2s[i] = (c < C) ? th[p.w2_off + (int64_t)h * C + c] : 0.f;
+  }
+  if (t < L2_CMAX) b2s[t] = (t < C) ? th[p.b2_off + t] : 0.f;
+  __syncthreads();
+  const uint32_t* ah = reinterpret_cast<const uint32_t*>(p.a_hi);
+  const uint32_t* al = reinterpret_cast<const uint32_t*>(p.a_lo);
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int r0 = tile * L2_ROWS + 2 * t;
+    const int64_t tile128 = (int64_t)b * p.k_tiles + tile * 2 + (t >> 6);
+    const int64_t col = tile128 * H * 64 + (t & 63);
+    float z0[L2_CMAX], z1[L2_CMAX];
+#pragma unroll
+    for (int c = 0; c < L2_CMAX; ++c) { z0[c] = b2s[c]; z1[c] = b2s[c]; }
+#pragma unroll 4
+    for (int h = 0; h < H; ++h) {
+      const float2 hi = unpack_bf16x2(ah[(int64_t)h * 64 + col]);
+      const float2 lo = unpack_bf16x2(al[(int64_t)h * 64 + col]);
+      const float a0 = hi.x + lo.x, a1v = hi.y + lo.y;
+      const float4* w = reinterpret_cast<const float4*>(&W2s[h * L2_CMAX]);
+#pragma unroll
+      for (int q4 = 0; q4 < L2_CMAX / 4; ++q4) {
+        const float4 wv = w[q4];
+        z0[q4 * 4 + 0] = fmaf(a0, wv.x, z0[q4 * 4 + 0]); z1[q4 * 4 + 0] = fmaf(a1v, wv.x, z1[q4 * 4 + 0]);
+        z0[q4 * 4 + 1] = fmaf(a0, wv.y, z0[q4 * 4 + 1]); z1[q4 * 4 + 1] = fmaf(a1v, wv.y, z1[q4 * 4 + 1]);
+        z0[q4 * 4 + 2] = fmaf(a0, wv.z, z0[q4 * 4 + 2]); z1[q4 * 4 + 2] = fmaf(a1v, wv.z, z1[q4 * 4 + 2]);
+        z0[q4 * 4 + 3] = fmaf(a0, wv.w, z0[q4 * 4 + 3]); z1[q4 * 4 + 3] = fmaf(a1v, wv.w, z1[q4 * 4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int r = r0 + rr;
+      if (r >= p.N) continue;
+      float* z = rr ? z1 : z0;
+      float* o = p.out + ((int64_t)b * p.N + r) * C;
+      if (p.out_act == PYB_ACT_SOFTMAX) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c) if (c < C) mx = fmaxf(mx, z[c]);
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c) if (c < C) se += expf(z[c] - mx);
+        const float inv = 1.0f / se;
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c) if (c < C) o[c] = expf(z[c] - mx) * inv;
+      } else {
+#pragma unroll
+        for (int c = 0; c < L2_CMAX; ++c) if (c < C) o[c] = act_apply(z[c], p.out_act);
+      }
+    }
+  }
+}
+
 // grad[b][b2_off + c] = sum_g b2_partial[b][g][c] (fixed order); loss[b] = sum_g loss_partial / N
 __global__ void k_layer2_reduce(const float* b2_partial, const double* loss_partial, int n_groups, int C, float* grad,
                                 int64_t P, int64_t b2_off, float* loss_out, int N) {
@@ -663,21 +732,24 @@ static CUtensorMap make_map(const void* base, int64_t k, int64_t rows, int64_t l
   return m;
 }
 
-struct TcState {
-  bool data_ready = false, bufs_ready = false;
-  int64_t N = 0, Npad = 0, Bc = 0;
-  int D = 0, H = 0, C = 0;
+struct TcData {   // split bf16 operands derived from one [N, D] fp32 matrix resident in HBM
+  bool ready = false;
+  int64_t N = 0, Npad = 0;
+  int D = 0;
   DevBuf<__nv_bfloat16> x_hi, x_lo, xt_hi, xt_lo;       // [N][D], [D+1][Npad]
-  DevBuf<__nv_bfloat16> w_hi, w_lo;                     // [Bc*H][D]
-  DevBuf<__nv_bfloat16> z_hi, z_lo;                     // dZ1^T [Bc*H][Npad]
-  DevBuf<__nv_bfloat16> a_hi, a_lo;                     // A1^T  [Bc*H][Npad]
-  DevBuf<__nv_bfloat16> z2_hi, z2_lo;                   // dZ2^T [Bc*16][Npad]
+  CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo;
+};
+struct TcState {
+  TcData train, aux;                                    // resident training set / minibatch or test inputs
+  int D = 0, H = 0, C = 0;
+  int64_t cap_chains = 0, cap_blocks = 0;               // capacity: chains, and 128-row blocks over all chains
+  DevBuf<__nv_bfloat16> w_hi, w_lo;                     // W1^T  [chains*H][D]
+  DevBuf<__nv_bfloat16> z_hi, z_lo;                     // dZ1^T blocked [block][H][128]
+  DevBuf<__nv_bfloat16> a_hi, a_lo;                     // A1^T  blocked [block][H][128]
+  DevBuf<__nv_bfloat16> z2_hi, z2_lo;                   // dZ2^T blocked [block][16][128]
   DevBuf<float> b2_partial;
   DevBuf<double> loss_partial;
-  CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo, mW_hi, mW_lo, mZ_hi, mZ_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
-  int n_tiles = 0;
-  int n_groups = 0;
-  bool attr_set = false;
+  CUtensorMap mW_hi, mW_lo, mZ_hi, mZ_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
 };
 static TcState* tc_state(pyb_handle* h) {
   if (!h->tc) h->tc = new TcState();
@@ -688,13 +760,13 @@ void tc_release(pyb_handle* h) {
   h->tc = nullptr;
 }
 void tc_invalidate_dataset(pyb_handle* h) {
-  if (h->tc) { ((TcState*)h->tc)->data_ready = false; ((TcState*)h->tc)->bufs_ready = false; }
+  if (h->tc) ((TcState*)h->tc)->train.ready = false;
 }
 
-bool tc_supported(pyb_handle* h, int64_t S) {
+// shape conditions of the tensor path for a batch of n_rows data rows
+bool tc_supported_rows(pyb_handle* h, int64_t n_rows) {
   const Model& m = h->model;
-  (void)S;
-  if (m.n_layers != 2 || !h->have_data) return false;
+  if (m.n_layers != 2) return false;
   const LayerDesc& L1 = m.layer[0];
   const LayerDesc& L2 = m.layer[1];
   if (!L1.use_bias || !L2.use_bias) return false;
@@ -702,8 +774,11 @@ bool tc_supported(pyb_handle* h, int64_t S) {
   if (L1.fan_in % 8 != 0 || L1.fan_in < 64) return false;
   if (L2.fan_out > L2_CMAX) return false;
   if (L1.act == PYB_ACT_SOFTMAX) return false;
-  if (h->N < 128) return false;
-  return true;
+  return n_rows >= 128;
+}
+bool tc_supported(pyb_handle* h, int64_t S) {
+  (void)S;
+  return h->have_data && tc_supported_rows(h, h->N);
 }
 
 template <int EPI, int ACT>
@@ -716,9 +791,8 @@ static void launch_gemm_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, c
   }
   tc_gemm_bf16x3<EPI, ACT><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
 }
-static void launch_gemm_tc(pyb_handle* h, TcState* st, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+static void launch_gemm_tc(pyb_handle* h, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                            const CUtensorMap& b_hi, const CUtensorMap& b_lo, TcGemmParams p, double flops) {
-  (void)st;
   int grid = std::min(p.total_items, h->sm_count);
   prof_begin(h);
   if (p.epi == EPI_STORE) launch_gemm_inst<EPI_STORE, 0>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
@@ -730,119 +804,127 @@ static void launch_gemm_tc(pyb_handle* h, TcState* st, const CUtensorMap& a_hi, 
   count_launch(h);
 }
 
-static void tc_prepare_data(pyb_handle* h, TcState* st) {
+
+static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N, bool need_xt) {
   const Model& m = h->model;
-  st->N = h->N; st->D = m.layer[0].fan_in; st->H = m.layer[0].fan_out; st->C = m.layer[1].fan_out;
-  st->Npad = ((st->N + L2_ROWS - 1) / L2_ROWS) * L2_ROWS;
-  const int64_t N = st->N, Npad = st->Npad;
-  const int D = st->D;
-  st->x_hi.alloc(N * D); st->x_lo.alloc(N * D);
-  st->xt_hi.alloc((int64_t)(D + 1) * Npad); st->xt_lo.alloc((int64_t)(D + 1) * Npad);
-  PYB_CUDA(cudaMemsetAsync(st->xt_hi.p, 0, st->xt_hi.bytes(), h->stream));
-  PYB_CUDA(cudaMemsetAsync(st->xt_lo.p, 0, st->xt_lo.bytes(), h->stream));
-  k_split_rows<<<(unsigned)std::min<int64_t>((N * D + 255) / 256, 65535), 256, 0, h->stream>>>(h->X.p, N, D, D, st->x_hi.p,
-                                                                                             st->x_lo.p, D);
-  dim3 g2((D + 31) / 32, (unsigned)((N + 31) / 32), 1), blk(32, 8);
-  k_split_transpose<<<g2, blk, 0, h->stream>>>(h->X.p, 0, (int)N, D, D, st->xt_hi.p, st->xt_lo.p, 0, Npad);
-  k_fill_bf16<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(st->xt_hi.p + (int64_t)D * Npad, N, 1.0f);  // ones row -> db1
-  count_launch(h, 3);
-  st->mX_hi = make_map(st->x_hi.p, D, N, D, 128);
-  st->mX_lo = make_map(st->x_lo.p, D, N, D, 128);
-  st->mXT_hi = make_map(st->xt_hi.p, Npad, D + 1, Npad, 128);
-  st->mXT_lo = make_map(st->xt_lo.p, Npad, D + 1, Npad, 128);
-  st->data_ready = true;
-  st->bufs_ready = false;
+  const int D = m.layer[0].fan_in;
+  d.N = N; d.D = D;
+  d.Npad = ((N + L2_ROWS - 1) / L2_ROWS) * L2_ROWS;
+  const int64_t Npad = d.Npad;
+  d.x_hi.alloc(N * D); d.x_lo.alloc(N * D);
+  k_split_rows<<<(unsigned)std::min<int64_t>((N * D + 255) / 256, 65535), 256, 0, h->stream>>>(X, N, D, D, d.x_hi.p, d.x_lo.p, D);
+  count_launch(h);
+  d.mX_hi = make_map(d.x_hi.p, D, N, D, 128);
+  d.mX_lo = make_map(d.x_lo.p, D, N, D, 128);
+  if (need_xt) {
+    d.xt_hi.alloc((int64_t)(D + 1) * Npad); d.xt_lo.alloc((int64_t)(D + 1) * Npad);
+    PYB_CUDA(cudaMemsetAsync(d.xt_hi.p, 0, (size_t)(D + 1) * Npad * 2, h->stream));
+    PYB_CUDA(cudaMemsetAsync(d.xt_lo.p, 0, (size_t)(D + 1) * Npad * 2, h->stream));
+    dim3 g2((D + 31) / 32, (unsigned)((N + 31) / 32), 1), blk(32, 8);
+    k_split_transpose<<<g2, blk, 0, h->stream>>>(X, 0, (int)N, D, D, d.xt_hi.p, d.xt_lo.p, 0, Npad);
+    k_fill_bf16<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(d.xt_hi.p + (int64_t)D * Npad, N, 1.0f);  // ones row -> db1
+    count_launch(h, 2);
+    d.mXT_hi = make_map(d.xt_hi.p, Npad, D + 1, Npad, 128);
+    d.mXT_lo = make_map(d.xt_lo.p, Npad, D + 1, Npad, 128);
+  }
+  d.ready = true;
 }
 
-static void tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S) {
-  // chain batch: intermediates are A1^T hi/lo + dZ1^T hi/lo = 8 bytes per (chain, hidden, row)
-  int64_t per_chain = (int64_t)st->H * st->Npad * 8;
+// chain batch for S chains over Npad rows; grows the shared buffers (and their tensor maps) on demand
+static int64_t tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S, int64_t Npad, bool backward) {
+  const Model& m = h->model;
+  st->D = m.layer[0].fan_in; st->H = m.layer[0].fan_out; st->C = m.layer[1].fan_out;
+  const int H = st->H, D = st->D;
+  const int64_t k_tiles = Npad / 128;
+  // intermediates: A1^T hi/lo (+ dZ1^T hi/lo) = 4 (+4) bytes per (chain, hidden, row)
+  int64_t per_chain = (int64_t)H * Npad * (backward ? 8 : 4) + (int64_t)H * D * 4;
   int64_t budget = (int64_t)(std::max(h->opt_workspace_mb, 20000.0) * 1024.0 * 1024.0);
   int64_t bc = std::max<int64_t>(1, budget / per_chain);
   if (h->opt_chain_batch > 0) bc = std::min<int64_t>(bc, h->opt_chain_batch);
   bc = std::min<int64_t>(bc, S);
-  if (bc >= h->sm_count) bc = (bc / h->sm_count) * h->sm_count;      // whole waves of G2 work
-  if (st->bufs_ready && st->Bc >= bc) return;
-  st->Bc = bc;
-  const int H = st->H, D = st->D;
-  st->w_hi.alloc(bc * H * D); st->w_lo.alloc(bc * H * D);
-  st->z_hi.alloc(bc * H * st->Npad); st->z_lo.alloc(bc * H * st->Npad);
-  st->a_hi.alloc(bc * H * st->Npad); st->a_lo.alloc(bc * H * st->Npad);
-  st->z2_hi.alloc(bc * L2_CMAX * st->Npad); st->z2_lo.alloc(bc * L2_CMAX * st->Npad);
-  // rows >= N of the transposed buffers are never written; keep them finite (they are read as packed pairs)
-  // the blocked buffers are read over whole 128-row tiles: rows >= N must hold zeros, not garbage
-  PYB_CUDA(cudaMemsetAsync(st->z_hi.p, 0, st->z_hi.bytes(), h->stream));
-  PYB_CUDA(cudaMemsetAsync(st->z_lo.p, 0, st->z_lo.bytes(), h->stream));
-  PYB_CUDA(cudaMemsetAsync(st->z2_hi.p, 0, st->z2_hi.bytes(), h->stream));
-  PYB_CUDA(cudaMemsetAsync(st->z2_lo.p, 0, st->z2_lo.bytes(), h->stream));
-  PYB_CUDA(cudaMemsetAsync(st->a_hi.p, 0, st->a_hi.bytes(), h->stream));
-  PYB_CUDA(cudaMemsetAsync(st->a_lo.p, 0, st->a_lo.bytes(), h->stream));
-  st->n_tiles = (int)(st->Npad / L2_ROWS);
-  st->n_groups = std::min(st->n_tiles, std::max(1, (int)((8 * (int64_t)h->sm_count + bc - 1) / bc)));
-  st->b2_partial.alloc((size_t)bc * st->n_groups * L2_CMAX);
-  st->loss_partial.alloc((size_t)bc * st->n_groups);
-  st->mW_hi = make_map(st->w_hi.p, D, bc * H, D, H);
-  st->mW_lo = make_map(st->w_lo.p, D, bc * H, D, H);
-  const int64_t blocks = bc * (st->Npad / 128);
-  st->mZ_hi = make_map_blocked(st->z_hi.p, blocks, H, H);
-  st->mZ_lo = make_map_blocked(st->z_lo.p, blocks, H, H);
-  st->mA_hi = make_map_blocked(st->a_hi.p, blocks, H, std::min(H, 128));
-  st->mA_lo = make_map_blocked(st->a_lo.p, blocks, H, std::min(H, 128));
-  st->mZ2_hi = make_map_blocked(st->z2_hi.p, blocks, L2_CMAX, L2_CMAX);
-  st->mZ2_lo = make_map_blocked(st->z2_lo.p, blocks, L2_CMAX, L2_CMAX);
-  st->bufs_ready = true;
+  if (bc >= h->sm_count) bc = (bc / h->sm_count) * h->sm_count;      // whole waves of per-chain GEMM work
+  bc = std::min<int64_t>(bc, 16384);
+  const int64_t need_blocks = bc * k_tiles;
+  if (bc > st->cap_chains || need_blocks > st->cap_blocks) {
+    PYB_CUDA(cudaStreamSynchronize(h->stream));
+    st->cap_chains = std::max(st->cap_chains, bc);
+    st->cap_blocks = std::max(st->cap_blocks, need_blocks);
+    const int64_t cb = st->cap_blocks, cc = st->cap_chains;
+    st->w_hi.alloc(cc * H * D); st->w_lo.alloc(cc * H * D);
+    st->a_hi.alloc(cb * H * 128); st->a_lo.alloc(cb * H * 128);
+    st->z_hi.alloc(cb * H * 128); st->z_lo.alloc(cb * H * 128);
+    st->z2_hi.alloc(cb * L2_CMAX * 128); st->z2_lo.alloc(cb * L2_CMAX * 128);
+    // every block a kernel reads is fully rewritten by the producer kernels of the same evaluation
+    // (G1 zero-fills rows >= N, k_layer2 writes whole 256-row tiles), so no clearing is needed
+    st->mW_hi = make_map(st->w_hi.p, D, cc * H, D, H);
+    st->mW_lo = make_map(st->w_lo.p, D, cc * H, D, H);
+    st->mZ_hi = make_map_blocked(st->z_hi.p, cb, H, H);
+    st->mZ_lo = make_map_blocked(st->z_lo.p, cb, H, H);
+    st->mA_hi = make_map_blocked(st->a_hi.p, cb, H, std::min(H, 128));
+    st->mA_lo = make_map_blocked(st->a_lo.p, cb, H, std::min(H, 128));
+    st->mZ2_hi = make_map_blocked(st->z2_hi.p, cb, L2_CMAX, L2_CMAX);
+    st->mZ2_lo = make_map_blocked(st->z2_lo.p, cb, L2_CMAX, L2_CMAX);
+  }
+  return bc;
 }
 
-void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
-  TcState* st = tc_state(h);
+static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* th, int nb) {
   const Model& m = h->model;
-  if (!st->data_ready) tc_prepare_data(h, st);
-  tc_prepare_bufs(h, st, S);
+  const LayerDesc& L1 = m.layer[0];
+  const int D = st->D, H = st->H;
+  const int64_t N = d.N, Npad = d.Npad, P = m.P;
+  // W1 [D,H] per chain -> W1^T hi/lo [H, D]
+  dim3 g((H + 31) / 32, (D + 31) / 32, nb), blk(32, 8);
+  k_split_transpose<<<g, blk, 0, h->stream>>>(th + L1.w_off, P, D, H, H, st->w_hi.p, st->w_lo.p, (int64_t)H * D, D);
+  count_launch(h);
+  // G1: A1^T = act(X W1 + b1)^T, split bf16 (all Npad/128 row tiles: rows >= N are written as zeros)
+  TcGemmParams p = {};
+  p.K = D; p.n_mtiles = (int)(Npad / 128); p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
+  p.a_batch_rows = 0; p.a_box_rows = 128; p.order = 1; p.sub_batch = 32; p.total_items = p.n_pairs * nb;
+  p.epi = EPI_BIAS_ACT_T_SPLIT;
+  p.bias = th + L1.b_off; p.bias_stride = P; p.act = L1.act;
+  p.out_hi = st->a_hi.p; p.out_lo = st->a_lo.p; p.out_tiles = (int)(Npad / 128);
+  p.M_valid = (int)N; p.N_valid = H;
+  launch_gemm_tc(h, d.mX_hi, d.mX_lo, st->mW_hi, st->mW_lo, p, 2.0 * N * D * (double)H * nb);
+}
+
+static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i, const float* y_f, const float* theta,
+                       int64_t S, float scale, float* loss_out, float* grad_out) {
+  const Model& m = h->model;
+  const int64_t Bc = tc_prepare_bufs(h, st, S, d.Npad, true);
   const LayerDesc& L1 = m.layer[0];
   const LayerDesc& L2 = m.layer[1];
   const int D = st->D, H = st->H, C = st->C;
-  const int64_t N = st->N, Npad = st->Npad, P = m.P;
-  for (int64_t b0 = 0; b0 < S; b0 += st->Bc) {
-    const int nb = (int)std::min<int64_t>(st->Bc, S - b0);
+  const int64_t N = d.N, Npad = d.Npad, P = m.P;
+  const int n_tiles = (int)(Npad / L2_ROWS);
+  const int n_groups = std::min(n_tiles, std::max(1, (int)((8 * (int64_t)h->sm_count + Bc - 1) / Bc)));
+  st->b2_partial.alloc((size_t)Bc * n_groups * L2_CMAX);
+  st->loss_partial.alloc((size_t)Bc * n_groups);
+  for (int64_t b0 = 0; b0 < S; b0 += Bc) {
+    const int nb = (int)std::min<int64_t>(Bc, S - b0);
     const float* th = theta + b0 * P;
     float* gr = grad_out + b0 * P;
-    // 1. W1 [D,H] per chain -> W1^T hi/lo [H, D]
-    {
-      dim3 g((H + 31) / 32, (D + 31) / 32, nb), blk(32, 8);
-      k_split_transpose<<<g, blk, 0, h->stream>>>(th + L1.w_off, P, D, H, H, st->w_hi.p, st->w_lo.p, (int64_t)H * D, D);
-      count_launch(h);
-    }
-    // 2. G1: A1^T = act(X W1 + b1)^T, split bf16
-    {
-      TcGemmParams p = {};
-      p.K = D; p.n_mtiles = (int)((N + 127) / 128); p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
-      p.a_batch_rows = 0; p.a_box_rows = 128; p.order = 1; p.sub_batch = 32; p.total_items = p.n_pairs * nb;
-      p.epi = EPI_BIAS_ACT_T_SPLIT;
-      p.bias = th + L1.b_off; p.bias_stride = P; p.act = L1.act;
-      p.out_hi = st->a_hi.p; p.out_lo = st->a_lo.p; p.out_tiles = (int)(Npad / 128);
-      p.M_valid = (int)N; p.N_valid = H;
-      launch_gemm_tc(h, st, st->mX_hi, st->mX_lo, st->mW_hi, st->mW_lo, p, 2.0 * N * D * (double)H * nb);
-    }
-    // 3. layer 2 + loss + dZ1^T, dZ2^T
+    tc_pack_and_g1(h, st, d, th, nb);
+    // layer 2 + loss + dZ1^T, dZ2^T
     {
       Layer2Params p = {};
       p.a_hi = st->a_hi.p; p.a_lo = st->a_lo.p; p.zt_hi = st->z_hi.p; p.zt_lo = st->z_lo.p;
       p.z2_hi = st->z2_hi.p; p.z2_lo = st->z2_lo.p; p.k_tiles = (int)(Npad / 128);
       p.theta = th; p.P = P; p.w2_off = L2.w_off; p.b2_off = L2.b_off;
       p.H = H; p.C = C; p.N = (int)N; p.act1 = L1.act; p.out_act = L2.act; p.loss_kind = h->loss_kind;
-      p.y_i = h->y_i.p; p.y_f = h->y_f.p; p.scale = scale;
-      p.loss_partial = st->loss_partial.p; p.b2_partial = st->b2_partial.p; p.n_groups = st->n_groups;
-      p.n_tiles = st->n_tiles;
-      dim3 g(st->n_groups, nb);
+      p.y_i = y_i; p.y_f = y_f; p.scale = scale;
+      p.loss_partial = st->loss_partial.p; p.b2_partial = st->b2_partial.p; p.n_groups = n_groups;
+      p.n_tiles = n_tiles;
+      dim3 g(n_groups, nb);
       if (C <= 4) k_layer2<4><<<g, 128, 0, h->stream>>>(p);
       else if (C <= 8) k_layer2<8><<<g, 128, 0, h->stream>>>(p);
       else if (C <= 12) k_layer2<12><<<g, 128, 0, h->stream>>>(p);
       else k_layer2<16><<<g, 128, 0, h->stream>>>(p);
-      k_layer2_reduce<<<nb, 64, 0, h->stream>>>(st->b2_partial.p, st->loss_partial.p, st->n_groups, C, gr, P, L2.b_off,
+      k_layer2_reduce<<<nb, 64, 0, h->stream>>>(st->b2_partial.p, st->loss_partial.p, n_groups, C, gr, P, L2.b_off,
                                                 loss_out ? loss_out + b0 : nullptr, (int)N);
       count_launch(h, 2);
     }
-    // 4. G3: dW2[h][c] = sum_r a1[r][h] dZ2[r][c]   (A = A1^T per chain, B = dZ2^T per chain, N = 16)
+    // G3: dW2[h][c] = sum_r a1[r][h] dZ2[r][c]   (A = A1^T per chain, B = dZ2^T per chain, N = 16)
     {
       TcGemmParams p = {};
       p.K = (int)Npad; p.n_mtiles = (H + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = L2_CMAX;
@@ -850,9 +932,9 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
       p.a_batch_rows = H; p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
       p.epi = EPI_STORE;
       p.out = gr + L2.w_off; p.out_stride = P; p.out_ld = C; p.M_valid = H; p.N_valid = C;
-      launch_gemm_tc(h, st, st->mA_hi, st->mA_lo, st->mZ2_hi, st->mZ2_lo, p, 2.0 * N * (double)H * C * nb);
+      launch_gemm_tc(h, st->mA_hi, st->mA_lo, st->mZ2_hi, st->mZ2_lo, p, 2.0 * N * (double)H * C * nb);
     }
-    // 5. G2: [dW1; db1] = [X^T; 1] dZ1
+    // G2: [dW1; db1] = [X^T; 1] dZ1
     {
       TcGemmParams p = {};
       p.K = (int)Npad; p.n_mtiles = (D + 1 + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
@@ -860,16 +942,81 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
       p.a_batch_rows = 0; p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
       p.epi = EPI_STORE;
       p.out = gr; p.out_stride = P; p.out_ld = H; p.M_valid = D + 1; p.N_valid = H;
-      launch_gemm_tc(h, st, st->mXT_hi, st->mXT_lo, st->mZ_hi, st->mZ_lo, p, 2.0 * N * (double)(D + 1) * H * nb);
+      launch_gemm_tc(h, d.mXT_hi, d.mXT_lo, st->mZ_hi, st->mZ_lo, p, 2.0 * N * (double)(D + 1) * H * nb);
     }
   }
   PYB_CUDA(cudaGetLastError());
 }
 
+void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
+  TcState* st = tc_state(h);
+  if (!st->train.ready) tc_prepare_data(h, st->train, h->X.p, h->N, true);
+  tc_eval_on(h, st, st->train, h->y_i.p, h->y_f.p, theta, S, scale, loss_out, grad_out);
+}
+
+// loss + gradient on an arbitrary device-resident batch (SVGD minibatches): operands are re-derived per call
+void tc_eval_batch(pyb_handle* h, const float* Xb, const int32_t* yb_i, const float* yb_f, int64_t Nb, const float* theta,
+                   int64_t S, float scale, float* loss_out, float* grad_out) {
+  TcState* st = tc_state(h);
+  tc_prepare_data(h, st->aux, Xb, Nb, true);
+  tc_eval_on(h, st, st->aux, yb_i, yb_f, theta, S, scale, loss_out, grad_out);
+}
+
+// forward only: out [S, N, C] (softmax / output activation applied) for device-resident inputs x [N, D]
+void tc_forward(pyb_handle* h, const float* theta, int64_t S, const float* x, int64_t N, float* out) {
+  TcState* st = tc_state(h);
+  const Model& m = h->model;
+  tc_prepare_data(h, st->aux, x, N, false);
+  TcData& d = st->aux;
+  const int64_t Bc = tc_prepare_bufs(h, st, S, d.Npad, false);
+  const LayerDesc& L2 = m.layer[1];
+  const int64_t P = m.P;
+  for (int64_t b0 = 0; b0 < S; b0 += Bc) {
+    const int nb = (int)std::min<int64_t>(Bc, S - b0);
+    const float* th = theta + b0 * P;
+    tc_pack_and_g1(h, st, d, th, nb);
+    Layer2FwdParams p = {};
+    p.a_hi = st->a_hi.p; p.a_lo = st->a_lo.p; p.k_tiles = (int)(d.Npad / 128);
+    p.theta = th; p.P = P; p.w2_off = L2.w_off; p.b2_off = L2.b_off;
+    p.H = st->H; p.C = st->C; p.N = (int)N; p.out_act = L2.act; p.n_tiles = (int)(d.Npad / L2_ROWS);
+    p.out = out + b0 * N * st->C;
+    dim3 g(std::min(p.n_tiles, 64), nb);
+    k_layer2_fwd<<<g, 128, 0, h->stream>>>(p);
+    count_launch(h);
+  }
+  PYB_CUDA(cudaGetLastError());
+}
+
+// ---- building blocks exported to svgd.cu (Gram matrix and Stein contraction on the tensor cores) ----
+void tc_split_rows(pyb_handle* h, const float* src, int64_t R, int C, int64_t lds, void* hi, void* lo, int64_t ldd) {
+  k_split_rows<<<(unsigned)std::min<int64_t>((R * C + 255) / 256, 65535), 256, 0, h->stream>>>(
+      src, R, C, lds, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldd);
+  count_launch(h);
+}
+// src [R, C] fp32 -> hi/lo [C, R] bf16 with row pitch ldd
+void tc_split_transpose(pyb_handle* h, const float* src, int R, int C, int64_t lds, void* hi, void* lo, int64_t ldd) {
+  dim3 g((C + 31) / 32, (R + 31) / 32, 1), blk(32, 8);
+  k_split_transpose<<<g, blk, 0, h->stream>>>(src, 0, R, C, lds, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, 0, ldd);
+  count_launch(h);
+}
+// out[m][n] = sum_k A[a_row0+m][k] B[n][k] for m < M, n < Nn; split operands, K-major, pitches in elements
+void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t lda, int64_t a_rows_total, int a_row0, int M,
+                   const void* b_hi, const void* b_lo, int64_t ldb, int Nn, int64_t K, float* out, int64_t ldc) {
+  PYB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, PYB_ERR_INVALID, "operand pitches must be multiples of 8 elements");
+  CUtensorMap ma_h = make_map(a_hi, K, a_rows_total, lda, 128), ma_l = make_map(a_lo, K, a_rows_total, lda, 128);
+  const int Hn = Nn >= 256 ? 256 : ((Nn + 15) / 16) * 16;
+  CUtensorMap mb_h = make_map(b_hi, K, Nn, ldb, Hn), mb_l = make_map(b_lo, K, Nn, ldb, Hn);
+  TcGemmParams p = {};
+  p.K = (int)K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = (Nn + Hn - 1) / Hn; p.H = Hn;
+  p.a_row0 = a_row0; p.a_batch_rows = 0; p.a_box_rows = 128; p.order = 1; p.sub_batch = 8;
+  p.total_items = p.n_pairs * p.n_batch;
+  p.epi = EPI_STORE; p.out = out; p.out_stride = Hn; p.out_ld = (int)ldc; p.M_valid = M; p.N_valid = Hn; p.n_cols_total = Nn;
+  launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * (double)Nn * (double)K);
+}
+
 // debug / unit-test entry: D[M,Nn] = A[M,K] B[Nn,K]^T through the tcgen05 kernel (host pointers)
 void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn, int K, float* Dout) {
   PYB_REQUIRE(Nn % 16 == 0 && Nn >= 16 && Nn <= 256 && K % 8 == 0, PYB_ERR_INVALID, "Nn%16, Nn<=256, K%8 required");
-  TcState* st = tc_state(h);
   DevBuf<float> dA, dB, dD;
   DevBuf<__nv_bfloat16> ah, al, bh, bl;
   dA.alloc((size_t)M * K); dB.alloc((size_t)Nn * K); dD.alloc((size_t)M * Nn);
@@ -885,7 +1032,7 @@ void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn,
   p.K = K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = 1; p.H = Nn;
   p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
   p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0; p.a_box_rows = 128;
-  launch_gemm_tc(h, st, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K);
+  launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K);
   PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
   PYB_CUDA(cudaStreamSynchronize(h->stream));
   PYB_CUDA(cudaGetLastError());

@@ -173,3 +173,75 @@ def test_tensor_path_reversibility_canonical(oracle):
     q2, p2 = eng.hmc_state()
     assert rel_err(q2, q) < 1e-5 and rel_err(-p2, p) < 1e-4
     assert np.abs(q1 - q).max() > 0
+
+
+def test_predictive_on_tensor_path(oracle):
+    """BayesianModel.predict shape (config C5 in small): tensor-core forward for every weight sample."""
+    O = oracle
+    D, H, Cc, Nt, n = 784, 256, 10, 300, 5
+    rng = np.random.default_rng(21)
+    spec = O.MLPSpec(D, [H, Cc], ["relu", "softmax"])
+    W = (rng.standard_normal((n, spec.n_params)) * 0.05).astype(np.float32)
+    x = rng.random((Nt, D)).astype(np.float32)
+    freq = np.float32([1, 2, 1, 3, 1])
+    mean64, var64 = O.predictive(spec, W, x, freq, np.float64)
+    eng = engine(D, H, Cc)
+    mean, var, allo = eng.predict(W, x, weights=freq, want_all=True)
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    np.testing.assert_allclose(mean, mean64, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(var, var64, rtol=2e-3, atol=1e-7)
+    np.testing.assert_allclose(allo, O.forward(spec, W, x, np.float64), rtol=1e-4, atol=1e-6)
+    eng.set_option("path", _lib.PATH_GENERIC)
+    mean_g, _, _ = eng.predict(W, x, weights=freq)
+    assert int(eng.info("path_used")) == _lib.PATH_GENERIC
+    np.testing.assert_allclose(mean, mean_g, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("sem", [_lib.SVGD_CANONICAL_MEDIAN, _lib.SVGD_REFERENCE_LIVE])
+def test_svgd_minibatch_gradients_on_tensor_path(oracle, sem):
+    """SVGD_mnist shape in small (784-128-10, minibatch from a resident pool): the per-particle gradients
+    come from the tcgen05 path on a re-split minibatch; the Stein update is checked against the oracle."""
+    O = oracle
+    D, H, Cc, N, S, B = 784, 128, 10, 600, 4, 256
+    spec, prob, q, out_act, rng = problem(O, D, H, Cc, N, S, seed=5)
+    idx = [rng.permutation(N)[:B].astype(np.int32) for _ in range(2)]
+    parts = q.astype(np.float64)
+    am, av = np.zeros((S, spec.n_params), np.float32), np.zeros((S, spec.n_params), np.float32)
+    want = parts.copy()
+    losses = []
+    for t, ix in enumerate(idx, 1):
+        if sem == _lib.SVGD_CANONICAL_MEDIAN:
+            want, am, av, loss, _, _ = O.svgd_canonical_step(prob, want, prob.X[ix], prob.y[ix], am, av, t, 1e-3)
+        else:
+            want, am, av, loss, _ = O.svgd_live_step(spec, want, prob.X[ix], prob.y[ix], prob.loss_kind, am, av, t, 1e-3)
+        losses.append(loss)
+    eng = engine(D, H, Cc)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.svgd_init(S, 1e-3, sem, particles0=parts)
+    got_losses = [eng.svgd_step(ix) for ix in idx]
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    np.testing.assert_allclose(got_losses, losses, rtol=1e-4)
+    # Adam's first steps are lr * phi / (|phi| + 1e-7): for the handful of coordinates with |phi| ~ 1e-7 (expected
+    # among 4e5) the step is ill-conditioned in phi, so bound the bulk tightly and the worst case by Adam's own bound
+    diff = np.abs(eng.svgd_particles() - want)
+    assert np.quantile(diff, 0.9995) < 2e-3 * 1e-3 * 2 + 1e-6
+    assert diff.max() <= 2.1 * 1e-3 * len(idx)
+
+
+@pytest.mark.parametrize("S", [256, 384])
+def test_svgd_canonical_phi_on_tensor_cores(oracle, S):
+    """Large particle sets: Gram matrix (bf16x3 GEMM) -> exact median bandwidth -> K Y contraction (bf16x3 GEMM)
+    against the float64 oracle of SVGD.baseline__kernel."""
+    rng = np.random.default_rng(S)
+    eng = engine(64, 32, 4)                      # P = 2212
+    P = eng.P
+    X = (rng.standard_normal((S, P)) * 0.3).astype(np.float32).astype(np.float64)
+    G = rng.standard_normal((S, P)).astype(np.float32)
+    want, h_ref, _ = oracle.svgd_phi_canonical(X, G)
+    phi, h = eng.svgd_phi(X, G, _lib.SVGD_CANONICAL_MEDIAN)
+    assert abs(h - h_ref) < 1e-5 * h_ref
+    assert rel_err(phi, want) < 1e-4
+    eng.set_option("path", _lib.PATH_GENERIC)    # float64 SIMT kernels on the same inputs
+    phi_g, h_g = eng.svgd_phi(X, G, _lib.SVGD_CANONICAL_MEDIAN)
+    assert abs(h_g - h_ref) < 1e-9 * h_ref and rel_err(phi_g, want) < 1e-5
