@@ -69,6 +69,16 @@ def measured_peaks():
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
 
 
+def ncu_traffic():
+    """dram__bytes_read+write per tc_gemm launch (mean over the G1/G3/G2 launches of one chain batch) from the
+    committed `ncu --set full` capture (profiles/r1_traffic.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p))["tc_gemm_bf16x3"]["dram_bytes_per_launch_mean"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -270,7 +280,8 @@ def main():
     if prof_ms > 0:
         achieved = prof_flops / (prof_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                "frac": achieved / peaks["bf16_sustained"], "traffic": ncu_traffic(),
+                "issued_mma_tflops": 3.0 * achieved, "issued_mma_frac": 3.0 * achieved / peaks["bf16_sustained"],
                 "peak_source": "%s bf16 dense sustained (cuBLAS)" % peaks["source"],
                 "kernel": {1: "k_sgemm (fp32 SIMT)", 2: "fused small", 3: "tc_gemm bf16x3 (tcgen05)"}.get(path_used, "?"),
                 "launches": int(prof_n), "avg_launch_ms": prof_ms / max(1, prof_n),
@@ -278,12 +289,12 @@ def main():
                 "whole_step_algorithmic_tflops": value / max(1, world) * algo_flops_per_eval / 1e12}
     cpu = None
     if not args.no_cpu_baseline:
-        # bounded sample: 1 chain, 2 iterations on a 6000-row slice scaled to the full row count
-        rows_s = min(args.rows, 6000)
-        v, dt = cpu_reference_run(args, 2, 1, rows_s)
-        cpu = {"value": v * rows_s / args.rows, "unit": "grad-evals/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "1 chain x 2 iterations (L=%d) on %d of %d rows, scaled by rows; numpy fp32 BLAS, reference "
-                         "loop shape (HMC.py:74-104); %.1f s" % (L, rows_s, args.rows, dt)}
+        # bounded sample (~10 s of CPU work): 1 chain, 3 timed iterations (+1 warm-up) on the full dataset
+        v, dt = cpu_reference_run(args, 3, 1, args.rows)
+        cpu = {"value": v, "unit": "grad-evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "1 chain x 3 iterations (L=%d, %d rows x 784, 784-256-10); numpy fp32 BLAS on all host cores, "
+                         "reference loop shape (HMC.py:74-104: L+2 gradient + 2 potential evaluations per iteration); "
+                         "%.1f s" % (L, args.rows, dt)}
     line = {
         "metric": "posterior_grad_evals_per_s", "value": value, "unit": "grad-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
