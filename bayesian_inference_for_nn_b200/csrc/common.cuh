@@ -249,6 +249,7 @@ struct pyb_handle {
   double prior_const = 0;  // sum_i log sigma_i + P/2 log 2pi (NaN when any sigma<0, as tfp's log_prob)
   // options
   int opt_path = PYB_PATH_AUTO;
+  int opt_tc_pair = 1;   // 1: use the CTA-pair (cta_group::2) GEMM kernel where it applies
   double opt_workspace_mb = 4096;
   int64_t opt_chain_batch = 0;
   int path_used = PYB_PATH_GENERIC;

@@ -69,8 +69,10 @@ __device__ inline float adam_update(float th, float g, float& m, float& v, float
 }
 
 // phi_i[e] = (wsum*g_i[e] + 2 gamma sum_k K_ik (x_i[e]-x_k[e])) / M ; Adam descent on particle i
+// theta holds ALL S particles (global order); g/am/av/phi_out hold only the local shard: row `il` of them
+// belongs to global particle i
 __global__ void k_live_update(float* theta, const float* g, float* am, float* av, float* phi_out, int64_t P,
-                              int S, int i, double gamma, const double* Krow, float lr_t) {
+                              int S, int i, int il, double gamma, const double* Krow, float lr_t) {
   __shared__ double Ks[1024];
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double xi = (e < P) ? (double)theta[(int64_t)i * P + e] : 0.0;
@@ -86,11 +88,11 @@ __global__ void k_live_update(float* theta, const float* g, float* am, float* av
     for (int k = 0; k < n; ++k) wsum += (float)Ks[k];
   }
   if (e < P) {
-    int64_t o = (int64_t)i * P + e;
+    const int64_t o = (int64_t)i * P + e, ol = (int64_t)il * P + e;
     float gk = (float)(2.0 * gamma * acc);
-    float phi = (wsum * g[o] + gk) / (float)S;
-    if (phi_out) phi_out[o] = phi;
-    theta[o] = adam_update(theta[o], phi, am[o], av[o], lr_t, 0.9f, 0.999f, 1e-7f);
+    float phi = (wsum * g[ol] + gk) / (float)S;
+    if (phi_out) phi_out[ol] = phi;
+    theta[o] = adam_update(theta[o], phi, am[ol], av[ol], lr_t, 0.9f, 0.999f, 1e-7f);
   }
 }
 
@@ -458,8 +460,7 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
           const int gi = r0 + i;
           k_live_row<<<(unsigned)St, 256, 0, h->stream>>>(th_all, P, gi, 1.0, sc.Krow.p);
           k_live_update<<<(unsigned)((P + 255) / 256), 256, 0, h->stream>>>(
-              th_all, sv.g.p - (int64_t)r0 * P, sv.adam_m.p - (int64_t)r0 * P, sv.adam_v.p - (int64_t)r0 * P,
-              sv.phi.p - (int64_t)r0 * P, P, St, gi, 1.0, sc.Krow.p, lr_t);
+              th_all, sv.g.p, sv.adam_m.p, sv.adam_v.p, sv.phi.p, P, St, gi, i, 1.0, sc.Krow.p, lr_t);
           count_launch(h, 2);
         }
       }

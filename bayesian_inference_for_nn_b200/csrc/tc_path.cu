@@ -363,6 +363,244 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x H tile per SM pair.  Each CTA owns 128 rows of A and HALF
+// of the B stage (the tensor core reads the peer's half through the pair), so the L2->SM traffic per
+// flop is the same as the two-accumulator kernel above, but an accumulator is only 128 x H per SM:
+// TMEM holds TWO of them and the epilogue of item i overlaps the MMAs of item i+1.
+// Roles per CTA: warp 0 TMA producer (own A rows, own half of B; completion is signalled on the
+// leader CTA's barrier), warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator, warps 4-11 epilogue.
+// ------------------------------------------------------------------------------------------
+constexpr int TP_STAGES = 6;
+constexpr int TP_STAGE_BYTES = 2 * TC_A_TILE_BYTES + 2 * 8192;     // A hi/lo (128 rows) + half of B hi/lo (<=128 rows)
+constexpr int TP_SMEM_BYTES = TP_STAGES * TP_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 2048 /*bias x2*/;
+constexpr int TP_THREADS = 384;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-SM TMA loads: executed by both CTAs, the transaction bytes land on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {       // arrive on the same barrier in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the leader CTA's copy of `bar`
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int EPI, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1)
+tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* bars = (uint64_t*)(smem + TP_STAGES * TP_STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [TP_STAGES]   (used in the leader CTA)
+  uint64_t* empty_bar = bars + TP_STAGES;        // [TP_STAGES]   (one per CTA: own smem slot is free)
+  uint64_t* tmem_full = bars + 2 * TP_STAGES;    // [2]           (one per CTA)
+  uint64_t* tmem_empty = bars + 2 * TP_STAGES + 2;   // [2]       (leader CTA: both epilogues have drained)
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * TP_STAGES + 4);
+  float* bias_s = (float*)(smem + TP_STAGES * TP_STAGE_BYTES + 1024);   // [2][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  const int half_rows = p.H >> 1;                // rows of B this CTA stages
+  const uint32_t cta_bytes = 2 * TC_A_TILE_BYTES + 2 * (uint32_t)half_rows * TC_BK * 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TP_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 16); mbar_init(&tmem_empty[1], 16);   // 8 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // peer barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+        int b, mp;
+        tc_decode(p, item, b, mp);
+        const int arow = p.a_row0 + (mp * 2 + (int)rank) * 128;
+        const int brow = b * p.H + (int)rank * half_rows;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = stage_base + stage * TP_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);     // bytes of BOTH CTAs
+          const int k0 = kc * TC_BK;
+          tma_load_2d_pair(st, &tmA_hi, &full_bar[stage], k0, arow);
+          tma_load_2d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, arow);
+          tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], k0, brow);
+          tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES + 8192, &tmB_lo, &full_bar[stage], k0, brow);
+          if (++stage == TP_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (rank == 0 && lane == 0) {
+      // D=F32, A=B=BF16, K-major, N = H, M = 256 across the pair
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.H >> 3) << 17) | ((256u >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const int k_tail = p.K - (nk - 1) * TC_BK;
+      for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);               // both epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)acc * 256;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + stage * TP_STAGE_BYTES);
+          const int nks = (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t koff = ks * 32;
+            const uint64_t ah = make_smem_desc_sw64(st + koff);
+            const uint64_t al = make_smem_desc_sw64(st + TC_A_TILE_BYTES + koff);
+            const uint64_t bh = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + koff);
+            const uint64_t bl = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + 8192 + koff);
+            tc_mma_bf16_pair(d, ah, bh, idesc, (kc | ks) != 0);
+            tc_mma_bf16_pair(d, al, bh, idesc, 1);
+            tc_mma_bf16_pair(d, ah, bl, idesc, 1);
+          }
+          tc_commit_pair(&empty_bar[stage]);                      // frees the slot in BOTH CTAs
+          if (++stage == TP_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(&tmem_full[acc]);                          // accumulator ready in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): 8 warps = 4 lane quadrants x 2 column halves of this CTA's 128 x H tile =====
+    const int half = (warp - 4) >> 2;
+    const int et = (threadIdx.x - 128) & 127;
+    const int eall = threadIdx.x - 128;                           // 0..255
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      int b, mp;
+      tc_decode(p, item, b, mp);
+      const int mt = mp * 2 + (int)rank;
+      float* bs = bias_s + acc * 256;
+      if (EPI == EPI_BIAS_ACT_T_SPLIT) {
+        // bias_s[acc] was last read two items ago; the tmem_empty/tmem_full hand-shake orders those reads
+        for (int c = eall; c < p.H; c += 256) bs[c] = p.bias ? p.bias[(int64_t)b * p.bias_stride + c] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      {
+        const int row = mt * 128 + et;
+        const bool valid = row < p.M_valid;
+        const int c_split = ((p.H + 63) >> 6) << 5;
+        for (int c0 = half ? c_split : 0; c0 < (half ? p.H : min(c_split, p.H)); c0 += 32) {
+          float v[32];
+          tc_ld32(tmem_base + lane_base + (uint32_t)(acc * 256 + c0), v);
+          if (EPI == EPI_BIAS_ACT_T_SPLIT) {
+            const int odd = lane & 1;
+            const bool v_even = (row & ~1) < p.M_valid, v_odd = (row | 1) < p.M_valid;
+            const int64_t w0 = ((((int64_t)b * p.out_tiles + mt) * p.H + c0 + odd) * 128 + (et & ~1)) >> 1;
+            uint32_t* ohi = reinterpret_cast<uint32_t*>(p.out_hi) + w0;
+            uint32_t* olo = reinterpret_cast<uint32_t*>(p.out_lo) + w0;
+            const bool full = (c0 + 32 <= p.H);
+            const bool in_range = mt < p.out_tiles;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float a_e = act_apply_t<ACT>(v[j] + bs[c0 + j]);
+              const float a_o = act_apply_t<ACT>(v[j + 1] + bs[c0 + j + 1]);
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? a_e : a_o, 1);
+              const float x0 = v_even ? (odd ? recv : a_e) : 0.f;
+              const float x1 = v_odd ? (odd ? a_o : recv) : 0.f;
+              if (in_range && (full || c0 + j + odd < p.H)) {
+                const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+                const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hp);
+                const float r0 = x0 - __uint_as_float(hw << 16);
+                const float r1 = x1 - __uint_as_float(hw & 0xffff0000u);
+                const __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
+                ohi[j * 64] = hw;
+                olo[j * 64] = *reinterpret_cast<const uint32_t*>(&lp);
+              }
+            }
+          } else {
+            if (valid) {
+              float* o = p.out + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
+              const int nvalid = p.n_cols_total > 0 ? min(p.N_valid, p.n_cols_total - b * p.H) : p.N_valid;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < nvalid) o[j] = v[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // the peer may still be reading this CTA's shared memory
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // SIMT helpers around the GEMMs
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -749,7 +987,7 @@ struct TcState {
   DevBuf<__nv_bfloat16> z2_hi, z2_lo;                   // dZ2^T blocked [block][16][128]
   DevBuf<float> b2_partial;
   DevBuf<double> loss_partial;
-  CUtensorMap mW_hi, mW_lo, mZ_hi, mZ_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
+  CUtensorMap mW_hi, mW_lo, mWp_hi, mWp_lo, mZ_hi, mZ_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
 };
 static TcState* tc_state(pyb_handle* h) {
   if (!h->tc) h->tc = new TcState();
@@ -784,17 +1022,38 @@ bool tc_supported(pyb_handle* h, int64_t S) {
 template <int EPI, int ACT>
 static void launch_gemm_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                              const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p) {
-  static bool attr_set = false;    // per instantiation
-  if (!attr_set) {
-    PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3<EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
+  // per device and per instantiation; cheap enough to repeat (a process may drive several GPUs)
+  PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3<EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   tc_gemm_bf16x3<EPI, ACT><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
 }
+template <int EPI, int ACT>
+static void launch_pair_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                             const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p) {
+  PYB_CUDA(cudaFuncSetAttribute(tc_gemm_pair_bf16x3<EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES));
+  tc_gemm_pair_bf16x3<EPI, ACT><<<grid, TP_THREADS, TP_SMEM_BYTES, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+}
+// CTA-pair kernel: plain 2-D operands, H a multiple of 32, an even number of M tiles' worth of work per item
+static bool pair_ok(const pyb_handle* h, const TcGemmParams& p) {
+  return h->opt_tc_pair && !p.a_blocked && !p.b_blocked && p.a_batch_rows == 0 && (p.H % 32) == 0 && p.H >= 32 &&
+         p.n_mtiles >= 2;
+}
+// bp_hi/bp_lo: the SAME B tensors described with half-height TMA boxes (H/2 rows) for the CTA-pair kernel, or null
 static void launch_gemm_tc(pyb_handle* h, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
-                           const CUtensorMap& b_hi, const CUtensorMap& b_lo, TcGemmParams p, double flops) {
+                           const CUtensorMap& b_hi, const CUtensorMap& b_lo, TcGemmParams p, double flops,
+                           const CUtensorMap* bp_hi = nullptr, const CUtensorMap* bp_lo = nullptr) {
   int grid = std::min(p.total_items, h->sm_count);
   prof_begin(h);
+  if (bp_hi && bp_lo && pair_ok(h, p)) {
+    grid = std::min(2 * p.total_items, (h->sm_count / 2) * 2);
+    if (p.epi == EPI_STORE) launch_pair_inst<EPI_STORE, 0>(h, grid, a_hi, a_lo, *bp_hi, *bp_lo, p);
+    else if (p.act == PYB_ACT_RELU) launch_pair_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_RELU>(h, grid, a_hi, a_lo, *bp_hi, *bp_lo, p);
+    else if (p.act == PYB_ACT_TANH) launch_pair_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_TANH>(h, grid, a_hi, a_lo, *bp_hi, *bp_lo, p);
+    else if (p.act == PYB_ACT_SIGMOID) launch_pair_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_SIGMOID>(h, grid, a_hi, a_lo, *bp_hi, *bp_lo, p);
+    else launch_pair_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_LINEAR>(h, grid, a_hi, a_lo, *bp_hi, *bp_lo, p);
+    prof_end(h, flops);
+    count_launch(h);
+    return;
+  }
   if (p.epi == EPI_STORE) launch_gemm_inst<EPI_STORE, 0>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
   else if (p.act == PYB_ACT_RELU) launch_gemm_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_RELU>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
   else if (p.act == PYB_ACT_TANH) launch_gemm_inst<EPI_BIAS_ACT_T_SPLIT, PYB_ACT_TANH>(h, grid, a_hi, a_lo, b_hi, b_lo, p);
@@ -858,6 +1117,8 @@ static int64_t tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S, int64_t Np
     // (G1 zero-fills rows >= N, k_layer2 writes whole 256-row tiles), so no clearing is needed
     st->mW_hi = make_map(st->w_hi.p, D, cc * H, D, H);
     st->mW_lo = make_map(st->w_lo.p, D, cc * H, D, H);
+    st->mWp_hi = make_map(st->w_hi.p, D, cc * H, D, std::max(H / 2, 8));
+    st->mWp_lo = make_map(st->w_lo.p, D, cc * H, D, std::max(H / 2, 8));
     st->mZ_hi = make_map_blocked(st->z_hi.p, cb, H, H);
     st->mZ_lo = make_map_blocked(st->z_lo.p, cb, H, H);
     st->mA_hi = make_map_blocked(st->a_hi.p, cb, H, std::min(H, 128));
@@ -885,7 +1146,7 @@ static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* t
   p.bias = th + L1.b_off; p.bias_stride = P; p.act = L1.act;
   p.out_hi = st->a_hi.p; p.out_lo = st->a_lo.p; p.out_tiles = (int)(Npad / 128);
   p.M_valid = (int)N; p.N_valid = H;
-  launch_gemm_tc(h, d.mX_hi, d.mX_lo, st->mW_hi, st->mW_lo, p, 2.0 * N * D * (double)H * nb);
+  launch_gemm_tc(h, d.mX_hi, d.mX_lo, st->mW_hi, st->mW_lo, p, 2.0 * N * D * (double)H * nb, &st->mWp_hi, &st->mWp_lo);
 }
 
 static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i, const float* y_f, const float* theta,
@@ -1011,7 +1272,8 @@ void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t ld
   p.a_row0 = a_row0; p.a_batch_rows = 0; p.a_box_rows = 128; p.order = 1; p.sub_batch = 8;
   p.total_items = p.n_pairs * p.n_batch;
   p.epi = EPI_STORE; p.out = out; p.out_stride = Hn; p.out_ld = (int)ldc; p.M_valid = M; p.N_valid = Hn; p.n_cols_total = Nn;
-  launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * (double)Nn * (double)K);
+  CUtensorMap mp_h = make_map(b_hi, K, Nn, ldb, std::max(Hn / 2, 8)), mp_l = make_map(b_lo, K, Nn, ldb, std::max(Hn / 2, 8));
+  launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * (double)Nn * (double)K, &mp_h, &mp_l);
 }
 
 // debug / unit-test entry: D[M,Nn] = A[M,K] B[Nn,K]^T through the tcgen05 kernel (host pointers)
@@ -1032,7 +1294,8 @@ void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn,
   p.K = K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = 1; p.H = Nn;
   p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
   p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0; p.a_box_rows = 128;
-  launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K);
+  CUtensorMap mp_h = make_map(bh.p, K, Nn, K, std::max(Nn / 2, 8)), mp_l = make_map(bl.p, K, Nn, K, std::max(Nn / 2, 8));
+  launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K, &mp_h, &mp_l);
   PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
   PYB_CUDA(cudaStreamSynchronize(h->stream));
   PYB_CUDA(cudaGetLastError());

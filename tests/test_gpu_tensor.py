@@ -31,13 +31,16 @@ def debug_gemm(eng, A, B):
     return D
 
 
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("M,Nn,K", [(128, 256, 32), (128, 256, 784), (300, 64, 96), (785, 256, 1000), (1000, 128, 40),
-                                     (2500, 16, 2048)])
-def test_split_bf16_gemm_matches_float64(M, Nn, K):
+                                     (2500, 16, 2048), (4096, 256, 800)])
+def test_split_bf16_gemm_matches_float64(M, Nn, K, pair):
+    """pair=1: the CTA-pair (cta_group::2, double-buffered TMEM) kernel where it applies."""
     rng = np.random.default_rng(M + Nn + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
     B = (rng.standard_normal((Nn, K)) * 0.3).astype(np.float32)
     eng = engine(64, 32, 4)
+    eng.set_option("tc_pair", pair)
     D = debug_gemm(eng, A, B)
     want = A.astype(np.float64) @ B.astype(np.float64).T
     scale = np.sqrt((A.astype(np.float64) ** 2).sum(1))[:, None] * np.sqrt((B.astype(np.float64) ** 2).sum(1))[None]
