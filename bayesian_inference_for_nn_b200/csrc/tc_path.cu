@@ -147,10 +147,23 @@ struct TcGemmParams {
   float* out; int64_t out_stride; int out_ld;
   int M_valid, N_valid;
   int a_row0;                  // first A row of this launch (row-sharded callers)
+  // split-K: the tcgen05 fp32 accumulator TRUNCATES on every accumulate (measured -4e-8 relative per MMA,
+  // -4.5e-4 after 60000-long reductions), so long K loops are cut into k_splits independent accumulations of
+  // chunks_per_split 32-element chunks whose partial results are summed afterwards in a fixed order
+  int k_splits, chunks_per_split; int64_t split_stride;
+  int vec_store;               // EPI_STORE: every output row segment is 16-byte aligned -> float4 stores
   int n_cols_total;            // >0: chain b owns columns [b*H, min((b+1)*H, n_cols_total)) of one wide output
 };
 
-__device__ __forceinline__ void tc_decode(const TcGemmParams& p, int item, int& b, int& mp) {
+__device__ __forceinline__ void tc_decode(const TcGemmParams& p, int item, int& b, int& mp, int& split) {
+  if (p.k_splits > 1) {          // [chain][split][pair]: the pairs sharing one B k-range run side by side
+    mp = item % p.n_pairs;
+    int r = item / p.n_pairs;
+    split = r % p.k_splits;
+    b = r / p.k_splits;
+    return;
+  }
+  split = 0;
   if (p.order == 0) {            // chain-major: the pairs of one chain run side by side (G2)
     b = item / p.n_pairs;
     mp = item - b * p.n_pairs;
@@ -221,12 +234,13 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        int b, mp;
-        tc_decode(p, item, b, mp);
+        int b, mp, split;
+        tc_decode(p, item, b, mp, split);
+        const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
         const int mt0 = mp * 2;
         const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
         const uint32_t bytes = (uint32_t)n_mt * 2 * (uint32_t)p.a_box_rows * TC_BK * 2 + 2 * b_bytes;
-        for (int kc = 0; kc < nk; ++kc) {
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], bytes);
@@ -253,13 +267,14 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t phase = 0, acc_phase = 0;
       const int k_tail = p.K - (nk - 1) * TC_BK;                 // valid K elements of the last chunk
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        int b, mp;
-        tc_decode(p, item, b, mp);
+        int b, mp, split;
+        tc_decode(p, item, b, mp, split);
+        const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
         const int mt0 = mp * 2;
         const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
         mbar_wait(tmem_empty, acc_phase ^ 1);                    // epilogue has drained the accumulators
         tc_fence_after();
-        for (int kc = 0; kc < nk; ++kc) {
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + stage * TC_STAGE_BYTES);
@@ -272,7 +287,7 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const uint64_t ah = make_smem_desc_sw64(st + mt * TC_A_TILE_BYTES + koff);
               const uint64_t al = make_smem_desc_sw64(st + (2 + mt) * TC_A_TILE_BYTES + koff);
               const uint32_t d = tmem_base + (uint32_t)mt * 256;
-              tc_mma_bf16(d, ah, bh, idesc, (kc | ks) != 0);
+              tc_mma_bf16(d, ah, bh, idesc, (kc != kc_begin) || (ks != 0));
               tc_mma_bf16(d, al, bh, idesc, 1);
               tc_mma_bf16(d, ah, bl, idesc, 1);
             }
@@ -293,8 +308,8 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int b, mp;
-      tc_decode(p, item, b, mp);
+      int b, mp, split;
+      tc_decode(p, item, b, mp, split);
       const int mt0 = mp * 2;
       const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
       if (EPI == EPI_BIAS_ACT_T_SPLIT) {
@@ -340,11 +355,17 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           } else {
             if (valid) {
-              float* o = p.out + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
+              float* o = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
               const int nvalid = p.n_cols_total > 0 ? min(p.N_valid, p.n_cols_total - b * p.H) : p.N_valid;
+              if (p.vec_store && c0 + 32 <= nvalid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < nvalid) o[j] = v[j];
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c0 + j < nvalid) o[j] = v[j];
+              }
             }
           }
         }
@@ -471,11 +492,12 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int item = cluster_id; item < p.total_items; item += n_clusters) {
-        int b, mp;
-        tc_decode(p, item, b, mp);
+        int b, mp, split;
+        tc_decode(p, item, b, mp, split);
+        const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
         const int arow = p.a_row0 + (mp * 2 + (int)rank) * 128;
         const int brow = b * p.H + (int)rank * half_rows;
-        for (int kc = 0; kc < nk; ++kc) {
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * TP_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);     // bytes of BOTH CTAs
@@ -497,10 +519,13 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       uint32_t phase = 0, acc_phase = 0;
       const int k_tail = p.K - (nk - 1) * TC_BK;
       for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+        int b, mp, split;
+        tc_decode(p, item, b, mp, split);
+        const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);               // both epilogues drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * 256;
-        for (int kc = 0; kc < nk; ++kc) {
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + stage * TP_STAGE_BYTES);
@@ -511,7 +536,7 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             const uint64_t al = make_smem_desc_sw64(st + TC_A_TILE_BYTES + koff);
             const uint64_t bh = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + koff);
             const uint64_t bl = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + 8192 + koff);
-            tc_mma_bf16_pair(d, ah, bh, idesc, (kc | ks) != 0);
+            tc_mma_bf16_pair(d, ah, bh, idesc, (kc != kc_begin) || (ks != 0));
             tc_mma_bf16_pair(d, al, bh, idesc, 1);
             tc_mma_bf16_pair(d, ah, bl, idesc, 1);
           }
@@ -531,8 +556,8 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < p.total_items; item += n_clusters) {
-      int b, mp;
-      tc_decode(p, item, b, mp);
+      int b, mp, split;
+      tc_decode(p, item, b, mp, split);
       const int mt = mp * 2 + (int)rank;
       float* bs = bias_s + acc * 256;
       if (EPI == EPI_BIAS_ACT_T_SPLIT) {
@@ -576,11 +601,17 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
           } else {
             if (valid) {
-              float* o = p.out + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
+              float* o = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
               const int nvalid = p.n_cols_total > 0 ? min(p.N_valid, p.n_cols_total - b * p.H) : p.N_valid;
+              if (p.vec_store && c0 + 32 <= nvalid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < nvalid) o[j] = v[j];
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c0 + j < nvalid) o[j] = v[j];
+              }
             }
           }
         }
@@ -925,6 +956,19 @@ __global__ void k_layer2_reduce(const float* b2_partial, const double* loss_part
   if (t == 0 && loss_out) loss_out[b] = (float)(tot / (double)N);
 }
 
+// out[b*out_stride + i] = sum_s part[s*split_stride + b*part_stride + i]   (fixed order => deterministic)
+__global__ void k_reduce_ksplits(const float* part, int splits, int64_t split_stride, int64_t part_stride, int64_t count,
+                                 float* out, int64_t out_stride) {
+  const int b = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[(int64_t)k * split_stride + (int64_t)b * part_stride + i];
+    out[(int64_t)b * out_stride + i] = s;
+  }
+}
+// one accumulator sees at most TC_SPLIT_CHUNKS chunks (8192 K elements): <= 1536 truncating accumulations
+constexpr int TC_SPLIT_CHUNKS = 256;
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -986,6 +1030,7 @@ struct TcState {
   DevBuf<__nv_bfloat16> a_hi, a_lo;                     // A1^T  blocked [block][H][128]
   DevBuf<__nv_bfloat16> z2_hi, z2_lo;                   // dZ2^T blocked [block][16][128]
   DevBuf<float> b2_partial;
+  DevBuf<float> kpart, gpart;                           // split-K partial sums (gradient GEMMs / exported GEMM)
   DevBuf<double> loss_partial;
   CUtensorMap mW_hi, mW_lo, mWp_hi, mWp_lo, mZ_hi, mZ_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
 };
@@ -1041,6 +1086,9 @@ static bool pair_ok(const pyb_handle* h, const TcGemmParams& p) {
 static void launch_gemm_tc(pyb_handle* h, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                            const CUtensorMap& b_hi, const CUtensorMap& b_lo, TcGemmParams p, double flops,
                            const CUtensorMap* bp_hi = nullptr, const CUtensorMap* bp_lo = nullptr) {
+  if (p.k_splits <= 1) { p.k_splits = 1; p.chunks_per_split = (p.K + TC_BK - 1) / TC_BK; p.split_stride = 0; }
+  p.vec_store = p.epi == EPI_STORE && ((uintptr_t)p.out % 16 == 0) && (p.out_stride % 4 == 0) && (p.out_ld % 4 == 0) &&
+                (p.split_stride % 4 == 0);
   int grid = std::min(p.total_items, h->sm_count);
   prof_begin(h);
   if (bp_hi && bp_lo && pair_ok(h, p)) {
@@ -1185,25 +1233,52 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
                                                 loss_out ? loss_out + b0 : nullptr, (int)N);
       count_launch(h, 2);
     }
+    // the two reductions over the data rows are split-K (accumulator truncation, see TcGemmParams)
+    const int nk_rows = (int)(Npad / TC_BK);
+    const int splits = (nk_rows + TC_SPLIT_CHUNKS - 1) / TC_SPLIT_CHUNKS;
+    const int64_t cnt1 = (int64_t)(D + 1) * H, cnt2 = (int64_t)H * C;
+    if (splits > 1) st->kpart.alloc((size_t)splits * nb * std::max(cnt1, cnt2));
     // G3: dW2[h][c] = sum_r a1[r][h] dZ2[r][c]   (A = A1^T per chain, B = dZ2^T per chain, N = 16)
     {
       TcGemmParams p = {};
       p.K = (int)Npad; p.n_mtiles = (H + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = L2_CMAX;
       p.a_blocked = 1; p.b_blocked = 1; p.k_tiles = (int)(Npad / 128); p.a_box_rows = std::min(H, 128);
-      p.a_batch_rows = H; p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
-      p.epi = EPI_STORE;
-      p.out = gr + L2.w_off; p.out_stride = P; p.out_ld = C; p.M_valid = H; p.N_valid = C;
+      p.a_batch_rows = H; p.order = 0; p.sub_batch = nb;
+      p.epi = EPI_STORE; p.out_ld = C; p.M_valid = H; p.N_valid = C;
+      if (splits > 1) {
+        p.k_splits = splits; p.chunks_per_split = TC_SPLIT_CHUNKS; p.split_stride = nb * cnt2;
+        p.out = st->kpart.p; p.out_stride = cnt2;
+      } else {
+        p.out = gr + L2.w_off; p.out_stride = P;
+      }
+      p.total_items = p.n_pairs * nb * std::max(splits, 1);
       launch_gemm_tc(h, st->mA_hi, st->mA_lo, st->mZ2_hi, st->mZ2_lo, p, 2.0 * N * (double)H * C * nb);
+      if (splits > 1) {
+        dim3 rg((unsigned)std::min<int64_t>((cnt2 + 255) / 256, 64), nb);
+        k_reduce_ksplits<<<rg, 256, 0, h->stream>>>(st->kpart.p, splits, nb * cnt2, cnt2, cnt2, gr + L2.w_off, P);
+        count_launch(h);
+      }
     }
     // G2: [dW1; db1] = [X^T; 1] dZ1
     {
       TcGemmParams p = {};
       p.K = (int)Npad; p.n_mtiles = (D + 1 + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
       p.a_blocked = 0; p.b_blocked = 1; p.k_tiles = (int)(Npad / 128); p.a_box_rows = 128;
-      p.a_batch_rows = 0; p.order = 0; p.sub_batch = nb; p.total_items = p.n_pairs * nb;
-      p.epi = EPI_STORE;
-      p.out = gr; p.out_stride = P; p.out_ld = H; p.M_valid = D + 1; p.N_valid = H;
+      p.a_batch_rows = 0; p.order = 0; p.sub_batch = nb;
+      p.epi = EPI_STORE; p.out_ld = H; p.M_valid = D + 1; p.N_valid = H;
+      if (splits > 1) {
+        p.k_splits = splits; p.chunks_per_split = TC_SPLIT_CHUNKS; p.split_stride = nb * cnt1;
+        p.out = st->kpart.p; p.out_stride = cnt1;
+      } else {
+        p.out = gr; p.out_stride = P;
+      }
+      p.total_items = p.n_pairs * nb * std::max(splits, 1);
       launch_gemm_tc(h, d.mXT_hi, d.mXT_lo, st->mZ_hi, st->mZ_lo, p, 2.0 * N * (double)(D + 1) * H * nb);
+      if (splits > 1) {
+        dim3 rg((unsigned)std::min<int64_t>((cnt1 + 255) / 256, 256), nb);
+        k_reduce_ksplits<<<rg, 256, 0, h->stream>>>(st->kpart.p, splits, nb * cnt1, cnt1, cnt1, gr, P);
+        count_launch(h);
+      }
     }
   }
   PYB_CUDA(cudaGetLastError());
@@ -1270,10 +1345,23 @@ void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t ld
   TcGemmParams p = {};
   p.K = (int)K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = (Nn + Hn - 1) / Hn; p.H = Hn;
   p.a_row0 = a_row0; p.a_batch_rows = 0; p.a_box_rows = 128; p.order = 1; p.sub_batch = 8;
-  p.total_items = p.n_pairs * p.n_batch;
   p.epi = EPI_STORE; p.out = out; p.out_stride = Hn; p.out_ld = (int)ldc; p.M_valid = M; p.N_valid = Hn; p.n_cols_total = Nn;
+  const int nk = (int)((K + TC_BK - 1) / TC_BK);
+  const int splits = (nk + TC_SPLIT_CHUNKS - 1) / TC_SPLIT_CHUNKS;
+  TcState* st = tc_state(h);
+  if (splits > 1) {      // long reductions (Gram over P = 1e5 parameters): split-K partials, fixed-order sum
+    st->gpart.alloc((size_t)splits * M * ldc);
+    p.k_splits = splits; p.chunks_per_split = TC_SPLIT_CHUNKS; p.split_stride = (int64_t)M * ldc; p.out = st->gpart.p;
+  }
+  p.total_items = p.n_pairs * p.n_batch * std::max(splits, 1);
   CUtensorMap mp_h = make_map(b_hi, K, Nn, ldb, std::max(Hn / 2, 8)), mp_l = make_map(b_lo, K, Nn, ldb, std::max(Hn / 2, 8));
   launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * (double)Nn * (double)K, &mp_h, &mp_l);
+  if (splits > 1) {
+    const int64_t cnt = (int64_t)M * ldc;
+    dim3 rg((unsigned)std::min<int64_t>((cnt + 255) / 256, 4096), 1);
+    k_reduce_ksplits<<<rg, 256, 0, h->stream>>>(st->gpart.p, splits, cnt, 0, cnt, out, 0);
+    count_launch(h);
+  }
 }
 
 // debug / unit-test entry: D[M,Nn] = A[M,K] B[Nn,K]^T through the tcgen05 kernel (host pointers)
