@@ -151,6 +151,9 @@ struct TcGemmParams {
   // -4.5e-4 after 60000-long reductions), so long K loops are cut into k_splits independent accumulations of
   // chunks_per_split 32-element chunks whose partial results are summed afterwards in a fixed order
   int k_splits, chunks_per_split; int64_t split_stride;
+  // pair kernel, 'hidden-major' gradient GEMM: chain b selects the (blocked) A operand, bt in [0, n_btiles) selects
+  // the B row tile [bt*H, bt*H+H) (+b_row0) and the output is stored transposed: out[(col0 + col)*out_ld + row]
+  int n_btiles, b_row0, transpose_out;
   int vec_store;               // EPI_STORE: every output row segment is 16-byte aligned -> float4 stores
   int n_cols_total;            // >0: chain b owns columns [b*H, min((b+1)*H, n_cols_total)) of one wide output
 };
@@ -440,6 +443,26 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
       : "memory");
 }
 
+__device__ __forceinline__ void tc_decode_pair(const TcGemmParams& p, int item, int& b, int& mp, int& split, int& bt) {
+  if (p.n_btiles > 0) {          // [chain][split][B tile]: the B tiles sharing one A k-range run side by side
+    bt = item % p.n_btiles;
+    int r = item / p.n_btiles;
+    split = r % p.k_splits;
+    b = r / p.k_splits;
+    mp = 0;
+    return;
+  }
+  bt = -1;
+  tc_decode(p, item, b, mp, split);
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 template <int EPI, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1)
 tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -492,18 +515,23 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int item = cluster_id; item < p.total_items; item += n_clusters) {
-        int b, mp, split;
-        tc_decode(p, item, b, mp, split);
+        int b, mp, split, bt;
+        tc_decode_pair(p, item, b, mp, split, bt);
         const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
-        const int arow = p.a_row0 + (mp * 2 + (int)rank) * 128;
-        const int brow = b * p.H + (int)rank * half_rows;
+        const int arow = (p.a_blocked ? 0 : p.a_row0) + (mp * 2 + (int)rank) * 128;
+        const int brow = (bt >= 0 ? p.b_row0 + bt * p.H : b * p.H) + (int)rank * half_rows;
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * TP_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);     // bytes of BOTH CTAs
           const int k0 = kc * TC_BK;
-          tma_load_2d_pair(st, &tmA_hi, &full_bar[stage], k0, arow);
-          tma_load_2d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, arow);
+          if (p.a_blocked) {
+            tma_load_3d_pair(st, &tmA_hi, &full_bar[stage], k0 & 127, arow, b * p.k_tiles + (k0 >> 7));
+            tma_load_3d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0 & 127, arow, b * p.k_tiles + (k0 >> 7));
+          } else {
+            tma_load_2d_pair(st, &tmA_hi, &full_bar[stage], k0, arow);
+            tma_load_2d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, arow);
+          }
           tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], k0, brow);
           tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES + 8192, &tmB_lo, &full_bar[stage], k0, brow);
           if (++stage == TP_STAGES) { stage = 0; phase ^= 1; }
@@ -519,8 +547,8 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       uint32_t phase = 0, acc_phase = 0;
       const int k_tail = p.K - (nk - 1) * TC_BK;
       for (int item = cluster_id; item < p.total_items; item += n_clusters) {
-        int b, mp, split;
-        tc_decode(p, item, b, mp, split);
+        int b, mp, split, bt;
+        tc_decode_pair(p, item, b, mp, split, bt);
         const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);               // both epilogues drained this accumulator
         tc_fence_after();
@@ -556,8 +584,8 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < p.total_items; item += n_clusters) {
-      int b, mp, split;
-      tc_decode(p, item, b, mp, split);
+      int b, mp, split, bt;
+      tc_decode_pair(p, item, b, mp, split, bt);
       const int mt = mp * 2 + (int)rank;
       float* bs = bias_s + acc * 256;
       if (EPI == EPI_BIAS_ACT_T_SPLIT) {
@@ -600,7 +628,16 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               }
             }
           } else {
-            if (valid) {
+            if (p.transpose_out) {
+              // out[(col0 + col) * out_ld + row]: consecutive lanes hold consecutive rows -> 128 B per warp store
+              if (valid) {
+                const int col0 = p.b_row0 + bt * p.H + c0;
+                float* o = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + (int64_t)col0 * p.out_ld + row;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.n_cols_total && c0 + j < p.H) o[(int64_t)j * p.out_ld] = v[j];
+              }
+            } else if (valid) {
               float* o = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
               const int nvalid = p.n_cols_total > 0 ? min(p.N_valid, p.n_cols_total - b * p.H) : p.N_valid;
               if (p.vec_store && c0 + 32 <= nvalid) {
@@ -1019,7 +1056,7 @@ struct TcData {   // split bf16 operands derived from one [N, D] fp32 matrix res
   int64_t N = 0, Npad = 0;
   int D = 0;
   DevBuf<__nv_bfloat16> x_hi, x_lo, xt_hi, xt_lo;       // [N][D], [D+1][Npad]
-  CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo;
+  CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo, mXTp_hi, mXTp_lo;   // mXTp: half-tile boxes for the hidden-major pair GEMM
 };
 struct TcState {
   TcData train, aux;                                    // resident training set / minibatch or test inputs
@@ -1032,7 +1069,7 @@ struct TcState {
   DevBuf<float> b2_partial;
   DevBuf<float> kpart, gpart;                           // split-K partial sums (gradient GEMMs / exported GEMM)
   DevBuf<double> loss_partial;
-  CUtensorMap mW_hi, mW_lo, mWp_hi, mWp_lo, mZ_hi, mZ_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
+  CUtensorMap mW_hi, mW_lo, mWp_hi, mWp_lo, mZ_hi, mZ_lo, mZa_hi, mZa_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
 };
 static TcState* tc_state(pyb_handle* h) {
   if (!h->tc) h->tc = new TcState();
@@ -1079,8 +1116,10 @@ static void launch_pair_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, c
 }
 // CTA-pair kernel: plain 2-D operands, H a multiple of 32, an even number of M tiles' worth of work per item
 static bool pair_ok(const pyb_handle* h, const TcGemmParams& p) {
-  return h->opt_tc_pair && !p.a_blocked && !p.b_blocked && p.a_batch_rows == 0 && (p.H % 32) == 0 && p.H >= 32 &&
-         p.n_mtiles >= 2;
+  if (!h->opt_tc_pair || p.b_blocked || p.H < 32 || p.n_mtiles < 2) return false;
+  if (p.n_btiles > 0) return p.a_blocked && p.n_mtiles == 2 && (p.H % 16) == 0;   // hidden-major gradient GEMM
+  if ((p.H % 32) != 0) return false;
+  return !p.a_blocked && p.a_batch_rows == 0;
 }
 // bp_hi/bp_lo: the SAME B tensors described with half-height TMA boxes (H/2 rows) for the CTA-pair kernel, or null
 static void launch_gemm_tc(pyb_handle* h, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
@@ -1133,6 +1172,9 @@ static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N,
     count_launch(h, 2);
     d.mXT_hi = make_map(d.xt_hi.p, Npad, D + 1, Npad, 128);
     d.mXT_lo = make_map(d.xt_lo.p, Npad, D + 1, Npad, 128);
+    const int n_t = (D + 1 + 255) / 256, Ht = (((D + 1 + n_t - 1) / n_t) + 15) / 16 * 16;
+    d.mXTp_hi = make_map(d.xt_hi.p, Npad, D + 1, Npad, Ht / 2);
+    d.mXTp_lo = make_map(d.xt_lo.p, Npad, D + 1, Npad, Ht / 2);
   }
   d.ready = true;
 }
@@ -1169,6 +1211,8 @@ static int64_t tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S, int64_t Np
     st->mWp_lo = make_map(st->w_lo.p, D, cc * H, D, std::max(H / 2, 8));
     st->mZ_hi = make_map_blocked(st->z_hi.p, cb, H, H);
     st->mZ_lo = make_map_blocked(st->z_lo.p, cb, H, H);
+    st->mZa_hi = make_map_blocked(st->z_hi.p, cb, H, std::min(H, 128));   // dZ1^T as an A operand (128-row boxes)
+    st->mZa_lo = make_map_blocked(st->z_lo.p, cb, H, std::min(H, 128));
     st->mA_hi = make_map_blocked(st->a_hi.p, cb, H, std::min(H, 128));
     st->mA_lo = make_map_blocked(st->a_lo.p, cb, H, std::min(H, 128));
     st->mZ2_hi = make_map_blocked(st->z2_hi.p, cb, L2_CMAX, L2_CMAX);
@@ -1260,7 +1304,28 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
       }
     }
     // G2: [dW1; db1] = [X^T; 1] dZ1
-    {
+    if (H == 256 && h->opt_tc_pair) {
+      // hidden-major on the CTA-pair kernel: D[h, f] = sum_r dZ1^T[h, r] [X^T;1][f, r].  M = 256 hidden units is
+      // exactly one CTA pair (no M padding), the D+1 feature rows are the N dimension in tiles of 256 plus one
+      // narrow remainder tile, the accumulators are double-buffered so the partial-sum stores overlap the MMAs
+      // (N = D+1 = 785 -> 4 tiles of 208 columns: 6 % padding instead of the 12.5 % of 7 x 128 M tiles)
+      const int n_t = (D + 1 + 255) / 256;
+      const int Ht = (((D + 1 + n_t - 1) / n_t) + 15) / 16 * 16;
+      TcGemmParams p = {};
+      p.K = (int)Npad; p.n_mtiles = 2; p.n_pairs = 1; p.n_batch = nb; p.H = Ht;
+      p.a_blocked = 1; p.b_blocked = 0; p.k_tiles = (int)(Npad / 128); p.a_box_rows = 128;
+      p.n_btiles = n_t; p.b_row0 = 0; p.transpose_out = 1; p.n_cols_total = D + 1;
+      p.epi = EPI_STORE; p.out_ld = H; p.M_valid = H; p.N_valid = Ht;
+      if (splits > 1) {
+        p.k_splits = splits; p.chunks_per_split = TC_SPLIT_CHUNKS; p.split_stride = nb * cnt1;
+        p.out = st->kpart.p; p.out_stride = cnt1;
+      } else {
+        p.out = gr; p.out_stride = P;
+      }
+      p.total_items = nb * std::max(splits, 1) * n_t;
+      launch_gemm_tc(h, st->mZa_hi, st->mZa_lo, d.mXT_hi, d.mXT_lo, p, 2.0 * N * (double)(D + 1) * H * nb, &d.mXTp_hi,
+                     &d.mXTp_lo);
+    } else {
       TcGemmParams p = {};
       p.K = (int)Npad; p.n_mtiles = (D + 1 + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
       p.a_blocked = 0; p.b_blocked = 1; p.k_tiles = (int)(Npad / 128); p.a_box_rows = 128;
@@ -1274,11 +1339,11 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
       }
       p.total_items = p.n_pairs * nb * std::max(splits, 1);
       launch_gemm_tc(h, d.mXT_hi, d.mXT_lo, st->mZ_hi, st->mZ_lo, p, 2.0 * N * (double)(D + 1) * H * nb);
-      if (splits > 1) {
-        dim3 rg((unsigned)std::min<int64_t>((cnt1 + 255) / 256, 256), nb);
-        k_reduce_ksplits<<<rg, 256, 0, h->stream>>>(st->kpart.p, splits, nb * cnt1, cnt1, cnt1, gr, P);
-        count_launch(h);
-      }
+    }
+    if (splits > 1) {
+      dim3 rg((unsigned)std::min<int64_t>((cnt1 + 255) / 256, 256), nb);
+      k_reduce_ksplits<<<rg, 256, 0, h->stream>>>(st->kpart.p, splits, nb * cnt1, cnt1, cnt1, gr, P);
+      count_launch(h);
     }
   }
   PYB_CUDA(cudaGetLastError());
