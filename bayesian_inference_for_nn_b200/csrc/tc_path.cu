@@ -159,11 +159,11 @@ struct TcGemmParams {
 };
 
 __device__ __forceinline__ void tc_decode(const TcGemmParams& p, int item, int& b, int& mp, int& split) {
-  if (p.k_splits > 1) {          // [chain][split][pair]: the pairs sharing one B k-range run side by side
-    mp = item % p.n_pairs;
+  if (p.k_splits > 1) {          // [split][chain][pair]: the pairs sharing one B k-range run side by side, and the
+    mp = item % p.n_pairs;       // k-range of the shared A operand stays L2-resident while all chains pass over it
     int r = item / p.n_pairs;
-    split = r % p.k_splits;
-    b = r / p.k_splits;
+    b = r % p.n_batch;
+    split = r / p.n_batch;
     return;
   }
   split = 0;
@@ -444,11 +444,11 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 }
 
 __device__ __forceinline__ void tc_decode_pair(const TcGemmParams& p, int item, int& b, int& mp, int& split, int& bt) {
-  if (p.n_btiles > 0) {          // [chain][split][B tile]: the B tiles sharing one A k-range run side by side
-    bt = item % p.n_btiles;
+  if (p.n_btiles > 0) {          // [split][chain][B tile]: the B tiles sharing one A k-range run side by side, and the
+    bt = item % p.n_btiles;      // k-range of the shared B operand (a few tens of MB) stays L2-resident for all chains
     int r = item / p.n_btiles;
-    split = r % p.k_splits;
-    b = r / p.k_splits;
+    b = r % p.n_batch;
+    split = r / p.n_batch;
     mp = 0;
     return;
   }
