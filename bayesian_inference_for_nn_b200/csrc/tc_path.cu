@@ -195,7 +195,7 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const TcGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint8_t* stage_base = smem;
   uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* full_bar = bars;                    // [TC_STAGES]
@@ -469,7 +469,7 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const TcGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint8_t* stage_base = smem;
   uint64_t* bars = (uint64_t*)(smem + TP_STAGES * TP_STAGE_BYTES);
   uint64_t* full_bar = bars;                     // [TP_STAGES]   (used in the leader CTA)
@@ -911,6 +911,299 @@ __global__ void __launch_bounds__(128, 4) k_layer2(Layer2Params p) {
   if (t == 0) p.loss_partial[(int64_t)b * p.n_groups + blockIdx.x] = tot;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// G1 + layer 2 in ONE kernel (relu hidden layer, H = 128 or 256): the CTA-pair GEMM above with an epilogue
+// that never lets the hidden activations leave the SM before layer 2 has consumed them.  Per 128-row tile
+// of one chain, straight out of the TMEM accumulator (thread == data row, 4 threads per row each owning a
+// quarter of the hidden units):
+//   phase A  a1 = relu(z1 + b1) -> A1^T hi/lo (kept for the dW2 GEMM), relu mask bits in registers,
+//            partial logits z2 += a1 * W2 (packed fp32x2 FMAs), TMEM accumulator released to the MMA warp
+//   exchange partial logits through shared memory; every thread of the row finishes softmax-CE / MSE and dZ2
+//   phase B  dZ1 = (dZ2 W2^T) * mask -> dZ1^T hi/lo for the dW1 GEMM
+// This replaces k_layer2's extra pass over A1^T (9.1 GB read per 148-chain batch) and hides layer 2's SIMT
+// work under the next tile's MMAs (double-buffered accumulators).
+// ------------------------------------------------------------------------------------------
+constexpr int TF_THREADS = 640;                 // 4 control warps + 16 epilogue warps
+template <int CP> struct TfCfg {
+  static constexpr int STAGES = CP > 12 ? 4 : 5;
+  static constexpr int W2_BYTES = 2 * 256 * CP * 4;            // [2][256][CP] fp32, double-buffered by accumulator
+  static constexpr int ZX_BYTES = 4 * CP * 128 * 4;            // [4 quarters][CP][128 rows] partial logits
+  static constexpr int SMEM = STAGES * TP_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 2048 /*bias x2*/ +
+                              128 /*b2 x2*/ + W2_BYTES + ZX_BYTES;
+};
+
+template <int CP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1)
+tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   const TcGemmParams p, const Layer2Params l2) {
+  constexpr int STAGES = TfCfg<CP>::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
+  uint8_t* stage_base = smem;
+  uint64_t* bars = (uint64_t*)(smem + STAGES * TP_STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]   (leader CTA)
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]   (one per CTA)
+  uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]        (leader CTA)
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
+  float* bias_s = (float*)(smem + STAGES * TP_STAGE_BYTES + 1024);          // [2][256]
+  float* b2_s = bias_s + 512;                                               // [2][16]
+  float* W2_s = b2_s + 32;                                                  // [2][256*CP]
+  float* zx_s = W2_s + 2 * 256 * CP;                                        // [4][CP][128]
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  const int H = p.H;
+  const int half_rows = H >> 1;
+  const uint32_t cta_bytes = 2 * TC_A_TILE_BYTES + 2 * (uint32_t)half_rows * TC_BK * 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 32); mbar_init(&tmem_empty[1], 32);   // 16 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 rows of X, own half of W1^T[b] =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+        int b, mp, split;
+        tc_decode(p, item, b, mp, split);
+        const int arow = p.a_row0 + (mp * 2 + (int)rank) * 128;
+        const int brow = b * H + (int)rank * half_rows;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = stage_base + stage * TP_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);
+          const int k0 = kc * TC_BK;
+          tma_load_2d_pair(st, &tmA_hi, &full_bar[stage], k0, arow);
+          tma_load_2d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, arow);
+          tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], k0, brow);
+          tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES + 8192, &tmB_lo, &full_bar[stage], k0, brow);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(H >> 3) << 17) | ((256u >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const int k_tail = p.K - (nk - 1) * TC_BK;
+      for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)acc * 256;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + stage * TP_STAGE_BYTES);
+          const int nks = (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t koff = ks * 32;
+            const uint64_t ah = make_smem_desc_sw64(st + koff);
+            const uint64_t al = make_smem_desc_sw64(st + TC_A_TILE_BYTES + koff);
+            const uint64_t bh = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + koff);
+            const uint64_t bl = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + 8192 + koff);
+            tc_mma_bf16_pair(d, ah, bh, idesc, (kc != 0) || (ks != 0));
+            tc_mma_bf16_pair(d, al, bh, idesc, 1);
+            tc_mma_bf16_pair(d, ah, bl, idesc, 1);
+          }
+          tc_commit_pair(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== fused epilogue (both CTAs): 16 warps = 4 lane quadrants x 4 quarters of the hidden units =====
+    const int q = (warp - 4) >> 2;                                // quarter of the hidden units
+    const int quad = warp & 3;                                    // TMEM lane quadrant (hardware: warp % 4)
+    const int et = quad * 32 + lane;                              // row inside the 128-row tile
+    const int eall = threadIdx.x - 128;                           // 0..511
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int Hq = H >> 2;                                        // hidden units per quarter: 32 or 64
+    const int C = l2.C;
+    const float invN = l2.scale / (float)l2.N;
+    uint16_t* a_hi = reinterpret_cast<uint16_t*>(p.out_hi);
+    uint16_t* a_lo = reinterpret_cast<uint16_t*>(p.out_lo);
+    uint16_t* zt_hi = reinterpret_cast<uint16_t*>(l2.zt_hi);
+    uint16_t* zt_lo = reinterpret_cast<uint16_t*>(l2.zt_lo);
+    uint16_t* z2_hi = reinterpret_cast<uint16_t*>(l2.z2_hi);
+    uint16_t* z2_lo = reinterpret_cast<uint16_t*>(l2.z2_lo);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      int b, mp, split;
+      tc_decode(p, item, b, mp, split);
+      const int mt = mp * 2 + (int)rank;
+      const int row = mt * 128 + et;
+      const bool valid = row < p.M_valid;
+      float* bs = bias_s + acc * 256;
+      float* b2b = b2_s + acc * 16;
+      float* W2b = W2_s + acc * 256 * CP;
+      {
+        // per-chain constants; buffer [acc] was last read two items ago (ordered by the barriers below)
+        const float* th = l2.theta + (int64_t)b * l2.P;
+        for (int i = eall; i < H * CP; i += 512) {
+          const int h = i / CP, c = i - h * CP;
+          W2b[i] = (c < C) ? th[l2.w2_off + (int64_t)h * C + c] : 0.f;
+        }
+        for (int c = eall; c < H; c += 512) bs[c] = p.bias[(int64_t)b * p.bias_stride + c];
+        if (eall < 16) b2b[eall] = (eall < C) ? th[l2.b2_off + eall] : 0.f;
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");             // constants visible; zx_s readers of the last item done
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      // ---- phase A
+      const int64_t blk = ((int64_t)b * p.out_tiles + mt) * H;    // first hidden-unit row of this (chain, tile) block
+      float2 z[CP / 2];
+#pragma unroll
+      for (int c = 0; c < CP / 2; ++c) z[c] = make_float2(0.f, 0.f);
+      uint32_t mask[2] = {0u, 0u};
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        if (ch * 32 < Hq) {
+          const int c0 = q * Hq + ch * 32;
+          float v[32];
+          tc_ld32(tmem_base + lane_base + (uint32_t)(acc * 256 + c0), v);
+          uint16_t* ohi = a_hi + (blk + c0) * 128 + et;
+          uint16_t* olo = a_lo + (blk + c0) * 128 + et;
+          const float4* bias4 = reinterpret_cast<const float4*>(bs + c0);
+          uint32_t m = 0u;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = bias4[j4];
+            const float bj[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 * 4 + jj;
+              float a = fmaxf(v[j] + bj[jj], 0.f);
+              a = valid ? a : 0.f;
+              m |= (a > 0.f ? 1u : 0u) << j;
+              __nv_bfloat16 hb, lb;
+              split_bf16(a, hb, lb);
+              ohi[j * 128] = __bfloat16_as_ushort(hb);
+              olo[j * 128] = __bfloat16_as_ushort(lb);
+              const float2 aa = make_float2(a, a);
+              const float4* w4 = reinterpret_cast<const float4*>(W2b + (c0 + j) * CP);
+#pragma unroll
+              for (int c4 = 0; c4 < CP / 4; ++c4) {
+                const float4 w = w4[c4];
+                z[2 * c4] = __ffma2_rn(aa, make_float2(w.x, w.y), z[2 * c4]);
+                z[2 * c4 + 1] = __ffma2_rn(aa, make_float2(w.z, w.w), z[2 * c4 + 1]);
+              }
+            }
+          }
+          mask[ch] = m;
+        }
+      }
+      // the accumulator is no longer needed: hand it back to the MMA warp before the rest of the epilogue
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      // ---- exchange the partial logits of the row's 4 threads
+#pragma unroll
+      for (int c = 0; c < CP / 2; ++c) {
+        zx_s[(q * CP + 2 * c) * 128 + et] = z[c].x;
+        zx_s[(q * CP + 2 * c + 1) * 128 + et] = z[c].y;
+      }
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      float zf[CP], dz[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        zf[c] = (((b2b[c] + zx_s[c * 128 + et]) + zx_s[(CP + c) * 128 + et]) + zx_s[(2 * CP + c) * 128 + et]) +
+                zx_s[(3 * CP + c) * 128 + et];
+      double loss_r = 0.0;
+      l2_loss_dz<CP>(l2, row, valid, zf, dz, loss_r, invN);
+      if (q == 0) {
+        // dZ2^T for the dW2 GEMM, per-warp partial sums of the loss and of db2
+        const int64_t blk2 = ((int64_t)b * p.out_tiles + mt) * L2_CMAX;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+          __nv_bfloat16 hb, lb;
+          split_bf16(dz[c], hb, lb);
+          z2_hi[(blk2 + c) * 128 + et] = __bfloat16_as_ushort(hb);
+          z2_lo[(blk2 + c) * 128 + et] = __bfloat16_as_ushort(lb);
+        }
+        const int64_t g = (int64_t)b * l2.n_groups + mt * 4 + quad;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+          const float s = warp_sum(dz[c]);
+          if (lane == 0) l2.b2_partial[g * L2_CMAX + c] = s;
+        }
+        double ls = loss_r;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+        if (lane == 0) l2.loss_partial[g] = ls;
+      }
+      // ---- phase B: dZ1 = (dZ2 W2^T) * relu'(z1)
+      float2 dzp[CP / 2];
+#pragma unroll
+      for (int c = 0; c < CP / 2; ++c) dzp[c] = make_float2(dz[2 * c], dz[2 * c + 1]);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        if (ch * 32 < Hq) {
+          const int c0 = q * Hq + ch * 32;
+          uint16_t* ohi = zt_hi + (blk + c0) * 128 + et;
+          uint16_t* olo = zt_lo + (blk + c0) * 128 + et;
+          const uint32_t m = mask[ch];
+#pragma unroll 8
+          for (int j = 0; j < 32; ++j) {
+            const float4* w4 = reinterpret_cast<const float4*>(W2b + (c0 + j) * CP);
+            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c4 = 0; c4 < CP / 4; ++c4) {
+              const float4 w = w4[c4];
+              s0 = __ffma2_rn(dzp[2 * c4], make_float2(w.x, w.y), s0);
+              s1 = __ffma2_rn(dzp[2 * c4 + 1], make_float2(w.z, w.w), s1);
+            }
+            float d = (s0.x + s0.y) + (s1.x + s1.y);
+            d = ((m >> j) & 1u) ? d : 0.f;
+            __nv_bfloat16 hb, lb;
+            split_bf16(d, hb, lb);
+            ohi[j * 128] = __bfloat16_as_ushort(hb);
+            olo[j * 128] = __bfloat16_as_ushort(lb);
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // forward-only layer 2 (posterior predictive): out[b][row][c] = softmax(a1 W2 + b2) or act(.)
 struct Layer2FwdParams {
   const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo; int k_tiles;
@@ -1151,6 +1444,17 @@ static void launch_gemm_tc(pyb_handle* h, const CUtensorMap& a_hi, const CUtenso
 }
 
 
+template <int CP>
+static void launch_fused_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                              const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p, const Layer2Params& l2) {
+  PYB_CUDA(cudaFuncSetAttribute(tc_g1_layer2_fused<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TfCfg<CP>::SMEM));
+  tc_g1_layer2_fused<CP><<<grid, TF_THREADS, TfCfg<CP>::SMEM, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p, l2);
+}
+// fused G1 + layer 2 applies to: relu hidden layer of 128 or 256 units, CTA pairs enabled
+static bool fused_ok(const pyb_handle* h, int H, int act1) {
+  return h->opt_tc_pair && h->opt_tc_fuse && act1 == PYB_ACT_RELU && (H == 128 || H == 256);
+}
+
 static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N, bool need_xt) {
   const Model& m = h->model;
   const int D = m.layer[0].fan_in;
@@ -1221,7 +1525,8 @@ static int64_t tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S, int64_t Np
   return bc;
 }
 
-static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* th, int nb) {
+static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* th, int nb,
+                           const Layer2Params* fused = nullptr) {
   const Model& m = h->model;
   const LayerDesc& L1 = m.layer[0];
   const int D = st->D, H = st->H;
@@ -1238,6 +1543,19 @@ static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* t
   p.bias = th + L1.b_off; p.bias_stride = P; p.act = L1.act;
   p.out_hi = st->a_hi.p; p.out_lo = st->a_lo.p; p.out_tiles = (int)(Npad / 128);
   p.M_valid = (int)N; p.N_valid = H;
+  if (fused) {
+    // G1 with layer 2 (+ loss, dZ2, dZ1) in its epilogue
+    const int grid = std::min(2 * p.total_items, (h->sm_count / 2) * 2);
+    const int C = fused->C;
+    prof_begin(h);
+    if (C <= 4) launch_fused_inst<4>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
+    else if (C <= 8) launch_fused_inst<8>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
+    else if (C <= 12) launch_fused_inst<12>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
+    else launch_fused_inst<16>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
+    prof_end(h, 2.0 * N * (D * (double)H + 3.0 * H * C) * nb);
+    count_launch(h);
+    return;
+  }
   launch_gemm_tc(h, d.mX_hi, d.mX_lo, st->mW_hi, st->mW_lo, p, 2.0 * N * D * (double)H * nb, &st->mWp_hi, &st->mWp_lo);
 }
 
@@ -1250,15 +1568,17 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
   const int D = st->D, H = st->H, C = st->C;
   const int64_t N = d.N, Npad = d.Npad, P = m.P;
   const int n_tiles = (int)(Npad / L2_ROWS);
-  const int n_groups = std::min(n_tiles, std::max(1, (int)((8 * (int64_t)h->sm_count + Bc - 1) / Bc)));
+  const bool fused = fused_ok(h, H, L1.act) && C <= L2_CMAX;
+  // fused: one partial per (128-row tile, lane quadrant); unfused: one per k_layer2 block
+  const int n_groups = fused ? (int)(Npad / 128) * 4
+                             : std::min(n_tiles, std::max(1, (int)((8 * (int64_t)h->sm_count + Bc - 1) / Bc)));
   st->b2_partial.alloc((size_t)Bc * n_groups * L2_CMAX);
   st->loss_partial.alloc((size_t)Bc * n_groups);
   for (int64_t b0 = 0; b0 < S; b0 += Bc) {
     const int nb = (int)std::min<int64_t>(Bc, S - b0);
     const float* th = theta + b0 * P;
     float* gr = grad_out + b0 * P;
-    tc_pack_and_g1(h, st, d, th, nb);
-    // layer 2 + loss + dZ1^T, dZ2^T
+    // layer 2 + loss + dZ1^T, dZ2^T: inside G1's epilogue when the shape allows, else a separate pass over A1^T
     {
       Layer2Params p = {};
       p.a_hi = st->a_hi.p; p.a_lo = st->a_lo.p; p.zt_hi = st->z_hi.p; p.zt_lo = st->z_lo.p;
@@ -1268,11 +1588,16 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
       p.y_i = y_i; p.y_f = y_f; p.scale = scale;
       p.loss_partial = st->loss_partial.p; p.b2_partial = st->b2_partial.p; p.n_groups = n_groups;
       p.n_tiles = n_tiles;
-      dim3 g(n_groups, nb);
-      if (C <= 4) k_layer2<4><<<g, 128, 0, h->stream>>>(p);
-      else if (C <= 8) k_layer2<8><<<g, 128, 0, h->stream>>>(p);
-      else if (C <= 12) k_layer2<12><<<g, 128, 0, h->stream>>>(p);
-      else k_layer2<16><<<g, 128, 0, h->stream>>>(p);
+      if (fused) {
+        tc_pack_and_g1(h, st, d, th, nb, &p);
+      } else {
+        tc_pack_and_g1(h, st, d, th, nb);
+        dim3 g(n_groups, nb);
+        if (C <= 4) k_layer2<4><<<g, 128, 0, h->stream>>>(p);
+        else if (C <= 8) k_layer2<8><<<g, 128, 0, h->stream>>>(p);
+        else if (C <= 12) k_layer2<12><<<g, 128, 0, h->stream>>>(p);
+        else k_layer2<16><<<g, 128, 0, h->stream>>>(p);
+      }
       k_layer2_reduce<<<nb, 64, 0, h->stream>>>(st->b2_partial.p, st->loss_partial.p, n_groups, C, gr, P, L2.b_off,
                                                 loss_out ? loss_out + b0 : nullptr, (int)N);
       count_launch(h, 2);

@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--leapfrog", type=int, default=int(os.environ.get("PYB_BENCH_L", 20)))
     ap.add_argument("--eps", type=float, default=2e-5)
     ap.add_argument("--path", default=os.environ.get("PYB_BENCH_PATH", "auto"))
+    ap.add_argument("--opt", action="append", default=[], help="development: library option key=value (e.g. tc_fuse=0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -171,7 +172,7 @@ def workload_config(args, world):
             "epsilon": args.eps, "evals_executed_per_step_per_chain": args.leapfrog + 1,
             "parallelism": "chains sharded x%d, no data-path collective" % world,
             "l2_policy": "inputs exceed L2 (X hi/lo 188 MB + per-chain operands >> 126 MB)",
-            "named_config": bool(args.chains == 1024 and args.rows == 60000 and args.leapfrog == 20)}
+            "named_config": bool(args.chains == 1024 and args.rows == 60000 and args.leapfrog == 20 and not args.opt)}
 
 
 def main():
@@ -218,6 +219,9 @@ def main():
     paths = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "fused": _lib.PATH_FUSED_SMALL,
              "tensor": _lib.PATH_TENSOR}
     eng.set_option("path", paths[args.path])
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, float(v))
     eng.set_dataset(X, y, _lib.LOSS_SPARSE_CE)          # inputs resident in HBM before the timed region
     eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
     eng.hmc_init(S, args.eps, 1.0, L, _lib.HMC_REFERENCE, chain_offset=rank * S)
