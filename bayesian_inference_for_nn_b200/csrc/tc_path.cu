@@ -443,6 +443,18 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
       : "memory");
 }
 
+// same, without release semantics: the caller has already ordered its TMEM reads with tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync and publishes no memory through this barrier (a cluster-scope release would
+// wait for every global store the warp has in flight)
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tc_decode_pair(const TcGemmParams& p, int item, int& b, int& mp, int& split, int& bt) {
   if (p.n_btiles > 0) {          // [split][chain][B tile]: the B tiles sharing one A k-range run side by side, and the
     bt = item % p.n_btiles;      // k-range of the shared B operand (a few tens of MB) stays L2-resident for all chains
@@ -743,9 +755,9 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-template <int CP>
+template <int CP, typename LT>
 __device__ __forceinline__ void l2_loss_dz(const Layer2Params& p, int r, bool valid, const float* z, float* dz,
-                                           double& loss_acc, float invN) {
+                                           LT& loss_acc, float invN) {
   const int C = p.C;
 #pragma unroll
   for (int c = 0; c < CP; ++c) dz[c] = 0.f;
@@ -761,7 +773,7 @@ __device__ __forceinline__ void l2_loss_dz(const Layer2Params& p, int r, bool va
     float zy = 0.f;
 #pragma unroll
     for (int c = 0; c < CP; ++c) if (c == yi) zy = z[c];
-    loss_acc += (double)(logf(se) - (zy - mx));
+    loss_acc += (LT)(logf(se) - (zy - mx));
     const float inv = 1.0f / se;
 #pragma unroll
     for (int c = 0; c < CP; ++c)
@@ -777,7 +789,7 @@ __device__ __forceinline__ void l2_loss_dz(const Layer2Params& p, int r, bool va
         acc += df * df;
         dz[c] = sc * df * act_grad_from_output(a, p.out_act);
       }
-    loss_acc += (double)(acc / (float)C);
+    loss_acc += (LT)(acc / (float)C);
   }
 }
 // CP = class count padded to a multiple of 4 (register tile of the per-row logits)
@@ -914,24 +926,54 @@ __global__ void __launch_bounds__(128, 4) k_layer2(Layer2Params p) {
 
 // ------------------------------------------------------------------------------------------
 // G1 + layer 2 in ONE kernel (relu hidden layer, H = 128 or 256): the CTA-pair GEMM above with an epilogue
-// that never lets the hidden activations leave the SM before layer 2 has consumed them.  Per 128-row tile
-// of one chain, straight out of the TMEM accumulator (thread == data row, 4 threads per row each owning a
-// quarter of the hidden units):
+// that never lets the hidden activations leave the SM before layer 2 has consumed them.
+// The epilogue reads the TMEM accumulator with tcgen05.ld.16x256b: lane (g = lane/4, t = lane%4) of a warp
+// receives, for each 8-column block, columns {2t, 2t+1} of rows g and g+8 (two loads: + rows g+16, g+24).
+// One thread therefore owns FOUR data rows x a quarter of the hidden units of its warp's column half, and every
+// W2 row it fetches from shared memory feeds 4 rows (the 32x32b layout, thread == row, re-reads W2 for every
+// row: measured shared-memory-bandwidth bound, 12.6 ms against 7.7 ms of MMA work).  Per 128-row tile of a chain:
 //   phase A  a1 = relu(z1 + b1) -> A1^T hi/lo (kept for the dW2 GEMM), relu mask bits in registers,
-//            partial logits z2 += a1 * W2 (packed fp32x2 FMAs), TMEM accumulator released to the MMA warp
-//   exchange partial logits through shared memory; every thread of the row finishes softmax-CE / MSE and dZ2
+//            partial logits z2 += a1 * W2 (packed fp32x2 FMAs); TMEM accumulator released to the MMA warp
+//   reduce   partial logits: quad reduce-scatter by shuffles (lane t ends up with ONE complete row), the two
+//            column halves meet in shared memory; softmax-CE / MSE and dZ2 once per row; quad all-gather of dZ2
 //   phase B  dZ1 = (dZ2 W2^T) * mask -> dZ1^T hi/lo for the dW1 GEMM
-// This replaces k_layer2's extra pass over A1^T (9.1 GB read per 148-chain batch) and hides layer 2's SIMT
-// work under the next tile's MMAs (double-buffered accumulators).
+// Transposed stores: lanes g and g^1 swap half of their rows so that each lane owns row PAIRS (one 32-bit bf16x2
+// word); per store instruction the 8 lanes sharing t write one full 32-byte sector of a hidden unit's row block.
 // ------------------------------------------------------------------------------------------
-constexpr int TF_THREADS = 640;                 // 4 control warps + 16 epilogue warps
+constexpr int TF_THREADS = 384;                 // 4 control warps + 8 epilogue warps
 template <int CP> struct TfCfg {
-  static constexpr int STAGES = CP > 12 ? 4 : 5;
-  static constexpr int W2_BYTES = 2 * 256 * CP * 4;            // [2][256][CP] fp32, double-buffered by accumulator
-  static constexpr int ZX_BYTES = 4 * CP * 128 * 4;            // [4 quarters][CP][128 rows] partial logits
+  static constexpr int STAGES = 5;
+  static constexpr int W2_BYTES = 2 * 256 * CP * 4;            // [2][256*CP] fp32 (fragment-interleaved), double-buffered
+  static constexpr int ZX_BYTES = 2 * CP * 128 * 4;            // [2 halves][CP][128 rows] partial logits
   static constexpr int SMEM = STAGES * TP_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 2048 /*bias x2*/ +
                               128 /*b2 x2*/ + W2_BYTES + ZX_BYTES;
 };
+// 16 accumulator columns... 32 columns x rows {g, g+8} of the 16 TMEM lanes starting at the address's lane
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// W2[h][c] inside the per-chain shared-memory copy: the 4 lanes of a quad (h = 8*kb + 2*t + i) read one
+// contiguous 64-byte segment per (kb, i, c/4) -> conflict-free for every class padding CP
+template <int CP>
+__device__ __forceinline__ int w2_slot(int h, int c) {
+  return ((((h >> 3) * 2 + (h & 1)) * (CP / 4) + (c >> 2)) * 4 + ((h >> 1) & 3)) * 4 + (c & 3);
+}
+// bf16 hi/lo words of a row pair (x0 = even row, x1 = odd row)
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hw, uint32_t& lw) {
+  const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+  hw = *reinterpret_cast<const uint32_t*>(&hp);
+  const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - __uint_as_float(hw << 16), x1 - __uint_as_float(hw & 0xffff0000u));
+  lw = *reinterpret_cast<const uint32_t*>(&lp);
+}
 
 template <int CP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1)
@@ -951,7 +993,7 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   float* bias_s = (float*)(smem + STAGES * TP_STAGE_BYTES + 1024);          // [2][256]
   float* b2_s = bias_s + 512;                                               // [2][16]
   float* W2_s = b2_s + 32;                                                  // [2][256*CP]
-  float* zx_s = W2_s + 2 * 256 * CP;                                        // [4][CP][128]
+  float* zx_s = W2_s + 2 * 256 * CP;                                        // [2][CP][128]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const uint32_t rank = cluster_ctarank();
@@ -970,7 +1012,7 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 32); mbar_init(&tmem_empty[1], 32);   // 16 epilogue warps x 2 CTAs
+    mbar_init(&tmem_empty[0], 16); mbar_init(&tmem_empty[1], 16);   // 8 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -1041,83 +1083,122 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ===== fused epilogue (both CTAs): 16 warps = 4 lane quadrants x 4 quarters of the hidden units =====
-    const int q = (warp - 4) >> 2;                                // quarter of the hidden units
+    // ===== fused epilogue (both CTAs): 8 warps = 4 TMEM lane quadrants x 2 halves of the hidden units =====
+    const int half = (warp - 4) >> 2;
     const int quad = warp & 3;                                    // TMEM lane quadrant (hardware: warp % 4)
-    const int et = quad * 32 + lane;                              // row inside the 128-row tile
-    const int eall = threadIdx.x - 128;                           // 0..511
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const int Hq = H >> 2;                                        // hidden units per quarter: 32 or 64
+    const int g = lane >> 2, t = lane & 3;
+    const int odd = g & 1;
+    const int eall = threadIdx.x - 128;                           // 0..255
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int Hh = H >> 1;                                        // hidden units per half: 64 or 128
     const int C = l2.C;
     const float invN = l2.scale / (float)l2.N;
-    uint16_t* a_hi = reinterpret_cast<uint16_t*>(p.out_hi);
-    uint16_t* a_lo = reinterpret_cast<uint16_t*>(p.out_lo);
-    uint16_t* zt_hi = reinterpret_cast<uint16_t*>(l2.zt_hi);
-    uint16_t* zt_lo = reinterpret_cast<uint16_t*>(l2.zt_lo);
+    const int r_own = 2 * (t & 1) + (t >> 1);                     // the row (of this thread's 4) whose logits it completes
+    const int row_own = quad * 32 + g + 8 * r_own;                // ... inside the 128-row tile
+    const int pair_off = quad * 32 + (odd ? g + 7 : g);           // tile row of this lane's first row pair (second: +16)
+    const int hbase = half * Hh + 2 * t;                          // this thread's first hidden unit
     uint16_t* z2_hi = reinterpret_cast<uint16_t*>(l2.z2_hi);
     uint16_t* z2_lo = reinterpret_cast<uint16_t*>(l2.z2_lo);
+    // per-chain constants (W2, b1, b2) travel global -> shared memory with cp.async, issued one item ahead into the
+    // buffer of the accumulator that item will use; slots of padded classes (c >= C) are zeroed once and never written
+    for (int i = eall; i < 2 * 256 * CP; i += 256) W2_s[i] = 0.f;
+    if (eall < 32) b2_s[eall] = 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    auto fetch_consts = [&](int item, int buf) {
+      int b, mp, split;
+      tc_decode(p, item, b, mp, split);
+      const float* th = l2.theta + (int64_t)b * l2.P;
+      if (eall < H) {
+        const int h = eall;
+        const float* src = th + l2.w2_off + (int64_t)h * C;
+        const uint32_t dst = smem_u32(W2_s + buf * 256 * CP + w2_slot<CP>(h, 0));
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+          if (c < C)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(((c >> 2) * 16 + (c & 3)) * 4)),
+                         "l"(src + c) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(bias_s + buf * 256 + h)),
+                     "l"(p.bias + (int64_t)b * p.bias_stride + h) : "memory");
+      }
+      if (eall < C)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(b2_s + buf * 16 + eall)),
+                     "l"(th + l2.b2_off + eall) : "memory");
+    };
+    if (cluster_id < p.total_items) fetch_consts(cluster_id, 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < p.total_items; item += n_clusters) {
       int b, mp, split;
       tc_decode(p, item, b, mp, split);
       const int mt = mp * 2 + (int)rank;
-      const int row = mt * 128 + et;
-      const bool valid = row < p.M_valid;
       float* bs = bias_s + acc * 256;
       float* b2b = b2_s + acc * 16;
       float* W2b = W2_s + acc * 256 * CP;
-      {
-        // per-chain constants; buffer [acc] was last read two items ago (ordered by the barriers below)
-        const float* th = l2.theta + (int64_t)b * l2.P;
-        for (int i = eall; i < H * CP; i += 512) {
-          const int h = i / CP, c = i - h * CP;
-          W2b[i] = (c < C) ? th[l2.w2_off + (int64_t)h * C + c] : 0.f;
-        }
-        for (int c = eall; c < H; c += 512) bs[c] = p.bias[(int64_t)b * p.bias_stride + c];
-        if (eall < 16) b2b[eall] = (eall < C) ? th[l2.b2_off + eall] : 0.f;
-      }
-      asm volatile("bar.sync 1, 512;" ::: "memory");             // constants visible; zx_s readers of the last item done
+      asm volatile("cp.async.wait_all;" ::: "memory");           // this thread's share of the constants has landed
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // constants visible; zx_s readers of the last item done
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      // ---- phase A
-      const int64_t blk = ((int64_t)b * p.out_tiles + mt) * H;    // first hidden-unit row of this (chain, tile) block
-      float2 z[CP / 2];
+      // (hidden unit hbase, this lane's first row pair) inside this (chain, tile) block, in bf16x2 words
+      const int64_t blk_w = (((((int64_t)b * p.out_tiles + mt) * H) + hbase) * 128 + pair_off) >> 1;
+      uint32_t* pa_hi = reinterpret_cast<uint32_t*>(p.out_hi) + blk_w;
+      uint32_t* pa_lo = reinterpret_cast<uint32_t*>(p.out_lo) + blk_w;
+      uint32_t* pz_hi = reinterpret_cast<uint32_t*>(l2.zt_hi) + blk_w;
+      uint32_t* pz_lo = reinterpret_cast<uint32_t*>(l2.zt_lo) + blk_w;
+      const float4* w4b = reinterpret_cast<const float4*>(W2b) + (((half * Hh) >> 3) * 2 * (CP / 4)) * 4 + t;
+      const float* bsb = bs + hbase;
+      // ---- phase A  (rows >= M_valid need no masking: their X rows are TMA zero fill, so a1 = relu(b1) stays
+      //      finite, and their dZ2 is zero, which zeroes dZ1 and every gradient contribution)
+      float2 z[4][CP / 2];
 #pragma unroll
-      for (int c = 0; c < CP / 2; ++c) z[c] = make_float2(0.f, 0.f);
-      uint32_t mask[2] = {0u, 0u};
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        if (ch * 32 < Hq) {
-          const int c0 = q * Hq + ch * 32;
-          float v[32];
-          tc_ld32(tmem_base + lane_base + (uint32_t)(acc * 256 + c0), v);
-          uint16_t* ohi = a_hi + (blk + c0) * 128 + et;
-          uint16_t* olo = a_lo + (blk + c0) * 128 + et;
-          const float4* bias4 = reinterpret_cast<const float4*>(bs + c0);
+        for (int c = 0; c < CP / 2; ++c) z[r][c] = make_float2(0.f, 0.f);
+      uint32_t mask[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch * 32 < Hh) {
+          const uint32_t col = (uint32_t)(acc * 256 + half * Hh + ch * 32);
+          float v[32];                                             // [rows g, g+8 | rows g+16, g+24][4 col blocks][2 rows][2 cols]
+          tc_ld_16x256b_x4(tmem_base + lane_addr + col, v);
+          tc_ld_16x256b_x4(tmem_base + lane_addr + (16u << 16) + col, v + 16);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           uint32_t m = 0u;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = bias4[j4];
-            const float bj[4] = {bb.x, bb.y, bb.z, bb.w};
+          for (int kb = 0; kb < 4; ++kb) {
+            const float2 bb = *reinterpret_cast<const float2*>(bsb + ch * 32 + 8 * kb);
+            float a[4][2];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 * 4 + jj;
-              float a = fmaxf(v[j] + bj[jj], 0.f);
-              a = valid ? a : 0.f;
-              m |= (a > 0.f ? 1u : 0u) << j;
-              __nv_bfloat16 hb, lb;
-              split_bf16(a, hb, lb);
-              ohi[j * 128] = __bfloat16_as_ushort(hb);
-              olo[j * 128] = __bfloat16_as_ushort(lb);
-              const float2 aa = make_float2(a, a);
-              const float4* w4 = reinterpret_cast<const float4*>(W2b + (c0 + j) * CP);
+            for (int r = 0; r < 4; ++r) {
+              const float* vv = v + (r >> 1) * 16 + kb * 4 + (r & 1) * 2;
+              a[r][0] = fmaxf(vv[0] + bb.x, 0.f);
+              a[r][1] = fmaxf(vv[1] + bb.y, 0.f);
+              m |= (a[r][0] > 0.f ? 1u : 0u) << (kb * 8 + r * 2);
+              m |= (a[r][1] > 0.f ? 1u : 0u) << (kb * 8 + r * 2 + 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              // logits: one W2 row from shared memory feeds this thread's 4 rows
+              const float4* w4 = w4b + (((ch * 4 + kb) * 2 + i) * (CP / 4)) * 4;
 #pragma unroll
               for (int c4 = 0; c4 < CP / 4; ++c4) {
-                const float4 w = w4[c4];
-                z[2 * c4] = __ffma2_rn(aa, make_float2(w.x, w.y), z[2 * c4]);
-                z[2 * c4 + 1] = __ffma2_rn(aa, make_float2(w.z, w.w), z[2 * c4 + 1]);
+                const float4 w = w4[c4 * 4];
+                const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const float2 aa = make_float2(a[r][i], a[r][i]);
+                  z[r][2 * c4] = __ffma2_rn(aa, w01, z[r][2 * c4]);
+                  z[r][2 * c4 + 1] = __ffma2_rn(aa, w23, z[r][2 * c4 + 1]);
+                }
               }
+              // A1^T: swap rows with lane g^1 so that this lane owns two row pairs of hidden unit hbase + ...
+              const float s0 = __shfl_xor_sync(0xffffffffu, odd ? a[0][i] : a[1][i], 4);
+              const float s1 = __shfl_xor_sync(0xffffffffu, odd ? a[2][i] : a[3][i], 4);
+              uint32_t hw0, lw0, hw1, lw1;
+              split_pair(odd ? s0 : a[0][i], odd ? a[1][i] : s0, hw0, lw0);
+              split_pair(odd ? s1 : a[2][i], odd ? a[3][i] : s1, hw1, lw1);
+              const int w_off = (ch * 32 + 8 * kb + i) * 64;
+              pa_hi[w_off] = hw0; pa_lo[w_off] = lw0;
+              pa_hi[w_off + 8] = hw1; pa_lo[w_off + 8] = lw1;
             }
           }
           mask[ch] = m;
@@ -1126,69 +1207,107 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       // the accumulator is no longer needed: hand it back to the MMA warp before the rest of the epilogue
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
-      // ---- exchange the partial logits of the row's 4 threads
+      if (lane == 0) mbar_arrive_leader_relaxed(&tmem_empty[acc]);
+      // next item's constants fly while this item's reductions and phase B run; buffer [acc ^ 1] was last read in
+      // the previous item, which every epilogue thread has left (they all passed this item's bar.sync 1)
+      if (item + n_clusters < p.total_items) fetch_consts(item + n_clusters, acc ^ 1);
+      // ---- partial logits: quad reduce-scatter (fixed order), lane t keeps row r_own
+      float zo[CP];
+      {
+        const bool b0 = t & 1, b1 = t & 2;
 #pragma unroll
-      for (int c = 0; c < CP / 2; ++c) {
-        zx_s[(q * CP + 2 * c) * 128 + et] = z[c].x;
-        zx_s[(q * CP + 2 * c + 1) * 128 + et] = z[c].y;
+        for (int c = 0; c < CP; ++c) {
+          const float z0 = (c & 1) ? z[0][c >> 1].y : z[0][c >> 1].x, z1 = (c & 1) ? z[1][c >> 1].y : z[1][c >> 1].x;
+          const float z2v = (c & 1) ? z[2][c >> 1].y : z[2][c >> 1].x, z3 = (c & 1) ? z[3][c >> 1].y : z[3][c >> 1].x;
+          // stage 1 (xor 1): lanes with t&1 == 0 keep rows {0,1}, the others rows {2,3}
+          float k0 = b0 ? z2v : z0, k1 = b0 ? z3 : z1;
+          const float g0 = __shfl_xor_sync(0xffffffffu, b0 ? z0 : z2v, 1);
+          const float g1 = __shfl_xor_sync(0xffffffffu, b0 ? z1 : z3, 1);
+          k0 = b0 ? g0 + k0 : k0 + g0;                            // always (t even) + (t odd)
+          k1 = b0 ? g1 + k1 : k1 + g1;
+          // stage 2 (xor 2): lanes with t&2 == 0 keep the first of their two rows
+          const float kk = b1 ? k1 : k0;
+          const float gg = __shfl_xor_sync(0xffffffffu, b1 ? k0 : k1, 2);
+          zo[c] = b1 ? gg + kk : kk + gg;                         // always (t < 2) + (t >= 2)
+        }
       }
-      asm volatile("bar.sync 2, 512;" ::: "memory");
+      // ---- the two column halves meet in shared memory
+#pragma unroll
+      for (int c = 0; c < CP; ++c) zx_s[(half * CP + c) * 128 + row_own] = zo[c];
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       float zf[CP], dz[CP];
 #pragma unroll
-      for (int c = 0; c < CP; ++c)
-        zf[c] = (((b2b[c] + zx_s[c * 128 + et]) + zx_s[(CP + c) * 128 + et]) + zx_s[(2 * CP + c) * 128 + et]) +
-                zx_s[(3 * CP + c) * 128 + et];
-      double loss_r = 0.0;
-      l2_loss_dz<CP>(l2, row, valid, zf, dz, loss_r, invN);
-      if (q == 0) {
-        // dZ2^T for the dW2 GEMM, per-warp partial sums of the loss and of db2
-        const int64_t blk2 = ((int64_t)b * p.out_tiles + mt) * L2_CMAX;
+      for (int c = 0; c < CP; ++c) zf[c] = (b2b[c] + zx_s[c * 128 + row_own]) + zx_s[(CP + c) * 128 + row_own];
+      float loss_r = 0.f;
+      const int row_g = mt * 128 + row_own;
+      l2_loss_dz<CP>(l2, row_g, row_g < p.M_valid, zf, dz, loss_r, invN);
+      if (half == 0) {
+        // dZ2^T for the dW2 GEMM, per-warp partial sums of the loss and of db2 (one warp == 32 rows)
+        const int64_t blk2 = (((int64_t)b * p.out_tiles + mt) * L2_CMAX) * 128 + row_own;
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
           __nv_bfloat16 hb, lb;
           split_bf16(dz[c], hb, lb);
-          z2_hi[(blk2 + c) * 128 + et] = __bfloat16_as_ushort(hb);
-          z2_lo[(blk2 + c) * 128 + et] = __bfloat16_as_ushort(lb);
+          z2_hi[blk2 + c * 128] = __bfloat16_as_ushort(hb);
+          z2_lo[blk2 + c * 128] = __bfloat16_as_ushort(lb);
         }
-        const int64_t g = (int64_t)b * l2.n_groups + mt * 4 + quad;
+        const int64_t grp = (int64_t)b * l2.n_groups + mt * 4 + quad;
+        float mine = 0.f;                                         // lane c keeps the sum of class c
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
-          const float s = warp_sum(dz[c]);
-          if (lane == 0) l2.b2_partial[g * L2_CMAX + c] = s;
+          const float sm = warp_sum(dz[c]);
+          if (lane == c) mine = sm;
         }
-        double ls = loss_r;
+        if (lane < CP) l2.b2_partial[grp * L2_CMAX + lane] = mine;
+        const float ls = warp_sum(loss_r);                        // 32 rows in fp32; the per-chain total is summed in fp64
+        if (lane == 0) l2.loss_partial[grp] = (double)ls;
+      }
+      // ---- quad all-gather of dZ2: row r lives in lane t = (r >> 1) | ((r & 1) << 1)
+      float2 dzp[4][CP / 2];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
-        if (lane == 0) l2.loss_partial[g] = ls;
+      for (int r = 0; r < 4; ++r) {
+        const int src = (lane & ~3) | ((r >> 1) | ((r & 1) << 1));
+#pragma unroll
+        for (int c = 0; c < CP / 2; ++c) {
+          dzp[r][c].x = __shfl_sync(0xffffffffu, dz[2 * c], src);
+          dzp[r][c].y = __shfl_sync(0xffffffffu, dz[2 * c + 1], src);
+        }
       }
       // ---- phase B: dZ1 = (dZ2 W2^T) * relu'(z1)
-      float2 dzp[CP / 2];
 #pragma unroll
-      for (int c = 0; c < CP / 2; ++c) dzp[c] = make_float2(dz[2 * c], dz[2 * c + 1]);
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        if (ch * 32 < Hq) {
-          const int c0 = q * Hq + ch * 32;
-          uint16_t* ohi = zt_hi + (blk + c0) * 128 + et;
-          uint16_t* olo = zt_lo + (blk + c0) * 128 + et;
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch * 32 < Hh) {
           const uint32_t m = mask[ch];
-#pragma unroll 8
-          for (int j = 0; j < 32; ++j) {
-            const float4* w4 = reinterpret_cast<const float4*>(W2b + (c0 + j) * CP);
-            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int c4 = 0; c4 < CP / 4; ++c4) {
-              const float4 w = w4[c4];
-              s0 = __ffma2_rn(dzp[2 * c4], make_float2(w.x, w.y), s0);
-              s1 = __ffma2_rn(dzp[2 * c4 + 1], make_float2(w.z, w.w), s1);
+          for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float4* w4 = w4b + (((ch * 4 + kb) * 2 + i) * (CP / 4)) * 4;
+              float2 s[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) s[r] = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int c4 = 0; c4 < CP / 4; ++c4) {
+                const float4 w = w4[c4 * 4];
+                const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  s[r] = __ffma2_rn(dzp[r][2 * c4], w01, s[r]);
+                  s[r] = __ffma2_rn(dzp[r][2 * c4 + 1], w23, s[r]);
+                }
+              }
+              float d[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) d[r] = ((m >> (kb * 8 + r * 2 + i)) & 1u) ? s[r].x + s[r].y : 0.f;
+              const float s0 = __shfl_xor_sync(0xffffffffu, odd ? d[0] : d[1], 4);
+              const float s1 = __shfl_xor_sync(0xffffffffu, odd ? d[2] : d[3], 4);
+              uint32_t hw0, lw0, hw1, lw1;
+              split_pair(odd ? s0 : d[0], odd ? d[1] : s0, hw0, lw0);
+              split_pair(odd ? s1 : d[2], odd ? d[3] : s1, hw1, lw1);
+              const int w_off = (ch * 32 + 8 * kb + i) * 64;
+              pz_hi[w_off] = hw0; pz_lo[w_off] = lw0;
+              pz_hi[w_off + 8] = hw1; pz_lo[w_off + 8] = lw1;
             }
-            float d = (s0.x + s0.y) + (s1.x + s1.y);
-            d = ((m >> j) & 1u) ? d : 0.f;
-            __nv_bfloat16 hb, lb;
-            split_bf16(d, hb, lb);
-            ohi[j * 128] = __bfloat16_as_ushort(hb);
-            olo[j * 128] = __bfloat16_as_ushort(lb);
           }
         }
       }
