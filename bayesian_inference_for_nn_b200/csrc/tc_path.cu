@@ -391,8 +391,8 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // of the B stage (the tensor core reads the peer's half through the pair), so the L2->SM traffic per
 // flop is the same as the two-accumulator kernel above, but an accumulator is only 128 x H per SM:
 // TMEM holds TWO of them and the epilogue of item i overlaps the MMAs of item i+1.
-// Roles per CTA: warp 0 TMA producer (own A rows, own half of B; completion is signalled on the
-// leader CTA's barrier), warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator, warps 4-11 epilogue.
+// Roles per CTA: warp 8 TMA producer (own A rows, own half of B; completion is signalled on the
+// leader CTA's barrier), warp 9 MMA issuer (leader CTA only), warp 10 TMEM allocator, warps 0-7 epilogue.
 // ------------------------------------------------------------------------------------------
 constexpr int TP_STAGES = 6;
 constexpr int TP_STAGE_BYTES = 2 * TC_A_TILE_BYTES + 2 * 8192;     // A hi/lo (128 rows) + half of B hi/lo (<=128 rows)
@@ -491,26 +491,26 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * TP_STAGES + 4);
   float* bias_s = (float*)(smem + TP_STAGES * TP_STAGE_BYTES + 1024);   // [2][256]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int nk = (p.K + TC_BK - 1) / TC_BK;
   const int half_rows = p.H >> 1;                // rows of B this CTA stages
   const uint32_t cta_bytes = 2 * TC_A_TILE_BYTES + 2 * (uint32_t)half_rows * TC_BK * 2;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < TP_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 16); mbar_init(&tmem_empty[1], 16);   // 8 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 10) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -521,7 +521,9 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  // warp roles: 0-7 epilogue, 8 TMA producer, 9 MMA issuer, 10 TMEM allocator (the SMSP arbiter favours the
+  // highest warp id: the single-thread issuers must not queue behind the epilogue warps)
+  if (warp == 8) {
     // ===== TMA producer (both CTAs) =====
     if (lane == 0) {
       int stage = 0;
@@ -550,7 +552,7 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ===== MMA issuer (leader CTA only) =====
     if (rank == 0 && lane == 0) {
       // D=F32, A=B=BF16, K-major, N = H, M = 256 across the pair
@@ -587,11 +589,11 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ===== epilogue (both CTAs): 8 warps = 4 lane quadrants x 2 column halves of this CTA's 128 x H tile =====
-    const int half = (warp - 4) >> 2;
-    const int et = (threadIdx.x - 128) & 127;
-    const int eall = threadIdx.x - 128;                           // 0..255
+    const int half = warp >> 2;
+    const int et = threadIdx.x & 127;
+    const int eall = threadIdx.x;                                 // 0..255
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -674,7 +676,7 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                            // the peer may still be reading this CTA's shared memory
-  if (warp == 2) {
+  if (warp == 10) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -704,8 +706,13 @@ __global__ void k_split_rows(const float* src, int64_t R, int C, int64_t lds, __
 
 // src [R, C] fp32 (batch stride sb) -> transposed hi/lo [C(+ones row), Rpad] bf16 per batch element.
 // grid (ceil(C/32), ceil(R/32), batch), block (32, 8)
+// Row order inside a 128-row block as the fused G1+layer-2 epilogue stores it: the 4 rows {g, g+8, g+16, g+24} of a
+// 32-row TMEM quadrant that one thread owns become 4 CONSECUTIVE elements (one 8-byte store).  Any operand that is
+// contracted against those arrays over the data rows ([X^T;1] in the dW1 GEMM) must use the same order.
+__host__ __device__ __forceinline__ int fused_row_pos(int r) { return (r & ~31) | ((r & 7) << 2) | ((r >> 3) & 3); }
+
 __global__ void k_split_transpose(const float* src, int64_t sb, int R, int C, int64_t lds, __nv_bfloat16* hi,
-                                  __nv_bfloat16* lo, int64_t db, int64_t ldd) {
+                                  __nv_bfloat16* lo, int64_t db, int64_t ldd, int perm = 0) {
   __shared__ float t[32][33];
   const float* s = src + (int64_t)blockIdx.z * sb;
   int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -719,13 +726,17 @@ __global__ void k_split_transpose(const float* src, int64_t sb, int R, int C, in
     if (c < C && r < R) {
       __nv_bfloat16 h, l;
       split_bf16(t[threadIdx.x][i], h, l);
-      int64_t o = (int64_t)blockIdx.z * db + (int64_t)c * ldd + r;
+      int64_t o = (int64_t)blockIdx.z * db + (int64_t)c * ldd + (perm ? fused_row_pos(r) : r);
       hi[o] = h;
       lo[o] = l;
     }
   }
 }
 
+__global__ void k_fill_ones_perm(__nv_bfloat16* p, int n) {      // p[fused_row_pos(r)] = 1 for r < n
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[fused_row_pos(i)] = __float2bfloat16_rn(1.0f);
+}
 __global__ void k_fill_bf16(__nv_bfloat16* p, int64_t n, float v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = __float2bfloat16_rn(v);
@@ -937,10 +948,12 @@ __global__ void __launch_bounds__(128, 4) k_layer2(Layer2Params p) {
 //   reduce   partial logits: quad reduce-scatter by shuffles (lane t ends up with ONE complete row), the two
 //            column halves meet in shared memory; softmax-CE / MSE and dZ2 once per row; quad all-gather of dZ2
 //   phase B  dZ1 = (dZ2 W2^T) * mask -> dZ1^T hi/lo for the dW1 GEMM
-// Transposed stores: lanes g and g^1 swap half of their rows so that each lane owns row PAIRS (one 32-bit bf16x2
-// word); per store instruction the 8 lanes sharing t write one full 32-byte sector of a hidden unit's row block.
+// Transposed stores: inside a 128-row block the rows are kept in the order fused_row_pos() — the 4 rows one thread
+// owns are adjacent, so a hidden unit's 4 values leave as ONE 8-byte store and the 8 lanes sharing t write 64
+// contiguous bytes; the dW2 GEMM contracts two arrays written this way, the dW1 GEMM uses an [X^T;1] copy in the
+// same row order.
 // ------------------------------------------------------------------------------------------
-constexpr int TF_THREADS = 384;                 // 4 control warps + 8 epilogue warps
+constexpr int TF_THREADS = 384;                 // 8 epilogue warps + 4 control warps
 template <int CP> struct TfCfg {
   static constexpr int STAGES = 5;
   static constexpr int W2_BYTES = 2 * 256 * CP * 4;            // [2][256*CP] fp32 (fragment-interleaved), double-buffered
@@ -1003,19 +1016,19 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   const int half_rows = H >> 1;
   const uint32_t cta_bytes = 2 * TC_A_TILE_BYTES + 2 * (uint32_t)half_rows * TC_BK * 2;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 16); mbar_init(&tmem_empty[1], 16);   // 8 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 10) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -1026,7 +1039,11 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  // warp roles: 0-7 epilogue, 8 TMA producer, 9 MMA issuer, 10 TMEM allocator.  The SMSP arbiter favours the
+  // highest warp id, so the single-thread issuers sit ABOVE the epilogue warps and never queue behind them.
+  if (warp >= 8) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");                  // the control warpgroup gives registers ...
+   if (warp == 8) {
     // ===== TMA producer (both CTAs): own 128 rows of X, own half of W1^T[b] =====
     if (lane == 0) {
       int stage = 0;
@@ -1049,7 +1066,7 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ===== MMA issuer (leader CTA only) =====
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(H >> 3) << 17) | ((256u >> 4) << 24);
@@ -1082,20 +1099,21 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+   }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");                // ... to the two epilogue warpgroups
     // ===== fused epilogue (both CTAs): 8 warps = 4 TMEM lane quadrants x 2 halves of the hidden units =====
-    const int half = (warp - 4) >> 2;
+    const int half = warp >> 2;
     const int quad = warp & 3;                                    // TMEM lane quadrant (hardware: warp % 4)
     const int g = lane >> 2, t = lane & 3;
-    const int odd = g & 1;
-    const int eall = threadIdx.x - 128;                           // 0..255
+    const int eall = threadIdx.x;                                 // 0..255
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int Hh = H >> 1;                                        // hidden units per half: 64 or 128
     const int C = l2.C;
     const float invN = l2.scale / (float)l2.N;
     const int r_own = 2 * (t & 1) + (t >> 1);                     // the row (of this thread's 4) whose logits it completes
     const int row_own = quad * 32 + g + 8 * r_own;                // ... inside the 128-row tile
-    const int pair_off = quad * 32 + (odd ? g + 7 : g);           // tile row of this lane's first row pair (second: +16)
+    const int pos0 = quad * 32 + 4 * g;                           // storage position of this thread's 4 rows (fused_row_pos)
     const int hbase = half * Hh + 2 * t;                          // this thread's first hidden unit
     uint16_t* z2_hi = reinterpret_cast<uint16_t*>(l2.z2_hi);
     uint16_t* z2_lo = reinterpret_cast<uint16_t*>(l2.z2_lo);
@@ -1138,12 +1156,12 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       asm volatile("bar.sync 1, 256;" ::: "memory");             // constants visible; zx_s readers of the last item done
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      // (hidden unit hbase, this lane's first row pair) inside this (chain, tile) block, in bf16x2 words
-      const int64_t blk_w = (((((int64_t)b * p.out_tiles + mt) * H) + hbase) * 128 + pair_off) >> 1;
-      uint32_t* pa_hi = reinterpret_cast<uint32_t*>(p.out_hi) + blk_w;
-      uint32_t* pa_lo = reinterpret_cast<uint32_t*>(p.out_lo) + blk_w;
-      uint32_t* pz_hi = reinterpret_cast<uint32_t*>(l2.zt_hi) + blk_w;
-      uint32_t* pz_lo = reinterpret_cast<uint32_t*>(l2.zt_lo) + blk_w;
+      // (hidden unit hbase, this thread's 4 rows) inside this (chain, tile) block, in 8-byte units (4 bf16)
+      const int64_t blk_w = (((((int64_t)b * p.out_tiles + mt) * H) + hbase) * 128 + pos0) >> 2;
+      uint2* pa_hi = reinterpret_cast<uint2*>(p.out_hi) + blk_w;
+      uint2* pa_lo = reinterpret_cast<uint2*>(p.out_lo) + blk_w;
+      uint2* pz_hi = reinterpret_cast<uint2*>(l2.zt_hi) + blk_w;
+      uint2* pz_lo = reinterpret_cast<uint2*>(l2.zt_lo) + blk_w;
       const float4* w4b = reinterpret_cast<const float4*>(W2b) + (((half * Hh) >> 3) * 2 * (CP / 4)) * 4 + t;
       const float* bsb = bs + hbase;
       // ---- phase A  (rows >= M_valid need no masking: their X rows are TMA zero fill, so a1 = relu(b1) stays
@@ -1190,15 +1208,13 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                   z[r][2 * c4 + 1] = __ffma2_rn(aa, w23, z[r][2 * c4 + 1]);
                 }
               }
-              // A1^T: swap rows with lane g^1 so that this lane owns two row pairs of hidden unit hbase + ...
-              const float s0 = __shfl_xor_sync(0xffffffffu, odd ? a[0][i] : a[1][i], 4);
-              const float s1 = __shfl_xor_sync(0xffffffffu, odd ? a[2][i] : a[3][i], 4);
+              // A1^T: this thread's 4 rows of hidden unit hbase + ... are adjacent in the block's row order
               uint32_t hw0, lw0, hw1, lw1;
-              split_pair(odd ? s0 : a[0][i], odd ? a[1][i] : s0, hw0, lw0);
-              split_pair(odd ? s1 : a[2][i], odd ? a[3][i] : s1, hw1, lw1);
-              const int w_off = (ch * 32 + 8 * kb + i) * 64;
-              pa_hi[w_off] = hw0; pa_lo[w_off] = lw0;
-              pa_hi[w_off + 8] = hw1; pa_lo[w_off + 8] = lw1;
+              split_pair(a[0][i], a[1][i], hw0, lw0);
+              split_pair(a[2][i], a[3][i], hw1, lw1);
+              const int w_off = (ch * 32 + 8 * kb + i) * 32;
+              __stcs(pa_hi + w_off, make_uint2(hw0, hw1));       // streaming: 18 GB per launch must not evict X / W1^T from L2
+              __stcs(pa_lo + w_off, make_uint2(lw0, lw1));
             }
           }
           mask[ch] = m;
@@ -1243,7 +1259,7 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       l2_loss_dz<CP>(l2, row_g, row_g < p.M_valid, zf, dz, loss_r, invN);
       if (half == 0) {
         // dZ2^T for the dW2 GEMM, per-warp partial sums of the loss and of db2 (one warp == 32 rows)
-        const int64_t blk2 = (((int64_t)b * p.out_tiles + mt) * L2_CMAX) * 128 + row_own;
+        const int64_t blk2 = (((int64_t)b * p.out_tiles + mt) * L2_CMAX) * 128 + pos0 + r_own;
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
           __nv_bfloat16 hb, lb;
@@ -1299,14 +1315,12 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               float d[4];
 #pragma unroll
               for (int r = 0; r < 4; ++r) d[r] = ((m >> (kb * 8 + r * 2 + i)) & 1u) ? s[r].x + s[r].y : 0.f;
-              const float s0 = __shfl_xor_sync(0xffffffffu, odd ? d[0] : d[1], 4);
-              const float s1 = __shfl_xor_sync(0xffffffffu, odd ? d[2] : d[3], 4);
               uint32_t hw0, lw0, hw1, lw1;
-              split_pair(odd ? s0 : d[0], odd ? d[1] : s0, hw0, lw0);
-              split_pair(odd ? s1 : d[2], odd ? d[3] : s1, hw1, lw1);
-              const int w_off = (ch * 32 + 8 * kb + i) * 64;
-              pz_hi[w_off] = hw0; pz_lo[w_off] = lw0;
-              pz_hi[w_off + 8] = hw1; pz_lo[w_off + 8] = lw1;
+              split_pair(d[0], d[1], hw0, lw0);
+              split_pair(d[2], d[3], hw1, lw1);
+              const int w_off = (ch * 32 + 8 * kb + i) * 32;
+              __stcs(pz_hi + w_off, make_uint2(hw0, hw1));
+              __stcs(pz_lo + w_off, make_uint2(lw0, lw1));
             }
           }
         }
@@ -1317,7 +1331,7 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 2) {
+  if (warp == 10) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -1468,7 +1482,9 @@ struct TcData {   // split bf16 operands derived from one [N, D] fp32 matrix res
   int64_t N = 0, Npad = 0;
   int D = 0;
   DevBuf<__nv_bfloat16> x_hi, x_lo, xt_hi, xt_lo;       // [N][D], [D+1][Npad]
+  DevBuf<__nv_bfloat16> xtq_hi, xtq_lo;                 // [D+1][Npad] with the fused epilogue's row order (fused_row_pos)
   CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo, mXTp_hi, mXTp_lo;   // mXTp: half-tile boxes for the hidden-major pair GEMM
+  CUtensorMap mXTq_hi, mXTq_lo, mXTqp_hi, mXTqp_lo;     // the same two views of xtq
 };
 struct TcState {
   TcData train, aux;                                    // resident training set / minibatch or test inputs
@@ -1598,6 +1614,18 @@ static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N,
     const int n_t = (D + 1 + 255) / 256, Ht = (((D + 1 + n_t - 1) / n_t) + 15) / 16 * 16;
     d.mXTp_hi = make_map(d.xt_hi.p, Npad, D + 1, Npad, Ht / 2);
     d.mXTp_lo = make_map(d.xt_lo.p, Npad, D + 1, Npad, Ht / 2);
+    if (fused_ok(h, m.layer[0].fan_out, m.layer[0].act)) {
+      d.xtq_hi.alloc((int64_t)(D + 1) * Npad); d.xtq_lo.alloc((int64_t)(D + 1) * Npad);
+      PYB_CUDA(cudaMemsetAsync(d.xtq_hi.p, 0, (size_t)(D + 1) * Npad * 2, h->stream));
+      PYB_CUDA(cudaMemsetAsync(d.xtq_lo.p, 0, (size_t)(D + 1) * Npad * 2, h->stream));
+      k_split_transpose<<<g2, blk, 0, h->stream>>>(X, 0, (int)N, D, D, d.xtq_hi.p, d.xtq_lo.p, 0, Npad, 1);
+      k_fill_ones_perm<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(d.xtq_hi.p + (int64_t)D * Npad, (int)N);
+      count_launch(h, 2);
+      d.mXTq_hi = make_map(d.xtq_hi.p, Npad, D + 1, Npad, 128);
+      d.mXTq_lo = make_map(d.xtq_lo.p, Npad, D + 1, Npad, 128);
+      d.mXTqp_hi = make_map(d.xtq_hi.p, Npad, D + 1, Npad, Ht / 2);
+      d.mXTqp_lo = make_map(d.xtq_lo.p, Npad, D + 1, Npad, Ht / 2);
+    }
   }
   d.ready = true;
 }
@@ -1767,8 +1795,8 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
         p.out = gr; p.out_stride = P;
       }
       p.total_items = nb * std::max(splits, 1) * n_t;
-      launch_gemm_tc(h, st->mZa_hi, st->mZa_lo, d.mXT_hi, d.mXT_lo, p, 2.0 * N * (double)(D + 1) * H * nb, &d.mXTp_hi,
-                     &d.mXTp_lo);
+      launch_gemm_tc(h, st->mZa_hi, st->mZa_lo, fused ? d.mXTq_hi : d.mXT_hi, fused ? d.mXTq_lo : d.mXT_lo, p,
+                     2.0 * N * (double)(D + 1) * H * nb, fused ? &d.mXTqp_hi : &d.mXTp_hi, fused ? &d.mXTqp_lo : &d.mXTp_lo);
     } else {
       TcGemmParams p = {};
       p.K = (int)Npad; p.n_mtiles = (D + 1 + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = nb; p.H = H;
@@ -1782,7 +1810,8 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
         p.out = gr; p.out_stride = P;
       }
       p.total_items = p.n_pairs * nb * std::max(splits, 1);
-      launch_gemm_tc(h, d.mXT_hi, d.mXT_lo, st->mZ_hi, st->mZ_lo, p, 2.0 * N * (double)(D + 1) * H * nb);
+      launch_gemm_tc(h, fused ? d.mXTq_hi : d.mXT_hi, fused ? d.mXTq_lo : d.mXT_lo, st->mZ_hi, st->mZ_lo, p,
+                     2.0 * N * (double)(D + 1) * H * nb);
     }
     if (splits > 1) {
       dim3 rg((unsigned)std::min<int64_t>((cnt1 + 255) / 256, 256), nb);
