@@ -176,6 +176,8 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_chain_batch = (int64_t)v;
   } else if (!strcmp(key, "tc_pair")) {
     h->opt_tc_pair = v != 0;
+  } else if (!strcmp(key, "tc_dual")) {
+    h->opt_tc_dual = v != 0;
   } else if (!strcmp(key, "tc_fuse")) {
     h->opt_tc_fuse = v != 0;
   } else if (!strcmp(key, "profile")) {

@@ -683,6 +683,180 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
+// Hidden-major gradient GEMM with TWO accumulators per CTA pair: D[h, f] = sum_r A[h, r] B[f, r] for two
+// adjacent feature tiles (bt, bt+1) of [X^T;1] at once.  The pair kernel above re-reads the chain's dZ1^T
+// (the A operand, 61 MB per chain) once per feature tile — 4 times at D+1 = 785 — and ncu shows it bound by
+// L2->SM bandwidth (64 GB per launch at ~5900 B/clk, tensor pipe 85.7 %).  Here every A stage feeds both
+// tiles (A traffic halves, 64 -> 47 GB); the two 256-column accumulators fill TMEM, so the epilogue is not
+// overlapped, which costs ~2 % at one epilogue per 8192-row split-K segment.
+// Roles: warps 0-7 epilogue (lane quadrant x accumulator), 8 TMA producer, 9 MMA issuer, 10 TMEM allocator.
+// ------------------------------------------------------------------------------------------
+constexpr int TD_STAGES = 4;
+constexpr int TD_STAGE_BYTES = 2 * TC_A_TILE_BYTES + 4 * 8192;     // A hi/lo (128 rows) + half of B hi/lo for two tiles
+constexpr int TD_SMEM_BYTES = TD_STAGES * TD_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
+
+__device__ __forceinline__ void td_decode(const TcGemmParams& p, int item, int& b, int& split, int& bt0, int& n_t) {
+  const int n_btp = (p.n_btiles + 1) >> 1;       // [split][chain][tile pair]: the shared operand's k-range stays in L2
+  const int btp = item % n_btp;
+  const int r = item / n_btp;
+  b = r % p.n_batch;
+  split = r / p.n_batch;
+  bt0 = 2 * btp;
+  n_t = (bt0 + 1 < p.n_btiles) ? 2 : 1;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1)
+tc_gemm_pair_dual_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                         const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stage_base = smem;
+  uint64_t* bars = (uint64_t*)(smem + TD_STAGES * TD_STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [TD_STAGES]   (leader CTA)
+  uint64_t* empty_bar = bars + TD_STAGES;        // [TD_STAGES]   (one per CTA)
+  uint64_t* tmem_full = bars + 2 * TD_STAGES;    // (one per CTA)
+  uint64_t* tmem_empty = bars + 2 * TD_STAGES + 1;   // (leader CTA: both epilogues have drained)
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * TD_STAGES + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  const int half_rows = p.H >> 1;                // rows of each B tile this CTA stages
+  const uint32_t b_bytes = (uint32_t)half_rows * TC_BK * 2;
+
+  if (warp == 8 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+  }
+  if (warp == 9 && lane == 0) {
+    for (int s = 0; s < TD_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 16);                   // 8 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 10) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    // ===== TMA producer (both CTAs): own 128 hidden units of dZ1^T[b], own half of each feature tile =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+        int b, split, bt0, n_t;
+        td_decode(p, item, b, split, bt0, n_t);
+        const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
+        const int arow = (int)rank * 128;
+        const uint32_t cta_bytes = 2 * TC_A_TILE_BYTES + 2 * (uint32_t)n_t * b_bytes;
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = stage_base + stage * TD_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);
+          const int k0 = kc * TC_BK;
+          tma_load_3d_pair(st, &tmA_hi, &full_bar[stage], k0 & 127, arow, b * p.k_tiles + (k0 >> 7));
+          tma_load_3d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0 & 127, arow, b * p.k_tiles + (k0 >> 7));
+          for (int j = 0; j < n_t; ++j) {
+            const int brow = p.b_row0 + (bt0 + j) * p.H + (int)rank * half_rows;
+            tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES + (2 * j) * 8192, &tmB_hi, &full_bar[stage], k0, brow);
+            tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES + (2 * j + 1) * 8192, &tmB_lo, &full_bar[stage], k0, brow);
+          }
+          if (++stage == TD_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.H >> 3) << 17) | ((256u >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const int k_tail = p.K - (nk - 1) * TC_BK;
+      for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+        int b, split, bt0, n_t;
+        td_decode(p, item, b, split, bt0, n_t);
+        const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
+        mbar_wait(tmem_empty, acc_phase ^ 1);                     // both epilogues drained the accumulators
+        tc_fence_after();
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + stage * TD_STAGE_BYTES);
+          const int nks = (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t koff = ks * 32;
+            const uint64_t ah = make_smem_desc_sw64(st + koff);
+            const uint64_t al = make_smem_desc_sw64(st + TC_A_TILE_BYTES + koff);
+            const uint32_t accum = (kc != kc_begin) || (ks != 0);
+            for (int j = 0; j < n_t; ++j) {
+              const uint64_t bh = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + (2 * j) * 8192 + koff);
+              const uint64_t bl = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + (2 * j + 1) * 8192 + koff);
+              const uint32_t d = tmem_base + (uint32_t)j * 256;
+              tc_mma_bf16_pair(d, ah, bh, idesc, accum);
+              tc_mma_bf16_pair(d, al, bh, idesc, 1);
+              tc_mma_bf16_pair(d, ah, bl, idesc, 1);
+            }
+          }
+          tc_commit_pair(&empty_bar[stage]);
+          if (++stage == TD_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(tmem_full);
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 8) {
+    // ===== epilogue (both CTAs): warp = (accumulator, lane quadrant); transposed partial-sum stores =====
+    const int j = warp >> 2;                                      // which accumulator / feature tile of the pair
+    const int et = threadIdx.x & 127;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      int b, split, bt0, n_t;
+      td_decode(p, item, b, split, bt0, n_t);
+      mbar_wait(tmem_full, acc_phase);
+      tc_fence_after();
+      if (j < n_t) {
+        const int row = (int)rank * 128 + et;                     // hidden unit
+        const int colbase = p.b_row0 + (bt0 + j) * p.H;
+        float* ob = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + row;
+        for (int c0 = 0; c0 < p.H; c0 += 32) {
+          float v[32];
+          tc_ld32(tmem_base + lane_base + (uint32_t)(j * 256 + c0), v);
+          if (row < p.M_valid) {
+            float* o = ob + (int64_t)(colbase + c0) * p.out_ld;
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (colbase + c0 + q < p.n_cols_total && c0 + q < p.H) o[(int64_t)q * p.out_ld] = v[q];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tmem_empty);
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 10) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // SIMT helpers around the GEMMs
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -1558,6 +1732,17 @@ static void launch_gemm_tc(pyb_handle* h, const CUtensorMap& a_hi, const CUtenso
                 (p.split_stride % 4 == 0);
   int grid = std::min(p.total_items, h->sm_count);
   prof_begin(h);
+  if (bp_hi && bp_lo && pair_ok(h, p) && p.n_btiles > 1 && p.epi == EPI_STORE && p.transpose_out && h->opt_tc_dual &&
+      p.H <= 256 && (p.H / 2) * TC_BK * 2 <= 8192) {
+    // hidden-major gradient GEMM: two feature tiles per item share every A stage
+    p.total_items = p.n_batch * p.k_splits * ((p.n_btiles + 1) / 2);
+    grid = std::min(2 * p.total_items, (h->sm_count / 2) * 2);
+    PYB_CUDA(cudaFuncSetAttribute(tc_gemm_pair_dual_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_BYTES));
+    tc_gemm_pair_dual_bf16x3<<<grid, TP_THREADS, TD_SMEM_BYTES, h->stream>>>(a_hi, a_lo, *bp_hi, *bp_lo, p);
+    prof_end(h, flops);
+    count_launch(h);
+    return;
+  }
   if (bp_hi && bp_lo && pair_ok(h, p)) {
     grid = std::min(2 * p.total_items, (h->sm_count / 2) * 2);
     if (p.epi == EPI_STORE) launch_pair_inst<EPI_STORE, 0>(h, grid, a_hi, a_lo, *bp_hi, *bp_lo, p);
