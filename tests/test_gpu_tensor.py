@@ -94,7 +94,11 @@ def move_off_relu_kinks(q, X, D, H, margin=1e-3):
 
 
 CASES = [(784, 256, 10, 512, 3, "relu", "ce"), (784, 128, 10, 300, 2, "relu", "ce"), (64, 32, 4, 1000, 5, "tanh", "ce"),
-         (128, 64, 3, 257, 2, "sigmoid", "mse"), (784, 256, 10, 128, 1, "relu", "ce")]
+         (128, 64, 3, 257, 2, "sigmoid", "mse"), (784, 256, 10, 128, 1, "relu", "ce"),
+         # the fused layer-1 GEMM + layer-2 epilogue (relu, H = 128/256) in every class padding CP = 4, 8, 12, 16,
+         # both losses, ragged row counts (last tile partly / wholly zero fill) and an odd chain count
+         (64, 128, 2, 129, 3, "relu", "ce"), (96, 256, 7, 1000, 2, "relu", "ce"), (64, 128, 16, 640, 2, "relu", "ce"),
+         (128, 256, 3, 385, 5, "relu", "mse"), (784, 256, 12, 257, 1, "relu", "ce")]
 
 
 @pytest.mark.parametrize("D,H,Cc,N,S,act,loss", CASES)
@@ -125,6 +129,33 @@ def test_tensor_path_logprob_and_gradient(oracle, D, H, Cc, N, S, act, loss):
     U1, _, g1 = eng.hmc_eval(q)
     np.testing.assert_array_equal(U, U1)
     np.testing.assert_array_equal(g, g1)
+
+
+@pytest.mark.parametrize("H,Cc,N,S", [(256, 10, 700, 4), (128, 5, 300, 3)])
+def test_fused_epilogue_agrees_with_the_unfused_kernels(oracle, H, Cc, N, S):
+    """tc_fuse=0 runs G1, k_layer2 and the dW2 GEMM as separate kernels, tc_dual=0 the single-accumulator dW1 GEMM:
+    same arithmetic in a different summation order, so the results agree far inside the parity budget."""
+    O = oracle
+    spec, prob, q, out_act, _ = problem(O, 784, H, Cc, N, S, seed=H + N)
+    eng = engine(784, H, Cc, "relu", out_act)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.set_option("path", _lib.PATH_TENSOR)
+    U, ls, g = eng.hmc_eval(q)
+    for key in ("tc_fuse", "tc_dual"):
+        eng.set_option(key, 0)
+        eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+        U0, ls0, g0 = eng.hmc_eval(q)
+        eng.set_option(key, 1)
+        np.testing.assert_allclose(U0, U, rtol=2e-6)
+        np.testing.assert_allclose(ls0, ls, rtol=2e-6)
+        for s in range(S):
+            assert rel_err(g0[s], g[s]) < 1e-5, (key, s, rel_err(g0[s], g[s]))
+    # repeatable bit for bit
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    U2, _, g2 = eng.hmc_eval(q)
+    np.testing.assert_array_equal(U, U2)
+    np.testing.assert_array_equal(g, g2)
 
 
 def test_tensor_path_hmc_iteration_matches_oracle(oracle):
