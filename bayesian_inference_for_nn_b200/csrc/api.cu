@@ -145,7 +145,13 @@ int pyb_destroy(pyb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   tc_release(h);
+  if (h->svgd.comm_stream) cudaStreamSynchronize(h->svgd.comm_stream);
   if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }
+  if (h->svgd.comm_stream) {
+    cudaStreamDestroy(h->svgd.comm_stream); h->svgd.comm_stream = nullptr;
+    cudaEventDestroy(h->svgd.ev_fork); cudaEventDestroy(h->svgd.ev_theta); cudaEventDestroy(h->svgd.ev_grad);
+    h->svgd.ev_fork = h->svgd.ev_theta = h->svgd.ev_grad = nullptr;
+  }
   for (auto* b : h->ws.act) delete b;
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   h->ws.act.clear();

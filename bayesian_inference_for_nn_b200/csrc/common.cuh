@@ -217,6 +217,10 @@ struct SvgdState {
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
   DevBuf<float> theta_all, g_all;
+  // the two all-gathers run on their own stream: particles while the local gradients are computed, gradients
+  // while the Gram matrix is built (the exchange step is comm-bound at 8 GPUs unless overlapped)
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_theta = nullptr, ev_grad = nullptr;
 };
 
 struct Workspace {

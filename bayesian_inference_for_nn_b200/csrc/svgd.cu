@@ -325,8 +325,9 @@ static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t
 }
 
 // phi for local rows [r0, r0+Sl) of the global particle matrix X_all [St,P] with gradients G_all
+// wait_g: event after which G_all is complete (sharded runs gather it on the comm stream while the Gram is built)
 static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all, int r0, int Sl, int St,
-                          float* phi_local, double* h_host_out) {
+                          float* phi_local, double* h_host_out, cudaEvent_t wait_g = nullptr) {
   SvgdState& sv = h->svgd;
   SvgdState& sc = h->svgd;
   const int64_t P = h->model.P;
@@ -355,6 +356,7 @@ static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all,
   median_bandwidth(h, sv.d2.p, (int64_t)Sl * St, (int64_t)St * St, St, sc.h2.p);
   k_kernel_rowsum<<<Sl, 256, 0, h->stream>>>(sv.d2.p, St, sc.h2.p, sv.rowsum.p);
   count_launch(h);
+  if (wait_g) PYB_CUDA(cudaStreamWaitEvent(h->stream, wait_g, 0));
   if (tensor) {
     // phi = (K Y + X rowsum/h2)/St with Y = G - X/h2: A = K [Sl, St] (K-major), B = Y^T [P, St]
     const int blocks = (int)std::min<int64_t>(((int64_t)St * P + 255) / 256, 16 * (int64_t)h->sm_count);
@@ -432,22 +434,46 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
   const float lr_t = (float)adam_lr_t(sv.lr, sv.t);
   const float scale = (sv.semantics == PYB_SVGD_REFERENCE_LIVE) ? 1.0f : (float)h->n_train;
   const int R = sv.world, St = (int)(S * R), r0 = (int)(S * sv.rank);
-  eval_on_batch(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
-  // particles / gradients of every rank (the one exchange step of the path)
+  // particles / gradients of every rank (the one exchange step of the path).  Jacobi (canonical) mode:
+  // the particle all-gather is issued before the local gradients are computed and the gradient all-gather before
+  // the Gram matrix is built, both on the comm stream, so each transfer hides behind the compute that does not
+  // need it; the sequential live sweep exchanges inside its own loop.
   const float* theta_all = sv.theta.p;
   const float* g_all = sv.g.p;
+  const bool overlap = R > 1 && sv.semantics != PYB_SVGD_REFERENCE_LIVE;
+  if (R > 1) {
+    sv.theta_all.alloc((size_t)St * P);
+    sv.g_all.alloc((size_t)St * P);
+    theta_all = sv.theta_all.p;
+    g_all = sv.g_all.p;
+  }
+  if (overlap) {
+    if (!sv.comm_stream) {
+      PYB_CUDA(cudaStreamCreateWithFlags(&sv.comm_stream, cudaStreamNonBlocking));
+      PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_fork, cudaEventDisableTiming));
+      PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_theta, cudaEventDisableTiming));
+      PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_grad, cudaEventDisableTiming));
+    }
+    PYB_CUDA(cudaEventRecord(sv.ev_fork, h->stream));                 // last step's update of theta is ordered before
+    PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_fork, 0));
+    nccl_all_gather_f32(sv.nccl_comm, sv.theta.p, sv.theta_all.p, (size_t)S * P, sv.comm_stream);
+    PYB_CUDA(cudaEventRecord(sv.ev_theta, sv.comm_stream));
+  }
+  eval_on_batch(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
   if (sv.semantics != PYB_SVGD_REFERENCE_LIVE) {
     dim3 gg((unsigned)std::min<int64_t>((P + 255) / 256, 1024), (unsigned)S);
     k_glogp<<<gg, 256, 0, h->stream>>>(sv.g.p, sv.theta.p, h->mu.p, h->inv_var.p, P);
     count_launch(h);
   }
-  if (R > 1) {
-    sv.theta_all.alloc((size_t)St * P);
-    sv.g_all.alloc((size_t)St * P);
+  if (overlap) {
+    PYB_CUDA(cudaEventRecord(sv.ev_fork, h->stream));
+    PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_fork, 0));
+    nccl_all_gather_f32(sv.nccl_comm, sv.g.p, sv.g_all.p, (size_t)S * P, sv.comm_stream);
+    PYB_CUDA(cudaEventRecord(sv.ev_grad, sv.comm_stream));
+    PYB_CUDA(cudaStreamWaitEvent(h->stream, sv.ev_theta, 0));        // the Gram matrix needs every rank's particles
+  } else if (R > 1) {
     nccl_all_gather_f32(sv.nccl_comm, sv.theta.p, sv.theta_all.p, (size_t)S * P, h->stream);
     nccl_all_gather_f32(sv.nccl_comm, sv.g.p, sv.g_all.p, (size_t)S * P, h->stream);
-    theta_all = sv.theta_all.p;
-    g_all = sv.g_all.p;
   }
   if (sv.semantics == PYB_SVGD_REFERENCE_LIVE) {
     // sequential sweep over ALL particles in global order: rank rr updates its rows (against the current
@@ -470,7 +496,7 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
       PYB_CUDA(cudaMemcpyAsync(sv.theta.p, th_all + (int64_t)r0 * P, (size_t)S * P * sizeof(float), cudaMemcpyDeviceToDevice,
                                h->stream));
   } else {
-    phi_canonical(h, theta_all, g_all, r0, (int)S, St, sv.phi.p, nullptr);
+    phi_canonical(h, theta_all, g_all, r0, (int)S, St, sv.phi.p, nullptr, overlap ? sv.ev_grad : nullptr);
     int blocks = (int)std::min<int64_t>((S * P + 255) / 256, 8 * (int64_t)h->sm_count);
     k_adam_all<<<blocks, 256, 0, h->stream>>>(sv.theta.p, sv.phi.p, sv.adam_m.p, sv.adam_v.p, S * P, -1.0f, lr_t);
     count_launch(h);
