@@ -84,7 +84,11 @@ int pyb_device_count(int32_t* n_out);
 int pyb_create(const pyb_model_desc* desc, int32_t device_id, uint64_t seed, pyb_handle** out);
 int pyb_destroy(pyb_handle* h);
 int pyb_param_count(const pyb_handle* h, int64_t* n_params_out);
-/* knobs: "path" (pyb_path), "workspace_mb", "chain_batch", "sync_each_iter" ... */
+/* knobs: "path" (pyb_path), "workspace_mb", "chain_batch", "profile" (per-launch CUDA-event timing of the
+ * tensor-core kernels, read back with "prof_ms"/"prof_flops"/"prof_launches"), and three A/B switches of the tensor
+ * path, all default 1: "tc_pair" (CTA-pair cta_group::2 kernels), "tc_fuse" (layer 2, loss and both deltas inside
+ * the layer-1 GEMM's epilogue), "tc_dual" (two feature tiles per item in the dW1 GEMM).  Switching them off selects
+ * the older kernels that compute the same quantities (used by the tests and by tools/kernel_cycles.sh). */
 int pyb_set_option(pyb_handle* h, const char* key, double value);
 /* read-outs: "path_used", "kernel_launches", "last_device_ms", "workspace_bytes", "tensor_path_ok" */
 int pyb_get_info(const pyb_handle* h, const char* key, double* value_out);
