@@ -14,6 +14,7 @@
 // Sharding: the kernels take the global particle matrix [S_tot, P] and a local row range, so the
 // same code serves one GPU (row range = everything) and the all-gathered multi-GPU layout.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
 #include <algorithm>
 
@@ -263,13 +264,54 @@ __global__ void k_stein_rhs(const float* X, const float* G, const double* h2, in
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     Y[i] = G[i] - X[i] * inv;
 }
-// phi = (KY + X_i rowsum_i / h2) / St   in place on the GEMM output
+// phi = (KY + X_i rowsum_i / h2) / St   in place on the GEMM output (fp32: the GEMM output already is)
 __global__ void k_phi_finish(float* phi, const float* X, int64_t P, int r0, int St, const double* h2, const double* rowsum) {
   const int i = blockIdx.y;
-  const double c = rowsum[i] / h2[0];
+  const float c = (float)(rowsum[i] / h2[0]), inv = 1.0f / (float)St;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t o = (int64_t)i * P + e;
-    phi[o] = (float)(((double)phi[o] + (double)X[(int64_t)(r0 + i) * P + e] * c) / (double)St);
+    phi[o] = fmaf(X[(int64_t)(r0 + i) * P + e], c, phi[o]) * inv;
+  }
+}
+// the same followed by the Adam ascent step on the local particles (theta_local = rows [r0, r0+Sl) of X): one pass
+// over phi / theta / m / v instead of two (the training step does not need phi afterwards)
+__device__ inline float adam_update(float th, float g, float& m, float& v, float lr_t, float b1, float b2, float eh);
+__global__ void k_phi_finish_adam(const float* ky, float* theta_local, float* am, float* av, int64_t P, int St,
+                                  const double* h2, const double* rowsum, float lr_t) {
+  const int i = blockIdx.y;
+  const float c = (float)(rowsum[i] / h2[0]), inv = 1.0f / (float)St;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = (int64_t)i * P + e;
+    const float th = theta_local[o];
+    const float phi = fmaf(th, c, ky[o]) * inv;
+    theta_local[o] = adam_update(th, -phi, am[o], av[o], lr_t, 0.9f, 0.999f, 1e-7f);
+  }
+}
+
+// Y^T = (G - X/h2)^T split into bf16 hi/lo [P, St] (K-major operand of the K*Y GEMM) in one pass.
+// grid (ceil(P/32), ceil(St/32)), block (32, 8)
+__global__ void k_stein_rhs_split_t(const float* X, const float* G, const double* h2, int St, int64_t P, uint16_t* hi,
+                                    uint16_t* lo, int64_t ldd) {
+  __shared__ float tile[32][33];
+  const float inv = (float)(1.0 / h2[0]);
+  const int64_t c0 = (int64_t)blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i;
+    const int64_t c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < St && c < P) ? G[(int64_t)r * P + c] - X[(int64_t)r * P + c] * inv : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t c = c0 + i;
+    const int r = r0 + threadIdx.x;
+    if (c < P && r < St) {
+      const float v = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      hi[c * ldd + r] = __bfloat16_as_ushort(h);
+      lo[c * ldd + r] = __bfloat16_as_ushort(l);
+    }
   }
 }
 
@@ -326,8 +368,11 @@ static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t
 
 // phi for local rows [r0, r0+Sl) of the global particle matrix X_all [St,P] with gradients G_all
 // wait_g: event after which G_all is complete (sharded runs gather it on the comm stream while the Gram is built)
+__global__ void k_adam_all(float* theta, const float* phi, float* am, float* av, int64_t n, float sign, float lr_t);
+struct AdamFuse { float* theta_local; float* am; float* av; float lr_t; };   // non-null: finish phi AND apply the update
 static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all, int r0, int Sl, int St,
-                          float* phi_local, double* h_host_out, cudaEvent_t wait_g = nullptr) {
+                          float* phi_local, double* h_host_out, cudaEvent_t wait_g = nullptr,
+                          const AdamFuse* adam = nullptr) {
   SvgdState& sv = h->svgd;
   SvgdState& sc = h->svgd;
   const int64_t P = h->model.P;
@@ -361,19 +406,29 @@ static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all,
     // phi = (K Y + X rowsum/h2)/St with Y = G - X/h2: A = K [Sl, St] (K-major), B = Y^T [P, St]
     const int blocks = (int)std::min<int64_t>(((int64_t)St * P + 255) / 256, 16 * (int64_t)h->sm_count);
     sv.kf.alloc((size_t)Sl * St); sv.kh.alloc((size_t)Sl * St); sv.kl.alloc((size_t)Sl * St);
-    sv.ybuf.alloc((size_t)St * P); sv.yth.alloc((size_t)P * St); sv.ytl.alloc((size_t)P * St);
+    sv.yth.alloc((size_t)P * St); sv.ytl.alloc((size_t)P * St);
     k_double_to_float<<<blocks, 256, 0, h->stream>>>(sv.d2.p, sv.kf.p, (int64_t)Sl * St);
     tc_split_rows(h, sv.kf.p, Sl, St, St, sv.kh.p, sv.kl.p, St);
-    k_stein_rhs<<<blocks, 256, 0, h->stream>>>(X_all, G_all, sc.h2.p, (int64_t)St * P, sv.ybuf.p);
-    tc_split_transpose(h, sv.ybuf.p, St, (int)P, P, sv.yth.p, sv.ytl.p, St);
+    dim3 gt((unsigned)((P + 31) / 32), (unsigned)((St + 31) / 32)), bt(32, 8);
+    k_stein_rhs_split_t<<<gt, bt, 0, h->stream>>>(X_all, G_all, sc.h2.p, St, P, sv.yth.p, sv.ytl.p, St);
     tc_gemm_split(h, sv.kh.p, sv.kl.p, St, Sl, 0, Sl, sv.yth.p, sv.ytl.p, St, (int)P, St, phi_local, P);
     dim3 gf((unsigned)std::min<int64_t>((P + 255) / 256, 1024), (unsigned)Sl);
-    k_phi_finish<<<gf, 256, 0, h->stream>>>(phi_local, X_all, P, r0, St, sc.h2.p, sv.rowsum.p);
+    if (adam)
+      k_phi_finish_adam<<<gf, 256, 0, h->stream>>>(phi_local, adam->theta_local, adam->am, adam->av, P, St, sc.h2.p,
+                                                  sv.rowsum.p, adam->lr_t);
+    else
+      k_phi_finish<<<gf, 256, 0, h->stream>>>(phi_local, X_all, P, r0, St, sc.h2.p, sv.rowsum.p);
     count_launch(h, 3);
   } else {
     dim3 g2((unsigned)((P + 255) / 256), (Sl + 7) / 8);
     k_phi_canonical<<<g2, 256, 0, h->stream>>>(sv.d2.p, X_all, G_all, P, r0, Sl, St, sc.h2.p, sv.rowsum.p, phi_local);
     count_launch(h);
+    if (adam) {
+      int blocks = (int)std::min<int64_t>(((int64_t)Sl * P + 255) / 256, 8 * (int64_t)h->sm_count);
+      k_adam_all<<<blocks, 256, 0, h->stream>>>(adam->theta_local, phi_local, adam->am, adam->av, (int64_t)Sl * P, -1.0f,
+                                                adam->lr_t);
+      count_launch(h);
+    }
   }
   if (h_host_out) {
     double v[2];
@@ -496,10 +551,8 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
       PYB_CUDA(cudaMemcpyAsync(sv.theta.p, th_all + (int64_t)r0 * P, (size_t)S * P * sizeof(float), cudaMemcpyDeviceToDevice,
                                h->stream));
   } else {
-    phi_canonical(h, theta_all, g_all, r0, (int)S, St, sv.phi.p, nullptr, overlap ? sv.ev_grad : nullptr);
-    int blocks = (int)std::min<int64_t>((S * P + 255) / 256, 8 * (int64_t)h->sm_count);
-    k_adam_all<<<blocks, 256, 0, h->stream>>>(sv.theta.p, sv.phi.p, sv.adam_m.p, sv.adam_v.p, S * P, -1.0f, lr_t);
-    count_launch(h);
+    const AdamFuse af = {sv.theta.p, sv.adam_m.p, sv.adam_v.p, lr_t};
+    phi_canonical(h, theta_all, g_all, r0, (int)S, St, sv.phi.p, nullptr, overlap ? sv.ev_grad : nullptr, &af);
   }
   sc.mean_loss.alloc(1);
   k_mean_float<<<1, 256, 0, h->stream>>>(sv.loss.p, S, sc.mean_loss.p);

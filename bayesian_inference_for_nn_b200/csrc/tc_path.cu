@@ -1577,14 +1577,25 @@ __global__ void __launch_bounds__(128) k_layer2_fwd(Layer2FwdParams p) {
   }
 }
 
-// grad[b][b2_off + c] = sum_g b2_partial[b][g][c] (fixed order); loss[b] = sum_g loss_partial / N
+// grad[b][b2_off + c] = sum_g b2_partial[b][g][c]; loss[b] = sum_g loss_partial / N.  Fixed summation order
+// (16 interleaved strands per class, combined in order): deterministic for any number of groups.  blockDim = 256.
 __global__ void k_layer2_reduce(const float* b2_partial, const double* loss_partial, int n_groups, int C, float* grad,
                                 int64_t P, int64_t b2_off, float* loss_out, int N) {
   __shared__ double scratch[32];
+  __shared__ float strands[16][L2_CMAX + 1];
   const int b = blockIdx.x, t = threadIdx.x;
+  {
+    const int c = t & 15, j = t >> 4;                 // class, strand
+    float s = 0.f;
+    if (c < C)
+      for (int g = j; g < n_groups; g += 16) s += b2_partial[((int64_t)b * n_groups + g) * L2_CMAX + c];
+    strands[j][c] = s;
+  }
+  __syncthreads();
   if (t < C) {
     float s = 0.f;
-    for (int g = 0; g < n_groups; ++g) s += b2_partial[((int64_t)b * n_groups + g) * L2_CMAX + t];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += strands[j][t];
     grad[(int64_t)b * P + b2_off + t] = s;
   }
   double a = 0.0;
@@ -1930,7 +1941,7 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
         else if (C <= 12) k_layer2<12><<<g, 128, 0, h->stream>>>(p);
         else k_layer2<16><<<g, 128, 0, h->stream>>>(p);
       }
-      k_layer2_reduce<<<nb, 64, 0, h->stream>>>(st->b2_partial.p, st->loss_partial.p, n_groups, C, gr, P, L2.b_off,
+      k_layer2_reduce<<<nb, 256, 0, h->stream>>>(st->b2_partial.p, st->loss_partial.p, n_groups, C, gr, P, L2.b_off,
                                                 loss_out ? loss_out + b0 : nullptr, (int)N);
       count_launch(h, 2);
     }
