@@ -42,6 +42,8 @@ struct TcGemmParams {
   int n_btiles, b_row0, transpose_out;
   int vec_store;               // EPI_STORE: every output row segment is 16-byte aligned -> float4 stores
   int n_cols_total;            // >0: chain b owns columns [b*H, min((b+1)*H, n_cols_total)) of one wide output
+  int sym_skip;                // pair kernel, A == B (Gram matrix): tiles strictly below the diagonal (256-col tile b <
+                               // 256-row tile mp) are skipped; the caller mirrors the upper triangle afterwards
 };
 
 __device__ __forceinline__ void tc_decode(const TcGemmParams& p, int item, int& b, int& mp, int& split) {
@@ -417,6 +419,7 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       for (int item = cluster_id; item < p.total_items; item += n_clusters) {
         int b, mp, split, bt;
         tc_decode_pair(p, item, b, mp, split, bt);
+        if (p.sym_skip && b < mp) continue;
         const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
         const int arow = (p.a_blocked ? 0 : p.a_row0) + (mp * 2 + (int)rank) * 128;
         const int brow = (bt >= 0 ? p.b_row0 + bt * p.H : b * p.H) + (int)rank * half_rows;
@@ -449,6 +452,7 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       for (int item = cluster_id; item < p.total_items; item += n_clusters) {
         int b, mp, split, bt;
         tc_decode_pair(p, item, b, mp, split, bt);
+        if (p.sym_skip && b < mp) continue;
         const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);               // both epilogues drained this accumulator
         tc_fence_after();
@@ -486,6 +490,7 @@ tc_gemm_pair_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     for (int item = cluster_id; item < p.total_items; item += n_clusters) {
       int b, mp, split, bt;
       tc_decode_pair(p, item, b, mp, split, bt);
+      if (p.sym_skip && b < mp) continue;
       const int mt = mp * 2 + (int)rank;
       float* bs = bias_s + acc * 256;
       if (EPI == EPI_BIAS_ACT_T_SPLIT) {

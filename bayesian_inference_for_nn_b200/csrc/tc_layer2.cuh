@@ -362,6 +362,22 @@ __global__ void k_reduce_ksplits(const float* part, int splits, int64_t split_st
     out[(int64_t)b * out_stride + i] = s;
   }
 }
+// Gram matrix: out[i][j] = out[j][i] for every element whose 256x256 tile lies strictly below the diagonal
+// (those tiles were skipped by the GEMM).  grid (n/32, n/32), block (32, 8); tiled through shared memory.
+__global__ void k_mirror_lower_tiles(float* out, int n, int64_t ld) {
+  __shared__ float t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;          // 32x32 block (rows bi, cols bj) of the LOWER part to fill
+  if ((bj * 32) / 256 >= (bi * 32) / 256) return;
+  for (int r = threadIdx.y; r < 32; r += 8) {           // read the mirrored block (rows bj, cols bi)
+    const int i = bj * 32 + r, j = bi * 32 + threadIdx.x;
+    t[r][threadIdx.x] = (i < n && j < n) ? out[(int64_t)i * ld + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + threadIdx.x;
+    if (i < n && j < n) out[(int64_t)i * ld + j] = t[threadIdx.x][r];
+  }
+}
 // one accumulator sees at most TC_SPLIT_CHUNKS chunks (8192 K elements): <= 1536 truncating accumulations
 constexpr int TC_SPLIT_CHUNKS = 256;
 

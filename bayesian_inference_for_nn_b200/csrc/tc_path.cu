@@ -472,6 +472,8 @@ void tc_split_transpose(pyb_handle* h, const float* src, int R, int C, int64_t l
   count_launch(h);
 }
 // out[m][n] = sum_k A[a_row0+m][k] B[n][k] for m < M, n < Nn; split operands, K-major, pitches in elements
+// A == B with a_row0 == 0 and M == Nn is a Gram matrix: the CTA-pair kernel then computes only the 256x256 tiles on and
+// above the diagonal and the rest is mirrored (exactly symmetric result, ~45 % fewer MMAs)
 void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t lda, int64_t a_rows_total, int a_row0, int M,
                    const void* b_hi, const void* b_lo, int64_t ldb, int Nn, int64_t K, float* out, int64_t ldc) {
   PYB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, PYB_ERR_INVALID, "operand pitches must be multiples of 8 elements");
@@ -491,11 +493,19 @@ void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t ld
   }
   p.total_items = p.n_pairs * p.n_batch * std::max(splits, 1);
   CUtensorMap mp_h = make_map(b_hi, K, Nn, ldb, std::max(Hn / 2, 8)), mp_l = make_map(b_lo, K, Nn, ldb, std::max(Hn / 2, 8));
+  const bool gram = a_hi == b_hi && a_lo == b_lo && a_row0 == 0 && M == Nn && lda == ldb && Hn == 256 && pair_ok(h, p) &&
+                    h->opt_tc_gram_sym;
+  p.sym_skip = gram ? 1 : 0;
   launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * (double)Nn * (double)K, &mp_h, &mp_l);
   if (splits > 1) {
     const int64_t cnt = (int64_t)M * ldc;
     dim3 rg((unsigned)std::min<int64_t>((cnt + 255) / 256, 4096), 1);
     k_reduce_ksplits<<<rg, 256, 0, h->stream>>>(st->gpart.p, splits, cnt, 0, cnt, out, 0);
+    count_launch(h);
+  }
+  if (gram) {
+    dim3 gm((unsigned)((M + 31) / 32), (unsigned)((M + 31) / 32)), bm(32, 8);
+    k_mirror_lower_tiles<<<gm, bm, 0, h->stream>>>(out, M, ldc);
     count_launch(h);
   }
 }

@@ -263,10 +263,10 @@ def test_svgd_minibatch_gradients_on_tensor_path(oracle, sem):
     assert diff.max() <= 2.1 * 1e-3 * len(idx)
 
 
-@pytest.mark.parametrize("S", [256, 384])
+@pytest.mark.parametrize("S", [256, 384, 1024])
 def test_svgd_canonical_phi_on_tensor_cores(oracle, S):
-    """Large particle sets: Gram matrix (bf16x3 GEMM) -> exact median bandwidth -> K Y contraction (bf16x3 GEMM)
-    against the float64 oracle of SVGD.baseline__kernel."""
+    """Large particle sets: Gram matrix (bf16x3 GEMM; S >= 512: upper tile triangle + mirror) -> exact median bandwidth
+    -> K Y contraction (bf16x3 GEMM) against the float64 oracle of SVGD.baseline__kernel."""
     rng = np.random.default_rng(S)
     eng = engine(64, 32, 4)                      # P = 2212
     P = eng.P
