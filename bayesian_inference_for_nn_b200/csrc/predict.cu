@@ -43,8 +43,20 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
   const int64_t P = m.P, C = m.out_dim, elems = Nt * C;
   DevBuf<float> dW, dx, dw, dout, dmean, dvar;
   DevBuf<double> s1, s2;
-  dx.alloc(Nt * m.in_dim);
-  PYB_CUDA(cudaMemcpyAsync(dx.p, x, Nt * m.in_dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  // W and x may be host pointers (copied chunk by chunk) or device pointers (used in place: samples that already
+  // live in HBM, e.g. DLPack tensors, skip the n*P*4-byte upload that otherwise dominates the call)
+  auto on_device = [](const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  };
+  const bool W_dev = on_device(W), x_dev = on_device(x);
+  const float* xd = x;
+  if (!x_dev) {
+    dx.alloc(Nt * m.in_dim);
+    PYB_CUDA(cudaMemcpyAsync(dx.p, x, Nt * m.in_dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    xd = dx.p;
+  }
   double wsum = 0.0;
   if (weight) {
     for (int64_t i = 0; i < n; ++i) wsum += weight[i];
@@ -59,7 +71,7 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
   int64_t out_cap = (int64_t)((512ull << 20) / (sizeof(float) * (size_t)elems));
   if (out_cap < 1) out_cap = 1;
   chunk = std::min(chunk, out_cap);
-  dW.alloc(chunk * P);
+  if (!W_dev) dW.alloc(chunk * P);
   dout.alloc(chunk * elems);
   s1.alloc(elems); s2.alloc(elems); dmean.alloc(elems); dvar.alloc(elems);
   PYB_CUDA(cudaMemsetAsync(s1.p, 0, elems * sizeof(double), h->stream));
@@ -69,9 +81,13 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
   PYB_CUDA(cudaEventRecord(h->ev0, h->stream));
   for (int64_t i0 = 0; i0 < n; i0 += chunk) {
     int64_t nb = std::min(chunk, n - i0);
-    PYB_CUDA(cudaMemcpyAsync(dW.p, W + i0 * P, nb * P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    if (use_tensor) tc_forward(h, dW.p, nb, dx.p, Nt, dout.p);
-    else generic_forward(h, dW.p, nb, dx.p, Nt, dout.p);
+    const float* Wd = W + i0 * P;
+    if (!W_dev) {
+      PYB_CUDA(cudaMemcpyAsync(dW.p, W + i0 * P, nb * P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+      Wd = dW.p;
+    }
+    if (use_tensor) tc_forward(h, Wd, nb, xd, Nt, dout.p);
+    else generic_forward(h, Wd, nb, xd, Nt, dout.p);
     k_pred_accum<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(dout.p, nb, elems, weight ? dw.p + i0 : nullptr,
                                                                          s1.p, s2.p);
     count_launch(h);

@@ -57,7 +57,9 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hw, uin
   lw = *reinterpret_cast<const uint32_t*>(&lp);
 }
 
-template <int CP>
+// FWD = false: training step (everything above).  FWD = true: forward only (posterior predictive): phase A, the logit
+// reduction and the output activation; out[b][row][c] is the only thing written — no A1^T, no deltas, no loss.
+template <int CP, bool FWD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1)
 tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -259,8 +261,10 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               const float* vv = v + (r >> 1) * 16 + kb * 4 + (r & 1) * 2;
               a[r][0] = fmaxf(vv[0] + bb.x, 0.f);
               a[r][1] = fmaxf(vv[1] + bb.y, 0.f);
-              m |= (a[r][0] > 0.f ? 1u : 0u) << (kb * 8 + r * 2);
-              m |= (a[r][1] > 0.f ? 1u : 0u) << (kb * 8 + r * 2 + 1);
+              if (!FWD) {
+                m |= (a[r][0] > 0.f ? 1u : 0u) << (kb * 8 + r * 2);
+                m |= (a[r][1] > 0.f ? 1u : 0u) << (kb * 8 + r * 2 + 1);
+              }
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -277,13 +281,15 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                   z[r][2 * c4 + 1] = __ffma2_rn(aa, w23, z[r][2 * c4 + 1]);
                 }
               }
-              // A1^T: this thread's 4 rows of hidden unit hbase + ... are adjacent in the block's row order
-              uint32_t hw0, lw0, hw1, lw1;
-              split_pair(a[0][i], a[1][i], hw0, lw0);
-              split_pair(a[2][i], a[3][i], hw1, lw1);
-              const int w_off = (ch * 32 + 8 * kb + i) * 32;
-              __stcs(pa_hi + w_off, make_uint2(hw0, hw1));       // streaming: 18 GB per launch must not evict X / W1^T from L2
-              __stcs(pa_lo + w_off, make_uint2(lw0, lw1));
+              if (!FWD) {
+                // A1^T: this thread's 4 rows of hidden unit hbase + ... are adjacent in the block's row order
+                uint32_t hw0, lw0, hw1, lw1;
+                split_pair(a[0][i], a[1][i], hw0, lw0);
+                split_pair(a[2][i], a[3][i], hw1, lw1);
+                const int w_off = (ch * 32 + 8 * kb + i) * 32;
+                __stcs(pa_hi + w_off, make_uint2(hw0, hw1));     // streaming: 18 GB per launch must not evict X / W1^T from L2
+                __stcs(pa_lo + w_off, make_uint2(lw0, lw1));
+              }
             }
           }
           mask[ch] = m;
@@ -323,8 +329,30 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       float zf[CP], dz[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) zf[c] = (b2b[c] + zx_s[c * 128 + row_own]) + zx_s[(CP + c) * 128 + row_own];
-      float loss_r = 0.f;
       const int row_g = mt * 128 + row_own;
+      if (FWD) {
+        // predictive: softmax / output activation of the finished row, one thread per row
+        if (half == 0 && row_g < p.M_valid) {
+          float* o = l2.fwd_out + ((int64_t)b * l2.N + row_g) * C;
+          if (l2.out_act == PYB_ACT_SOFTMAX) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) if (c < C) mx = fmaxf(mx, zf[c]);
+            float se = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) if (c < C) se += expf(zf[c] - mx);
+            const float inv = 1.0f / se;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) if (c < C) o[c] = expf(zf[c] - mx) * inv;
+          } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) if (c < C) o[c] = act_apply(zf[c], l2.out_act);
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      float loss_r = 0.f;
       l2_loss_dz<CP>(l2, row_g, row_g < p.M_valid, zf, dz, loss_r, invN);
       if (half == 0) {
         // dZ2^T for the dW2 GEMM, per-warp partial sums of the loss and of db2 (one warp == 32 rows)

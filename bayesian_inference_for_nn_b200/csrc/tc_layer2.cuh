@@ -83,6 +83,7 @@ struct Layer2Params {
   double* loss_partial;        // [Bc][n_groups]
   float* b2_partial;           // [Bc][n_groups][16]
   int n_groups, n_tiles;
+  float* fwd_out;              // fused forward-only mode: [Bc][N][C] outputs (softmax / output activation applied)
 };
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));

@@ -180,8 +180,13 @@ static void launch_gemm_tc(pyb_handle* h, const CUtensorMap& a_hi, const CUtenso
 template <int CP>
 static void launch_fused_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                               const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p, const Layer2Params& l2) {
-  PYB_CUDA(cudaFuncSetAttribute(tc_g1_layer2_fused<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TfCfg<CP>::SMEM));
-  tc_g1_layer2_fused<CP><<<grid, TF_THREADS, TfCfg<CP>::SMEM, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p, l2);
+  if (l2.fwd_out) {
+    PYB_CUDA(cudaFuncSetAttribute(tc_g1_layer2_fused<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TfCfg<CP>::SMEM));
+    tc_g1_layer2_fused<CP, true><<<grid, TF_THREADS, TfCfg<CP>::SMEM, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p, l2);
+    return;
+  }
+  PYB_CUDA(cudaFuncSetAttribute(tc_g1_layer2_fused<CP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TfCfg<CP>::SMEM));
+  tc_g1_layer2_fused<CP, false><<<grid, TF_THREADS, TfCfg<CP>::SMEM, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p, l2);
 }
 // fused G1 + layer 2 applies to: relu hidden layer of 128 or 256 units, CTA pairs enabled
 static bool fused_ok(const pyb_handle* h, int H, int act1) {
@@ -297,7 +302,7 @@ static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* t
     else if (C <= 8) launch_fused_inst<8>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
     else if (C <= 12) launch_fused_inst<12>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
     else launch_fused_inst<16>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
-    prof_end(h, 2.0 * N * (D * (double)H + 3.0 * H * C) * nb);
+    prof_end(h, 2.0 * N * (D * (double)H + (fused->fwd_out ? 1.0 : 3.0) * H * C) * nb);
     count_launch(h);
     return;
   }
@@ -443,9 +448,19 @@ void tc_forward(pyb_handle* h, const float* theta, int64_t S, const float* x, in
   const int64_t Bc = tc_prepare_bufs(h, st, S, d.Npad, false);
   const LayerDesc& L2 = m.layer[1];
   const int64_t P = m.P;
+  const bool fused = fused_ok(h, st->H, m.layer[0].act) && st->C <= L2_CMAX;
   for (int64_t b0 = 0; b0 < S; b0 += Bc) {
     const int nb = (int)std::min<int64_t>(Bc, S - b0);
     const float* th = theta + b0 * P;
+    if (fused) {
+      // layer 2 and the output activation inside the layer-1 GEMM's epilogue: A1 never leaves the SM
+      Layer2Params f = {};
+      f.theta = th; f.P = P; f.w2_off = L2.w_off; f.b2_off = L2.b_off;
+      f.H = st->H; f.C = st->C; f.N = (int)N; f.out_act = L2.act; f.scale = 1.0f;
+      f.fwd_out = out + b0 * N * st->C;
+      tc_pack_and_g1(h, st, d, th, nb, &f);
+      continue;
+    }
     tc_pack_and_g1(h, st, d, th, nb);
     Layer2FwdParams p = {};
     p.a_hi = st->a_hi.p; p.a_lo = st->a_lo.p; p.k_tiles = (int)(d.Npad / 128);

@@ -181,17 +181,23 @@ class Engine:
 
     # ---- predictive
     def predict(self, W, x, weights=None, want_all=False):
-        W = _f32(W)
-        if W.ndim != 2 or W.shape[1] != self.P:
+        """W [n, P] weight samples, x [Nt, in_dim...] inputs: NumPy arrays, or device tensors (DLPack / tf.Tensor), which
+        the library reads in place instead of uploading."""
+        if isinstance(W, (np.ndarray, list, tuple)):
+            W = _f32(W)
+        Wa, _, wptr = ingest(W, np.float32)
+        if len(Wa.shape) != 2 or int(Wa.shape[1]) != self.P:
             raise ValueError("W must be [n, P]")
-        x = _f32(x)
-        x = x.reshape(x.shape[0], -1)
-        if x.shape[1] != self.spec.in_dim:
-            raise ValueError("x has %d features per row, the model expects %d" % (x.shape[1], self.spec.in_dim))
-        n, Nt, Cc = W.shape[0], x.shape[0], self.spec.out_dim
+        if isinstance(x, (np.ndarray, list, tuple)):
+            x = _f32(x)
+            x = x.reshape(x.shape[0], -1)
+        xa, _, xptr = ingest(x, np.float32)
+        if int(np.prod(xa.shape[1:])) != self.spec.in_dim:
+            raise ValueError("x has %d features per row, the model expects %d" % (int(np.prod(xa.shape[1:])), self.spec.in_dim))
+        n, Nt, Cc = int(Wa.shape[0]), int(xa.shape[0]), self.spec.out_dim
         w = None if weights is None else _f32(weights, (n,))
         mean = np.empty((Nt, Cc), np.float32)
         var = np.empty((Nt, Cc), np.float32)
         allo = np.empty((n, Nt, Cc), np.float32) if want_all else None
-        check(self.lib.pyb_predict(self.h, _ptr(W), n, _ptr(w), _ptr(x), Nt, _ptr(mean), _ptr(var), _ptr(allo)))
+        check(self.lib.pyb_predict(self.h, wptr, n, _ptr(w), xptr, Nt, _ptr(mean), _ptr(var), _ptr(allo)))
         return mean, var, allo

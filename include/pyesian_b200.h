@@ -150,7 +150,9 @@ int pyb_nccl_unique_id(void* out_128);
 
 /* ---- posterior predictive (BayesianModel.predict BayesianModel.py:106-129; Plotter.py:244) ----
  * W [n,P] weight samples, weight [n] or NULL (=1), x [Nt,in_dim]; mean/var [Nt,out_dim] with
- * NaN->0 per element and population variance; all_out [n,Nt,out_dim] or NULL.  Host pointers. */
+ * NaN->0 per element and population variance; all_out [n,Nt,out_dim] or NULL.  weight and the outputs are host
+ * pointers; W and x may be host OR device pointers (device memory is read in place: weight samples that already
+ * live in HBM skip the n*P*4-byte upload). */
 int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x,
                 int64_t Nt, float* mean_out, float* var_out, float* all_out);
 

@@ -229,6 +229,17 @@ def test_predictive_on_tensor_path(oracle):
     mean_g, _, _ = eng.predict(W, x, weights=freq)
     assert int(eng.info("path_used")) == _lib.PATH_GENERIC
     np.testing.assert_allclose(mean, mean_g, rtol=1e-4, atol=1e-6)
+    # weight samples and inputs already resident in HBM (DLPack): read in place, same numbers bit for bit;
+    # the unfused kernels (tc_fuse=0: G1 + k_layer2_fwd through A1^T) agree with the fused forward epilogue
+    torch = pytest.importorskip("torch")
+    eng.set_option("path", _lib.PATH_TENSOR)
+    mean_d, var_d, all_d = eng.predict(torch.from_numpy(W).cuda(), torch.from_numpy(x).cuda(), weights=freq, want_all=True)
+    np.testing.assert_array_equal(mean_d, mean)
+    np.testing.assert_array_equal(all_d, allo)
+    eng.set_option("tc_fuse", 0)
+    mean_u, _, all_u = eng.predict(W, x, weights=freq, want_all=True)
+    np.testing.assert_allclose(all_u, allo, rtol=2e-5, atol=1e-7)      # the unfused path carries a1 as bf16 hi + lo (2^-17)
+    np.testing.assert_allclose(mean_u, mean, rtol=2e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("sem", [_lib.SVGD_CANONICAL_MEDIAN, _lib.SVGD_REFERENCE_LIVE])
