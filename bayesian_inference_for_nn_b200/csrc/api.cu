@@ -495,4 +495,38 @@ int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, c
   PYB_CATCH
 }
 
+int pyb_buffer_create(pyb_handle* h, const void* host_or_null, int64_t bytes, void** dev_out) {
+  PYB_TRY
+  PYB_REQUIRE(h && dev_out && bytes > 0, PYB_ERR_INVALID, "bad arguments");
+  use_device(h);
+  void* d = nullptr;
+  PYB_CUDA(cudaMalloc(&d, (size_t)bytes));
+  if (host_or_null) {
+    cudaError_t e = cudaMemcpyAsync(d, host_or_null, (size_t)bytes, cudaMemcpyDefault, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { cudaFree(d); PYB_CUDA(e); }
+  }
+  *dev_out = d;
+  PYB_CATCH
+}
+
+int pyb_buffer_destroy(pyb_handle* h, void* dev) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  if (dev) {
+    PYB_CUDA(cudaStreamSynchronize(h->stream));
+    PYB_CUDA(cudaFree(dev));
+  }
+  PYB_CATCH
+}
+
+int pyb_gather_rows(pyb_handle* h, const float* src, const int64_t* idx, int64_t n, int64_t row_len, float* dst) {
+  PYB_TRY
+  PYB_REQUIRE(h && src && idx && dst && n > 0 && row_len > 0, PYB_ERR_INVALID, "bad arguments");
+  use_device(h);
+  gather_rows_f32(h, src, idx, n, row_len, dst);
+  PYB_CATCH
+}
+
 }  // extern "C"

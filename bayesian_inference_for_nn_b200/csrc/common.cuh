@@ -322,6 +322,7 @@ bool tc_supported_rows(pyb_handle* h, int64_t n_rows);
 void tc_eval_batch(pyb_handle* h, const float* Xb, const int32_t* yb_i, const float* yb_f, int64_t Nb, const float* theta,
                    int64_t S, float scale, float* loss_out, float* grad_out);
 void tc_forward(pyb_handle* h, const float* theta, int64_t S, const float* x, int64_t N, float* out);
+void gather_rows_f32(pyb_handle* h, const float* src, const int64_t* idx_host, int64_t n, int64_t row_len, float* dst);
 void tc_split_rows(pyb_handle* h, const float* src, int64_t R, int C, int64_t lds, void* hi, void* lo, int64_t ldd);
 void tc_split_transpose(pyb_handle* h, const float* src, int R, int C, int64_t lds, void* hi, void* lo, int64_t ldd);
 void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t lda, int64_t a_rows_total, int a_row0, int M,

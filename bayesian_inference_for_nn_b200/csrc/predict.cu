@@ -35,6 +35,27 @@ __global__ void k_pred_finish(const double* s1, const double* s2, double wsum, i
   var[e] = (float)(v > 0.0 ? v : 0.0);
 }
 
+// dst[k][:] = src[idx[k]][:]   (device rows of row_len floats; idx arrives from the host)
+__global__ void k_gather_rows_f32(const float* src, const int64_t* idx, int64_t row_len, float* dst) {
+  const int64_t k = blockIdx.y;
+  const float* s = src + idx[k] * row_len;
+  float* d = dst + k * row_len;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_len; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+void gather_rows_f32(pyb_handle* h, const float* src, const int64_t* idx_host, int64_t n, int64_t row_len, float* dst) {
+  DevBuf<int64_t> di;
+  di.alloc(n);
+  PYB_CUDA(cudaMemcpyAsync(di.p, idx_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  for (int64_t k0 = 0; k0 < n; k0 += 65535) {
+    const int64_t nk = std::min<int64_t>(65535, n - k0);
+    dim3 g((unsigned)std::min<int64_t>((row_len + 255) / 256, 256), (unsigned)nk);
+    k_gather_rows_f32<<<g, 256, 0, h->stream>>>(src, di.p + k0, row_len, dst + k0 * row_len);
+    count_launch(h);
+  }
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+}
+
 void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
              float* mean, float* var, float* all) {
   PYB_REQUIRE(n > 0 && Nt > 0, PYB_ERR_INVALID, "n and Nt must be > 0");

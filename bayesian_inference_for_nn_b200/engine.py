@@ -27,6 +27,26 @@ def _f32(a, shape=None):
     return a
 
 
+class DeviceArray:
+    """A float32 array owned by the caller and resident in the engine's HBM (pyb_buffer_create).  Anything that takes
+    weight samples or inputs (``Engine.predict``) reads it in place.  Freed with the object."""
+
+    def __init__(self, engine: "Engine", ptr: int, shape):
+        self._engine, self.ptr, self.shape, self.dtype = engine, ptr, tuple(int(v) for v in shape), np.float32
+
+    def free(self):
+        eng = self._engine
+        if self.ptr and eng is not None and getattr(eng, "h", None):
+            eng.lib.pyb_buffer_destroy(eng.h, self.ptr)
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, spec: ModelSpec, device: int = 0, seed: int = 0):
         self.lib = _lib.load()
@@ -178,6 +198,26 @@ class Engine:
         out = np.empty((self.S, self.P), np.float64)
         check(self.lib.pyb_svgd_get_particles(self.h, _ptr(out)))
         return out
+
+    # ---- caller-owned device arrays
+    def device_array(self, a) -> DeviceArray:
+        """Upload a float32 array once; the result can be passed wherever weight samples / inputs are taken."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        out = C.c_void_p()
+        check(self.lib.pyb_buffer_create(self.h, a.ctypes.data, int(a.nbytes), C.byref(out)))
+        return DeviceArray(self, out.value, a.shape)
+
+    def gather_rows(self, src: DeviceArray, idx) -> DeviceArray:
+        """rows src[idx] as a new device array (the distinct weight vectors of a posterior draw)."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        if idx.size == 0 or idx.min() < 0 or idx.max() >= src.shape[0]:
+            raise IndexError("row index out of range")
+        row_len = int(np.prod(src.shape[1:]))
+        out = C.c_void_p()
+        check(self.lib.pyb_buffer_create(self.h, None, int(idx.size) * row_len * 4, C.byref(out)))
+        dst = DeviceArray(self, out.value, (int(idx.size),) + tuple(src.shape[1:]))
+        check(self.lib.pyb_gather_rows(self.h, src.ptr, idx.ctypes.data, int(idx.size), row_len, dst.ptr))
+        return dst
 
     # ---- predictive
     def predict(self, W, x, weights=None, want_all=False):

@@ -83,6 +83,15 @@ class BayesianModel:
             self._engine = Engine(self._spec, device=self._device)
         return self._engine
 
+    def _samples_on_device(self, d: Sampled):
+        """The Sampled distribution's [n, P] matrix, uploaded once and kept in HBM: every predict() call re-draws
+        from the same stored samples (BayesianModel.py:106-129), so only indices and counts travel after that."""
+        key = (id(d), d.samples.shape)
+        if getattr(self, "_dev_samples_key", None) != key:
+            self._dev_samples = self._engine_for_predict().device_array(d.samples)
+            self._dev_samples_key = key
+        return self._dev_samples
+
     def _draw_flat(self):
         """One flat [P] weight vector assembled from every interval's distribution
         (``_sample_weights`` BayesianModel.py:63-77)."""
@@ -110,14 +119,16 @@ class BayesianModel:
                   and self._spec.layer_param_range(*self._layers_dtbn_intervals[0]) == (0, self._spec.n_params))
         if single and mode == "exact":
             d = self._distributions[0]
-            mean, var, _ = eng.predict(d.samples, x, weights=np.asarray(d.frequencies, np.float32))
+            mean, var, _ = eng.predict(self._samples_on_device(d), x, weights=np.asarray(d.frequencies, np.float32))
             self.last_variance = var
             return [mean], mean
         if single:
             d = self._distributions[0]
             draws = np.fromiter((d.sample_index() for _ in range(nb_samples)), dtype=np.int64, count=nb_samples)
             uniq, inverse, counts = np.unique(draws, return_inverse=True, return_counts=True)
-            mean, var, allo = eng.predict(d.samples[uniq], x, weights=counts.astype(np.float32), want_all=True)
+            Wd = eng.gather_rows(self._samples_on_device(d), uniq)     # distinct draws, gathered in HBM
+            mean, var, allo = eng.predict(Wd, x, weights=counts.astype(np.float32), want_all=True)
+            Wd.free()
             self.last_variance = var
             return [allo[i] for i in inverse], mean
         W = np.stack([self._draw_flat() for _ in range(nb_samples)])

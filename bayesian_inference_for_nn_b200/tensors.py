@@ -93,6 +93,10 @@ def ingest(obj, want_dtype):
         return a, _lib.MEM_HOST, a.ctypes.data
     if _is_capsule(obj):
         return _from_capsule(obj, None, want_dtype)
+    if type(obj).__name__ == "DeviceArray" and hasattr(obj, "ptr"):      # engine.DeviceArray: already in HBM
+        if np.dtype(obj.dtype) != np.dtype(want_dtype):
+            raise TypeError("device array has dtype %s, expected %s" % (np.dtype(obj.dtype), np.dtype(want_dtype)))
+        return obj, _lib.MEM_DEVICE, obj.ptr
     mod = type(obj).__module__ or ""
     if mod.startswith("tensorflow"):
         import tensorflow as tf  # lazy: only when the caller already handed us a tf.Tensor

@@ -156,6 +156,16 @@ int pyb_nccl_unique_id(void* out_128);
 int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x,
                 int64_t Nt, float* mean_out, float* var_out, float* all_out);
 
+/* ---- device-resident arrays owned by the caller (posterior samples kept in HBM between predict calls:
+ *      BayesianModel.predict re-draws nb_samples weight vectors from the SAME Sampled on every call,
+ *      BayesianModel.py:106-129 / Sampled.py:29-32) ----
+ * pyb_buffer_create allocates `bytes` on the handle's device and, if host_or_null is given, uploads them;
+ * pyb_gather_rows writes dst[k] = src[idx[k]] for rows of row_len floats (src, dst device pointers, idx on the host);
+ * buffers outlive nothing: free them with pyb_buffer_destroy before pyb_destroy. */
+int pyb_buffer_create(pyb_handle* h, const void* host_or_null, int64_t bytes, void** dev_out);
+int pyb_buffer_destroy(pyb_handle* h, void* dev);
+int pyb_gather_rows(pyb_handle* h, const float* src, const int64_t* idx, int64_t n, int64_t row_len, float* dst);
+
 #ifdef __cplusplus
 }
 #endif
