@@ -256,6 +256,7 @@ struct pyb_handle {
   int opt_tc_pair = 1;   // 1: use the CTA-pair (cta_group::2) GEMM kernel where it applies
   int opt_tc_dual = 1;   // 1: the hidden-major dW1 GEMM computes two feature tiles per item (shared A stages)
   int opt_tc_gram_sym = 1;   // 1: Gram matrices (A == B) compute the upper tile triangle only and mirror it
+  int opt_fs_cluster = 1;   // 1: the small-width HMC kernel spreads a chain over a CTA cluster when there are few chains
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
   double opt_workspace_mb = 4096;
   int64_t opt_chain_batch = 0;

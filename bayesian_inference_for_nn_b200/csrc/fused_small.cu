@@ -11,7 +11,13 @@
 //   phase 2  thread == (hidden unit, row slice): recompute a1 from the unit's own weights (registers),
 //            dZ1 = (dZ2 W2^T) act'(a1), accumulate dW1[:,h], db1[h], dW2[h,:] in registers
 //   slices are combined in a fixed order (deterministic), db2 by one warp per class.
+//
+// Few chains (the reference runs ONE, HMC.py:74): a chain is then spread over a thread-block CLUSTER of up to 8
+// CTAs.  Each CTA keeps the whole state (q, p: a few hundred floats, updated redundantly and identically) and
+// evaluates an eighth of the data rows; after every evaluation the partial gradients and loss meet through
+// distributed shared memory (one cluster barrier per evaluation, double-buffered exchange, fixed summation order).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 
 namespace pyb {
@@ -32,6 +38,7 @@ struct FsParams {
   float* q; float* p; float* q0; const float* inj_p; const float* inj_u;
   float eps, half_eps, drift, stdv, inv2m, prior_const;
   int L, semantics, burning;
+  int cluster;                   // CTAs per chain (1, 2, 4 or 8)
   uint64_t seed; uint32_t iter; int64_t chain_offset;
   float* U0; float* U1; float* K0; float* K1; float* log_alpha; float* ret_loss; int32_t* accepted;
   unsigned long long* counters; double* loss_sum;
@@ -44,6 +51,7 @@ struct FsSmem {
   float* qs; float* ps; float* gs;   // [P]
   float* pk;      // [H][PKW] packed per-unit parameters
   float* part;    // [n_slices][H*(D+1+C)]
+  float* gx;      // [2][GX] cluster exchange: partial gradient [P] + loss sum (double) of this CTA's rows
   double* red;    // [32]
 };
 
@@ -60,9 +68,10 @@ __device__ __forceinline__ T fs_block_sum_all(T v, T* scratch) {
   return r;
 }
 
-// loss (mean over rows) and gs = scale * d(mean loss)/d theta for the parameters in sm.qs
+// over the data rows [rb, re): loss SUM (returned to every thread) and gout = scale/N * d(sum loss)/d theta for the
+// parameters in sm.qs (N = all rows of the dataset: partial results of disjoint row ranges simply add up)
 template <int D, int C>
-__device__ float fs_eval(const FsParams& p, const FsSmem& sm, float scale) {
+__device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale, int rb, int re, float* gout) {
   constexpr int PKW = D + 1 + C;
   const int t = threadIdx.x, H = p.H, N = p.N;
   // pack per-unit parameters: {W1[0..D)[h], b1[h], W2[h][0..C)}
@@ -81,7 +90,7 @@ __device__ float fs_eval(const FsParams& p, const FsSmem& sm, float scale) {
   // ---- phase 1: thread == row
   double loss_acc = 0.0;
   const float sc = scale / (float)N;
-  for (int r = t; r < N; r += FS_THREADS) {
+  for (int r = rb + t; r < re; r += FS_THREADS) {
     float x[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) x[d] = sm.xs[r * D + d];
@@ -140,7 +149,7 @@ __device__ float fs_eval(const FsParams& p, const FsSmem& sm, float scale) {
     for (int d = 0; d < D; ++d) { w1[d] = w[d]; gw1[d] = 0.f; }
 #pragma unroll
     for (int c = 0; c < C; ++c) { w2[c] = w[D + 1 + c]; gw2[c] = 0.f; }
-    for (int r = slice; r < N; r += n_slices) {
+    for (int r = rb + slice; r < re; r += n_slices) {
       float z = b1;
       float x[D];
 #pragma unroll
@@ -171,20 +180,49 @@ __device__ float fs_eval(const FsParams& p, const FsSmem& sm, float scale) {
     for (int sl = 0; sl < n_slices; ++sl) s += sm.part[sl * NG + i];
     int hh = i / PKW, k = i - hh * PKW;
     int64_t dst = (k < D) ? p.w1_off + (int64_t)k * H + hh : (k == D ? p.b1_off + hh : p.w2_off + (int64_t)hh * C + (k - D - 1));
-    sm.gs[dst] = s;
+    gout[dst] = s;
   }
   // db2[c] = sum_r dZ2[r][c]: one warp per class
   {
     const int wid = t >> 5, lane = t & 31;
     if (wid < C) {
       float s = 0.f;
-      for (int r = lane; r < N; r += 32) s += sm.dz2[r * C + wid];
+      for (int r = rb + lane; r < re; r += 32) s += sm.dz2[r * C + wid];
       s = warp_sum(s);
-      if (lane == 0) sm.gs[p.b2_off + wid] = s;
+      if (lane == 0) gout[p.b2_off + wid] = s;
     }
   }
   __syncthreads();
-  return (float)(loss_tot / (double)N);
+  return loss_tot;
+}
+// whole dataset in this CTA: mean loss, gradient in sm.gs
+template <int D, int C>
+__device__ float fs_eval(const FsParams& p, const FsSmem& sm, float scale) {
+  return (float)(fs_eval_rows<D, C>(p, sm, scale, 0, p.N, sm.gs) / (double)p.N);
+}
+// this CTA's share of the rows, then the cluster-wide sum through distributed shared memory.  `n_eval` alternates the
+// exchange buffer: a CTA may already write the next evaluation's partials while a slower one still reads these
+template <int D, int C>
+__device__ float fs_eval_cluster(const FsParams& p, const FsSmem& sm, float scale, int rank, int n_ctas, int& n_eval) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const int t = threadIdx.x;
+  const int64_t P = p.P, GX = ((P + 1) & ~(int64_t)1) + 2;
+  float* gx = sm.gx + (n_eval & 1) * GX;
+  ++n_eval;
+  const int rb = (int)((int64_t)p.N * rank / n_ctas), re = (int)((int64_t)p.N * (rank + 1) / n_ctas);
+  const double lsum = fs_eval_rows<D, C>(p, sm, scale, rb, re, gx);
+  if (t == 0) *reinterpret_cast<double*>(gx + GX - 2) = lsum;
+  cl.sync();
+  for (int64_t i = t; i < P; i += FS_THREADS) {
+    float sacc = 0.f;
+    for (int rr = 0; rr < n_ctas; ++rr) sacc += cl.map_shared_rank(gx, rr)[i];     // fixed order: identical in every CTA
+    sm.gs[i] = sacc;
+  }
+  double lt = 0.0;
+  for (int rr = 0; rr < n_ctas; ++rr) lt += *reinterpret_cast<const double*>(cl.map_shared_rank(gx, rr) + GX - 2);
+  __syncthreads();
+  return (float)(lt / (double)p.N);
 }
 
 template <int D, int C>
@@ -203,6 +241,8 @@ __device__ void fs_setup(const FsParams& p, FsSmem& sm, float* base) {
   sm.gs = cur; cur += P;
   sm.pk = cur; cur += p.H * PKW;
   sm.part = cur; cur += n_slices * p.H * PKW;
+  cur = (float*)(((uintptr_t)cur + 7) & ~(uintptr_t)7);
+  sm.gx = cur; cur += 2 * (((P + 1) & ~(int64_t)1) + 2);
   for (int i = threadIdx.x; i < N * D; i += FS_THREADS) sm.xs[i] = p.X[i];
   if (p.loss_kind == PYB_LOSS_SPARSE_CE) {
     for (int i = threadIdx.x; i < N; i += FS_THREADS) sm.ys[i] = __int_as_float(p.y_i[i]);
@@ -232,8 +272,15 @@ __global__ void __launch_bounds__(FS_THREADS) k_fs_hmc(FsParams p) {
   extern __shared__ __align__(16) float fs_smem[];
   FsSmem sm;
   fs_setup<D, C>(p, sm, fs_smem);
-  const int64_t s = blockIdx.x, P = p.P;
+  const int n_ctas = p.cluster;
+  const int rank = n_ctas > 1 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
+  const int64_t s = blockIdx.x / n_ctas, P = p.P;
   const int t = threadIdx.x;
+  const bool writer = rank == 0;          // every CTA of the cluster holds the same state; one writes it back
+  int n_eval = 0;
+  auto eval = [&]() -> float {
+    return n_ctas > 1 ? fs_eval_cluster<D, C>(p, sm, p.n_train, rank, n_ctas, n_eval) : fs_eval<D, C>(p, sm, p.n_train);
+  };
   // q, momentum (HMC.py:78), K0 (:79)
   double k0 = 0.0;
   for (int64_t i = t; i < P; i += FS_THREADS) sm.qs[i] = p.q[s * P + i];
@@ -251,12 +298,12 @@ __global__ void __launch_bounds__(FS_THREADS) k_fs_hmc(FsParams p) {
   for (int64_t i = t; i < P; i += FS_THREADS) k0 += (double)sm.ps[i] * (double)sm.ps[i];
   const float K0 = (float)(fs_block_sum_all<double>(k0, sm.red) * (double)p.inv2m);
   // U0 and the first half kick share the evaluation at q0 (HMC.py:80-82)
-  const float loss0 = fs_eval<D, C>(p, sm, p.n_train);
+  const float loss0 = eval();
   double e0 = 0.0;
   for (int64_t i = t; i < P; i += FS_THREADS) {
     float q = sm.qs[i], d = q - p.mu[i], iv = p.inv_var[i];
     e0 += 0.5 * (double)(d * d * iv);
-    p.q0[s * P + i] = q;
+    if (writer) p.q0[s * P + i] = q;
     float pp = sm.ps[i] - p.half_eps * (sm.gs[i] + d * iv);
     sm.ps[i] = pp;
     sm.qs[i] = q + p.drift * pp;
@@ -264,7 +311,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fs_hmc(FsParams p) {
   const float Up0 = (float)fs_block_sum_all<double>(e0, sm.red);
   float loss1 = loss0, Up1 = 0.f, K1 = 0.f;
   for (int step = 1; step <= p.L; ++step) {
-    loss1 = fs_eval<D, C>(p, sm, p.n_train);
+    loss1 = eval();
     if (step < p.L) {
       for (int64_t i = t; i < P; i += FS_THREADS) {
         float q = sm.qs[i], d = q - p.mu[i];
@@ -293,11 +340,13 @@ __global__ void __launch_bounds__(FS_THREADS) k_fs_hmc(FsParams p) {
       K1 = (float)(fs_block_sum_all<double>(k1, sm.red) * (double)p.inv2m);
     }
   }
-  for (int64_t i = t; i < P; i += FS_THREADS) {
-    p.q[s * P + i] = sm.qs[i];
-    p.p[s * P + i] = sm.ps[i];
-  }
-  if (t == 0) {
+  if (writer)
+    for (int64_t i = t; i < P; i += FS_THREADS) {
+      p.q[s * P + i] = sm.qs[i];
+      p.p[s * P + i] = sm.ps[i];
+    }
+  if (n_ctas > 1) cooperative_groups::this_cluster().sync();     // nobody leaves while a peer may still read its shared memory
+  if (t == 0 && writer) {
     // Metropolis test (HMC.py:91), same expression order as k_accept
     float U0 = (Up0 + p.prior_const) + loss0 * p.n_train;
     float U1 = (Up1 + p.prior_const) + loss1 * p.n_train;
@@ -321,7 +370,7 @@ static size_t fs_smem_bytes(const pyb_handle* h) {
   const int D = m.layer[0].fan_in, H = m.layer[0].fan_out, C = m.layer[1].fan_out;
   const int n_slices = FS_THREADS / H > 0 ? FS_THREADS / H : 1;
   size_t f = 64 + (size_t)h->N * D + (size_t)h->N * (h->loss_kind == PYB_LOSS_SPARSE_CE ? 1 : C) + (size_t)h->N * C +
-             3 * (size_t)m.P + (size_t)H * (D + 1 + C) * (1 + n_slices);
+             3 * (size_t)m.P + (size_t)H * (D + 1 + C) * (1 + n_slices) + 2 * (((size_t)m.P + 1) / 2 * 2 + 2) + 2;
   return f * sizeof(float) + 16;
 }
 
@@ -342,7 +391,18 @@ static void fs_launch(pyb_handle* h, const FsParams& p, int64_t S, bool hmc) {
   size_t smem = fs_smem_bytes(h);
   if (hmc) {
     PYB_CUDA(cudaFuncSetAttribute(k_fs_hmc<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fs_hmc<D, C><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
+    if (p.cluster > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(S * p.cluster)); cfg.blockDim = dim3(FS_THREADS);
+      cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      PYB_CUDA(cudaLaunchKernelEx(&cfg, k_fs_hmc<D, C>, p));
+    } else {
+      k_fs_hmc<D, C><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
+    }
   } else {
     PYB_CUDA(cudaFuncSetAttribute(k_fs_eval<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fs_eval<D, C><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
@@ -395,6 +455,11 @@ void fused_small_hmc_iteration(pyb_handle* h, bool burning) {
   p.prior_const = (float)h->prior_const;
   p.L = st.L; p.semantics = st.semantics; p.burning = burning ? 1 : 0;
   p.seed = h->seed; p.iter = (uint32_t)st.iter; p.chain_offset = st.chain_offset;
+  // few chains: spread each over a cluster (the row ranges must stay worth a CTA: >= 64 rows each)
+  p.cluster = 1;
+  if (h->opt_fs_cluster)
+    for (int c = 8; c >= 2; c >>= 1)
+      if (st.S * c <= h->sm_count && h->N / c >= 64) { p.cluster = c; break; }
   p.U0 = st.U0.p; p.U1 = st.U1.p; p.K0 = st.K0.p; p.K1 = st.K1.p; p.log_alpha = st.log_alpha.p;
   p.ret_loss = st.ret_loss.p; p.accepted = st.accepted.p; p.counters = st.counters.p; p.loss_sum = st.loss_sum.p;
   fs_dispatch(h, p, st.S, true);

@@ -200,6 +200,45 @@ def test_sharded_chains_reproduce_the_unsharded_run(oracle, path):
     np.testing.assert_allclose(np.concatenate(parts), qf, rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("S", [1, 5, 30, 200])
+def test_cluster_spread_small_chains_match_the_one_cta_kernel(oracle, S):
+    """Few chains: the small-width kernel spreads each chain over a cluster of 8/4/2 CTAs (row ranges + DSMEM sum of
+    the partial gradients).  Same trajectory as one CTA per chain up to summation order, same accept decisions, and
+    the one-chain case still matches the float64 oracle."""
+    O = oracle
+    rng = np.random.default_rng(S)
+    N, D, H, Cc, L, eps = 1600, 2, 50, 2, 6, 5e-3
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    y = (X[:, 0] * X[:, 1] > 0).astype(np.int32)
+    spec_o = O.MLPSpec(D, [H, Cc], ["relu", "softmax"])
+    q = (rng.standard_normal((S, spec_o.n_params)) * 0.3).astype(np.float32)
+    p0 = rng.standard_normal((S, spec_o.n_params)).astype(np.float32)
+    u = rng.random(S).astype(np.float32)
+    outs = []
+    for cluster in (1, 0):
+        eng = Engine(keras_json.parse_model_json(keras_json.make_sequential_json(D, [H, Cc], ["relu", "softmax"])))
+        eng.set_option("fs_cluster", cluster)
+        eng.set_dataset(X, y, _lib.LOSS_SPARSE_CE)
+        eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+        eng.hmc_init(S, eps, 1.0, L, _lib.HMC_REFERENCE, q0=q)
+        eng.hmc_inject(p=p0, u=u)
+        eng.hmc_run(1, burning=False, sampling=True)
+        assert int(eng.info("path_used")) == _lib.PATH_FUSED_SMALL
+        qs, ps = eng.hmc_state()
+        outs.append((qs, ps, eng.hmc_last()))
+        eng.close()
+    (qa, pa, la), (qb, pb, lb) = outs
+    np.testing.assert_allclose(qa, qb, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(pa, pb, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(la["U1"], lb["U1"], rtol=1e-5)
+    np.testing.assert_array_equal(la["accept"], lb["accept"])
+    if S == 1:
+        mu, sg = O.expand_prior(spec_o, 0.0, 1.0)
+        want = O.hmc_iteration(O.Problem(spec_o, X, y, O.LOSS_SPARSE_CE, mu, sg), q, p0, u, eps, 1.0, L, False,
+                               O.HMC_REFERENCE, np.float64)
+        assert rel_err(pa, want["pL"]) < 1e-3 and abs(la["U1"][0] - want["U1"][0]) < 1e-4 * abs(want["U1"][0])
+
+
 def test_chain_batching_does_not_change_results(oracle):
     g = load_golden("hmc_c1_mini")
     a, _ = make_engine(g, oracle)
