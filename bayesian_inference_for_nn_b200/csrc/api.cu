@@ -188,6 +188,8 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_tc_gram_sym = v != 0;
   } else if (!strcmp(key, "fs_cluster")) {
     h->opt_fs_cluster = v != 0;
+  } else if (!strcmp(key, "live_fused")) {
+    h->opt_live_fused = v != 0;
   } else if (!strcmp(key, "tc_fuse")) {
     h->opt_tc_fuse = v != 0;
   } else if (!strcmp(key, "profile")) {

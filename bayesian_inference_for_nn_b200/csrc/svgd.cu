@@ -15,6 +15,7 @@
 // same code serves one GPU (row range = everything) and the all-gathered multi-GPU layout.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cooperative_groups.h>
 #include <math.h>
 #include <algorithm>
 
@@ -94,6 +95,58 @@ __global__ void k_live_update(float* theta, const float* g, float* am, float* av
     float phi = (wsum * g[ol] + gk) / (float)S;
     if (phi_out) phi_out[ol] = phi;
     theta[o] = adam_update(theta[o], phi, am[ol], av[ol], lr_t, 0.9f, 0.999f, 1e-7f);
+  }
+}
+
+// The whole sequential sweep of one step in ONE cooperative launch (single GPU): for i = 0..S-1 {kernel row of
+// particle i against the current state; grid barrier; phi_i and the Adam step of particle i; grid barrier}.
+// Same arithmetic, block shape and summation order as k_live_row / k_live_update (bit-identical results); what goes
+// away is 2 S kernel launches per step (the reference's own configuration is launch-bound: S = 10..64, P = 252).
+__global__ void __launch_bounds__(256) k_live_sweep(float* theta, const float* g, float* am, float* av, float* phi_out,
+                                                    int64_t P, int S, double gamma, double* Krow, float lr_t) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double scratch[32];
+  __shared__ double Ks[1024];
+  for (int i = 0; i < S; ++i) {
+    // ---- K_ik for every k (one block per k, float64)
+    const float* xi_row = theta + (int64_t)i * P;
+    for (int k = blockIdx.x; k < S; k += gridDim.x) {
+      const float* xk = theta + (int64_t)k * P;
+      double a = 0.0;
+      for (int64_t e = threadIdx.x; e < P; e += blockDim.x) {
+        double d = (double)xi_row[e] - (double)xk[e];
+        a += d * d;
+      }
+      double t = block_sum<double>(a, scratch);
+      if (threadIdx.x == 0) Krow[k] = exp(-gamma * t);
+      __syncthreads();
+    }
+    grid.sync();
+    // ---- phi_i and the update of particle i (one thread per parameter)
+    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x; e0 < P; e0 += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t e = e0 + threadIdx.x;
+      double xi = (e < P) ? (double)theta[(int64_t)i * P + e] : 0.0;
+      double acc = 0.0;
+      float wsum = 0.f;
+      for (int k0 = 0; k0 < S; k0 += 1024) {
+        int n = min(1024, S - k0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += blockDim.x) Ks[k] = Krow[k0 + k];
+        __syncthreads();
+        if (e < P)
+          for (int k = 0; k < n; ++k) acc += Ks[k] * (xi - (double)theta[(int64_t)(k0 + k) * P + e]);
+        for (int k = 0; k < n; ++k) wsum += (float)Ks[k];
+      }
+      if (e < P) {
+        const int64_t o = (int64_t)i * P + e;
+        float gk = (float)(2.0 * gamma * acc);
+        float phi = (wsum * g[o] + gk) / (float)S;
+        if (phi_out) phi_out[o] = phi;
+        theta[o] = adam_update(theta[o], phi, am[o], av[o], lr_t, 0.9f, 0.999f, 1e-7f);
+      }
+    }
+    grid.sync();
   }
 }
 
@@ -535,7 +588,23 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
     // global state) and broadcasts them before the next rank starts
     sc.Krow.alloc(St);
     float* th_all = (R > 1) ? sv.theta_all.p : sv.theta.p;
-    for (int rr = 0; rr < R; ++rr) {
+    bool swept = false;
+    if (R == 1 && h->opt_live_fused) {
+      // one cooperative launch for the whole sweep (falls back to the per-particle launches if it cannot be co-resident)
+      int per_sm = 0;
+      PYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_live_sweep, 256, 0));
+      const int64_t want = std::max<int64_t>(St, (P + 255) / 256);
+      const int grid = (int)std::min<int64_t>(want, (int64_t)per_sm * h->sm_count);
+      if (grid >= 1) {
+        float* th = sv.theta.p; const float* gp = sv.g.p; float* am = sv.adam_m.p; float* av = sv.adam_v.p;
+        float* ph = sv.phi.p; int64_t Pp = P; int Sp = St; double gam = 1.0; double* kr = sc.Krow.p; float lrt = lr_t;
+        void* args[] = {&th, &gp, &am, &av, &ph, &Pp, &Sp, &gam, &kr, &lrt};
+        PYB_CUDA(cudaLaunchCooperativeKernel((void*)k_live_sweep, dim3(grid), dim3(256), args, 0, h->stream));
+        count_launch(h);
+        swept = true;
+      }
+    }
+    for (int rr = 0; rr < R && !swept; ++rr) {
       if (rr == sv.rank) {
         for (int i = 0; i < (int)S; ++i) {
           const int gi = r0 + i;
