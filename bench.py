@@ -290,7 +290,11 @@ def main():
                 "kernel": {1: "k_sgemm (fp32 SIMT)", 2: "fused small", 3: "tc_gemm bf16x3 (tcgen05)"}.get(path_used, "?"),
                 "launches": int(prof_n), "avg_launch_ms": prof_ms / max(1, prof_n),
                 "kernel_share_of_step": prof_ms / d["device_ms"],
-                "whole_step_algorithmic_tflops": value / max(1, world) * algo_flops_per_eval / 1e12}
+                "whole_step_algorithmic_tflops": value / max(1, world) * algo_flops_per_eval / 1e12,
+                "note": "fp32-grade products cost 3 bf16 MMA passes (hi*hi + lo*hi + hi*lo): algorithmic frac <= 1/3 of the "
+                        "bf16 peak, issued_mma_frac is the tensor-pipe view; ncu (profiles/): the dW1 GEMM runs the tensor "
+                        "pipe 95 % active, the fused layer-1 GEMM + layer-2 kernel is bound by the SM's 128 B/clk "
+                        "shared-memory data path (MMA operand reads + TMA fills + epilogue stores), see DESIGN.md section 4"}
     cpu = None
     if not args.no_cpu_baseline:
         # bounded sample (~10 s of CPU work): 1 chain, 3 timed iterations (+1 warm-up) on the full dataset
