@@ -68,6 +68,8 @@ SIGNATURES = {
     "pyb_svgd_set_comm": [_P, C.c_int32, C.c_int32, C.c_void_p],
     "pyb_nccl_unique_id": [C.c_void_p],
     "pyb_predict": [_P, _f32p, C.c_int64, _f32p, _f32p, C.c_int64, _f32p, _f32p, _f32p],
+    "pyb_predict_uncertainty": [_P, _f32p, C.c_int64, _f32p, _f32p, C.c_int64, _i32p, C.c_int32, C.c_double, _f32p, _f32p,
+                                _f32p, _f32p],
     "pyb_buffer_create": [_P, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)],
     "pyb_buffer_destroy": [_P, C.c_void_p],
     "pyb_gather_rows": [_P, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p],

@@ -499,6 +499,17 @@ int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, c
   PYB_CATCH
 }
 
+int pyb_predict_uncertainty(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
+                            const int32_t* y, int32_t cumulative_rows, double divisor, float* total_out,
+                            float* aleatoric_out, float* epistemic_out, float* mean_out) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  UncertaintyReq uq{y, cumulative_rows, divisor, total_out, aleatoric_out, epistemic_out};
+  predict(h, W, n, weight, x, Nt, mean_out, nullptr, nullptr, &uq);
+  PYB_CATCH
+}
+
 int pyb_buffer_create(pyb_handle* h, const void* host_or_null, int64_t bytes, void** dev_out) {
   PYB_TRY
   PYB_REQUIRE(h && dev_out && bytes > 0, PYB_ERR_INVALID, "bad arguments");

@@ -354,6 +354,13 @@ void nccl_all_reduce_f64(void* comm, double* buf, size_t count, cudaStream_t s);
 void nccl_broadcast_f32(void* comm, float* buf, size_t count, int root, cudaStream_t s);
 
 // predict.cu
+// optional classification-uncertainty request (Metrics.py:344-375): host labels [Nt], host outputs [Nt, Ce, Ce]
+struct UncertaintyReq {
+  const int32_t* y;
+  int cumulative;     // 1: running sum over the rows, as the reference computes it; 0: per-row matrices
+  double divisor;     // the reference divides by its n_samples ARGUMENT (Metrics.py:368-369)
+  float *total, *aleatoric, *epistemic;
+};
 void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
-             float* mean, float* var, float* all);
+             float* mean, float* var, float* all, const UncertaintyReq* uq = nullptr);
 }  // namespace pyb

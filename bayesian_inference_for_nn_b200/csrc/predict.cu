@@ -35,6 +35,75 @@ __global__ void k_pred_finish(const double* s1, const double* s2, double wsum, i
   var[e] = (float)(v > 0.0 ? v : 0.0);
 }
 
+// ---- Metrics.classification_uncertainty (Metrics.py:344-375) --------------------------------------------------
+// Per data row r and weight sample k with class probabilities p (NaN -> 0 as BayesianModel.py:125):
+//   aleatoric_r += w_k (diag(p) - p p^T)        epistemic_r += w_k (p - onehot(y_r)) (p - onehot(y_r))^T
+// One thread per (row, i, j); j is the fastest index, so p_j loads are coalesced and p_i loads are warp broadcasts.
+// A one-unit (sigmoid) output is widened to the two classes [1-p, p] (Metrics.py:357-359).
+__device__ inline float uq_prob(const float* o, int C, int c) {
+  float v = (C == 1) ? o[0] : o[c];
+  if (v != v) v = 0.f;
+  return (C == 1 && c == 0) ? 1.f - v : v;
+}
+__global__ void k_uncert_accum(const float* out, int64_t n_chunk, int64_t Nt, int C, int Ce, const int32_t* y,
+                               const float* w, double* alea, double* epi) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Nt * Ce * Ce) return;
+  const int j = (int)(e % Ce), i = (int)((e / Ce) % Ce);
+  const int64_t r = e / ((int64_t)Ce * Ce);
+  const int label = y[r];
+  const float oi = (i == label) ? 1.f : 0.f, oj = (j == label) ? 1.f : 0.f;
+  double a = 0.0, b = 0.0;
+  for (int64_t k = 0; k < n_chunk; ++k) {
+    const float* o = out + (k * Nt + r) * C;
+    const float pi = uq_prob(o, C, i), pj = uq_prob(o, C, j);
+    const double ww = w ? (double)w[k] : 1.0;
+    a += ww * ((i == j ? (double)pi : 0.0) - (double)pi * (double)pj);
+    b += ww * (double)(pi - oi) * (double)(pj - oj);
+  }
+  alea[e] += a;
+  epi[e] += b;
+}
+// The reference never resets its accumulators between rows (Metrics.py:352-366: `aleatoric +=` inside the row loop,
+// appended per row), so row r of its result is the running sum over rows 0..r.  Three passes over 256-row segments:
+// segment sums, exclusive scan of the segment sums, running prefix written out (fixed order => deterministic).
+constexpr int kUqSeg = 256;
+__global__ void k_uncert_segsum(const double* acc, int64_t Nt, int CC, double* seg) {
+  const int e = threadIdx.x;
+  if (e >= CC) return;
+  const int64_t r0 = (int64_t)blockIdx.x * kUqSeg, r1 = min(r0 + (int64_t)kUqSeg, Nt);
+  double s = 0.0;
+  for (int64_t r = r0; r < r1; ++r) s += acc[r * CC + e];
+  seg[(int64_t)blockIdx.x * CC + e] = s;
+}
+__global__ void k_uncert_segscan(double* seg, int64_t nseg, int CC) {
+  const int e = threadIdx.x;
+  if (e >= CC) return;
+  double run = 0.0;
+  for (int64_t s = 0; s < nseg; ++s) {
+    const double v = seg[s * CC + e];
+    seg[s * CC + e] = run;
+    run += v;
+  }
+}
+__global__ void k_uncert_finish(const double* alea, const double* epi, const double* seg_a, const double* seg_e,
+                                int64_t Nt, int CC, int cumulative, double inv_div, float* total, float* alea_out,
+                                float* epi_out) {
+  const int e = threadIdx.x;
+  if (e >= CC) return;
+  const int64_t r0 = (int64_t)blockIdx.x * kUqSeg, r1 = min(r0 + (int64_t)kUqSeg, Nt);
+  double ra = cumulative ? seg_a[(int64_t)blockIdx.x * CC + e] : 0.0;
+  double re = cumulative ? seg_e[(int64_t)blockIdx.x * CC + e] : 0.0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const double a = alea[r * CC + e], b = epi[r * CC + e];
+    if (cumulative) { ra += a; re += b; } else { ra = a; re = b; }
+    const float fa = (float)(ra * inv_div), fe = (float)(re * inv_div);
+    alea_out[r * CC + e] = fa;
+    epi_out[r * CC + e] = fe;
+    total[r * CC + e] = fe + fa;     // epistemics + aleatorics in float32, as Metrics.py:370
+  }
+}
+
 // dst[k][:] = src[idx[k]][:]   (device rows of row_len floats; idx arrives from the host)
 __global__ void k_gather_rows_f32(const float* src, const int64_t* idx, int64_t row_len, float* dst) {
   const int64_t k = blockIdx.y;
@@ -57,13 +126,31 @@ void gather_rows_f32(pyb_handle* h, const float* src, const int64_t* idx_host, i
 }
 
 void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
-             float* mean, float* var, float* all) {
+             float* mean, float* var, float* all, const UncertaintyReq* uq) {
   PYB_REQUIRE(n > 0 && Nt > 0, PYB_ERR_INVALID, "n and Nt must be > 0");
-  PYB_REQUIRE(W && x && mean && var, PYB_ERR_INVALID, "null pointer");
+  PYB_REQUIRE(W && x && (uq || (mean && var)), PYB_ERR_INVALID, "null pointer");
   const Model& m = h->model;
   const int64_t P = m.P, C = m.out_dim, elems = Nt * C;
   DevBuf<float> dW, dx, dw, dout, dmean, dvar;
   DevBuf<double> s1, s2;
+  // classification-uncertainty accumulators [Nt, Ce, Ce] (Ce = 2 for a one-unit output)
+  const int Ce = (C == 1) ? 2 : (int)C, CC = Ce * Ce;
+  DevBuf<double> ua, ue, seg_a, seg_e;
+  DevBuf<float> ut, uao, ueo;
+  DevBuf<int32_t> uy;
+  const int64_t nseg = (Nt + kUqSeg - 1) / kUqSeg;
+  if (uq) {
+    PYB_REQUIRE(uq->y && uq->total && uq->aleatoric && uq->epistemic, PYB_ERR_INVALID, "null pointer");
+    PYB_REQUIRE(CC <= 1024, PYB_ERR_UNSUPPORTED, "classification uncertainty supports at most 32 classes");
+    PYB_REQUIRE(uq->divisor != 0.0, PYB_ERR_INVALID, "divisor must not be 0");
+    for (int64_t r = 0; r < Nt; ++r)
+      PYB_REQUIRE(uq->y[r] >= 0 && uq->y[r] < Ce, PYB_ERR_INVALID, "label out of range");
+    ua.alloc(Nt * CC); ue.alloc(Nt * CC); seg_a.alloc(nseg * CC); seg_e.alloc(nseg * CC);
+    ut.alloc(Nt * CC); uao.alloc(Nt * CC); ueo.alloc(Nt * CC); uy.alloc(Nt);
+    PYB_CUDA(cudaMemsetAsync(ua.p, 0, Nt * CC * sizeof(double), h->stream));
+    PYB_CUDA(cudaMemsetAsync(ue.p, 0, Nt * CC * sizeof(double), h->stream));
+    PYB_CUDA(cudaMemcpyAsync(uy.p, uq->y, Nt * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  }
   // W and x may be host pointers (copied chunk by chunk) or device pointers (used in place: samples that already
   // live in HBM, e.g. DLPack tensors, skip the n*P*4-byte upload that otherwise dominates the call)
   auto on_device = [](const void* ptr) {
@@ -112,6 +199,11 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
     k_pred_accum<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(dout.p, nb, elems, weight ? dw.p + i0 : nullptr,
                                                                          s1.p, s2.p);
     count_launch(h);
+    if (uq) {
+      k_uncert_accum<<<(unsigned)((Nt * CC + 255) / 256), 256, 0, h->stream>>>(dout.p, nb, Nt, (int)C, Ce, uy.p,
+                                                                              weight ? dw.p + i0 : nullptr, ua.p, ue.p);
+      count_launch(h);
+    }
     if (all) {
       k_nan_to_zero<<<(unsigned)std::min<int64_t>((nb * elems + 255) / 256, 4096), 256, 0, h->stream>>>(dout.p, nb * elems);
       count_launch(h);
@@ -120,9 +212,26 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
   }
   k_pred_finish<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(s1.p, s2.p, wsum, elems, dmean.p, dvar.p);
   count_launch(h);
+  if (uq) {
+    if (uq->cumulative) {
+      k_uncert_segsum<<<(unsigned)nseg, CC, 0, h->stream>>>(ua.p, Nt, CC, seg_a.p);
+      k_uncert_segsum<<<(unsigned)nseg, CC, 0, h->stream>>>(ue.p, Nt, CC, seg_e.p);
+      k_uncert_segscan<<<1, CC, 0, h->stream>>>(seg_a.p, nseg, CC);
+      k_uncert_segscan<<<1, CC, 0, h->stream>>>(seg_e.p, nseg, CC);
+      count_launch(h, 4);
+    }
+    k_uncert_finish<<<(unsigned)nseg, CC, 0, h->stream>>>(ua.p, ue.p, seg_a.p, seg_e.p, Nt, CC, uq->cumulative ? 1 : 0,
+                                                         1.0 / uq->divisor, ut.p, uao.p, ueo.p);
+    count_launch(h);
+  }
   PYB_CUDA(cudaEventRecord(h->ev1, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(mean, dmean.p, elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(var, dvar.p, elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (uq) {
+    PYB_CUDA(cudaMemcpyAsync(uq->total, ut.p, Nt * CC * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    PYB_CUDA(cudaMemcpyAsync(uq->aleatoric, uao.p, Nt * CC * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    PYB_CUDA(cudaMemcpyAsync(uq->epistemic, ueo.p, Nt * CC * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (mean) PYB_CUDA(cudaMemcpyAsync(mean, dmean.p, elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (var) PYB_CUDA(cudaMemcpyAsync(var, dvar.p, elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   PYB_CUDA(cudaStreamSynchronize(h->stream));
   PYB_CUDA(cudaGetLastError());
   float ms = 0.f;

@@ -220,6 +220,37 @@ class Engine:
         return dst
 
     # ---- predictive
+    def _predict_args(self, W, x):
+        if isinstance(W, (np.ndarray, list, tuple)):
+            W = _f32(W)
+        Wa, _, wptr = ingest(W, np.float32)
+        if len(Wa.shape) != 2 or int(Wa.shape[1]) != self.P:
+            raise ValueError("W must be [n, P]")
+        if isinstance(x, (np.ndarray, list, tuple)):
+            x = _f32(x)
+            x = x.reshape(x.shape[0], -1)
+        xa, _, xptr = ingest(x, np.float32)
+        if int(np.prod(xa.shape[1:])) != self.spec.in_dim:
+            raise ValueError("x has %d features per row, the model expects %d" % (int(np.prod(xa.shape[1:])), self.spec.in_dim))
+        return (Wa, W, wptr), (xa, x, xptr)
+
+    def predict_uncertainty(self, W, x, y, weights=None, cumulative=True, divisor=None):
+        """Metrics.classification_uncertainty on the device (pyb_predict_uncertainty): -> (total, aleatoric, epistemic,
+        mean), the first three [Nt, Ce, Ce].  ``divisor`` defaults to the number of rows."""
+        (Wa, _Wk, wptr), (xa, _xk, xptr) = self._predict_args(W, x)
+        n, Nt, Cc = int(Wa.shape[0]), int(xa.shape[0]), self.spec.out_dim
+        Ce = 2 if Cc == 1 else Cc
+        ya = np.ascontiguousarray(np.asarray(y).reshape(-1), dtype=np.int32)
+        if ya.shape[0] != Nt:
+            raise ValueError("x and y disagree on the number of rows")
+        w = None if weights is None else _f32(weights, (n,))
+        tot, al, ep = (np.empty((Nt, Ce, Ce), np.float32) for _ in range(3))
+        mean = np.empty((Nt, Cc), np.float32)
+        check(self.lib.pyb_predict_uncertainty(self.h, wptr, n, _ptr(w), xptr, Nt, _ptr(ya), int(bool(cumulative)),
+                                               float(Nt if divisor is None else divisor), _ptr(tot), _ptr(al), _ptr(ep),
+                                               _ptr(mean)))
+        return tot, al, ep, mean
+
     def predict(self, W, x, weights=None, want_all=False):
         """W [n, P] weight samples, x [Nt, in_dim...] inputs: NumPy arrays, or device tensors (DLPack / tf.Tensor), which
         the library reads in place instead of uploading."""

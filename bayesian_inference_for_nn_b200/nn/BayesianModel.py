@@ -44,6 +44,18 @@ class ParticleModel:
     __call__ = predict
 
 
+class WeightDraws:
+    """Distinct weight vectors of a posterior draw, resident in HBM, with their multiplicities."""
+
+    def __init__(self, W, weights, inverse, exact=False):
+        self.W, self.weights, self.inverse, self.exact = W, weights, inverse, exact
+
+    def free(self):
+        if not self.exact and self.W is not None:     # exact mode borrows the model's resident sample matrix
+            self.W.free()
+        self.W = None
+
+
 class BayesianModel:
     def __init__(self, model_config: str, device: int = 0):
         self._model_config = model_config
@@ -109,32 +121,57 @@ class BayesianModel:
         return [self.sample_model() for _ in range(n)]
 
     # ---- predictive -----------------------------------------------------------------------
-    def predict(self, x, nb_samples: int, y_true=None, loss_func=None, mode: str = "reference"):
+    def _is_single_sampled(self):
+        return (len(self._distributions) == 1 and isinstance(self._distributions[0], Sampled)
+                and self._spec.layer_param_range(*self._layers_dtbn_intervals[0]) == (0, self._spec.n_params))
+
+    def draw(self, nb_samples: int, mode: str = "reference"):
+        """The nb_samples weight draws of one ``predict`` call (BayesianModel.py:121-122), made up front.  Returns a
+        ``WeightDraws`` that ``predict`` / ``classification_uncertainty`` accept as ``draws=`` so that several
+        quantities can be computed on the SAME draws — what the reference's Metrics/Plotter get from caching the
+        per-draw outputs (Metrics.py:27-45)."""
+        eng = self._engine_for_predict()
+        if self._is_single_sampled():
+            d = self._distributions[0]
+            if mode == "exact":
+                return WeightDraws(self._samples_on_device(d), np.asarray(d.frequencies, np.float32), None, exact=True)
+            draws = np.fromiter((d.sample_index() for _ in range(nb_samples)), dtype=np.int64, count=nb_samples)
+            uniq, inverse, counts = np.unique(draws, return_inverse=True, return_counts=True)
+            Wd = eng.gather_rows(self._samples_on_device(d), uniq)     # distinct draws, gathered in HBM
+            return WeightDraws(Wd, counts.astype(np.float32), inverse)
+        W = np.stack([self._draw_flat() for _ in range(nb_samples)])
+        return WeightDraws(eng.device_array(W), None, np.arange(nb_samples))
+
+    def predict(self, x, nb_samples: int, y_true=None, loss_func=None, mode: str = "reference", draws=None):
         """-> (list of nb_samples arrays [N,C], mean [N,C]).  ``self.last_variance`` holds the
         population variance over the draws (what Plotter.regression_uncertainty takes with np.var)."""
         x = to_numpy(x, np.float32)
         x = x.reshape(x.shape[0], -1)
         eng = self._engine_for_predict()
-        single = (len(self._distributions) == 1 and isinstance(self._distributions[0], Sampled)
-                  and self._spec.layer_param_range(*self._layers_dtbn_intervals[0]) == (0, self._spec.n_params))
-        if single and mode == "exact":
-            d = self._distributions[0]
-            mean, var, _ = eng.predict(self._samples_on_device(d), x, weights=np.asarray(d.frequencies, np.float32))
+        dr = draws if draws is not None else self.draw(nb_samples, mode)
+        if dr.exact:
+            mean, var, _ = eng.predict(dr.W, x, weights=dr.weights)
             self.last_variance = var
             return [mean], mean
-        if single:
-            d = self._distributions[0]
-            draws = np.fromiter((d.sample_index() for _ in range(nb_samples)), dtype=np.int64, count=nb_samples)
-            uniq, inverse, counts = np.unique(draws, return_inverse=True, return_counts=True)
-            Wd = eng.gather_rows(self._samples_on_device(d), uniq)     # distinct draws, gathered in HBM
-            mean, var, allo = eng.predict(Wd, x, weights=counts.astype(np.float32), want_all=True)
-            Wd.free()
-            self.last_variance = var
-            return [allo[i] for i in inverse], mean
-        W = np.stack([self._draw_flat() for _ in range(nb_samples)])
-        mean, var, allo = eng.predict(W, x, want_all=True)
+        mean, var, allo = eng.predict(dr.W, x, weights=dr.weights, want_all=True)
+        if draws is None:
+            dr.free()
         self.last_variance = var
-        return [allo[i] for i in range(nb_samples)], mean
+        return [allo[i] for i in dr.inverse], mean
+
+    def classification_uncertainty(self, x, y_true, nb_samples: int, divisor=None, cumulative=True,
+                                   mode: str = "reference", draws=None):
+        """Metrics.classification_uncertainty (Metrics.py:344-375) evaluated on the device for nb_samples weight draws:
+        -> (epistemic + aleatoric, aleatoric, epistemic), each [N, C, C].  ``cumulative=True`` keeps the reference's
+        running sum over the rows, ``divisor`` is the n_samples argument it divides by (default: the number of rows)."""
+        x = to_numpy(x, np.float32)
+        x = x.reshape(x.shape[0], -1)
+        dr = draws if draws is not None else self.draw(nb_samples, mode)
+        tot, al, ep, _ = self._engine_for_predict().predict_uncertainty(
+            dr.W, x, to_numpy(y_true).reshape(-1), weights=dr.weights, cumulative=cumulative, divisor=divisor)
+        if draws is None:
+            dr.free()
+        return tot, al, ep
 
     def uncertainty_mask(self, x, nb_samples, threshold, mode="reference"):
         """max_c mean_c < threshold — the 'uncertainty area' of Plotter.py:71-72."""

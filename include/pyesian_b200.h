@@ -156,6 +156,17 @@ int pyb_nccl_unique_id(void* out_128);
 int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x,
                 int64_t Nt, float* mean_out, float* var_out, float* all_out);
 
+/* Metrics.classification_uncertainty (Metrics.py:344-375): for the same n weight samples and inputs, with integer
+ * labels y [Nt] (host), the per-row matrices  aleatoric = sum_k w_k (diag(p_k) - p_k p_k^T)  and
+ * epistemic = sum_k w_k (p_k - onehot(y)) (p_k - onehot(y))^T, divided by `divisor` (the reference divides by its
+ * n_samples ARGUMENT, :368-369).  cumulative_rows = 1 reproduces the reference, whose accumulators are never reset
+ * between rows (row r holds the running sum over rows 0..r, :352-366); 0 gives the per-row matrices.  Outputs are host
+ * float32 [Nt, Ce, Ce] with Ce = out_dim, or 2 for a one-unit output widened to [1-p, p] (:357-359);
+ * total = epistemic + aleatoric; mean_out [Nt, out_dim] may be NULL.  At most 32 classes. */
+int pyb_predict_uncertainty(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
+                            const int32_t* y, int32_t cumulative_rows, double divisor, float* total_out,
+                            float* aleatoric_out, float* epistemic_out, float* mean_out);
+
 /* ---- device-resident arrays owned by the caller (posterior samples kept in HBM between predict calls:
  *      BayesianModel.predict re-draws nb_samples weight vectors from the SAME Sampled on every call,
  *      BayesianModel.py:106-129 / Sampled.py:29-32) ----
