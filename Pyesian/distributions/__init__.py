@@ -1,1 +1,3 @@
-from bayesian_inference_for_nn_b200.distributions import Distribution, GaussianPrior, Sampled  # noqa: F401
+from bayesian_inference_for_nn_b200.distributions import (Distribution, GaussianPrior, Sampled, Normal,  # noqa: F401
+                                                          TensorflowProbabilityDistribution,
+                                                          MultivariateNormalDiagPlusLowRank, Mixture)

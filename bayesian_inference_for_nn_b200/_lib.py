@@ -18,6 +18,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 PRIOR_SCALAR, PRIOR_PER_VARIABLE, PRIOR_PER_ELEMENT = 0, 1, 2
 HMC_REFERENCE, HMC_CANONICAL = 0, 1
 SVGD_REFERENCE_LIVE, SVGD_CANONICAL_MEDIAN = 0, 1
+SG_SGLD, SG_SWAG = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_FUSED_SMALL, PATH_TENSOR = 0, 1, 2, 3
 
 
@@ -67,6 +68,9 @@ SIGNATURES = {
     "pyb_svgd_get_particles": [_P, _f64p],
     "pyb_svgd_set_comm": [_P, C.c_int32, C.c_int32, C.c_void_p],
     "pyb_nccl_unique_id": [C.c_void_p],
+    "pyb_sg_init": [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_int32],
+    "pyb_sg_step": [_P, _i32p, C.c_int64, C.c_double, _f32p, _f32p, C.POINTER(C.c_double)],
+    "pyb_sg_get": [_P, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
     "pyb_predict": [_P, _f32p, C.c_int64, _f32p, _f32p, C.c_int64, _f32p, _f32p, _f32p],
     "pyb_predict_uncertainty": [_P, _f32p, C.c_int64, _f32p, _f32p, C.c_int64, _i32p, C.c_int32, C.c_double, _f32p, _f32p,
                                 _f32p, _f32p],

@@ -490,6 +490,35 @@ int pyb_nccl_unique_id(void* out_128) {
   PYB_CATCH
 }
 
+int pyb_sg_init(pyb_handle* h, int64_t S, int64_t chain_offset, int32_t kind, int32_t k_dev, int32_t frequency,
+                const float* theta0, int32_t theta0_rows) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  sg_init(h, S, chain_offset, kind, k_dev, frequency, theta0, theta0_rows);
+  PYB_CATCH
+}
+
+int pyb_sg_step(pyb_handle* h, const int32_t* idx, int64_t B, double lr, const float* noise, float* loss_out,
+                double* mean_loss_out) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  if (idx)
+    for (int64_t i = 0; i < B; ++i)
+      PYB_REQUIRE(idx[i] >= 0 && idx[i] < h->N, PYB_ERR_INVALID, "batch index out of range");
+  sg_step(h, idx, B, lr, noise, loss_out, mean_loss_out);
+  PYB_CATCH
+}
+
+int pyb_sg_get(pyb_handle* h, float* theta, float* mean, float* sq_mean, float* dev, int32_t* n_cols, int64_t* n_steps) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  sg_get(h, theta, mean, sq_mean, dev, n_cols, n_steps);
+  PYB_CATCH
+}
+
 int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt, float* mean,
                 float* var, float* all) {
   PYB_TRY

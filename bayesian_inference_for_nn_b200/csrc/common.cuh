@@ -85,7 +85,7 @@ struct Model {
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011).  counter = (block, chain, iteration, stream), key = seed.
 // ------------------------------------------------------------------------------------------
-enum { STREAM_MOMENTUM = 0, STREAM_UNIFORM = 1, STREAM_INIT = 2 };
+enum { STREAM_MOMENTUM = 0, STREAM_UNIFORM = 1, STREAM_INIT = 2, STREAM_SGLD = 3 };
 
 __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                uint32_t k0, uint32_t k1, uint32_t out[4]) {
@@ -223,6 +223,17 @@ struct SvgdState {
   cudaEvent_t ev_fork = nullptr, ev_theta = nullptr, ev_grad = nullptr;
 };
 
+// S stochastic-gradient chains (sgmc.cu): SGLD / SWAG state per chain
+struct SgState {
+  bool inited = false;
+  int kind = 0, k = 0, freq = 1, cols = 0;
+  int64_t S = 0, offset = 0, n = 0;
+  DevBuf<float> theta, g, mean, sq, dev, loss;   // dev [S, k, P]: column c of chain s is contiguous
+  DevBuf<double> mean_loss;
+  DevBuf<float> Xb, yb_f;
+  DevBuf<int32_t> yb_i, idx;
+};
+
 struct Workspace {
   // generic-path activations for a chain batch: act[l] = [Bc, N, width_l], dz ping-pong
   std::vector<DevBuf<float>*> act;
@@ -267,6 +278,7 @@ struct pyb_handle {
   pyb::Workspace ws;
   pyb::HmcState hmc;
   pyb::SvgdState svgd;
+  pyb::SgState sg;
   // live per-kernel timing of the dominant (GEMM) kernels: CUDA events on the launching stream
   bool prof_enabled = false;
   std::vector<cudaEvent_t> prof_events;   // begin/end pairs, resolved by prof_resolve()
@@ -343,6 +355,16 @@ void hmc_flush_arena(pyb_handle* h);
 void svgd_init(pyb_handle* h, int64_t S, int64_t offset, double lr, int sem, const double* p0);
 void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out);
 void svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int sem, float* phi, double* h_out);
+
+// rows idx[0..B) of the resident dataset gathered into a contiguous minibatch (device index list)
+void gather_batch(pyb_handle* h, const int32_t* idx_dev, int64_t B, float* Xb, int32_t* yb_i, float* yb_f);
+
+// sgmc.cu
+void sg_init(pyb_handle* h, int64_t S, int64_t chain_offset, int kind, int k_dev, int frequency, const float* theta0,
+             int theta0_rows);
+void sg_step(pyb_handle* h, const int32_t* idx, int64_t B, double lr, const float* noise, float* loss_out,
+             double* mean_loss_out);
+void sg_get(pyb_handle* h, float* theta, float* mean, float* sq, float* dev, int32_t* n_cols, int64_t* n_steps);
 
 // nccl_shim.cu (NCCL resolved with dlopen; only sharded SVGD uses it)
 void nccl_unique_id(void* out_128);

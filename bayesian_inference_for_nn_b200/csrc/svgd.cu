@@ -48,6 +48,14 @@ __global__ void k_gather_rows(const float* X, const int32_t* y_i, const float* y
     for (int c = threadIdx.x; c < C; c += blockDim.x) yb_f[b * C + c] = y_f[r * C + c];
 }
 
+void gather_batch(pyb_handle* h, const int32_t* idx_dev, int64_t B, float* Xb, int32_t* yb_i, float* yb_f) {
+  const Model& m = h->model;
+  k_gather_rows<<<(unsigned)B, 128, 0, h->stream>>>(h->X.p, h->loss_kind == PYB_LOSS_SPARSE_CE ? h->y_i.p : nullptr,
+                                                    h->loss_kind == PYB_LOSS_MSE ? h->y_f.p : nullptr, idx_dev, B,
+                                                    m.in_dim, m.out_dim, Xb, yb_i, yb_f);
+  count_launch(h);
+}
+
 // ---- live sweep ---------------------------------------------------------------------------
 // Krow[k] = exp(-gamma * ||x_i - x_k||^2), float64; one block per k
 __global__ void k_live_row(const float* theta, int64_t P, int i, double gamma, double* Krow) {
@@ -532,10 +540,7 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
     sv.Xb.alloc(B * m.in_dim);
     if (h->loss_kind == PYB_LOSS_SPARSE_CE) sv.yb_i.alloc(B); else sv.yb_f.alloc(B * m.out_dim);
     PYB_CUDA(cudaMemcpyAsync(sv.idx.p, idx, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    k_gather_rows<<<(unsigned)B, 128, 0, h->stream>>>(h->X.p, h->loss_kind == PYB_LOSS_SPARSE_CE ? h->y_i.p : nullptr,
-                                                      h->loss_kind == PYB_LOSS_MSE ? h->y_f.p : nullptr, sv.idx.p, B,
-                                                      m.in_dim, m.out_dim, sv.Xb.p, sv.yb_i.p, sv.yb_f.p);
-    count_launch(h);
+    gather_batch(h, sv.idx.p, B, sv.Xb.p, sv.yb_i.p, sv.yb_f.p);
     Xb = sv.Xb.p; yb_i = sv.yb_i.p; yb_f = sv.yb_f.p; Nb = B;
   }
   sv.t += 1;

@@ -199,6 +199,35 @@ class Engine:
         check(self.lib.pyb_svgd_get_particles(self.h, _ptr(out)))
         return out
 
+    # ---- S-batched SGLD / SWAG chains
+    def sg_init(self, S, kind, k_dev=0, frequency=1, theta0=None, chain_offset=0):
+        t0, rows = None, 0
+        if theta0 is not None:
+            t0 = _f32(np.atleast_2d(theta0))
+            rows = int(t0.shape[0])
+            if t0.shape[1] != self.P or rows not in (1, int(S)):
+                raise ValueError("theta0 must be [1, P] or [S, P]")
+        check(self.lib.pyb_sg_init(self.h, int(S), int(chain_offset), int(kind), int(k_dev), int(frequency), _ptr(t0), rows))
+        self.S, self._sg_k = int(S), (int(k_dev) if kind == _lib.SG_SWAG else 0)
+
+    def sg_step(self, lr, batch_idx=None, noise=None):
+        """-> (per-chain minibatch losses [S], their mean)."""
+        loss = np.empty(self.S, np.float32)
+        mean = C.c_double()
+        z = None if noise is None else _f32(noise, (self.S, self.P))
+        idx = None if batch_idx is None else np.ascontiguousarray(batch_idx, dtype=np.int32)
+        check(self.lib.pyb_sg_step(self.h, _ptr(idx), 0 if idx is None else int(idx.shape[0]), float(lr), _ptr(z),
+                                   _ptr(loss), C.byref(mean)))
+        return loss, mean.value
+
+    def sg_state(self):
+        S, P, k = self.S, self.P, self._sg_k
+        theta, mean, sq = (np.empty((S, P), np.float32) for _ in range(3))
+        dev = np.zeros((S, k, P), np.float32) if k else None
+        cols, n = C.c_int32(), C.c_int64()
+        check(self.lib.pyb_sg_get(self.h, _ptr(theta), _ptr(mean), _ptr(sq), _ptr(dev), C.byref(cols), C.byref(n)))
+        return dict(theta=theta, mean=mean, sq_mean=sq, dev=None if dev is None else dev[:, :cols.value], n=n.value)
+
     # ---- caller-owned device arrays
     def device_array(self, a) -> DeviceArray:
         """Upload a float32 array once; the result can be passed wherever weight samples / inputs are taken."""

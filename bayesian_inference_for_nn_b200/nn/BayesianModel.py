@@ -16,7 +16,7 @@ import shutil
 
 import numpy as np
 
-from ..distributions import Distribution, Sampled
+from ..distributions import Distribution, Mixture, MultivariateNormalDiagPlusLowRank, Normal, Sampled
 from ..engine import Engine
 from ..keras_json import parse_model_json
 from ..tensors import to_numpy
@@ -179,7 +179,8 @@ class BayesianModel:
         return mean.max(axis=-1) < threshold
 
     # ---- persistence (BayesianModel.py:132-203) ---------------------------------------------
-    _REGISTRY = {"Sampled": Sampled}
+    _REGISTRY = {"Sampled": Sampled, "Normal": Normal, "TensorflowProbabilityDistribution": Normal,
+                 "MultivariateNormalDiagPlusLowRank": MultivariateNormalDiagPlusLowRank, "Mixture": Mixture}
 
     @classmethod
     def load(cls, model_path: str, custom_distribution_register=None) -> "BayesianModel":
@@ -218,7 +219,8 @@ class BayesianModel:
         with open(os.path.join(model_path, "layers_config.txt"), "w") as f:
             f.write(str(len(self._layers_dtbn_intervals)) + "\n")
             for (start, end), d in zip(self._layers_dtbn_intervals, self._distributions):
-                f.write(d.__class__.__name__ + "\n" + str(start) + "\n" + str(end) + "\n")
+                name = "TensorflowProbabilityDistribution" if isinstance(d, Normal) else d.__class__.__name__
+                f.write(name + "\n" + str(start) + "\n" + str(end) + "\n")
         for i, d in enumerate(self._distributions):
             os.mkdir(os.path.join(model_path, "distribution%d" % i))
             d.store(os.path.join(model_path, "distribution%d" % i))

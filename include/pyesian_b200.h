@@ -51,6 +51,8 @@ typedef enum { PYB_SVGD_REFERENCE_LIVE = 0, PYB_SVGD_CANONICAL_MEDIAN = 1 } pyb_
 /* which device path evaluates the MLP; AUTO picks by shape */
 typedef enum { PYB_PATH_AUTO = 0, PYB_PATH_GENERIC = 1, PYB_PATH_FUSED_SMALL = 2, PYB_PATH_TENSOR = 3 } pyb_path;
 
+typedef enum { PYB_SG_SGLD = 0, PYB_SG_SWAG = 1 } pyb_sg_kind;
+
 typedef struct pyb_handle pyb_handle;
 
 /* Dense stack parsed from the Keras model JSON (model.to_json(); consumed at HMC.py:56,
@@ -147,6 +149,26 @@ int pyb_svgd_get_particles(pyb_handle* h, double* particles_out);
 /* NCCL plumbing for sharded particles: all ranks pass the same 128-byte ncclUniqueId. */
 int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id_128);
 int pyb_nccl_unique_id(void* out_128);
+
+/* ---- S-batched stochastic-gradient chains: SGLD (SGLD.py:46-95 step, :115-121 schedule on the host, :133-143
+ *      compile) and SWAG (SWAG.py:43-94 step, :97-113 compile) on the same minibatch gradient kernels ----
+ * S local chains with global ids chain_offset.. (Philox counters use the global id).  theta0 NULL => Keras Dense
+ * defaults per chain (glorot_uniform kernels, zero biases: what model_from_json builds, SGLD.py:138); else host
+ * float32 [theta0_rows, P] with theta0_rows = 1 (every chain starts from the same weights: SWAG's starting_model,
+ * SWAG.py:105-106) or S.  k_dev / frequency: SWAG's deviation-matrix width and moment update period (ignored by SGLD,
+ * whose moments are updated every step and whose deviation matrix is never read, SGLD.py:146-161). */
+int pyb_sg_init(pyb_handle* h, int64_t S, int64_t chain_offset, int32_t kind, int32_t k_dev, int32_t frequency,
+                const float* theta0, int32_t theta0_rows);
+/* One step of every chain on the minibatch batch_idx (host int32 [B] row indices into the resident dataset; NULL =>
+ * the full dataset).  SGLD: theta -= lr * (g + lr * z) (the reference draws its noise with stddev = lr and multiplies
+ * by lr again, SGLD.py:67-68); noise = host float32 [S, P] standard normals injected for this step (test hook) or
+ * NULL => Philox.  SWAG: theta -= lr * g.  Then the running moments / deviation column as the reference updates
+ * them.  loss_out [S] (host, may be NULL) = each chain's minibatch loss BEFORE the update; mean_loss_out = their mean. */
+int pyb_sg_step(pyb_handle* h, const int32_t* batch_idx, int64_t B, double lr, const float* noise, float* loss_out,
+                double* mean_loss_out);
+/* State read-back (any pointer may be NULL): theta, mean, sq_mean host float32 [S, P]; dev [S, k_dev, P] (column c of
+ * chain s contiguous; columns >= *n_cols are zero); n_cols = deviation columns filled; n_steps = steps taken. */
+int pyb_sg_get(pyb_handle* h, float* theta, float* mean, float* sq_mean, float* dev, int32_t* n_cols, int64_t* n_steps);
 
 /* ---- posterior predictive (BayesianModel.predict BayesianModel.py:106-129; Plotter.py:244) ----
  * W [n,P] weight samples, weight [n] or NULL (=1), x [Nt,in_dim]; mean/var [Nt,out_dim] with
