@@ -38,36 +38,118 @@ __global__ void k_pred_finish(const double* s1, const double* s2, double wsum, i
 // ---- Metrics.classification_uncertainty (Metrics.py:344-375) --------------------------------------------------
 // Per data row r and weight sample k with class probabilities p (NaN -> 0 as BayesianModel.py:125):
 //   aleatoric_r += w_k (diag(p) - p p^T)        epistemic_r += w_k (p - onehot(y_r)) (p - onehot(y_r))^T
-// One thread per (row, i, j); j is the fastest index, so p_j loads are coalesced and p_i loads are warp broadcasts.
-// A one-unit (sigmoid) output is widened to the two classes [1-p, p] (Metrics.py:357-359).
-__device__ inline float uq_prob(const float* o, int C, int c) {
-  float v = (C == 1) ? o[0] : o[c];
-  if (v != v) v = 0.f;
-  return (C == 1 && c == 0) ? 1.f - v : v;
+// Both follow from the first and second moments over the samples, S1 = sum_k w_k p (k_pred_accum already has it) and
+// S2 = sum_k w_k p p^T:   aleatoric = diag(S1) - S2,   epistemic = S2 - S1 e^T - e S1^T + W e e^T  (e = onehot, W = sum w),
+// so the only extra pass over the [n, Nt, C] outputs is the S2 accumulation below.  A block owns 128/C data rows and
+// stages 32 samples of their class probabilities in shared memory with coalesced loads (every output byte is read from
+// HBM exactly once, ~15 KB in flight per block); thread = (row, class i) then keeps row i of that row's C x C block in
+// registers and reads its row's C values back as shared-memory broadcasts: float32 products, flushed into float64
+// every 32 samples.  (First version: the same register tile fed by direct global loads - 10 of 11 loads redundant,
+// 360 GB/s, long-scoreboard bound at 20 % occupancy; profiles/r1_ncu_full_next.txt.)
+// A one-unit (sigmoid) output is widened to the two classes [1-p, p] (Metrics.py:357-359); its moments follow from
+// s1 = sum w p and s2 = sum w p^2 alone, no extra pass.
+template <int C>
+__global__ void __launch_bounds__(128) k_uncert_s2(const float* __restrict__ out, int64_t n_chunk, int64_t Nt,
+                                                   const float* __restrict__ w, double* __restrict__ S2) {
+  constexpr int R = 128 / C, RC = R * C, KT = 32, PER = (KT * RC + 127) / 128;
+  __shared__ float tile[KT * RC];
+  __shared__ float wt[KT];
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * R;
+  const int nrows = (int)min((int64_t)R, Nt - r0);
+  const int nvalid = nrows * C;                 // this block's contiguous floats per sample
+  const int lr = tid / C, i = tid % C;          // compute role: row lr of the block, class i
+  const bool active = tid < RC && lr < nrows;
+  const float* src = out + r0 * C;
+  const int64_t stride = Nt * C;
+  double acc[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) acc[j] = 0.0;
+  for (int64_t k0 = 0; k0 < n_chunk; k0 += KT) {
+    const int kt = (int)min((int64_t)KT, n_chunk - k0);
+    // stage kt samples x nvalid floats, coalesced; all of a thread's loads are issued before the first store
+    float v[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * 128, kk = e / RC, c = e % RC;
+      v[q] = (kk < kt && c < nvalid) ? src[(k0 + kk) * stride + c] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * 128;
+      if (e < KT * RC) tile[e] = (v[q] != v[q]) ? 0.f : v[q];
+    }
+    if (tid < KT) wt[tid] = (tid < kt) ? (w ? w[k0 + tid] : 1.f) : 0.f;
+    __syncthreads();
+    if (active) {
+      float f[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) f[j] = 0.f;
+#pragma unroll 8
+      for (int kk = 0; kk < KT; ++kk) {          // samples beyond kt were staged as zeros with zero weight
+        const float* row = tile + kk * RC + lr * C;
+        const float wp = wt[kk] * row[i];
+#pragma unroll
+        for (int j = 0; j < C; ++j) f[j] = fmaf(wp, row[j], f[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < C; ++j) acc[j] += (double)f[j];
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < C; ++j) S2[((r0 + lr) * C + i) * C + j] += acc[j];
+  }
 }
-__global__ void k_uncert_accum(const float* out, int64_t n_chunk, int64_t Nt, int C, int Ce, const int32_t* y,
-                               const float* w, double* alea, double* epi) {
+// any other class count (<= 32): thread = (row, i, j)
+__global__ void k_uncert_s2_generic(const float* out, int64_t n_chunk, int64_t Nt, int C, const float* w, double* S2) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Nt * C * C) return;
+  const int j = (int)(e % C), i = (int)((e / C) % C);
+  const int64_t r = e / ((int64_t)C * C);
+  double a = 0.0;
+  for (int64_t k = 0; k < n_chunk; ++k) {
+    const float* o = out + (k * Nt + r) * C;
+    float pi = o[i], pj = o[j];
+    if (pi != pi) pi = 0.f;
+    if (pj != pj) pj = 0.f;
+    a += (w ? (double)w[k] : 1.0) * (double)(pi * pj);
+  }
+  S2[e] += a;
+}
+// per-row matrices from the moments; s1/s2 are k_pred_accum's sums over out_dim C, S2 the block above (C > 1)
+__global__ void k_uncert_rows(const double* s1, const double* s2, const double* S2, double wsum, int64_t Nt, int C, int Ce,
+                              const int32_t* y, double* alea, double* epi) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Nt * Ce * Ce) return;
   const int j = (int)(e % Ce), i = (int)((e / Ce) % Ce);
   const int64_t r = e / ((int64_t)Ce * Ce);
-  const int label = y[r];
-  const float oi = (i == label) ? 1.f : 0.f, oj = (j == label) ? 1.f : 0.f;
-  double a = 0.0, b = 0.0;
-  for (int64_t k = 0; k < n_chunk; ++k) {
-    const float* o = out + (k * Nt + r) * C;
-    const float pi = uq_prob(o, C, i), pj = uq_prob(o, C, j);
-    const double ww = w ? (double)w[k] : 1.0;
-    a += ww * ((i == j ? (double)pi : 0.0) - (double)pi * (double)pj);
-    b += ww * (double)(pi - oi) * (double)(pj - oj);
+  double m1i, m1j, m2;
+  if (C == 1) {           // classes [1 - p, p]
+    const double a = s1[r], b = s2[r];
+    m1i = i ? a : wsum - a;
+    m1j = j ? a : wsum - a;
+    m2 = (i && j) ? b : ((i || j) ? a - b : wsum - 2.0 * a + b);
+  } else {
+    m1i = s1[r * C + i];
+    m1j = s1[r * C + j];
+    m2 = S2[e];
   }
-  alea[e] += a;
-  epi[e] += b;
+  const int label = y[r];
+  const double ei = (i == label) ? 1.0 : 0.0, ej = (j == label) ? 1.0 : 0.0;
+  alea[e] = (i == j ? m1i : 0.0) - m2;
+  epi[e] = m2 - m1i * ej - ei * m1j + wsum * ei * ej;
+}
+template <int C>
+static void launch_uncert_s2(pyb_handle* h, const float* out, int64_t nb, int64_t Nt, const float* w, double* S2) {
+  constexpr int R = 128 / C;
+  k_uncert_s2<C><<<(unsigned)((Nt + R - 1) / R), 128, 0, h->stream>>>(out, nb, Nt, w, S2);
 }
 // The reference never resets its accumulators between rows (Metrics.py:352-366: `aleatoric +=` inside the row loop,
-// appended per row), so row r of its result is the running sum over rows 0..r.  Three passes over 256-row segments:
+// appended per row), so row r of its result is the running sum over rows 0..r.  Three passes over 32-row segments:
 // segment sums, exclusive scan of the segment sums, running prefix written out (fixed order => deterministic).
-constexpr int kUqSeg = 256;
+constexpr int kUqSeg = 32;
 __global__ void k_uncert_segsum(const double* acc, int64_t Nt, int CC, double* seg) {
   const int e = threadIdx.x;
   if (e >= CC) return;
@@ -76,14 +158,14 @@ __global__ void k_uncert_segsum(const double* acc, int64_t Nt, int CC, double* s
   for (int64_t r = r0; r < r1; ++r) s += acc[r * CC + e];
   seg[(int64_t)blockIdx.x * CC + e] = s;
 }
-__global__ void k_uncert_segscan(double* seg, int64_t nseg, int CC) {
+__global__ void k_uncert_segscan(const double* __restrict__ seg, double* __restrict__ excl, int64_t nseg, int CC) {
   const int e = threadIdx.x;
   if (e >= CC) return;
-  double run = 0.0;
+  double run = 0.0;                       // out of place, so the loads of the next segments do not wait for the stores
+#pragma unroll 8
   for (int64_t s = 0; s < nseg; ++s) {
-    const double v = seg[s * CC + e];
-    seg[s * CC + e] = run;
-    run += v;
+    excl[s * CC + e] = run;
+    run += seg[s * CC + e];
   }
 }
 __global__ void k_uncert_finish(const double* alea, const double* epi, const double* seg_a, const double* seg_e,
@@ -135,7 +217,7 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
   DevBuf<double> s1, s2;
   // classification-uncertainty accumulators [Nt, Ce, Ce] (Ce = 2 for a one-unit output)
   const int Ce = (C == 1) ? 2 : (int)C, CC = Ce * Ce;
-  DevBuf<double> ua, ue, seg_a, seg_e;
+  DevBuf<double> ua, ue, uS2, seg_a, seg_e, exc_a, exc_e;
   DevBuf<float> ut, uao, ueo;
   DevBuf<int32_t> uy;
   const int64_t nseg = (Nt + kUqSeg - 1) / kUqSeg;
@@ -145,10 +227,12 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
     PYB_REQUIRE(uq->divisor != 0.0, PYB_ERR_INVALID, "divisor must not be 0");
     for (int64_t r = 0; r < Nt; ++r)
       PYB_REQUIRE(uq->y[r] >= 0 && uq->y[r] < Ce, PYB_ERR_INVALID, "label out of range");
-    ua.alloc(Nt * CC); ue.alloc(Nt * CC); seg_a.alloc(nseg * CC); seg_e.alloc(nseg * CC);
+    ua.alloc(Nt * CC); ue.alloc(Nt * CC); seg_a.alloc(nseg * CC); seg_e.alloc(nseg * CC); exc_a.alloc(nseg * CC); exc_e.alloc(nseg * CC);
     ut.alloc(Nt * CC); uao.alloc(Nt * CC); ueo.alloc(Nt * CC); uy.alloc(Nt);
-    PYB_CUDA(cudaMemsetAsync(ua.p, 0, Nt * CC * sizeof(double), h->stream));
-    PYB_CUDA(cudaMemsetAsync(ue.p, 0, Nt * CC * sizeof(double), h->stream));
+    if (C > 1) {
+      uS2.alloc(Nt * CC);
+      PYB_CUDA(cudaMemsetAsync(uS2.p, 0, Nt * CC * sizeof(double), h->stream));
+    }
     PYB_CUDA(cudaMemcpyAsync(uy.p, uq->y, Nt * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   }
   // W and x may be host pointers (copied chunk by chunk) or device pointers (used in place: samples that already
@@ -199,9 +283,17 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
     k_pred_accum<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(dout.p, nb, elems, weight ? dw.p + i0 : nullptr,
                                                                          s1.p, s2.p);
     count_launch(h);
-    if (uq) {
-      k_uncert_accum<<<(unsigned)((Nt * CC + 255) / 256), 256, 0, h->stream>>>(dout.p, nb, Nt, (int)C, Ce, uy.p,
-                                                                              weight ? dw.p + i0 : nullptr, ua.p, ue.p);
+    if (uq && C > 1) {
+      const float* wk = weight ? dw.p + i0 : nullptr;
+      switch ((int)C) {
+        case 2: launch_uncert_s2<2>(h, dout.p, nb, Nt, wk, uS2.p); break;
+        case 3: launch_uncert_s2<3>(h, dout.p, nb, Nt, wk, uS2.p); break;
+        case 4: launch_uncert_s2<4>(h, dout.p, nb, Nt, wk, uS2.p); break;
+        case 5: launch_uncert_s2<5>(h, dout.p, nb, Nt, wk, uS2.p); break;
+        case 10: launch_uncert_s2<10>(h, dout.p, nb, Nt, wk, uS2.p); break;
+        default:
+          k_uncert_s2_generic<<<(unsigned)((Nt * CC + 255) / 256), 256, 0, h->stream>>>(dout.p, nb, Nt, (int)C, wk, uS2.p);
+      }
       count_launch(h);
     }
     if (all) {
@@ -213,14 +305,17 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
   k_pred_finish<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(s1.p, s2.p, wsum, elems, dmean.p, dvar.p);
   count_launch(h);
   if (uq) {
+    k_uncert_rows<<<(unsigned)((Nt * CC + 255) / 256), 256, 0, h->stream>>>(s1.p, s2.p, uS2.p, wsum, Nt, (int)C, Ce, uy.p,
+                                                                           ua.p, ue.p);
+    count_launch(h);
     if (uq->cumulative) {
       k_uncert_segsum<<<(unsigned)nseg, CC, 0, h->stream>>>(ua.p, Nt, CC, seg_a.p);
       k_uncert_segsum<<<(unsigned)nseg, CC, 0, h->stream>>>(ue.p, Nt, CC, seg_e.p);
-      k_uncert_segscan<<<1, CC, 0, h->stream>>>(seg_a.p, nseg, CC);
-      k_uncert_segscan<<<1, CC, 0, h->stream>>>(seg_e.p, nseg, CC);
+      k_uncert_segscan<<<1, CC, 0, h->stream>>>(seg_a.p, exc_a.p, nseg, CC);
+      k_uncert_segscan<<<1, CC, 0, h->stream>>>(seg_e.p, exc_e.p, nseg, CC);
       count_launch(h, 4);
     }
-    k_uncert_finish<<<(unsigned)nseg, CC, 0, h->stream>>>(ua.p, ue.p, seg_a.p, seg_e.p, Nt, CC, uq->cumulative ? 1 : 0,
+    k_uncert_finish<<<(unsigned)nseg, CC, 0, h->stream>>>(ua.p, ue.p, exc_a.p, exc_e.p, Nt, CC, uq->cumulative ? 1 : 0,
                                                          1.0 / uq->divisor, ut.p, uao.p, ueo.p);
     count_launch(h);
   }

@@ -36,36 +36,85 @@ __global__ void k_sg_broadcast(float* theta, const float* src, int64_t P, int ro
     theta[s * P + e] = src[(rows == 1 ? 0 : s) * P + e];
 }
 
-// the fused update; dev_col = nullptr: no deviation column this step; moments = 0: parameters only
-__global__ void k_sg_update(float* theta, const float* g, float* mean, float* sq, float* dev_col, int64_t dev_stride,
-                            const float* inj, int64_t P, float lr, float noise_scale, int kind, int moments, float n,
-                            uint64_t seed, int64_t chain_offset, uint32_t iter) {
-  const int64_t s = blockIdx.y;
+// the fused update over the FLAT [S*P] arrays (they are contiguous, so a thread's four elements are one 16-byte access
+// whatever P is; they may straddle two chains or two Philox blocks).  dev_col = nullptr: no deviation column this step;
+// moments = 0: parameters only.  All loads are issued before the first store.
+__global__ void __launch_bounds__(256) k_sg_update(float* __restrict__ theta, const float* __restrict__ g,
+                                                   float* __restrict__ mean, float* __restrict__ sq,
+                                                   float* __restrict__ dev_col, int64_t dev_stride,
+                                                   const float* __restrict__ inj, int64_t P, int64_t total, float lr,
+                                                   float noise_scale, int kind, int moments, float n, uint64_t seed,
+                                                   int64_t chain_offset, uint32_t iter) {
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (base >= P) return;
-  float z[4] = {0.f, 0.f, 0.f, 0.f};
-  if (kind == PYB_SG_SGLD) {
-    if (inj) {
-      for (int j = 0; j < 4; ++j) if (base + j < P) z[j] = inj[s * P + base + j];
-    } else {
-      philox_normal4((uint32_t)(base >> 2), (uint32_t)(chain_offset + s), iter, STREAM_SGLD, seed, z);
+  if (base >= total) return;
+  const bool full = base + 4 <= total;
+  float t[4], gg[4], m[4], q[4], z[4] = {0.f, 0.f, 0.f, 0.f};
+  auto ld4 = [](const float* p, float* o) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  };
+  auto st4 = [](float* p, const float* o) { *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]); };
+  if (full) {
+    ld4(theta + base, t);
+    ld4(g + base, gg);
+    if (moments) { ld4(mean + base, m); ld4(sq + base, q); }
+    if (kind == PYB_SG_SGLD && inj) ld4(inj + base, z);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = base + j < total;
+      t[j] = ok ? theta[base + j] : 0.f;
+      gg[j] = ok ? g[base + j] : 0.f;
+      m[j] = (ok && moments) ? mean[base + j] : 0.f;
+      q[j] = (ok && moments) ? sq[base + j] : 0.f;
+      if (kind == PYB_SG_SGLD && inj && ok) z[j] = inj[base + j];
+    }
+  }
+  int64_t s = base / P, e = base - s * P;       // chain and element of the first of the four
+  if (kind == PYB_SG_SGLD && !inj) {
+    float zz[4];
+    int64_t have_s = -1, have_b = -1;
+    int64_t ss = s, ee = e;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((ee >> 2) != have_b || ss != have_s) {
+        philox_normal4((uint32_t)(ee >> 2), (uint32_t)(chain_offset + ss), iter, STREAM_SGLD, seed, zz);
+        have_b = ee >> 2; have_s = ss;
+      }
+      const int l = (int)(ee & 3);
+      z[j] = l == 0 ? zz[0] : (l == 1 ? zz[1] : (l == 2 ? zz[2] : zz[3]));
+      if (++ee == P) { ee = 0; ++ss; }
     }
   }
   // every product and sum is rounded on its own (no FMA contraction), like the eager float32 ops of the reference
+  float d[4];
+#pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int64_t e = base + j;
-    if (e >= P) break;
-    const int64_t i = s * P + e;
-    float t = theta[i];
     // var.assign_add(-lr * (grad + noise)), noise = stddev * z with stddev = lr (SGLD.py:67-68); SWAG: assign_sub(lr * g)
-    t = (kind == PYB_SG_SGLD) ? __fadd_rn(t, __fmul_rn(-lr, __fadd_rn(g[i], __fmul_rn(noise_scale, z[j]))))
-                              : __fsub_rn(t, __fmul_rn(lr, g[i]));
-    theta[i] = t;
+    t[j] = (kind == PYB_SG_SGLD) ? __fadd_rn(t[j], __fmul_rn(-lr, __fadd_rn(gg[j], __fmul_rn(noise_scale, z[j]))))
+                                 : __fsub_rn(t[j], __fmul_rn(lr, gg[j]));
     if (moments) {
-      const float m = __fdiv_rn(__fadd_rn(__fmul_rn(mean[i], n), t), n + 1.0f);
-      mean[i] = m;
-      sq[i] = __fdiv_rn(__fadd_rn(__fmul_rn(sq[i], n), __fmul_rn(t, t)), n + 1.0f);
-      if (dev_col) dev_col[s * dev_stride + e] = __fsub_rn(t, m);
+      m[j] = __fdiv_rn(__fadd_rn(__fmul_rn(m[j], n), t[j]), n + 1.0f);
+      q[j] = __fdiv_rn(__fadd_rn(__fmul_rn(q[j], n), __fmul_rn(t[j], t[j])), n + 1.0f);
+      d[j] = __fsub_rn(t[j], m[j]);
+    }
+  }
+  if (full) {
+    st4(theta + base, t);
+    if (moments) { st4(mean + base, m); st4(sq + base, q); }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (base + j < total) {
+        theta[base + j] = t[j];
+        if (moments) { mean[base + j] = m[j]; sq[base + j] = q[j]; }
+      }
+  }
+  if (moments && dev_col) {          // column c of chain s sits at s * k * P + c * P: not 16-byte aligned in general
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (base + j < total) dev_col[s * dev_stride + e] = d[j];
+      if (++e == P) { e = 0; ++s; }
     }
   }
 }
@@ -154,10 +203,10 @@ void sg_step(pyb_handle* h, const int32_t* idx, int64_t B, double lr, const floa
     dev_col = sg.dev.p + (int64_t)col * P;
     if (sg.cols < sg.k) sg.cols += 1;
   }
-  dim3 grid((unsigned)((P + 1023) / 1024), (unsigned)S);
-  k_sg_update<<<grid, 256, 0, h->stream>>>(sg.theta.p, sg.g.p, sg.mean.p, sg.sq.p, dev_col, (int64_t)sg.k * P,
-                                           inj.p, P, (float)lr, (float)lr, sg.kind, moments, (float)sg.n, h->seed,
-                                           sg.offset, (uint32_t)sg.n);
+  const int64_t total = S * P;
+  k_sg_update<<<(unsigned)((total + 1023) / 1024), 256, 0, h->stream>>>(
+      sg.theta.p, sg.g.p, sg.mean.p, sg.sq.p, dev_col, (int64_t)sg.k * P, inj.p, P, total, (float)lr, (float)lr, sg.kind,
+      moments, (float)sg.n, h->seed, sg.offset, (uint32_t)sg.n);
   count_launch(h);
   k_sg_loss_mean<<<1, 256, 0, h->stream>>>(sg.loss.p, S, sg.mean_loss.p);
   count_launch(h);
