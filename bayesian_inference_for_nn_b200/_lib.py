@@ -67,6 +67,7 @@ SIGNATURES = {
     "pyb_svgd_phi": [_P, _f64p, _f32p, C.c_int64, C.c_int32, _f32p, C.POINTER(C.c_double)],
     "pyb_svgd_get_particles": [_P, _f64p],
     "pyb_svgd_set_comm": [_P, C.c_int32, C.c_int32, C.c_void_p],
+    "pyb_set_comm": [_P, C.c_int32, C.c_int32, C.c_void_p],
     "pyb_nccl_unique_id": [C.c_void_p],
     "pyb_sg_init": [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_int32],
     "pyb_sg_step": [_P, _i32p, C.c_int64, C.c_double, _f32p, _f32p, C.POINTER(C.c_double)],

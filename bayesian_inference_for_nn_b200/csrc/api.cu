@@ -190,6 +190,8 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_fs_cluster = v != 0;
   } else if (!strcmp(key, "live_fused")) {
     h->opt_live_fused = v != 0;
+  } else if (!strcmp(key, "predict_sharded")) {
+    h->opt_predict_sharded = v != 0;
   } else if (!strcmp(key, "tc_fuse")) {
     h->opt_tc_fuse = v != 0;
   } else if (!strcmp(key, "profile")) {
@@ -482,6 +484,8 @@ int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* id
   h->svgd.rank = rank; h->svgd.world = world;
   PYB_CATCH
 }
+
+int pyb_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* id) { return pyb_svgd_set_comm(h, rank, world, id); }
 
 int pyb_nccl_unique_id(void* out_128) {
   PYB_TRY

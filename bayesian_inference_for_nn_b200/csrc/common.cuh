@@ -269,6 +269,7 @@ struct pyb_handle {
   int opt_tc_gram_sym = 1;   // 1: Gram matrices (A == B) compute the upper tile triangle only and mirror it
   int opt_fs_cluster = 1;   // 1: the small-width HMC kernel spreads a chain over a CTA cluster when there are few chains
   int opt_live_fused = 1;   // 1: the reference-live SVGD sweep is one cooperative launch on a single GPU
+  int opt_predict_sharded = 0;   // 1: pyb_predict all-reduces its moment sums over the handle's communicator
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
   double opt_workspace_mb = 4096;
   int64_t opt_chain_batch = 0;

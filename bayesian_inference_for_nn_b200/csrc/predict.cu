@@ -302,6 +302,19 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
       PYB_CUDA(cudaMemcpyAsync(all + i0 * elems, dout.p, nb * elems * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
   }
+  // weight samples sharded over ranks: the only exchange is the all-reduce of the moment sums
+  // ([Nt, C] doubles, 0.8 MB each at C5) and of the total weight; per-draw outputs stay with the rank that made them
+  if (h->opt_predict_sharded && h->svgd.nccl_comm && h->svgd.world > 1) {
+    DevBuf<double> dws;
+    dws.alloc(1);
+    PYB_CUDA(cudaMemcpyAsync(dws.p, &wsum, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    nccl_all_reduce_f64(h->svgd.nccl_comm, s1.p, (size_t)elems, h->stream);
+    nccl_all_reduce_f64(h->svgd.nccl_comm, s2.p, (size_t)elems, h->stream);
+    if (uq && C > 1) nccl_all_reduce_f64(h->svgd.nccl_comm, uS2.p, (size_t)(Nt * CC), h->stream);
+    nccl_all_reduce_f64(h->svgd.nccl_comm, dws.p, 1, h->stream);
+    PYB_CUDA(cudaMemcpyAsync(&wsum, dws.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PYB_CUDA(cudaStreamSynchronize(h->stream));
+  }
   k_pred_finish<<<(unsigned)((elems + 255) / 256), 256, 0, h->stream>>>(s1.p, s2.p, wsum, elems, dmean.p, dvar.p);
   count_launch(h);
   if (uq) {

@@ -177,6 +177,15 @@ class Engine:
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         check(self.lib.pyb_svgd_set_comm(self.h, int(rank), int(world), buf))
 
+    def set_comm(self, rank: int, world: int, unique_id: bytes = None, predict_sharded: bool = True):
+        """Join `world` ranks (one process per GPU).  With ``predict_sharded`` every later ``predict`` /
+        ``predict_uncertainty`` call treats W as this rank's share of the weight samples and returns the moments over
+        all ranks' samples (one all-reduce of the [Nt, C] sums); all ranks must make the call."""
+        _lib.preload_nccl()
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        check(self.lib.pyb_set_comm(self.h, int(rank), int(world), buf))
+        self.set_option("predict_sharded", 1.0 if (predict_sharded and world > 1) else 0.0)
+
     def svgd_step(self, batch_idx=None):
         loss = C.c_double()
         if batch_idx is None:

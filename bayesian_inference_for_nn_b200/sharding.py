@@ -34,3 +34,26 @@ def reduce_hmc_diag(diag: dict, dist=None, device=None) -> dict:
     return {"n_accepted": int(s[0]), "n_total": int(s[1]), "n_nan": int(s[2]), "grad_evals": int(s[3]),
             "kernel_launches": int(s[4]), "mean_loss": s[5] / max(1.0, s[1]),
             "accept_rate": s[0] / max(1.0, s[1]), "device_ms": float(mx.item())}
+
+
+def shard_weight_samples(W, weights, rank: int, world: int):
+    """This rank's contiguous share of the weight samples of a posterior-predictive call (and of their integer
+    multiplicities, if any): the partition `Engine.set_comm(..., predict_sharded=True)` + `Engine.predict` expects."""
+    lo, hi = shard_range(len(W), rank, world)
+    return W[lo:hi], (None if weights is None else weights[lo:hi])
+
+
+def combine_predictive_moments(mean, var, wsum, dist=None):
+    """Host-side equivalent of the device all-reduce, for ranks WITHOUT a shared NCCL communicator: each rank passes
+    the mean / population variance / total weight of its own samples and gets the moments over all samples
+    (sum of w, sum of w*o and sum of w*o^2 are additive).  `dist` = torch.distributed (any backend) or None."""
+    import numpy as np
+    mean, var = np.asarray(mean, np.float64), np.asarray(var, np.float64)
+    s = np.stack([np.full_like(mean, float(wsum)), wsum * mean, wsum * (var + mean * mean)])
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        import torch
+        t = torch.from_numpy(s)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        s = t.numpy()
+    m = s[1] / s[0]
+    return m.astype(np.float32), np.maximum(s[2] / s[0] - m * m, 0.0).astype(np.float32), float(s[0].flat[0])

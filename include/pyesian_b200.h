@@ -90,7 +90,8 @@ int pyb_param_count(const pyb_handle* h, int64_t* n_params_out);
  * tensor-core kernels, read back with "prof_ms"/"prof_flops"/"prof_launches"), and three A/B switches of the tensor
  * path, all default 1: "tc_pair" (CTA-pair cta_group::2 kernels), "tc_fuse" (layer 2, loss and both deltas inside
  * the layer-1 GEMM's epilogue), "tc_dual" (two feature tiles per item in the dW1 GEMM).  Switching them off selects
- * the older kernels that compute the same quantities (used by the tests and by tools/kernel_cycles.sh). */
+ * the older kernels that compute the same quantities (used by the tests and by tools/kernel_cycles.sh);
+ * "predict_sharded" (default 0, see pyb_set_comm). */
 int pyb_set_option(pyb_handle* h, const char* key, double value);
 /* read-outs: "path_used", "kernel_launches", "last_device_ms", "workspace_bytes", "tensor_path_ok" */
 int pyb_get_info(const pyb_handle* h, const char* key, double* value_out);
@@ -148,6 +149,11 @@ int pyb_svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int3
 int pyb_svgd_get_particles(pyb_handle* h, double* particles_out);
 /* NCCL plumbing for sharded particles: all ranks pass the same 128-byte ncclUniqueId. */
 int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id_128);
+/* The same communicator under its general name.  With option "predict_sharded" = 1, pyb_predict and
+ * pyb_predict_uncertainty treat W as this rank's share of the weight samples (BayesianModel.predict's nb_samples
+ * draws split over the ranks) and all-reduce their moment sums: every rank returns the mean / variance / uncertainty
+ * matrices over ALL ranks' samples; all_out stays local.  All ranks must make the call. */
+int pyb_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id_128);
 int pyb_nccl_unique_id(void* out_128);
 
 /* ---- S-batched stochastic-gradient chains: SGLD (SGLD.py:46-95 step, :115-121 schedule on the host, :133-143

@@ -51,3 +51,56 @@ def test_svgd_sharded_over_two_gpus_matches_golden(sem, key):
     np.testing.assert_allclose(res[1][2], g[key + "_losses"], rtol=1e-4)
     lr, n = float(g["lr"]), len(g["idx"])
     assert np.abs(parts - g[key + "_particles"]).max() < 2e-3 * lr * n + 1e-6
+
+
+def _predict_worker(rank, world, uid, out):
+    import numpy as np
+    from bayesian_inference_for_nn_b200 import keras_json
+    from bayesian_inference_for_nn_b200.engine import Engine
+    from bayesian_inference_for_nn_b200.sharding import shard_weight_samples
+    rng = np.random.default_rng(3)
+    js = keras_json.make_sequential_json(784, [128, 10], ["relu", "softmax"])
+    eng = Engine(keras_json.parse_model_json(js), device=rank)
+    W = rng.normal(0, 0.05, (9, eng.P)).astype(np.float32)
+    freq = rng.integers(1, 4, 9).astype(np.float32)
+    x = rng.uniform(0, 1, (512, 784)).astype(np.float32)
+    y = rng.integers(0, 10, 512)
+    eng.set_comm(rank, world, uid)
+    Wl, fl = shard_weight_samples(W, freq, rank, world)           # 5 + 4 weight samples
+    mean, var, allo = eng.predict(Wl, x, weights=fl, want_all=True)
+    tot, al, ep, _ = eng.predict_uncertainty(Wl, x, y, weights=fl)
+    out.put((rank, mean, var, allo.shape[0], tot))
+    eng.close()
+
+
+def test_predictive_sharded_over_two_gpus_matches_one_gpu():
+    """weight samples split over ranks, moment sums all-reduced over NCCL"""
+    from bayesian_inference_for_nn_b200 import _lib, keras_json
+    from bayesian_inference_for_nn_b200.engine import Engine
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    uid = _lib.nccl_unique_id()
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_predict_worker, args=(r, 2, uid, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(3)
+    js = keras_json.make_sequential_json(784, [128, 10], ["relu", "softmax"])
+    eng = Engine(keras_json.parse_model_json(js))
+    W = rng.normal(0, 0.05, (9, eng.P)).astype(np.float32)
+    freq = rng.integers(1, 4, 9).astype(np.float32)
+    x = rng.uniform(0, 1, (512, 784)).astype(np.float32)
+    y = rng.integers(0, 10, 512)
+    mean, var, _ = eng.predict(W, x, weights=freq)
+    tot, _, _, _ = eng.predict_uncertainty(W, x, y, weights=freq)
+    assert [r[3] for r in res] == [5, 4]                      # per-draw outputs stay local
+    for r in res:                                             # both ranks hold the full answer
+        np.testing.assert_allclose(r[1], mean, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(r[2], var, rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(r[4], tot, rtol=1e-5, atol=1e-7)

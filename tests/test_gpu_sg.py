@@ -162,3 +162,32 @@ def test_swag_script_flow():
     xt, yt = next(iter(ds.test_data.batch(ds.test_size)))
     _, preds = bm.predict(xt, nb_samples=30)
     assert (preds.argmax(1) == yt).mean() > 0.8 and opt.step() < first
+
+
+def test_errors_and_edge_cases(oracle):
+    """status codes across the boundary; a partial last minibatch; full-dataset steps (batch_idx = NULL)"""
+    from bayesian_inference_for_nn_b200._lib import PyesianB200Error
+    eng, spec, X, y, theta0, rng, B, loss = setup(oracle, SHAPES[0], 2)
+    with pytest.raises(PyesianB200Error) as e:
+        eng.sg_step(0.1)
+    assert e.value.code == -3                                   # PYB_ERR_STATE: step before init
+    with pytest.raises(PyesianB200Error) as e:
+        eng.sg_init(2, _lib.SG_SWAG, k_dev=1, frequency=1)
+    assert e.value.code == -1                                   # SWAG needs k >= 2
+    with pytest.raises(PyesianB200Error):
+        eng.sg_init(2, 7)
+    with pytest.raises(ValueError):
+        eng.sg_init(3, _lib.SG_SGLD, theta0=theta0)              # 2 rows for 3 chains
+    eng.sg_init(2, _lib.SG_SGLD, theta0=theta0)
+    with pytest.raises(PyesianB200Error) as e:
+        eng.sg_step(0.1, np.array([0, X.shape[0]], np.int32))
+    assert e.value.code == -1                                   # row index out of range
+    st = oracle.sg_init_state(theta0)
+    z = np.zeros((2, spec.n_params), np.float32)
+    for idx in (np.arange(7, dtype=np.int32), None):            # ragged 7-row batch, then the whole dataset
+        Xb, yb = (X, y) if idx is None else (X[idx], y[idx])
+        want = oracle.sg_step(spec, st, Xb, yb, loss, oracle.SG_SGLD, 0.05, z=z)
+        got, _ = eng.sg_step(0.05, idx, noise=z)
+        np.testing.assert_allclose(got, want, rtol=1e-4)
+    assert rel_err(eng.sg_state()["theta"], st.theta) < 2e-5
+    eng.close()
