@@ -337,41 +337,88 @@ __global__ void k_phi_finish(float* phi, const float* X, int64_t P, int r0, int 
 // the same followed by the Adam ascent step on the local particles (theta_local = rows [r0, r0+Sl) of X): one pass
 // over phi / theta / m / v instead of two (the training step does not need phi afterwards)
 __device__ inline float adam_update(float th, float g, float& m, float& v, float lr_t, float b1, float b2, float eh);
-__global__ void k_phi_finish_adam(const float* ky, float* theta_local, float* am, float* av, int64_t P, int St,
-                                  const double* h2, const double* rowsum, float lr_t) {
-  const int i = blockIdx.y;
-  const float c = (float)(rowsum[i] / h2[0]), inv = 1.0f / (float)St;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t o = (int64_t)i * P + e;
-    const float th = theta_local[o];
-    const float phi = fmaf(th, c, ky[o]) * inv;
-    theta_local[o] = adam_update(th, -phi, am[o], av[o], lr_t, 0.9f, 0.999f, 1e-7f);
+// Flat [Sl*P] indexing: a thread's four elements are one 16-byte access per stream (7 streams: ky, theta, m, v read;
+// theta, m, v written) whatever P is; they may straddle two particle rows, so the row constant is looked up per element.
+__global__ void __launch_bounds__(256) k_phi_finish_adam(const float* __restrict__ ky, float* __restrict__ theta_local,
+                                                         float* __restrict__ am, float* __restrict__ av, int64_t P,
+                                                         int64_t total, int St, const double* __restrict__ h2,
+                                                         const double* __restrict__ rowsum, float lr_t) {
+  const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (base >= total) return;
+  const float inv = 1.0f / (float)St;
+  const double ih2 = 1.0 / h2[0];
+  int64_t i = base / P;
+  int64_t e = base - i * P;
+  float c = (float)(rowsum[i] * ih2);
+  if (base + 4 <= total) {
+    const float4 k4 = *reinterpret_cast<const float4*>(ky + base);
+    const float4 t4 = *reinterpret_cast<const float4*>(theta_local + base);
+    float4 m4 = *reinterpret_cast<const float4*>(am + base);
+    float4 v4 = *reinterpret_cast<const float4*>(av + base);
+    float kk[4] = {k4.x, k4.y, k4.z, k4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float phi = fmaf(tt[j], c, kk[j]) * inv;
+      tt[j] = adam_update(tt[j], -phi, mm[j], vv[j], lr_t, 0.9f, 0.999f, 1e-7f);
+      if (++e == P) { e = 0; ++i; if (j < 3) c = (float)(rowsum[i] * ih2); }
+    }
+    *reinterpret_cast<float4*>(theta_local + base) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+    *reinterpret_cast<float4*>(am + base) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(av + base) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  } else {
+    for (int64_t o = base; o < total; ++o) {
+      const float th = theta_local[o];
+      const float phi = fmaf(th, c, ky[o]) * inv;
+      theta_local[o] = adam_update(th, -phi, am[o], av[o], lr_t, 0.9f, 0.999f, 1e-7f);
+      if (++e == P) { e = 0; ++i; if (o + 1 < total) c = (float)(rowsum[i] * ih2); }
+    }
   }
 }
 
 // Y^T = (G - X/h2)^T split into bf16 hi/lo [P, St] (K-major operand of the K*Y GEMM) in one pass.
-// grid (ceil(P/32), ceil(St/32)), block (32, 8)
-__global__ void k_stein_rhs_split_t(const float* X, const float* G, const double* h2, int St, int64_t P, uint16_t* hi,
-                                    uint16_t* lo, int64_t ldd) {
-  __shared__ float tile[32][33];
+// mu != nullptr: G holds the raw scaled loss gradient and the log-posterior gradient is formed here,
+// G_eff = -(G + (X - mu) inv_var) — the separate k_glogp pass (one more read and write of [St, P]) goes away.
+// grid (ceil(P/32), ceil(St/64)), block (32, 8): a warp stores 64 particles x 2 bytes = one 128-byte line per parameter
+__global__ void k_stein_rhs_split_t(const float* __restrict__ X, const float* __restrict__ G, const double* h2, int St,
+                                    int64_t P, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t ldd,
+                                    const float* __restrict__ mu, const float* __restrict__ inv_var) {
+  __shared__ float tile[64][33];
   const float inv = (float)(1.0 / h2[0]);
   const int64_t c0 = (int64_t)blockIdx.x * 32;
-  const int r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
+  const int r0 = blockIdx.y * 64;
+  const int64_t c = c0 + threadIdx.x;
+  float m = 0.f, iv = 0.f;
+  if (mu && c < P) { m = mu[c]; iv = inv_var[c]; }
+#pragma unroll
+  for (int i = threadIdx.y; i < 64; i += 8) {
     const int r = r0 + i;
-    const int64_t c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < St && c < P) ? G[(int64_t)r * P + c] - X[(int64_t)r * P + c] * inv : 0.f;
+    float v = 0.f;
+    if (r < St && c < P) {
+      const float x = X[(int64_t)r * P + c];
+      float g = G[(int64_t)r * P + c];
+      if (mu) g = -(g + (x - m) * iv);
+      v = g - x * inv;
+    }
+    tile[i][threadIdx.x] = v;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
-    const int64_t c = c0 + i;
-    const int r = r0 + threadIdx.x;
-    if (c < P && r < St) {
-      const float v = tile[threadIdx.x][i];
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-      hi[c * ldd + r] = __bfloat16_as_ushort(h);
-      lo[c * ldd + r] = __bfloat16_as_ushort(l);
+    const int64_t cc = c0 + i;
+    const int r = r0 + 2 * threadIdx.x;
+    if (cc < P && r < St) {
+      const float v0 = tile[2 * threadIdx.x][i], v1 = tile[2 * threadIdx.x + 1][i];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+      if (r + 1 < St && ((cc * ldd + r) & 1) == 0) {
+        *reinterpret_cast<uint32_t*>(hi + cc * ldd + r) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        *reinterpret_cast<uint32_t*>(lo + cc * ldd + r) = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      } else {
+        hi[cc * ldd + r] = __bfloat16_as_ushort(h0);
+        lo[cc * ldd + r] = __bfloat16_as_ushort(l0);
+        if (r + 1 < St) { hi[cc * ldd + r + 1] = __bfloat16_as_ushort(h1); lo[cc * ldd + r + 1] = __bfloat16_as_ushort(l1); }
+      }
     }
   }
 }
@@ -431,9 +478,16 @@ static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t
 // wait_g: event after which G_all is complete (sharded runs gather it on the comm stream while the Gram is built)
 __global__ void k_adam_all(float* theta, const float* phi, float* am, float* av, int64_t n, float sign, float lr_t);
 struct AdamFuse { float* theta_local; float* am; float* av; float lr_t; };   // non-null: finish phi AND apply the update
+// large particle sets: Gram matrix and the K*Y contraction run on the tensor cores (bf16x3 split);
+// small ones keep the direct float64 kernels (bit-for-bit the formulation scipy's pdist uses)
+static bool svgd_tensor_ok(const pyb_handle* h, int St) {
+  return St >= 256 && h->model.P >= 64 && (St % 8) == 0 && (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_TENSOR);
+}
+// raw_loss_grad: G_all is the scaled LOSS gradient and the prior term is folded into the Stein right-hand side
+// (tensor path only); otherwise G_all already is the log-posterior gradient
 static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all, int r0, int Sl, int St,
                           float* phi_local, double* h_host_out, cudaEvent_t wait_g = nullptr,
-                          const AdamFuse* adam = nullptr) {
+                          const AdamFuse* adam = nullptr, bool raw_loss_grad = false) {
   SvgdState& sv = h->svgd;
   SvgdState& sc = h->svgd;
   const int64_t P = h->model.P;
@@ -441,10 +495,8 @@ static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all,
   sv.d2.alloc((size_t)Sl * St);
   sv.rowsum.alloc(Sl);
   sc.h2.alloc(2);
-  // large particle sets: Gram matrix and the K*Y contraction run on the tensor cores (bf16x3 split);
-  // small ones keep the direct float64 kernels (bit-for-bit the formulation scipy's pdist uses)
-  const bool tensor = St >= 256 && P >= 64 && (St % 8) == 0 &&
-                      (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_TENSOR);
+  const bool tensor = svgd_tensor_ok(h, St);
+  PYB_REQUIRE(tensor || !raw_loss_grad, PYB_ERR_STATE, "the prior term is only folded on the tensor path");
   const int64_t Ppad = (P + 7) / 8 * 8;
   if (tensor) {
     sv.xh.alloc((size_t)St * Ppad); sv.xl.alloc((size_t)St * Ppad);
@@ -470,13 +522,14 @@ static void phi_canonical(pyb_handle* h, const float* X_all, const float* G_all,
     sv.yth.alloc((size_t)P * St); sv.ytl.alloc((size_t)P * St);
     k_double_to_float<<<blocks, 256, 0, h->stream>>>(sv.d2.p, sv.kf.p, (int64_t)Sl * St);
     tc_split_rows(h, sv.kf.p, Sl, St, St, sv.kh.p, sv.kl.p, St);
-    dim3 gt((unsigned)((P + 31) / 32), (unsigned)((St + 31) / 32)), bt(32, 8);
-    k_stein_rhs_split_t<<<gt, bt, 0, h->stream>>>(X_all, G_all, sc.h2.p, St, P, sv.yth.p, sv.ytl.p, St);
+    dim3 gt((unsigned)((P + 31) / 32), (unsigned)((St + 63) / 64)), bt(32, 8);
+    k_stein_rhs_split_t<<<gt, bt, 0, h->stream>>>(X_all, G_all, sc.h2.p, St, P, sv.yth.p, sv.ytl.p, St,
+                                                 raw_loss_grad ? h->mu.p : nullptr, raw_loss_grad ? h->inv_var.p : nullptr);
     tc_gemm_split(h, sv.kh.p, sv.kl.p, St, Sl, 0, Sl, sv.yth.p, sv.ytl.p, St, (int)P, St, phi_local, P);
     dim3 gf((unsigned)std::min<int64_t>((P + 255) / 256, 1024), (unsigned)Sl);
     if (adam)
-      k_phi_finish_adam<<<gf, 256, 0, h->stream>>>(phi_local, adam->theta_local, adam->am, adam->av, P, St, sc.h2.p,
-                                                  sv.rowsum.p, adam->lr_t);
+      k_phi_finish_adam<<<(unsigned)(((int64_t)Sl * P + 1023) / 1024), 256, 0, h->stream>>>(
+          phi_local, adam->theta_local, adam->am, adam->av, P, (int64_t)Sl * P, St, sc.h2.p, sv.rowsum.p, adam->lr_t);
     else
       k_phi_finish<<<gf, 256, 0, h->stream>>>(phi_local, X_all, P, r0, St, sc.h2.p, sv.rowsum.p);
     count_launch(h, 3);
@@ -573,7 +626,8 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
     PYB_CUDA(cudaEventRecord(sv.ev_theta, sv.comm_stream));
   }
   eval_on_batch(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
-  if (sv.semantics != PYB_SVGD_REFERENCE_LIVE) {
+  const bool fold_prior = sv.semantics != PYB_SVGD_REFERENCE_LIVE && svgd_tensor_ok(h, St);
+  if (sv.semantics != PYB_SVGD_REFERENCE_LIVE && !fold_prior) {
     dim3 gg((unsigned)std::min<int64_t>((P + 255) / 256, 1024), (unsigned)S);
     k_glogp<<<gg, 256, 0, h->stream>>>(sv.g.p, sv.theta.p, h->mu.p, h->inv_var.p, P);
     count_launch(h);
@@ -626,7 +680,7 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
                                h->stream));
   } else {
     const AdamFuse af = {sv.theta.p, sv.adam_m.p, sv.adam_v.p, lr_t};
-    phi_canonical(h, theta_all, g_all, r0, (int)S, St, sv.phi.p, nullptr, overlap ? sv.ev_grad : nullptr, &af);
+    phi_canonical(h, theta_all, g_all, r0, (int)S, St, sv.phi.p, nullptr, overlap ? sv.ev_grad : nullptr, &af, fold_prior);
   }
   sc.mean_loss.alloc(1);
   k_mean_float<<<1, 256, 0, h->stream>>>(sv.loss.p, S, sc.mean_loss.p);

@@ -27,6 +27,22 @@ __global__ void k_split_rows(const float* src, int64_t R, int C, int64_t lds, __
     lo[r * ldd + c] = l;
   }
 }
+// the same for even C, lds, ldd and 8-byte aligned bases (every row then starts 8-byte aligned in src and 4-byte aligned
+// in hi/lo): two elements per thread, 8-byte loads and 4-byte stores
+__global__ void k_split_rows2(const float* __restrict__ src, int64_t R, int C2, int64_t lds, __nv_bfloat16* __restrict__ hi,
+                              __nv_bfloat16* __restrict__ lo, int64_t ldd) {
+  const int64_t total = R * C2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C2;
+    const int c = 2 * (int)(i - r * C2);
+    const float2 v = *reinterpret_cast<const float2*>(src + r * lds + c);
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v.x, h0, l0);
+    split_bf16(v.y, h1, l1);
+    *reinterpret_cast<__nv_bfloat162*>(hi + r * ldd + c) = __nv_bfloat162(h0, h1);
+    *reinterpret_cast<__nv_bfloat162*>(lo + r * ldd + c) = __nv_bfloat162(l0, l1);
+  }
+}
 
 // src [R, C] fp32 (batch stride sb) -> transposed hi/lo [C(+ones row), Rpad] bf16 per batch element.
 // grid (ceil(C/32), ceil(R/32), batch), block (32, 8)
