@@ -66,6 +66,8 @@ SIGNATURES = {
     "pyb_svgd_step": [_P, _i32p, C.c_int64, C.POINTER(C.c_double)],
     "pyb_svgd_phi": [_P, _f64p, _f32p, C.c_int64, C.c_int32, _f32p, C.POINTER(C.c_double)],
     "pyb_svgd_get_particles": [_P, _f64p],
+    "pyb_svgd_set_validation": [_P, _f32p, C.c_void_p, C.c_int64],
+    "pyb_svgd_validation_loss": [_P, C.POINTER(C.c_double), _f32p],
     "pyb_svgd_set_comm": [_P, C.c_int32, C.c_int32, C.c_void_p],
     "pyb_set_comm": [_P, C.c_int32, C.c_int32, C.c_void_p],
     "pyb_nccl_unique_id": [C.c_void_p],

@@ -450,6 +450,22 @@ int pyb_svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int3
   PYB_CATCH
 }
 
+int pyb_svgd_set_validation(pyb_handle* h, const float* X, const void* y, int64_t N) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  svgd_set_validation(h, X, y, N);
+  PYB_CATCH
+}
+
+int pyb_svgd_validation_loss(pyb_handle* h, double* mean_loss_out, float* per_particle_out) {
+  PYB_TRY
+  PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
+  use_device(h);
+  svgd_validation_loss(h, mean_loss_out, per_particle_out);
+  PYB_CATCH
+}
+
 __global__ void k_f32_to_f64(const float* a, double* b, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     b[i] = (double)a[i];

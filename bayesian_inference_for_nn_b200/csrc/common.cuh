@@ -213,6 +213,10 @@ struct SvgdState {
   DevBuf<float> Xb;
   DevBuf<int32_t> yb_i, idx;
   DevBuf<float> yb_f;
+  // held-out set for the per-step validation loss (SVGD.py:126-129), resident in HBM
+  DevBuf<float> val_X, val_yf;
+  DevBuf<int32_t> val_yi;
+  int64_t val_N = 0;
   // comm
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
@@ -356,6 +360,8 @@ void hmc_flush_arena(pyb_handle* h);
 void svgd_init(pyb_handle* h, int64_t S, int64_t offset, double lr, int sem, const double* p0);
 void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out);
 void svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int sem, float* phi, double* h_out);
+void svgd_set_validation(pyb_handle* h, const float* X, const void* y, int64_t N);
+void svgd_validation_loss(pyb_handle* h, double* mean_loss_out, float* per_particle_out);
 
 // rows idx[0..B) of the resident dataset gathered into a contiguous minibatch (device index list)
 void gather_batch(pyb_handle* h, const int32_t* idx_dev, int64_t B, float* Xb, int32_t* yb_i, float* yb_f);

@@ -697,6 +697,50 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
   if (loss_out) *loss_out = ml / (double)R;
 }
 
+// mean over the particles of the loss on a held-out set (SVGD.py:126-129: the reference runs one forward pass per
+// particle over the whole validation split inside every step).  The set is uploaded once and stays in HBM; the
+// particles never leave the device.  The gradient buffer is free between steps and serves as the tensor path's scratch.
+void svgd_set_validation(pyb_handle* h, const float* X, const void* y, int64_t N) {
+  SvgdState& sv = h->svgd;
+  const Model& m = h->model;
+  PYB_REQUIRE(h->have_data, PYB_ERR_STATE, "pyb_set_dataset fixes the loss kind: call it first");
+  PYB_REQUIRE(X && y && N > 0, PYB_ERR_INVALID, "bad validation set");
+  sv.val_X.alloc(N * m.in_dim);
+  PYB_CUDA(cudaMemcpyAsync(sv.val_X.p, X, N * m.in_dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (h->loss_kind == PYB_LOSS_SPARSE_CE) {
+    const int32_t* yi = (const int32_t*)y;
+    for (int64_t i = 0; i < N; ++i) PYB_REQUIRE(yi[i] >= 0 && yi[i] < m.out_dim, PYB_ERR_INVALID, "label out of range");
+    sv.val_yi.alloc(N);
+    PYB_CUDA(cudaMemcpyAsync(sv.val_yi.p, y, N * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    sv.val_yf.alloc(N * m.out_dim);
+    PYB_CUDA(cudaMemcpyAsync(sv.val_yf.p, y, N * m.out_dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  sv.val_N = N;
+}
+void svgd_validation_loss(pyb_handle* h, double* mean_loss_out, float* per_particle_out) {
+  SvgdState& sv = h->svgd;
+  PYB_REQUIRE(sv.inited, PYB_ERR_STATE, "pyb_svgd_init must be called first");
+  PYB_REQUIRE(sv.val_N > 0, PYB_ERR_STATE, "pyb_svgd_set_validation must be called first");
+  DevBuf<float> vloss;
+  vloss.alloc(sv.S);
+  const bool tensor = tc_supported_rows(h, sv.val_N) && (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_TENSOR);
+  eval_on_batch(h, sv.theta.p, sv.S, sv.val_X.p, sv.val_yi.p, sv.val_yf.p, sv.val_N, 1.0f, vloss.p,
+                tensor ? sv.g.p : nullptr);
+  sv.mean_loss.alloc(1);
+  k_mean_float<<<1, 256, 0, h->stream>>>(vloss.p, sv.S, sv.mean_loss.p);
+  count_launch(h);
+  if (sv.world > 1) nccl_all_reduce_f64(sv.nccl_comm, sv.mean_loss.p, 1, h->stream);
+  double ml = 0.0;
+  PYB_CUDA(cudaMemcpyAsync(&ml, sv.mean_loss.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (per_particle_out)
+    PYB_CUDA(cudaMemcpyAsync(per_particle_out, vloss.p, sv.S * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+  if (mean_loss_out) *mean_loss_out = ml / (double)sv.world;
+}
+
 void svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int sem, float* phi, double* h_out) {
   PYB_REQUIRE(S > 0 && S <= 65535, PYB_ERR_INVALID, "S must be in [1, 65535]");
   const int64_t P = h->model.P;

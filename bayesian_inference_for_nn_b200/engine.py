@@ -102,6 +102,7 @@ class Engine:
             raise ValueError("X and y must both be host or both be device tensors")
         check(self.lib.pyb_set_dataset(self.h, xptr, N, yptr, int(loss_kind), int(xmem), int(n_train)))
         self.N = N
+        self._loss_kind = int(loss_kind)
 
     def set_prior(self, mean, sigma, form: int):
         m = _f32(np.atleast_1d(mean).reshape(-1))
@@ -194,6 +195,26 @@ class Engine:
             idx = np.ascontiguousarray(batch_idx, dtype=np.int32)
             check(self.lib.pyb_svgd_step(self.h, _ptr(idx), int(idx.shape[0]), C.byref(loss)))
         return loss.value
+
+    def svgd_set_validation(self, X, y):
+        """held-out set for ``svgd_validation_loss`` (uploaded once; labels as in ``set_dataset``)"""
+        X = _f32(X)
+        X = X.reshape(X.shape[0], -1)
+        if getattr(self, "_loss_kind", None) is None:
+            raise RuntimeError("set_dataset must be called first (it fixes the loss kind)")
+        if self._loss_kind == _lib.LOSS_SPARSE_CE:
+            y = np.ascontiguousarray(np.asarray(y).reshape(-1), dtype=np.int32)
+        else:
+            y = np.ascontiguousarray(y, dtype=np.float32).reshape(X.shape[0], -1)
+        if y.shape[0] != X.shape[0] or X.shape[1] != self.spec.in_dim:
+            raise ValueError("validation set has the wrong shape")
+        check(self.lib.pyb_svgd_set_validation(self.h, _ptr(X), _ptr(y), int(X.shape[0])))
+
+    def svgd_validation_loss(self, per_particle=False):
+        mean = C.c_double()
+        pp = np.empty(self.S, np.float32) if per_particle else None
+        check(self.lib.pyb_svgd_validation_loss(self.h, C.byref(mean), _ptr(pp)))
+        return (mean.value, pp) if per_particle else mean.value
 
     def svgd_phi(self, X, G, semantics):
         X = np.ascontiguousarray(X, dtype=np.float64)

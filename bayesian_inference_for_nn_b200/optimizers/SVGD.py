@@ -50,7 +50,7 @@ class SVGD(Optimizer):
         self.train_losses = []
         self.valid_losses = []
         self._engine = None
-        self._valid_engine = None
+        self._valid_ready = False
 
     def compile_extra_components(self, **kwargs):
         self._batch_size = int(self._hyperparameters.batch_size)
@@ -81,16 +81,15 @@ class SVGD(Optimizer):
         return b
 
     def _validation_loss(self):
-        """mean over particles of the loss on the whole validation split (SVGD.py:126-129)."""
+        """mean over particles of the loss on the whole validation split (SVGD.py:126-129), evaluated on the device
+        against the resident particles: the split is uploaded once, nothing but the scalar comes back."""
         if self._dataset.valid_size == 0:
             return 0.0
-        if self._valid_engine is None:
-            self._valid_engine = Engine(self._spec, device=int(self._hp("device", 0)))
+        if not self._valid_ready:
             xv, yv = self._dataset.split_arrays("valid")
-            self._valid_engine.set_dataset(xv, yv, self._dataset.loss_kind)
-            self._valid_engine.set_prior(np.float32([0.0]), np.float32([1.0]), _lib.PRIOR_SCALAR)
-        _, loss, _ = self._valid_engine.hmc_eval(self._engine.svgd_particles().astype(np.float32), want_grad=False)
-        return float(loss.mean())
+            self._engine.svgd_set_validation(xv, yv)
+            self._valid_ready = True
+        return float(self._engine.svgd_validation_loss())
 
     def step(self, save_document_path=None):
         self._step += 1

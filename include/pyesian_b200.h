@@ -147,6 +147,12 @@ int pyb_svgd_step(pyb_handle* h, const int32_t* batch_idx, int64_t B, double* lo
 int pyb_svgd_phi(pyb_handle* h, const double* X, const float* G, int64_t S, int32_t semantics,
                  float* phi_out, double* h_out);
 int pyb_svgd_get_particles(pyb_handle* h, double* particles_out);
+/* The validation pass of SVGD.step (SVGD.py:126-129: every particle's loss over the whole validation split, summed
+ * / M) without moving the particles: the held-out set (host X [N, in_dim] float32, y as in pyb_set_dataset) is uploaded
+ * once, pyb_svgd_validation_loss evaluates the mean loss of every resident particle on it (per_particle_out [S] host,
+ * may be NULL) and returns their mean (all-reduced over the ranks of a sharded run). */
+int pyb_svgd_set_validation(pyb_handle* h, const float* X, const void* y, int64_t N);
+int pyb_svgd_validation_loss(pyb_handle* h, double* mean_loss_out, float* per_particle_out);
 /* NCCL plumbing for sharded particles: all ranks pass the same 128-byte ncclUniqueId. */
 int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id_128);
 /* The same communicator under its general name.  With option "predict_sharded" = 1, pyb_predict and

@@ -108,3 +108,38 @@ def test_svgd_script_flow(semantics):
     _, mean = res.predict(xt, mode="exact")
     np.testing.assert_allclose(preds, mean, rtol=1e-4, atol=1e-5)
     assert (mean.argmax(1) == yt).mean() > 0.8
+
+
+@pytest.mark.parametrize("shape", [(2, [50, 2], ["relu", "softmax"], 333, "ce"),       # generic forward
+                                   (4, [8, 3], ["tanh", "linear"], 100, "mse"),
+                                   (784, [128, 10], ["relu", "softmax"], 640, "ce")])  # tensor path (scratch gradient)
+def test_svgd_validation_loss_on_device(oracle, shape):
+    """SVGD.py:126-129: every particle's loss over the whole validation split, evaluated against the resident particles"""
+    from bayesian_inference_for_nn_b200 import _lib
+    from bayesian_inference_for_nn_b200.engine import Engine
+    D, units, acts, Nv, kind = shape
+    rng = np.random.default_rng(0)
+    S = 6
+    spec_o = oracle.MLPSpec(D, units, acts)
+    eng = Engine(keras_json.parse_model_json(keras_json.make_sequential_json(D, units, acts)))
+    loss = _lib.LOSS_SPARSE_CE if kind == "ce" else _lib.LOSS_MSE
+    mk_y = (lambda n: rng.integers(0, units[-1], n).astype(np.int32)) if kind == "ce" else \
+        (lambda n: rng.normal(size=(n, units[-1])).astype(np.float32))
+    X, y = rng.uniform(0, 1, (256, D)).astype(np.float32), mk_y(256)
+    eng.set_dataset(X, y, loss)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    parts = rng.normal(0, 0.3 if D < 100 else 0.05, (S, spec_o.n_params))
+    eng.svgd_init(S, 1e-3, _lib.SVGD_CANONICAL_MEDIAN, particles0=parts)
+    with pytest.raises(_lib.PyesianB200Error):
+        eng.svgd_validation_loss()                          # no validation set yet
+    Xv, yv = rng.uniform(0, 1, (Nv, D)).astype(np.float32), mk_y(Nv)
+    eng.svgd_set_validation(Xv, yv)
+    want, _ = oracle.mean_loss_and_grad(spec_o, parts.astype(np.float32), Xv, yv, loss, dtype=np.float64, want_grad=False)
+    mean, per = eng.svgd_validation_loss(per_particle=True)
+    np.testing.assert_allclose(per, want, rtol=1e-4)
+    assert abs(mean - want.mean()) < 1e-4 * abs(want.mean())
+    eng.svgd_step(np.arange(64, dtype=np.int32))              # the scratch gradient must not disturb the next step
+    before = eng.svgd_particles()
+    eng.svgd_validation_loss()
+    np.testing.assert_array_equal(eng.svgd_particles(), before)
+    eng.close()

@@ -15,9 +15,10 @@ def launches(path):
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     cols = rows[hdr]
     ki, vi = cols.index("Kernel Name"), cols.index("Metric Value")
+    mi = cols.index("Metric Name") if "Metric Name" in cols else None
     agg = collections.defaultdict(list)
     for r in rows[hdr + 1:]:
-        if len(r) > vi:
+        if len(r) > vi and (mi is None or r[mi] == "gpu__time_duration.sum"):
             agg[r[ki].split("(")[0]].append(float(r[vi].replace(",", "")) / 1e6)
     tot = sum(sum(v) for v in agg.values())
     print("# per-kernel device time, cold-cache and serialised under ncu: compare SHARES, not absolutes")
