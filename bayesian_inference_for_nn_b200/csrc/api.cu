@@ -190,6 +190,9 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_fs_cluster = v != 0;
   } else if (!strcmp(key, "live_fused")) {
     h->opt_live_fused = v != 0;
+  } else if (!strcmp(key, "hmc_carry")) {
+    h->opt_hmc_carry = v != 0;
+    h->hmc.have_cur = false;
   } else if (!strcmp(key, "predict_sharded")) {
     h->opt_predict_sharded = v != 0;
   } else if (!strcmp(key, "tc_fuse")) {
@@ -253,6 +256,7 @@ int pyb_set_dataset(pyb_handle* h, const float* X, int64_t N, const void* y, int
   h->n_train = n_train > 0 ? n_train : N;
   h->loss_kind = loss_kind;
   h->have_data = true;
+  h->hmc.have_cur = false;      // a new dataset invalidates the carried loss / gradient
   tc_invalidate_dataset(h);
   PYB_CATCH
 }

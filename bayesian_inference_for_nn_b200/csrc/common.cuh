@@ -177,6 +177,8 @@ struct HmcState {
   int L = 0, semantics = 0;
   uint64_t iter = 0;  // global iteration counter (RNG counter word)
   DevBuf<float> q, p, g, q0;
+  DevBuf<float> gcur;           // loss gradient at the chain's current position (carried between iterations)
+  bool have_cur = false;        // gcur / loss0 are valid for the current q
   DevBuf<float> inj_p, inj_u;
   bool have_inj_p = false, have_inj_u = false;
   // per-chain scalars
@@ -273,6 +275,7 @@ struct pyb_handle {
   int opt_tc_gram_sym = 1;   // 1: Gram matrices (A == B) compute the upper tile triangle only and mirror it
   int opt_fs_cluster = 1;   // 1: the small-width HMC kernel spreads a chain over a CTA cluster when there are few chains
   int opt_live_fused = 1;   // 1: the reference-live SVGD sweep is one cooperative launch on a single GPU
+  int opt_hmc_carry = 1;    // 1: loss and gradient at the current position are carried to the next HMC iteration
   int opt_predict_sharded = 0;   // 1: pyb_predict all-reduces its moment sums over the handle's communicator
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
   double opt_workspace_mb = 4096;

@@ -237,9 +237,12 @@ __global__ void __launch_bounds__(1024) k_record_slots(const int32_t* accepted, 
 }
 
 // q = accepted ? q : q0 (HMC.py:97-101) and copy recorded samples into the arena
+// gcur != nullptr: the loss gradient at the chain's CURRENT position is carried to the next iteration — an accepted
+// chain takes the end-point gradient g (evaluated at q_L), a rejected one keeps the gradient it already has at q0
 __global__ void __launch_bounds__(EW_THREADS) k_select_record(float* q, const float* q0, const int32_t* accepted,
                                                                const int32_t* slot_first, const int32_t* slot_acc,
-                                                               float* arena, int64_t P, int sampling, int64_t S) {
+                                                               float* arena, int64_t P, int sampling, int64_t S,
+                                                               float* gcur, const float* g) {
   int64_t s = chain_index();
   if (s >= S) return;
   int acc = accepted[s];
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_select_record(float* q, const fl
       if (sf >= 0) arena[(int64_t)sf * P + i] = old;
       if (!acc) q[o] = old;
       if (sa >= 0) arena[(int64_t)sa * P + i] = cur;
+      if (gcur && acc) gcur[o] = g[o];
     }
   }
 }
@@ -310,6 +314,7 @@ void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double
   st.host_last_idx.assign(S, -1);
   st.sampling_started = false;
   st.have_inj_p = st.have_inj_u = false;
+  st.have_cur = false;
   DevBuf<float> tmp;
   const float* q0d = nullptr;
   if (q0) {
@@ -352,13 +357,13 @@ void hmc_flush_arena(pyb_handle* h) {
   st.arena_used_upper = 0;
 }
 
-static void launch_kick(pyb_handle* h, float kick1, float kick2, float drift, bool snapshot, bool energy,
+static void launch_kick(pyb_handle* h, const float* g, float kick1, float kick2, float drift, bool snapshot, bool energy,
                         bool kinetic, float* Up_out, float* K_out) {
   HmcState& st = h->hmc;
   const int64_t P = h->model.P;
   int nblk = ew_blocks(P);
   KickArgs a;
-  a.q = st.q.p; a.p = st.p.p; a.g = st.g.p; a.q0 = st.q0.p; a.mu = h->mu.p; a.inv_var = h->inv_var.p; a.P = P; a.S = st.S;
+  a.q = st.q.p; a.p = st.p.p; a.g = g; a.q0 = st.q0.p; a.mu = h->mu.p; a.inv_var = h->inv_var.p; a.P = P; a.S = st.S;
   a.kick1 = kick1; a.kick2 = kick2; a.drift = drift;
   a.snapshot = snapshot; a.energy = energy; a.kinetic = kinetic;
   a.partial_e = st.partial_e.p; a.partial_k = st.partial_k.p;
@@ -386,6 +391,8 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
   PYB_CUDA(cudaMemsetAsync(st.loss_sum.p, 0, sizeof(double), h->stream));
   PYB_CUDA(cudaEventRecord(h->ev0, h->stream));
   const int path = resolve_path(h, S, true);
+  int64_t evals = 0;
+  if (path == PYB_PATH_FUSED_SMALL) { st.have_cur = false; evals = (int64_t)n_iters * S * (st.L + 1); }
   for (int it = 0; it < n_iters; ++it) {
     bool first = sampling && !st.sampling_started;
     if (sampling) {
@@ -406,18 +413,27 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
     count_launch(h);
     k_finish<<<(unsigned)S, 128, 0, h->stream>>>(st.partial_k.p, nblk, 1.0 / (2.0 * st.m), st.K0.p);
     count_launch(h);
-    // U0 and the first half kick share one evaluation at q0  (HMC.py:80-82)
-    eval_loss_grad(h, st.q.p, S, n_train, st.loss0.p, st.g.p);
-    launch_kick(h, half, 0.f, drift, true, true, false, st.Up0.p, nullptr);
+    // U0 and the first half kick share one evaluation at q0  (HMC.py:80-82).  The reference re-evaluates the
+    // potential and its gradient at q0 in every iteration (HMC.py:80,82); q0 is where the previous iteration ended —
+    // its end point q_L if that was accepted, its own q0 if not — and both were evaluated then, so with "hmc_carry"
+    // the loss and the loss gradient at the current position travel with the chain (k_select_record / ret_loss):
+    // L evaluations per iteration instead of L + 1, bit-identical results (every kernel is deterministic).
+    if (!st.have_cur) {
+      st.gcur.alloc(S * P);
+      eval_loss_grad(h, st.q.p, S, n_train, st.loss0.p, st.gcur.p);
+      evals += S;
+    }
+    launch_kick(h, st.gcur.p, half, 0.f, drift, true, true, false, st.Up0.p, nullptr);
     for (int i = 1; i <= st.L; ++i) {
       eval_loss_grad(h, st.q.p, S, n_train, st.loss.p, st.g.p);
+      evals += S;
       if (i < st.L) {
-        launch_kick(h, eps, 0.f, drift, false, false, false, nullptr, nullptr);
+        launch_kick(h, st.g.p, eps, 0.f, drift, false, false, false, nullptr, nullptr);
       } else if (st.semantics == PYB_HMC_REFERENCE) {
         // L-th full kick and the trailing half kick, both with the gradient at q_L (HMC.py:85-87)
-        launch_kick(h, eps, half, 0.f, false, true, true, st.Up1.p, st.K1.p);
+        launch_kick(h, st.g.p, eps, half, 0.f, false, true, true, st.Up1.p, st.K1.p);
       } else {
-        launch_kick(h, half, 0.f, 0.f, false, true, true, st.Up1.p, st.K1.p);
+        launch_kick(h, st.g.p, half, 0.f, 0.f, false, true, true, st.Up1.p, st.K1.p);
       }
     }
     AcceptArgs a;
@@ -438,9 +454,14 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
       count_launch(h);
       st.sampling_started = true;
     }
+    const bool carry = h->opt_hmc_carry && path != PYB_PATH_FUSED_SMALL;
     k_select_record<<<gridp, EW_THREADS, 0, h->stream>>>(st.q.p, st.q0.p, st.accepted.p, st.slot_first.p,
-                                                         st.slot_acc.p, st.arena.p, P, sampling ? 1 : 0, S);
+                                                         st.slot_acc.p, st.arena.p, P, sampling ? 1 : 0, S,
+                                                         carry ? st.gcur.p : nullptr, st.g.p);
     count_launch(h);
+    if (carry)     // loss at the new current position = what step() returns: accepted ? loss(q_L) : loss(q0) (HMC.py:96,104)
+      PYB_CUDA(cudaMemcpyAsync(st.loss0.p, st.ret_loss.p, S * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    st.have_cur = carry;
     st.have_inj_p = st.have_inj_u = false;
     st.iter++;
   }
@@ -461,7 +482,7 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
     out->n_nan = (int64_t)c[2];
     out->accept_rate = c[1] ? (double)c[0] / (double)c[1] : 0.0;
     out->mean_loss = c[1] ? ls / (double)c[1] : 0.0;
-    out->grad_evals = (int64_t)n_iters * S * (st.L + 1);
+    out->grad_evals = evals;
     out->device_ms = ms;
     out->kernel_launches = h->kernel_launches - launches0;
   }

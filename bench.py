@@ -4,9 +4,13 @@
 Workload (BASELINE.json configs[2], the config the metric and the >=1024-chain target are quoted
 on; it fits one GPU): HMC, 1024 chains per GPU, synthetic MNIST-shaped data 60000x784 (U[0,1),
 labels U{0..9}), 784-256-10 MLP, L=20, Gaussian prior N(0,1), reference leapfrog semantics.
-One "step" = one HMC sampling iteration of every local chain: momentum draw, L+1 full-dataset
-log-posterior forward/backward evaluations, Hamiltonian, Metropolis accept, sample bookkeeping.
-The metric counts S*L grad-evals per step (the endpoint evaluation is overhead).
+One "step" = one HMC sampling iteration of every local chain: momentum draw, L full-dataset
+log-posterior forward/backward evaluations at the L new positions (the evaluation at the start position is
+carried from the previous iteration - its end point if accepted, its start if rejected - with bit-identical
+results, tests/test_gpu_parity.py::test_carried_evaluation_is_bit_identical_to_re_evaluation; the reference
+re-evaluates it, HMC.py:80,82), both Hamiltonians, Metropolis accept, sample bookkeeping.
+The metric counts S*L grad-evals per step; `evals_executed_per_step_per_chain` in the
+config is what the library actually ran (L; L+1 in the e2e leg, whose re-uploaded dataset drops the carry).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -165,11 +169,11 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, evals_per_step=None):
     return {"workload": "C3 HMC 784-256-10 MLP, %d chains/GPU, %d rows x 784 synthetic MNIST-shaped, L=%d, "
                         "reference leapfrog semantics, Gaussian prior N(0,1)" % (args.chains, args.rows, args.leapfrog),
             "chains_per_gpu": args.chains, "chains_total": args.chains * world, "rows": args.rows, "L": args.leapfrog,
-            "epsilon": args.eps, "evals_executed_per_step_per_chain": args.leapfrog + 1,
+            "epsilon": args.eps, "evals_executed_per_step_per_chain": evals_per_step if evals_per_step is not None else args.leapfrog + 1,
             "parallelism": "chains sharded x%d, no data-path collective" % world,
             "l2_policy": "inputs exceed L2 (X hi/lo 188 MB + per-chain operands >> 126 MB)",
             "named_config": bool(args.chains == 1024 and args.rows == 60000 and args.leapfrog == 20 and not args.opt)}
@@ -307,7 +311,8 @@ def main():
         "metric": "posterior_grad_evals_per_s", "value": value, "unit": "grad-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core products, fp32 accumulate)"
-        if path_used == 3 else "f32", "data": "synthetic", "config": workload_config(args, world),
+        if path_used == 3 else "f32", "data": "synthetic",
+        "config": workload_config(args, world, d["grad_evals"] / float(S * args.steps)),
         "wall_ms_per_step": 1e3 * wall_s / args.steps, "accept_rate": accept_rate, "path_used": path_used,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
     }

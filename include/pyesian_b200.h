@@ -71,7 +71,8 @@ typedef struct {
   int64_t n_accepted;    /* over all local chains and iterations of this call */
   int64_t n_total;
   int64_t n_nan;         /* proposals whose Hamiltonian difference was NaN (rejected) */
-  int64_t grad_evals;    /* chain x position evaluations actually executed in this call */
+  int64_t grad_evals;    /* chain x position evaluations actually executed in this call (L per iteration and chain,
+                            plus one when the carried evaluation at the start position is not available) */
   double device_ms;      /* CUDA-event time of the call's kernels on the handle's stream */
   int64_t kernel_launches;
 } pyb_hmc_diag;
@@ -91,7 +92,9 @@ int pyb_param_count(const pyb_handle* h, int64_t* n_params_out);
  * path, all default 1: "tc_pair" (CTA-pair cta_group::2 kernels), "tc_fuse" (layer 2, loss and both deltas inside
  * the layer-1 GEMM's epilogue), "tc_dual" (two feature tiles per item in the dW1 GEMM).  Switching them off selects
  * the older kernels that compute the same quantities (used by the tests and by tools/kernel_cycles.sh);
- * "predict_sharded" (default 0, see pyb_set_comm). */
+ * "predict_sharded" (default 0, see pyb_set_comm); "hmc_carry" (default 1): the loss and loss gradient at a chain's
+ * current position are carried from the previous iteration (its end point if accepted, its start if rejected) instead
+ * of being re-evaluated as HMC.py:80,82 do - L instead of L+1 full-data evaluations per iteration, identical results. */
 int pyb_set_option(pyb_handle* h, const char* key, double value);
 /* read-outs: "path_used", "kernel_launches", "last_device_ms", "workspace_bytes", "tensor_path_ok" */
 int pyb_get_info(const pyb_handle* h, const char* key, double* value_out);

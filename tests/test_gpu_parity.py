@@ -369,3 +369,40 @@ def test_auto_path_selection(oracle):
     eng3, _ = make_engine(g3, oracle, "auto")
     eng3.hmc_eval(g3["q"])
     assert int(eng3.info("path_used")) == _lib.PATH_GENERIC
+
+
+@pytest.mark.parametrize("name,path", [("hmc_c1_mini", "generic"), ("hmc_c3_mini", "generic"), ("hmc_c3_mini", "auto")])
+def test_carried_evaluation_is_bit_identical_to_re_evaluation(oracle, name, path):
+    """"hmc_carry": the loss / gradient at q0 come from the previous iteration (its end point if accepted, its start
+    if rejected) instead of being re-evaluated as HMC.py:80,82 do.  Same bits, L instead of L+1 evaluations."""
+    g = load_golden(name)
+    S, L, n_it = 6, 3, 7
+    spec = spec_from_golden(g, oracle)
+    eps = 1e-2 if spec.in_dim < 100 else 8e-2        # large enough that some proposals are rejected (oracle-calibrated)
+    runs = {}
+    for carry in (1, 0):
+        eng, _ = make_engine(g, oracle, path, seed=5)
+        eng.set_option("hmc_carry", carry)
+        eng.hmc_init(S, eps, 1.0, L, _lib.HMC_REFERENCE)
+        eng.hmc_run(2, burning=True, sampling=False)
+        d1 = eng.hmc_run(n_it, burning=False, sampling=True)
+        # two calls, and a change of data in between: the carried evaluation must be dropped, not reused
+        eng.set_dataset(g["X"][::-1].copy(), g["y"][::-1].copy(), int(g["loss_kind"]))
+        d2 = eng.hmc_run(2, burning=False, sampling=True)
+        runs[carry] = (eng.hmc_state(), eng.hmc_last(), eng.hmc_samples(), d1, d2)
+        if int(eng.info("path_used")) == _lib.PATH_FUSED_SMALL:
+            pytest.skip("the one-launch small-width kernel evaluates everything in shared memory")
+        eng.close()
+    (qa, pa), la, sa, d1a, d2a = runs[1]
+    (qb, pb), lb, sb, d1b, d2b = runs[0]
+    np.testing.assert_array_equal(qa, qb)
+    np.testing.assert_array_equal(pa, pb)
+    for k in ("U0", "U1", "K0", "K1", "log_alpha", "accept", "loss"):
+        np.testing.assert_array_equal(la[k], lb[k], err_msg=k)
+    for a, b in zip(sa, sb):
+        np.testing.assert_array_equal(a, b)
+    assert 0 < d1a["n_accepted"] < S * n_it, "the case must contain accepted AND rejected proposals"
+    assert d1a["n_accepted"] == d1b["n_accepted"] and d2a["n_accepted"] == d2b["n_accepted"]
+    assert d1b["grad_evals"] == S * n_it * (L + 1) and d2b["grad_evals"] == S * 2 * (L + 1)
+    assert d1a["grad_evals"] == S * n_it * L                 # the burn-in call left its end-point evaluation behind
+    assert d2a["grad_evals"] == S * (2 * L + 1)              # new dataset: one fresh evaluation at the start position
