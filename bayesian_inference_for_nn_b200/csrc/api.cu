@@ -184,6 +184,8 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_tc_pair = v != 0;
   } else if (!strcmp(key, "tc_dual")) {
     h->opt_tc_dual = v != 0;
+  } else if (!strcmp(key, "tc_h128_pairs")) {
+    h->opt_tc_h128_pairs = v != 0;
   } else if (!strcmp(key, "tc_gram_sym")) {
     h->opt_tc_gram_sym = v != 0;
   } else if (!strcmp(key, "fs_cluster")) {

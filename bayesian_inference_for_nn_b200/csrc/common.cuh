@@ -272,6 +272,7 @@ struct pyb_handle {
   int opt_path = PYB_PATH_AUTO;
   int opt_tc_pair = 1;   // 1: use the CTA-pair (cta_group::2) GEMM kernel where it applies
   int opt_tc_dual = 1;   // 1: the hidden-major dW1 GEMM computes two feature tiles per item (shared A stages)
+  int opt_tc_h128_pairs = 1;   // 1: 128-unit hidden layers use the dual hidden-major dW1 GEMM with two chains per CTA pair
   int opt_tc_gram_sym = 1;   // 1: Gram matrices (A == B) compute the upper tile triangle only and mirror it
   int opt_fs_cluster = 1;   // 1: the small-width HMC kernel spreads a chain over a CTA cluster when there are few chains
   int opt_live_fused = 1;   // 1: the reference-live SVGD sweep is one cooperative launch on a single GPU

@@ -42,6 +42,8 @@ struct TcGemmParams {
   int n_btiles, b_row0, transpose_out;
   int vec_store;               // EPI_STORE: every output row segment is 16-byte aligned -> float4 stores
   int n_cols_total;            // >0: chain b owns columns [b*H, min((b+1)*H, n_cols_total)) of one wide output
+  int chain_pairs, n_chains;   // dual hidden-major kernel with 128 hidden units: the two CTAs of a pair take two CHAINS
+                               // (2b, 2b+1 < n_chains) instead of the two halves of one chain's 256 hidden units
   int sym_skip;                // pair kernel, A == B (Gram matrix): tiles strictly below the diagonal (256-col tile b <
                                // 256-row tile mp) are skipped; the caller mirrors the upper triangle afterwards
 };
@@ -649,15 +651,16 @@ tc_gemm_pair_dual_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         int b, split, bt0, n_t;
         td_decode(p, item, b, split, bt0, n_t);
         const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
-        const int arow = (int)rank * 128;
-        const uint32_t cta_bytes = 2 * TC_A_TILE_BYTES + 2 * (uint32_t)n_t * b_bytes;
+        const int arow = p.chain_pairs ? 0 : (int)rank * 128;
+        const int ab = p.chain_pairs ? 2 * b + (int)rank : b;     // (an odd batch's last partner reads another chain's
+        const uint32_t cta_bytes = 2 * TC_A_TILE_BYTES + 2 * (uint32_t)n_t * b_bytes;   // block or zeros: never stored)
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * TD_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);
           const int k0 = kc * TC_BK;
-          tma_load_3d_pair(st, &tmA_hi, &full_bar[stage], k0 & 127, arow, b * p.k_tiles + (k0 >> 7));
-          tma_load_3d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0 & 127, arow, b * p.k_tiles + (k0 >> 7));
+          tma_load_3d_pair(st, &tmA_hi, &full_bar[stage], k0 & 127, arow, ab * p.k_tiles + (k0 >> 7));
+          tma_load_3d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0 & 127, arow, ab * p.k_tiles + (k0 >> 7));
           for (int j = 0; j < n_t; ++j) {
             const int brow = p.b_row0 + (bt0 + j) * p.H + (int)rank * half_rows;
             tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES + (2 * j) * 8192, &tmB_hi, &full_bar[stage], k0, brow);
@@ -718,13 +721,14 @@ tc_gemm_pair_dual_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       mbar_wait(tmem_full, acc_phase);
       tc_fence_after();
       if (j < n_t) {
-        const int row = (int)rank * 128 + et;                     // hidden unit
+        const int row = p.chain_pairs ? et : (int)rank * 128 + et;          // hidden unit
+        const int oc = p.chain_pairs ? 2 * b + (int)rank : b;               // chain whose gradient this CTA holds
         const int colbase = p.b_row0 + (bt0 + j) * p.H;
-        float* ob = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + row;
+        float* ob = p.out + (int64_t)split * p.split_stride + (int64_t)oc * p.out_stride + row;
         for (int c0 = 0; c0 < p.H; c0 += 32) {
           float v[32];
           tc_ld32(tmem_base + lane_base + (uint32_t)(j * 256 + c0), v);
-          if (row < p.M_valid) {
+          if (row < p.M_valid && (!p.chain_pairs || oc < p.n_chains)) {
             float* o = ob + (int64_t)(colbase + c0) * p.out_ld;
 #pragma unroll
             for (int q = 0; q < 32; ++q)

@@ -379,7 +379,9 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
       }
     }
     // G2: [dW1; db1] = [X^T; 1] dZ1
-    if (H == 256 && h->opt_tc_pair) {
+    // two 128-unit chains per CTA pair: only the dual kernel knows that mode, and it needs at least two feature tiles
+    const bool chain_pairs = H == 128 && h->opt_tc_dual && h->opt_tc_h128_pairs && (D + 1 + 255) / 256 > 1;
+    if ((H == 256 || chain_pairs) && h->opt_tc_pair) {
       // hidden-major on the CTA-pair kernel: D[h, f] = sum_r dZ1^T[h, r] [X^T;1][f, r].  M = 256 hidden units is
       // exactly one CTA pair (no M padding), the D+1 feature rows are the N dimension in tiles of 256 plus one
       // narrow remainder tile, the accumulators are double-buffered so the partial-sum stores overlap the MMAs
@@ -387,7 +389,8 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
       const int n_t = (D + 1 + 255) / 256;
       const int Ht = (((D + 1 + n_t - 1) / n_t) + 15) / 16 * 16;
       TcGemmParams p = {};
-      p.K = (int)Npad; p.n_mtiles = 2; p.n_pairs = 1; p.n_batch = nb; p.H = Ht;
+      p.K = (int)Npad; p.n_mtiles = 2; p.n_pairs = 1; p.n_batch = chain_pairs ? (nb + 1) / 2 : nb; p.H = Ht;
+      p.chain_pairs = chain_pairs ? 1 : 0; p.n_chains = nb;
       p.a_blocked = 1; p.b_blocked = 0; p.k_tiles = (int)(Npad / 128); p.a_box_rows = 128;
       p.n_btiles = n_t; p.b_row0 = 0; p.transpose_out = 1; p.n_cols_total = D + 1;
       p.epi = EPI_STORE; p.out_ld = H; p.M_valid = H; p.N_valid = Ht;
@@ -397,7 +400,7 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
       } else {
         p.out = gr; p.out_stride = P;
       }
-      p.total_items = nb * std::max(splits, 1) * n_t;
+      p.total_items = p.n_batch * std::max(splits, 1) * n_t;
       launch_gemm_tc(h, st->mZa_hi, st->mZa_lo, fused ? d.mXTq_hi : d.mXT_hi, fused ? d.mXTq_lo : d.mXT_lo, p,
                      2.0 * N * (double)(D + 1) * H * nb, fused ? &d.mXTqp_hi : &d.mXTp_hi, fused ? &d.mXTqp_lo : &d.mXTp_lo);
     } else {

@@ -98,7 +98,10 @@ CASES = [(784, 256, 10, 512, 3, "relu", "ce"), (784, 128, 10, 300, 2, "relu", "c
          # the fused layer-1 GEMM + layer-2 epilogue (relu, H = 128/256) in every class padding CP = 4, 8, 12, 16,
          # both losses, ragged row counts (last tile partly / wholly zero fill) and an odd chain count
          (64, 128, 2, 129, 3, "relu", "ce"), (96, 256, 7, 1000, 2, "relu", "ce"), (64, 128, 16, 640, 2, "relu", "ce"),
-         (128, 256, 3, 385, 5, "relu", "mse"), (784, 256, 12, 257, 1, "relu", "ce")]
+         (128, 256, 3, 385, 5, "relu", "mse"), (784, 256, 12, 257, 1, "relu", "ce"),
+         # 128 hidden units: dW1 on the dual hidden-major kernel with two CHAINS per CTA pair; odd chain count (the last
+         # pair has one partner) and more than 8192 rows (split-K partial sums per chain)
+         (784, 128, 10, 9000, 3, "relu", "ce"), (300, 128, 4, 640, 5, "relu", "mse")]
 
 
 @pytest.mark.parametrize("D,H,Cc,N,S,act,loss", CASES)
@@ -184,6 +187,20 @@ def test_tensor_path_hmc_iteration_matches_oracle(oracle):
             assert rel_err(qd[s], want["q"][s]) < 1e-3
             assert rel_err(pd[s], want["pL"][s]) < 1e-3
     assert d["grad_evals"] == S * (L + 1)
+
+
+def test_h128_chain_pair_dw1_agrees_with_the_feature_major_kernel(oracle):
+    """A/B of the two dW1 kernels for 128 hidden units ("tc_h128_pairs"): same products, same k order"""
+    spec, prob, q, out_act, _ = problem(oracle, 784, 128, 10, 1024, 7, seed=3, act="relu", loss="ce")
+    eng = engine(784, 128, 10, "relu", out_act)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.set_option("path", _lib.PATH_TENSOR)
+    _, _, g_pairs = eng.hmc_eval(q)
+    eng.set_option("tc_h128_pairs", 0)
+    _, _, g_fm = eng.hmc_eval(q)
+    for s in range(7):
+        assert rel_err(g_pairs[s], g_fm[s]) < 2e-6
 
 
 def test_tensor_path_reversibility_canonical(oracle):
