@@ -101,7 +101,7 @@ CASES = [(784, 256, 10, 512, 3, "relu", "ce"), (784, 128, 10, 300, 2, "relu", "c
          (128, 256, 3, 385, 5, "relu", "mse"), (784, 256, 12, 257, 1, "relu", "ce"),
          # 128 hidden units: dW1 on the dual hidden-major kernel with two CHAINS per CTA pair; odd chain count (the last
          # pair has one partner) and more than 8192 rows (split-K partial sums per chain)
-         (784, 128, 10, 9000, 3, "relu", "ce"), (300, 128, 4, 640, 5, "relu", "mse")]
+         (784, 128, 10, 9000, 3, "relu", "ce"), (320, 128, 4, 640, 5, "relu", "mse")]
 
 
 @pytest.mark.parametrize("D,H,Cc,N,S,act,loss", CASES)
