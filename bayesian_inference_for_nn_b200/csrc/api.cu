@@ -46,7 +46,12 @@ void eval_on_batch(pyb_handle* h, const float* theta, int64_t S, const float* Xb
                    int64_t Nb, float scale, float* loss_out, float* grad_out) {
   if (Xb == h->X.p && Nb == h->N) { eval_loss_grad(h, theta, S, scale, loss_out, grad_out); return; }
   const bool tensor_ok = grad_out && tc_supported_rows(h, Nb) && (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_TENSOR);
+  const bool small_ok = grad_out && Nb <= h->N && fused_small_supported(h) &&
+                        (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_FUSED_SMALL);
   if (tensor_ok) { tc_eval_batch(h, Xb, yb_i, yb_f, Nb, theta, S, scale, loss_out, grad_out); h->path_used = PYB_PATH_TENSOR; }
+  else if (small_ok) {   // small-width nets: one launch, parameters and the batch in shared memory
+    fused_small_eval_on(h, theta, S, Xb, yb_i, yb_f, Nb, scale, loss_out, grad_out); h->path_used = PYB_PATH_FUSED_SMALL;
+  }
   else { generic_eval(h, theta, S, Xb, yb_i, yb_f, Nb, scale, loss_out, grad_out); h->path_used = PYB_PATH_GENERIC; }
 }
 }  // namespace pyb

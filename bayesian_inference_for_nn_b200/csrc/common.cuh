@@ -339,6 +339,8 @@ void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, f
 int resolve_path(pyb_handle* h, int64_t S, bool with_grad);
 bool fused_small_supported(pyb_handle* h);
 void fused_small_hmc_iteration(pyb_handle* h, bool burning);
+void fused_small_eval_on(pyb_handle* h, const float* theta, int64_t S, const float* Xb, const int32_t* yb_i,
+                         const float* yb_f, int64_t Nb, float scale, float* loss, float* grad);
 
 // tc_path.cu
 bool tc_supported_rows(pyb_handle* h, int64_t n_rows);

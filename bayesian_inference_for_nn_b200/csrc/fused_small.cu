@@ -442,6 +442,18 @@ void fused_small_eval(pyb_handle* h, const float* theta, int64_t S, float scale,
   PYB_CUDA(cudaGetLastError());
 }
 
+// the same on an arbitrary device-resident batch of at most h->N rows (minibatches gathered from the resident dataset:
+// SVGD / SGLD / SWAG steps); the shared-memory plan is the one sized for the full dataset
+void fused_small_eval_on(pyb_handle* h, const float* theta, int64_t S, const float* Xb, const int32_t* yb_i,
+                         const float* yb_f, int64_t Nb, float scale, float* loss, float* grad) {
+  PYB_REQUIRE(Nb > 0 && Nb <= h->N, PYB_ERR_INVALID, "fused small path: batch larger than the resident dataset");
+  FsParams p = fs_base(h);
+  p.X = Xb; p.y_i = yb_i; p.y_f = yb_f; p.N = (int)Nb;
+  p.theta = theta; p.loss_out = loss; p.grad_out = grad; p.scale = scale;
+  fs_dispatch(h, p, S, false);
+  PYB_CUDA(cudaGetLastError());
+}
+
 // one HMC iteration for all chains in ONE launch (sampler.cu records samples afterwards)
 void fused_small_hmc_iteration(pyb_handle* h, bool burning) {
   HmcState& st = h->hmc;
