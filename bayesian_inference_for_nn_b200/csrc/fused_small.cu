@@ -70,10 +70,13 @@ __device__ __forceinline__ T fs_block_sum_all(T v, T* scratch) {
 
 // over the data rows [rb, re): loss SUM (returned to every thread) and gout = scale/N * d(sum loss)/d theta for the
 // parameters in sm.qs (N = all rows of the dataset: partial results of disjoint row ranges simply add up)
-template <int D, int C>
+template <int D, int C, int ACT>
 __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale, int rb, int re, float* gout) {
   constexpr int PKW = D + 1 + C;
   const int t = threadIdx.x, H = p.H, N = p.N;
+  // ACT >= 0: the hidden activation is a compile-time constant (relu: the shipped models) and the per-(row, unit)
+  // switches in act_apply / act_grad_from_output fold away; ACT < 0: any activation, selected at run time
+  const int act1 = ACT >= 0 ? ACT : p.act1;
   // pack per-unit parameters: {W1[0..D)[h], b1[h], W2[h][0..C)}
   for (int i = t; i < H * PKW; i += FS_THREADS) {
     int h = i / PKW, k = i - h * PKW;
@@ -102,7 +105,7 @@ __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale,
       float z = w[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) z = fmaf(x[d], w[d], z);
-      float a = act_apply(z, p.act1);
+      float a = act_apply(z, act1);
 #pragma unroll
       for (int c = 0; c < C; ++c) z2[c] = fmaf(a, w[D + 1 + c], z2[c]);
     }
@@ -154,12 +157,12 @@ __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale,
       float x[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) { x[d] = sm.xs[r * D + d]; z = fmaf(x[d], w1[d], z); }
-      const float a = act_apply(z, p.act1);
+      const float a = act_apply(z, act1);
       float da = 0.f;
       float dzr[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) { dzr[c] = sm.dz2[r * C + c]; da = fmaf(dzr[c], w2[c], da); }
-      const float d1 = da * act_grad_from_output(a, p.act1);
+      const float d1 = da * act_grad_from_output(a, act1);
 #pragma unroll
       for (int d = 0; d < D; ++d) gw1[d] = fmaf(x[d], d1, gw1[d]);
       gb1 += d1;
@@ -196,13 +199,13 @@ __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale,
   return loss_tot;
 }
 // whole dataset in this CTA: mean loss, gradient in sm.gs
-template <int D, int C>
+template <int D, int C, int ACT>
 __device__ float fs_eval(const FsParams& p, const FsSmem& sm, float scale) {
-  return (float)(fs_eval_rows<D, C>(p, sm, scale, 0, p.N, sm.gs) / (double)p.N);
+  return (float)(fs_eval_rows<D, C, ACT>(p, sm, scale, 0, p.N, sm.gs) / (double)p.N);
 }
 // this CTA's share of the rows, then the cluster-wide sum through distributed shared memory.  `n_eval` alternates the
 // exchange buffer: a CTA may already write the next evaluation's partials while a slower one still reads these
-template <int D, int C>
+template <int D, int C, int ACT>
 __device__ float fs_eval_cluster(const FsParams& p, const FsSmem& sm, float scale, int rank, int n_ctas, int& n_eval) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster();
@@ -211,7 +214,7 @@ __device__ float fs_eval_cluster(const FsParams& p, const FsSmem& sm, float scal
   float* gx = sm.gx + (n_eval & 1) * GX;
   ++n_eval;
   const int rb = (int)((int64_t)p.N * rank / n_ctas), re = (int)((int64_t)p.N * (rank + 1) / n_ctas);
-  const double lsum = fs_eval_rows<D, C>(p, sm, scale, rb, re, gx);
+  const double lsum = fs_eval_rows<D, C, ACT>(p, sm, scale, rb, re, gx);
   if (t == 0) *reinterpret_cast<double*>(gx + GX - 2) = lsum;
   cl.sync();
   for (int64_t i = t; i < P; i += FS_THREADS) {
@@ -252,7 +255,7 @@ __device__ void fs_setup(const FsParams& p, FsSmem& sm, float* base) {
 }
 
 // eval-only: loss + scale * d(mean loss)/d theta  (parity hook, SVGD gradients)
-template <int D, int C>
+template <int D, int C, int ACT>
 __global__ void __launch_bounds__(FS_THREADS) k_fs_eval(FsParams p) {
   extern __shared__ __align__(16) float fs_smem[];
   FsSmem sm;
@@ -260,14 +263,14 @@ __global__ void __launch_bounds__(FS_THREADS) k_fs_eval(FsParams p) {
   const int64_t s = blockIdx.x;
   for (int64_t i = threadIdx.x; i < p.P; i += FS_THREADS) sm.qs[i] = p.theta[s * p.P + i];
   __syncthreads();
-  float loss = fs_eval<D, C>(p, sm, p.scale);
+  float loss = fs_eval<D, C, ACT>(p, sm, p.scale);
   if (p.grad_out)
     for (int64_t i = threadIdx.x; i < p.P; i += FS_THREADS) p.grad_out[s * p.P + i] = sm.gs[i];
   if (threadIdx.x == 0 && p.loss_out) p.loss_out[s] = loss;
 }
 
 // one full HMC iteration of one chain
-template <int D, int C>
+template <int D, int C, int ACT>
 __global__ void __launch_bounds__(FS_THREADS) k_fs_hmc(FsParams p) {
   extern __shared__ __align__(16) float fs_smem[];
   FsSmem sm;
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fs_hmc(FsParams p) {
   const bool writer = rank == 0;          // every CTA of the cluster holds the same state; one writes it back
   int n_eval = 0;
   auto eval = [&]() -> float {
-    return n_ctas > 1 ? fs_eval_cluster<D, C>(p, sm, p.n_train, rank, n_ctas, n_eval) : fs_eval<D, C>(p, sm, p.n_train);
+    return n_ctas > 1 ? fs_eval_cluster<D, C, ACT>(p, sm, p.n_train, rank, n_ctas, n_eval) : fs_eval<D, C, ACT>(p, sm, p.n_train);
   };
   // q, momentum (HMC.py:78), K0 (:79)
   double k0 = 0.0;
@@ -386,11 +389,11 @@ bool fused_small_supported(pyb_handle* h) {
   return true;
 }
 
-template <int D, int C>
+template <int D, int C, int ACT>
 static void fs_launch(pyb_handle* h, const FsParams& p, int64_t S, bool hmc) {
   size_t smem = fs_smem_bytes(h);
   if (hmc) {
-    PYB_CUDA(cudaFuncSetAttribute(k_fs_hmc<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PYB_CUDA(cudaFuncSetAttribute(k_fs_hmc<D, C, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (p.cluster > 1) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(S * p.cluster)); cfg.blockDim = dim3(FS_THREADS);
@@ -399,13 +402,13 @@ static void fs_launch(pyb_handle* h, const FsParams& p, int64_t S, bool hmc) {
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = (unsigned)p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      PYB_CUDA(cudaLaunchKernelEx(&cfg, k_fs_hmc<D, C>, p));
+      PYB_CUDA(cudaLaunchKernelEx(&cfg, k_fs_hmc<D, C, ACT>, p));
     } else {
-      k_fs_hmc<D, C><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
+      k_fs_hmc<D, C, ACT><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
     }
   } else {
-    PYB_CUDA(cudaFuncSetAttribute(k_fs_eval<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fs_eval<D, C><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
+    PYB_CUDA(cudaFuncSetAttribute(k_fs_eval<D, C, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fs_eval<D, C, ACT><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
   }
   count_launch(h);
 }
@@ -414,7 +417,7 @@ static void fs_dispatch(pyb_handle* h, const FsParams& p, int64_t S, bool hmc) {
   const int D = h->model.layer[0].fan_in, C = h->model.layer[1].fan_out;
   const double flops = 1.0;  // roofline for this path is reported per grad-eval by bench/tests, not per launch
   prof_begin(h);
-#define FS_CASE(d, c) if (D == d && C == c) fs_launch<d, c>(h, p, S, hmc); else
+#define FS_CASE(d, c) if (D == d && C == c) { if (p.act1 == PYB_ACT_RELU) fs_launch<d, c, PYB_ACT_RELU>(h, p, S, hmc); else fs_launch<d, c, -1>(h, p, S, hmc); } else
   FS_CASE(1, 1) FS_CASE(1, 2) FS_CASE(1, 3) FS_CASE(1, 4)
   FS_CASE(2, 1) FS_CASE(2, 2) FS_CASE(2, 3) FS_CASE(2, 4)
   FS_CASE(3, 1) FS_CASE(3, 2) FS_CASE(3, 3) FS_CASE(3, 4)

@@ -191,3 +191,27 @@ def test_errors_and_edge_cases(oracle):
         np.testing.assert_allclose(got, want, rtol=1e-4)
     assert rel_err(eng.sg_state()["theta"], st.theta) < 2e-5
     eng.close()
+
+
+def test_sharded_sgld_chains_reproduce_the_unsharded_run(oracle):
+    """chains never interact and the Philox counters use the GLOBAL chain id (chain_offset): two shards of 3 chains
+    driven with the same minibatches give exactly the 6-chain run (first row, applied to the SG chains)"""
+    S = 6
+    eng, spec, X, y, _, rng, B, loss = setup(oracle, SHAPES[0], S)
+    batches = [rng.permutation(X.shape[0])[:B].astype(np.int32) for _ in range(5)]
+    eng.sg_init(S, _lib.SG_SGLD)
+    for n, idx in enumerate(batches):
+        eng.sg_step(0.05 / (n + 1), idx)
+    whole = eng.sg_state()
+    parts = []
+    for r in range(2):
+        e2 = Engine(keras_json.parse_model_json(keras_json.make_sequential_json(2, [50, 2], ["relu", "softmax"])), seed=11)
+        e2.set_dataset(X, y, loss)
+        e2.sg_init(S // 2, _lib.SG_SGLD, chain_offset=r * (S // 2))
+        for n, idx in enumerate(batches):
+            e2.sg_step(0.05 / (n + 1), idx)
+        parts.append(e2.sg_state())
+        e2.close()
+    for k in ("theta", "mean", "sq_mean"):
+        np.testing.assert_array_equal(np.concatenate([p[k] for p in parts]), whole[k])
+    eng.close()
