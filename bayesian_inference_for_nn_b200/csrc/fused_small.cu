@@ -1,381 +1,7 @@
-// fused_small.cu — small-width path (BASELINE configs C1/C2: make_moons 2-50-2, 1-D regression
-// 1-1-1): ONE CTA per chain, dataset + q/p/grad resident in shared memory, the whole HMC iteration
-// (Philox momentum draw, K0, L+1 full-data forward/backward evaluations with the prior, leapfrog
-// kicks/drifts, K1/U1, Metropolis test) in ONE launch.  fp32 SIMT, warp-shuffle block reductions.
-//
-// Reference: HMC.step HMC.py:74-104 (one chain, ~8 eager TF ops per leapfrog step and two host
-// syncs per iteration); _potential_energy :149-159; _step_p :128-136; _step_q :138-141.
-//
-// Evaluation inside the CTA (N rows, D inputs, H hidden, C outputs):
-//   phase 1  thread == data row:  z1, a1, z2 -> loss, dZ2 (kept in smem for all rows)
-//   phase 2  thread == (hidden unit, row slice): recompute a1 from the unit's own weights (registers),
-//            dZ1 = (dZ2 W2^T) act'(a1), accumulate dW1[:,h], db1[h], dW2[h,:] in registers
-//   slices are combined in a fixed order (deterministic), db2 by one warp per class.
-//
-// Few chains (the reference runs ONE, HMC.py:74): a chain is then spread over a thread-block CLUSTER of up to 8
-// CTAs.  Each CTA keeps the whole state (q, p: a few hundred floats, updated redundantly and identically) and
-// evaluates an eighth of the data rows; after every evaluation the partial gradients and loss meet through
-// distributed shared memory (one cluster barrier per evaluation, double-buffered exchange, fixed summation order).
-#include "common.cuh"
-#include <cooperative_groups.h>
-#include <algorithm>
+// fused_small.cu — host side of the small-width path (kernels: fused_small.cuh, instantiated in fused_small_d*.cu)
+#include "fused_small.cuh"
 
 namespace pyb {
-
-constexpr int FS_THREADS = 256;
-constexpr int FS_HMAX = 256;
-
-struct FsParams {
-  // model / data
-  int N, H, act1, out_act, loss_kind;
-  int64_t P, w1_off, b1_off, w2_off, b2_off;
-  const float* X; const int32_t* y_i; const float* y_f;
-  const float* mu; const float* inv_var;
-  float n_train;                 // scale of the mean loss in U (HMC.py:158)
-  // eval-only mode
-  const float* theta; float* loss_out; float* grad_out; float scale;
-  // HMC iteration mode
-  float* q; float* p; float* q0; const float* inj_p; const float* inj_u;
-  float eps, half_eps, drift, stdv, inv2m, prior_const;
-  int L, semantics, burning;
-  int cluster;                   // CTAs per chain (1, 2, 4 or 8)
-  uint64_t seed; uint32_t iter; int64_t chain_offset;
-  float* U0; float* U1; float* K0; float* K1; float* log_alpha; float* ret_loss; int32_t* accepted;
-  unsigned long long* counters; double* loss_sum;
-};
-
-struct FsSmem {
-  float* xs;      // [N][D]
-  float* ys;      // labels as float bits (int) or targets [N][C]
-  float* dz2;     // [N][C]
-  float* qs; float* ps; float* gs;   // [P]
-  float* pk;      // [H][PKW] packed per-unit parameters
-  float* part;    // [n_slices][H*(D+1+C)]
-  float* gx;      // [2][GX] cluster exchange: partial gradient [P] + loss sum (double) of this CTA's rows
-  double* red;    // [32]
-};
-
-template <typename T>
-__device__ __forceinline__ T fs_block_sum_all(T v, T* scratch) {
-  // block-wide sum broadcast to every thread
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) scratch[w] = v;
-  __syncthreads();
-  T r = (lane < (FS_THREADS >> 5)) ? scratch[lane] : T(0);
-  r = warp_sum(r);
-  return r;
-}
-
-// over the data rows [rb, re): loss SUM (returned to every thread) and gout = scale/N * d(sum loss)/d theta for the
-// parameters in sm.qs (N = all rows of the dataset: partial results of disjoint row ranges simply add up)
-template <int D, int C, int ACT>
-__device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale, int rb, int re, float* gout) {
-  constexpr int PKW = D + 1 + C;
-  const int t = threadIdx.x, H = p.H, N = p.N;
-  // ACT >= 0: the hidden activation is a compile-time constant (relu: the shipped models) and the per-(row, unit)
-  // switches in act_apply / act_grad_from_output fold away; ACT < 0: any activation, selected at run time
-  const int act1 = ACT >= 0 ? ACT : p.act1;
-  // pack per-unit parameters: {W1[0..D)[h], b1[h], W2[h][0..C)}
-  for (int i = t; i < H * PKW; i += FS_THREADS) {
-    int h = i / PKW, k = i - h * PKW;
-    float v;
-    if (k < D) v = sm.qs[p.w1_off + (int64_t)k * H + h];
-    else if (k == D) v = sm.qs[p.b1_off + h];
-    else v = sm.qs[p.w2_off + (int64_t)h * C + (k - D - 1)];
-    sm.pk[i] = v;
-  }
-  __syncthreads();
-  float b2[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) b2[c] = sm.qs[p.b2_off + c];
-  // ---- phase 1: thread == row
-  double loss_acc = 0.0;
-  const float sc = scale / (float)N;
-  for (int r = rb + t; r < re; r += FS_THREADS) {
-    float x[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) x[d] = sm.xs[r * D + d];
-    float z2[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) z2[c] = b2[c];
-    for (int h = 0; h < H; ++h) {
-      const float* w = sm.pk + h * PKW;
-      float z = w[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) z = fmaf(x[d], w[d], z);
-      float a = act_apply(z, act1);
-#pragma unroll
-      for (int c = 0; c < C; ++c) z2[c] = fmaf(a, w[D + 1 + c], z2[c]);
-    }
-    float dz[C];
-    if (p.loss_kind == PYB_LOSS_SPARSE_CE) {
-      float mx = z2[0];
-#pragma unroll
-      for (int c = 1; c < C; ++c) mx = fmaxf(mx, z2[c]);
-      float se = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) se += expf(z2[c] - mx);
-      const int yi = __float_as_int(sm.ys[r]);
-      float zy = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) if (c == yi) zy = z2[c];
-      loss_acc += (double)(logf(se) - (zy - mx));
-      const float inv = 1.0f / se;
-#pragma unroll
-      for (int c = 0; c < C; ++c) dz[c] = (expf(z2[c] - mx) * inv - (c == yi ? 1.f : 0.f)) * sc;
-    } else {
-      float acc = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float a = act_apply(z2[c], p.out_act);
-        float df = a - sm.ys[r * C + c];
-        acc += df * df;
-        dz[c] = (2.0f * sc / (float)C) * df * act_grad_from_output(a, p.out_act);
-      }
-      loss_acc += (double)(acc / (float)C);
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) sm.dz2[r * C + c] = dz[c];
-  }
-  const double loss_tot = fs_block_sum_all<double>(loss_acc, sm.red);   // contains the __syncthreads dz2 needs
-  // ---- phase 2: thread == (hidden unit, row slice)
-  const int n_slices = FS_THREADS / H > 0 ? FS_THREADS / H : 1;
-  const int h = t % H, slice = t / H;
-  const int NG = H * PKW;
-  if (slice < n_slices && t < n_slices * H) {
-    const float* w = sm.pk + h * PKW;
-    float w1[D], w2[C], gw1[D], gw2[C], gb1 = 0.f;
-    const float b1 = w[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) { w1[d] = w[d]; gw1[d] = 0.f; }
-#pragma unroll
-    for (int c = 0; c < C; ++c) { w2[c] = w[D + 1 + c]; gw2[c] = 0.f; }
-    for (int r = rb + slice; r < re; r += n_slices) {
-      float z = b1;
-      float x[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) { x[d] = sm.xs[r * D + d]; z = fmaf(x[d], w1[d], z); }
-      const float a = act_apply(z, act1);
-      float da = 0.f;
-      float dzr[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) { dzr[c] = sm.dz2[r * C + c]; da = fmaf(dzr[c], w2[c], da); }
-      const float d1 = da * act_grad_from_output(a, act1);
-#pragma unroll
-      for (int d = 0; d < D; ++d) gw1[d] = fmaf(x[d], d1, gw1[d]);
-      gb1 += d1;
-#pragma unroll
-      for (int c = 0; c < C; ++c) gw2[c] = fmaf(a, dzr[c], gw2[c]);
-    }
-    float* o = sm.part + slice * NG + h * PKW;
-#pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = gw1[d];
-    o[D] = gb1;
-#pragma unroll
-    for (int c = 0; c < C; ++c) o[D + 1 + c] = gw2[c];
-  }
-  __syncthreads();
-  // combine slices in a fixed order and scatter into the flat gradient layout
-  for (int i = t; i < NG; i += FS_THREADS) {
-    float s = 0.f;
-    for (int sl = 0; sl < n_slices; ++sl) s += sm.part[sl * NG + i];
-    int hh = i / PKW, k = i - hh * PKW;
-    int64_t dst = (k < D) ? p.w1_off + (int64_t)k * H + hh : (k == D ? p.b1_off + hh : p.w2_off + (int64_t)hh * C + (k - D - 1));
-    gout[dst] = s;
-  }
-  // db2[c] = sum_r dZ2[r][c]: one warp per class
-  {
-    const int wid = t >> 5, lane = t & 31;
-    if (wid < C) {
-      float s = 0.f;
-      for (int r = rb + lane; r < re; r += 32) s += sm.dz2[r * C + wid];
-      s = warp_sum(s);
-      if (lane == 0) gout[p.b2_off + wid] = s;
-    }
-  }
-  __syncthreads();
-  return loss_tot;
-}
-// whole dataset in this CTA: mean loss, gradient in sm.gs
-template <int D, int C, int ACT>
-__device__ float fs_eval(const FsParams& p, const FsSmem& sm, float scale) {
-  return (float)(fs_eval_rows<D, C, ACT>(p, sm, scale, 0, p.N, sm.gs) / (double)p.N);
-}
-// this CTA's share of the rows, then the cluster-wide sum through distributed shared memory.  `n_eval` alternates the
-// exchange buffer: a CTA may already write the next evaluation's partials while a slower one still reads these
-template <int D, int C, int ACT>
-__device__ float fs_eval_cluster(const FsParams& p, const FsSmem& sm, float scale, int rank, int n_ctas, int& n_eval) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cl = cg::this_cluster();
-  const int t = threadIdx.x;
-  const int64_t P = p.P, GX = ((P + 1) & ~(int64_t)1) + 2;
-  float* gx = sm.gx + (n_eval & 1) * GX;
-  ++n_eval;
-  const int rb = (int)((int64_t)p.N * rank / n_ctas), re = (int)((int64_t)p.N * (rank + 1) / n_ctas);
-  const double lsum = fs_eval_rows<D, C, ACT>(p, sm, scale, rb, re, gx);
-  if (t == 0) *reinterpret_cast<double*>(gx + GX - 2) = lsum;
-  cl.sync();
-  for (int64_t i = t; i < P; i += FS_THREADS) {
-    float sacc = 0.f;
-    for (int rr = 0; rr < n_ctas; ++rr) sacc += cl.map_shared_rank(gx, rr)[i];     // fixed order: identical in every CTA
-    sm.gs[i] = sacc;
-  }
-  double lt = 0.0;
-  for (int rr = 0; rr < n_ctas; ++rr) lt += *reinterpret_cast<const double*>(cl.map_shared_rank(gx, rr) + GX - 2);
-  __syncthreads();
-  return (float)(lt / (double)p.N);
-}
-
-template <int D, int C>
-__device__ void fs_setup(const FsParams& p, FsSmem& sm, float* base) {
-  const int N = p.N;
-  const int64_t P = p.P;
-  constexpr int PKW = D + 1 + C;
-  const int n_slices = FS_THREADS / p.H > 0 ? FS_THREADS / p.H : 1;
-  float* cur = base;
-  sm.red = (double*)cur; cur += 64;
-  sm.xs = cur; cur += (int64_t)N * D;
-  sm.ys = cur; cur += (int64_t)N * (p.loss_kind == PYB_LOSS_SPARSE_CE ? 1 : C);
-  sm.dz2 = cur; cur += (int64_t)N * C;
-  sm.qs = cur; cur += P;
-  sm.ps = cur; cur += P;
-  sm.gs = cur; cur += P;
-  sm.pk = cur; cur += p.H * PKW;
-  sm.part = cur; cur += n_slices * p.H * PKW;
-  cur = (float*)(((uintptr_t)cur + 7) & ~(uintptr_t)7);
-  sm.gx = cur; cur += 2 * (((P + 1) & ~(int64_t)1) + 2);
-  for (int i = threadIdx.x; i < N * D; i += FS_THREADS) sm.xs[i] = p.X[i];
-  if (p.loss_kind == PYB_LOSS_SPARSE_CE) {
-    for (int i = threadIdx.x; i < N; i += FS_THREADS) sm.ys[i] = __int_as_float(p.y_i[i]);
-  } else {
-    for (int i = threadIdx.x; i < N * C; i += FS_THREADS) sm.ys[i] = p.y_f[i];
-  }
-}
-
-// eval-only: loss + scale * d(mean loss)/d theta  (parity hook, SVGD gradients)
-template <int D, int C, int ACT>
-__global__ void __launch_bounds__(FS_THREADS) k_fs_eval(FsParams p) {
-  extern __shared__ __align__(16) float fs_smem[];
-  FsSmem sm;
-  fs_setup<D, C>(p, sm, fs_smem);
-  const int64_t s = blockIdx.x;
-  for (int64_t i = threadIdx.x; i < p.P; i += FS_THREADS) sm.qs[i] = p.theta[s * p.P + i];
-  __syncthreads();
-  float loss = fs_eval<D, C, ACT>(p, sm, p.scale);
-  if (p.grad_out)
-    for (int64_t i = threadIdx.x; i < p.P; i += FS_THREADS) p.grad_out[s * p.P + i] = sm.gs[i];
-  if (threadIdx.x == 0 && p.loss_out) p.loss_out[s] = loss;
-}
-
-// one full HMC iteration of one chain
-template <int D, int C, int ACT>
-__global__ void __launch_bounds__(FS_THREADS) k_fs_hmc(FsParams p) {
-  extern __shared__ __align__(16) float fs_smem[];
-  FsSmem sm;
-  fs_setup<D, C>(p, sm, fs_smem);
-  const int n_ctas = p.cluster;
-  const int rank = n_ctas > 1 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
-  const int64_t s = blockIdx.x / n_ctas, P = p.P;
-  const int t = threadIdx.x;
-  const bool writer = rank == 0;          // every CTA of the cluster holds the same state; one writes it back
-  int n_eval = 0;
-  auto eval = [&]() -> float {
-    return n_ctas > 1 ? fs_eval_cluster<D, C, ACT>(p, sm, p.n_train, rank, n_ctas, n_eval) : fs_eval<D, C, ACT>(p, sm, p.n_train);
-  };
-  // q, momentum (HMC.py:78), K0 (:79)
-  double k0 = 0.0;
-  for (int64_t i = t; i < P; i += FS_THREADS) sm.qs[i] = p.q[s * P + i];
-  if (p.inj_p) {
-    for (int64_t i = t; i < P; i += FS_THREADS) sm.ps[i] = p.inj_p[s * P + i];
-  } else {
-    for (int64_t blk = t; blk * 4 < P; blk += FS_THREADS) {
-      float z[4];
-      philox_normal4((uint32_t)blk, (uint32_t)(p.chain_offset + s), p.iter, STREAM_MOMENTUM, p.seed, z);
-      for (int j = 0; j < 4; ++j)
-        if (blk * 4 + j < P) sm.ps[blk * 4 + j] = z[j] * p.stdv;
-    }
-  }
-  __syncthreads();
-  for (int64_t i = t; i < P; i += FS_THREADS) k0 += (double)sm.ps[i] * (double)sm.ps[i];
-  const float K0 = (float)(fs_block_sum_all<double>(k0, sm.red) * (double)p.inv2m);
-  // U0 and the first half kick share the evaluation at q0 (HMC.py:80-82)
-  const float loss0 = eval();
-  double e0 = 0.0;
-  for (int64_t i = t; i < P; i += FS_THREADS) {
-    float q = sm.qs[i], d = q - p.mu[i], iv = p.inv_var[i];
-    e0 += 0.5 * (double)(d * d * iv);
-    if (writer) p.q0[s * P + i] = q;
-    float pp = sm.ps[i] - p.half_eps * (sm.gs[i] + d * iv);
-    sm.ps[i] = pp;
-    sm.qs[i] = q + p.drift * pp;
-  }
-  const float Up0 = (float)fs_block_sum_all<double>(e0, sm.red);
-  float loss1 = loss0, Up1 = 0.f, K1 = 0.f;
-  for (int step = 1; step <= p.L; ++step) {
-    loss1 = eval();
-    if (step < p.L) {
-      for (int64_t i = t; i < P; i += FS_THREADS) {
-        float q = sm.qs[i], d = q - p.mu[i];
-        float pp = sm.ps[i] - p.eps * (sm.gs[i] + d * p.inv_var[i]);
-        sm.ps[i] = pp;
-        sm.qs[i] = q + p.drift * pp;
-      }
-      __syncthreads();
-    } else {
-      double e1 = 0.0, k1 = 0.0;
-      for (int64_t i = t; i < P; i += FS_THREADS) {
-        float q = sm.qs[i], d = q - p.mu[i], iv = p.inv_var[i];
-        float gt = sm.gs[i] + d * iv;
-        e1 += 0.5 * (double)(d * d * iv);
-        float pp = sm.ps[i];
-        if (p.semantics == PYB_HMC_REFERENCE) {   // L-th full kick, then the trailing half kick (HMC.py:85-87)
-          pp = pp - p.eps * gt;
-          pp = pp - p.half_eps * gt;
-        } else {
-          pp = pp - p.half_eps * gt;
-        }
-        sm.ps[i] = pp;
-        k1 += (double)pp * (double)pp;
-      }
-      Up1 = (float)fs_block_sum_all<double>(e1, sm.red);
-      K1 = (float)(fs_block_sum_all<double>(k1, sm.red) * (double)p.inv2m);
-    }
-  }
-  if (writer)
-    for (int64_t i = t; i < P; i += FS_THREADS) {
-      p.q[s * P + i] = sm.qs[i];
-      p.p[s * P + i] = sm.ps[i];
-    }
-  if (n_ctas > 1) cooperative_groups::this_cluster().sync();     // nobody leaves while a peer may still read its shared memory
-  if (t == 0 && writer) {
-    // Metropolis test (HMC.py:91), same expression order as k_accept
-    float U0 = (Up0 + p.prior_const) + loss0 * p.n_train;
-    float U1 = (Up1 + p.prior_const) + loss1 * p.n_train;
-    float la = ((K0 + U0) - K1) - U1;
-    float alpha = expf(la);
-    float u = p.inj_u ? p.inj_u[s] : philox_uniform((uint32_t)(p.chain_offset + s), p.iter, STREAM_UNIFORM, p.seed);
-    int acc = p.burning ? 1 : ((u < alpha) ? 1 : 0);
-    p.U0[s] = U0; p.U1[s] = U1; p.K0[s] = K0; p.K1[s] = K1; p.log_alpha[s] = la; p.accepted[s] = acc;
-    float rl = acc ? loss1 : loss0;
-    p.ret_loss[s] = rl;
-    if (acc) atomicAdd(&p.counters[0], 1ull);
-    atomicAdd(&p.counters[1], 1ull);
-    if (la != la) atomicAdd(&p.counters[2], 1ull);
-    atomicAdd(p.loss_sum, (double)rl);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-static size_t fs_smem_bytes(const pyb_handle* h) {
-  const Model& m = h->model;
-  const int D = m.layer[0].fan_in, H = m.layer[0].fan_out, C = m.layer[1].fan_out;
-  const int n_slices = FS_THREADS / H > 0 ? FS_THREADS / H : 1;
-  size_t f = 64 + (size_t)h->N * D + (size_t)h->N * (h->loss_kind == PYB_LOSS_SPARSE_CE ? 1 : C) + (size_t)h->N * C +
-             3 * (size_t)m.P + (size_t)H * (D + 1 + C) * (1 + n_slices) + 2 * (((size_t)m.P + 1) / 2 * 2 + 2) + 2;
-  return f * sizeof(float) + 16;
-}
 
 bool fused_small_supported(pyb_handle* h) {
   const Model& m = h->model;
@@ -389,41 +15,17 @@ bool fused_small_supported(pyb_handle* h) {
   return true;
 }
 
-template <int D, int C, int ACT>
-static void fs_launch(pyb_handle* h, const FsParams& p, int64_t S, bool hmc) {
-  size_t smem = fs_smem_bytes(h);
-  if (hmc) {
-    PYB_CUDA(cudaFuncSetAttribute(k_fs_hmc<D, C, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (p.cluster > 1) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(S * p.cluster)); cfg.blockDim = dim3(FS_THREADS);
-      cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = (unsigned)p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      PYB_CUDA(cudaLaunchKernelEx(&cfg, k_fs_hmc<D, C, ACT>, p));
-    } else {
-      k_fs_hmc<D, C, ACT><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
-    }
-  } else {
-    PYB_CUDA(cudaFuncSetAttribute(k_fs_eval<D, C, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fs_eval<D, C, ACT><<<(unsigned)S, FS_THREADS, smem, h->stream>>>(p);
-  }
-  count_launch(h);
-}
-
 static void fs_dispatch(pyb_handle* h, const FsParams& p, int64_t S, bool hmc) {
-  const int D = h->model.layer[0].fan_in, C = h->model.layer[1].fan_out;
+  const int D = h->model.layer[0].fan_in;
   const double flops = 1.0;  // roofline for this path is reported per grad-eval by bench/tests, not per launch
   prof_begin(h);
-#define FS_CASE(d, c) if (D == d && C == c) { if (p.act1 == PYB_ACT_RELU) fs_launch<d, c, PYB_ACT_RELU>(h, p, S, hmc); else fs_launch<d, c, -1>(h, p, S, hmc); } else
-  FS_CASE(1, 1) FS_CASE(1, 2) FS_CASE(1, 3) FS_CASE(1, 4)
-  FS_CASE(2, 1) FS_CASE(2, 2) FS_CASE(2, 3) FS_CASE(2, 4)
-  FS_CASE(3, 1) FS_CASE(3, 2) FS_CASE(3, 3) FS_CASE(3, 4)
-  FS_CASE(4, 1) FS_CASE(4, 2) FS_CASE(4, 3) FS_CASE(4, 4)
-  throw Error(PYB_ERR_UNSUPPORTED, "fused small path: unsupported (D, C)");
-#undef FS_CASE
+  switch (D) {
+    case 1: fs_launch_d1(h, p, S, hmc); break;
+    case 2: fs_launch_d2(h, p, S, hmc); break;
+    case 3: fs_launch_d3(h, p, S, hmc); break;
+    case 4: fs_launch_d4(h, p, S, hmc); break;
+    default: throw Error(PYB_ERR_UNSUPPORTED, "fused small path: unsupported input width");
+  }
   prof_end(h, flops);
 }
 
