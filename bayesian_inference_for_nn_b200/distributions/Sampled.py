@@ -1,51 +1,57 @@
-"""Sampled — empirical posterior: flat weight vectors with integer frequencies.
+"""Sampled — the empirical posterior HMC / SVGD return: flat weight vectors with integer multiplicities.
 
-Mirrors Pyesian/distributions/Sampled.py:8-60: weighted draw through ``random.randint(1, total)``
-+ ``bisect_left`` on the cumulative frequencies (:29-32) so that P(index) is proportional to its
-frequency; the same validation errors (:11-16, :24-25).  Samples are kept as one ``[n, P]``
-float32 matrix (what the device returns) instead of a list of tensors.
+Behavioural mirror of Pyesian/distributions/Sampled.py:8-60.  A draw picks sample k with probability proportional to
+its frequency, by the reference's own recipe — ``random.randint(1, total)`` looked up in the running totals with
+``bisect_left`` (:29-32) — so a seeded ``random`` reproduces the reference's choices.  The constructor rejects the same
+inputs with the same messages (:11-16, :24-25).  The folder format is the reference's (:34-60): ``info.json`` with
+``size / n_samples / frequencies / dtypes`` and one TensorProto file ``samples/sample<i>.tf`` per sample.
+
+Unlike the reference, which keeps a Python list of tensors, the samples live in ONE ``[n, P]`` float32 matrix: that is
+what the device hands back and what ``BayesianModel.predict`` uploads once and gathers rows from.
 """
-import bisect
 import json
 import os
 import random
+from bisect import bisect_left
+from itertools import accumulate
 
 import numpy as np
 
 from .Distribution import Distribution
 
 
+def _as_matrix(samples):
+    if isinstance(samples, np.ndarray):
+        return np.ascontiguousarray(samples)
+    return np.ascontiguousarray(np.stack([np.asarray(s) for s in samples]))
+
+
 class Sampled(Distribution):
     def __init__(self, samples, frequencies):
-        if len(samples) == 0:
+        n = len(samples)
+        if n == 0:
             raise ValueError("Can't have distribution Sampled with 0 samples")
-        if len(samples) != len(frequencies):
+        if n != len(frequencies):
             raise ValueError("Number of samples and list frequency do not have the same size")
-        mat = np.ascontiguousarray(np.stack([np.asarray(s) for s in samples]) if not isinstance(samples, np.ndarray)
-                                   else samples)
-        if mat.ndim != 2:
+        matrix = _as_matrix(samples)
+        if matrix.ndim != 2:
             raise ValueError("Samples must have only one dimension")
-        super().__init__(int(mat.shape[1]))
-        self._n_samples = int(mat.shape[0])
-        self._samples = mat
-        self._frequencies = [int(f) for f in frequencies]
-        self._acc_frequencies = []
-        acc = 0
-        for f in self._frequencies:
-            if f == 0:
-                raise ValueError("Samples frequencies can't sum up to zero")
-            acc += f
-            self._acc_frequencies.append(acc)
+        counts = [int(f) for f in frequencies]
+        if not all(counts):
+            raise ValueError("Samples frequencies can't sum up to zero")
+        super().__init__(int(matrix.shape[1]))
+        self._samples, self._n_samples, self._frequencies = matrix, n, counts
+        self._acc_frequencies = list(accumulate(counts))          # running totals: the draw's lookup table
 
-    # reference semantics ------------------------------------------------------------------
+    # ---- drawing ---------------------------------------------------------------------------------------------------
     def sample_index(self) -> int:
-        w = random.randint(1, self._acc_frequencies[-1])
-        return bisect.bisect_left(self._acc_frequencies, w)
+        ticket = random.randint(1, self._acc_frequencies[-1])
+        return bisect_left(self._acc_frequencies, ticket)
 
     def sample(self):
         return self._samples[self.sample_index()]
 
-    # batched views used by BayesianModel.predict --------------------------------------------
+    # ---- whole-posterior views for the device path ----------------------------------------------------------------
     @property
     def samples(self):
         return self._samples
@@ -54,27 +60,27 @@ class Sampled(Distribution):
     def frequencies(self):
         return list(self._frequencies)
 
-    # persistence (format of Sampled.store :34-48; the per-sample payload is a TensorProto) ----
+    # ---- persistence ----------------------------------------------------------------------------------------------
     def store(self, path: str):
         from ..nn.tensorproto import serialize_tensor
-        info = {"size": self._size, "n_samples": self._n_samples, "frequencies": self._frequencies,
-                "dtypes": [str(self._samples.dtype.name)] * self._n_samples}
+        meta = dict(size=self._size, n_samples=self._n_samples, frequencies=self._frequencies,
+                    dtypes=[self._samples.dtype.name] * self._n_samples)
         with open(os.path.join(path, "info.json"), "w") as f:
-            f.write(json.dumps(info))
-        sdir = os.path.join(path, "samples")
-        os.makedirs(sdir, exist_ok=True)
-        for i in range(self._n_samples):
-            with open(os.path.join(sdir, "sample%d.tf" % i), "wb") as f:
-                f.write(serialize_tensor(self._samples[i]))
+            json.dump(meta, f)
+        folder = os.path.join(path, "samples")
+        os.makedirs(folder, exist_ok=True)
+        for i, row in enumerate(self._samples):
+            with open(os.path.join(folder, "sample%d.tf" % i), "wb") as f:
+                f.write(serialize_tensor(row))
 
     @classmethod
     def load(cls, path: str) -> "Sampled":
         from ..nn.tensorproto import parse_tensor
-        with open(os.path.join(path, "info.json"), "r") as f:
-            info = json.load(f)
-        sdir = os.path.join(path, "samples")
-        rows = []
-        for i in range(info["n_samples"]):
-            with open(os.path.join(sdir, "sample%d.tf" % i), "rb") as f:
-                rows.append(parse_tensor(f.read()))
-        return Sampled(np.stack(rows), info["frequencies"])
+        with open(os.path.join(path, "info.json")) as f:
+            meta = json.load(f)
+        folder = os.path.join(path, "samples")
+
+        def read(i):
+            with open(os.path.join(folder, "sample%d.tf" % i), "rb") as f:
+                return parse_tensor(f.read())
+        return cls(np.stack([read(i) for i in range(meta["n_samples"])]), meta["frequencies"])

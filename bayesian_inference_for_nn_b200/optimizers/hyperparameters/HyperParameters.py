@@ -7,6 +7,7 @@ format ``key value key value`` (:32-62).  HMC reads ``m, L, epsilon`` (HMC.py:53
 => reference behaviour): ``n_chains``, ``seed``, ``semantics``, ``device``, ``path``.
 """
 import copy
+import re
 
 
 class HyperParameters:
@@ -29,28 +30,51 @@ class HyperParameters:
         with open(fn, "r") as f:
             return self.parse(f.read())
 
+    _NUMBER = re.compile(r"[0-9.\-]+")
+
     def parse(self, text: str):
-        """Two-state scanner: a key is a run of [alnum . _ -], a value a run of [digit - .]."""
-        keys, values = [], []
-        key, val, reading_value = "", "", False
-        for ch in text:
-            if not reading_value:
-                if ch.isalnum() or ch in self.connectors:
-                    key += ch
-                elif key:
-                    keys.append(key)
-                    key, reading_value = "", True
-            else:
-                if ch.isdigit() or ch in "-.":
-                    val += ch
-                elif val:
-                    values.append(float(val))
-                    val, reading_value = "", False
-        if key:
-            keys.append(key)
-            values.extend([0.0] * (len(keys) - len(values)))
-        elif val:
-            values.append(float(val))
-        for k, v in zip(keys, values):
-            self._params[k] = v
+        """``name number name number ...`` as the GUI writes it (``static/hyperparams/*.txt``).  Same reading as the
+        reference's character scanner (:32-62): a name is a run of alphanumerics and ``. _ -``; the character that ends
+        it is dropped; whatever precedes the next run of digits / ``-`` / ``.`` is skipped; the character that ends a
+        number is dropped too; a name at the very end of the text gets 0.0 (and so does every name still without a
+        number then)."""
+        names, numbers, pos, end = [], [], 0, len(text)
+        while pos < end:
+            m = self._name_at_or_after(text, pos)
+            if m is None:
+                break
+            names.append(m.group())
+            if m.end() == end:                                    # unterminated last name: pad with zeros
+                numbers.extend([0.0] * (len(names) - len(numbers)))
+                break
+            v = self._NUMBER.search(text, m.end() + 1)
+            if v is None:
+                break
+            numbers.append(float(v.group()))
+            pos = v.end() + 1
+        for i, name in enumerate(names):
+            self._params[name] = numbers[i]        # a name left without a number is an IndexError, as in the reference
         return self
+
+    def _name_at_or_after(self, text, pos):
+        """first maximal run of name characters starting at or after pos (str.isalnum decides what a letter is)"""
+        n = len(text)
+        while pos < n and not (text[pos].isalnum() or text[pos] in self.connectors):
+            pos += 1
+        if pos == n:
+            return None
+        stop = pos
+        while stop < n and (text[stop].isalnum() or text[stop] in self.connectors):
+            stop += 1
+        return _Span(text, pos, stop)
+
+
+class _Span:
+    def __init__(self, text, start, stop):
+        self._text, self._start, self._stop = text, start, stop
+
+    def group(self):
+        return self._text[self._start:self._stop]
+
+    def end(self):
+        return self._stop

@@ -187,3 +187,22 @@ def test_compile_fails_loudly_without_gpu_and_only_once():
         opt.compile(HyperParameters(epsilon=0.01, m=1, L=2), mj, ds, prior=GaussianPrior(0.0, 1.0))
     with pytest.raises(AttributeError):
         HMC().compile(HyperParameters(epsilon=0.01), mj, ds, prior=GaussianPrior(0.0, 1.0))
+
+
+def test_hyperparameters_parse_matches_the_reference_goldens():
+    """tests/golden/hyperparams_parse.json was produced by importing the REFERENCE's HyperParameters.py (pure Python) in the
+    build container (tests/golden/make_hyperparams_golden.py): same parameters, same failure modes, case by case."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from Pyesian.optimizers.hyperparameters import HyperParameters
+    cases = json.load(open(os.path.join(GOLDEN, "hyperparams_parse.json")))
+    assert len(cases) > 400
+    for c in cases:
+        try:
+            got = ("ok", dict(HyperParameters(seed_kw=3).parse(c["text"])._params))
+        except Exception as e:
+            got = ("err", type(e).__name__)
+        want = ("ok", c["params"]) if c["status"] == "ok" else ("err", c["error"])
+        assert got == want, (c["text"], got, want)
+    assert any(c["status"] == "err" for c in cases)            # a name without a number is an IndexError, kept
