@@ -19,6 +19,7 @@ PRIOR_SCALAR, PRIOR_PER_VARIABLE, PRIOR_PER_ELEMENT = 0, 1, 2
 HMC_REFERENCE, HMC_CANONICAL = 0, 1
 SVGD_REFERENCE_LIVE, SVGD_CANONICAL_MEDIAN = 0, 1
 SG_SGLD, SG_SWAG = 0, 1
+UQ_CANONICAL, UQ_REFERENCE = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_FUSED_SMALL, PATH_TENSOR = 0, 1, 2, 3
 
 

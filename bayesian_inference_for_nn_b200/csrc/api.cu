@@ -560,12 +560,13 @@ int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, c
 }
 
 int pyb_predict_uncertainty(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
-                            const int32_t* y, int32_t cumulative_rows, double divisor, float* total_out,
+                            const int32_t* y, int32_t semantics, double divisor, float* total_out,
                             float* aleatoric_out, float* epistemic_out, float* mean_out) {
   PYB_TRY
   PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
   use_device(h);
-  UncertaintyReq uq{y, cumulative_rows, divisor, total_out, aleatoric_out, epistemic_out};
+  PYB_REQUIRE(semantics == PYB_UQ_REFERENCE || semantics == PYB_UQ_CANONICAL, PYB_ERR_INVALID, "bad semantics");
+  UncertaintyReq uq{y, semantics == PYB_UQ_REFERENCE ? 1 : 0, divisor, total_out, aleatoric_out, epistemic_out};
   predict(h, W, n, weight, x, Nt, mean_out, nullptr, nullptr, &uq);
   PYB_CATCH
 }

@@ -392,7 +392,7 @@ void nccl_broadcast_f32(void* comm, float* buf, size_t count, int root, cudaStre
 // optional classification-uncertainty request (Metrics.py:344-375): host labels [Nt], host outputs [Nt, Ce, Ce]
 struct UncertaintyReq {
   const int32_t* y;
-  int cumulative;     // 1: running sum over the rows, as the reference computes it; 0: per-row matrices
+  int cumulative;     // 1: reference semantics (running sum over the rows, broadcast epistemic term); 0: canonical per-row matrices
   double divisor;     // the reference divides by its n_samples ARGUMENT (Metrics.py:368-369)
   float *total, *aleatoric, *epistemic;
 };

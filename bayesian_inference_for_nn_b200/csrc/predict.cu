@@ -37,9 +37,10 @@ __global__ void k_pred_finish(const double* s1, const double* s2, double wsum, i
 
 // ---- Metrics.classification_uncertainty (Metrics.py:344-375) --------------------------------------------------
 // Per data row r and weight sample k with class probabilities p (NaN -> 0 as BayesianModel.py:125):
-//   aleatoric_r += w_k (diag(p) - p p^T)        epistemic_r += w_k (p - onehot(y_r)) (p - onehot(y_r))^T
+//   aleatoric_r += w_k (diag(p) - p p^T)        epistemic_r += w_k (p - onehot(y_r)) (p - onehot(y_r))^T   (canonical)
 // Both follow from the first and second moments over the samples, S1 = sum_k w_k p (k_pred_accum already has it) and
-// S2 = sum_k w_k p p^T:   aleatoric = diag(S1) - S2,   epistemic = S2 - S1 e^T - e S1^T + W e e^T  (e = onehot, W = sum w),
+// S2 = sum_k w_k p p^T:   aleatoric = diag(S1) - S2,   epistemic = S2 - S1 e^T - e S1^T + W e e^T  (e = onehot, W = sum w);
+// the reference's own epistemic term (a broadcast, see k_uncert_rows) is C S2 - S1 1^T - 1 S1^T + W 1 1^T,
 // so the only extra pass over the [n, Nt, C] outputs is the S2 accumulation below.  A block owns 128/C data rows and
 // stages 32 samples of their class probabilities in shared memory with coalesced loads (every output byte is read from
 // HBM exactly once, ~15 KB in flight per block); thread = (row, class i) then keeps row i of that row's C x C block in
@@ -119,8 +120,10 @@ __global__ void k_uncert_s2_generic(const float* out, int64_t n_chunk, int64_t N
   S2[e] += a;
 }
 // per-row matrices from the moments; s1/s2 are k_pred_accum's sums over out_dim C, S2 the block above (C > 1)
+// reference != 0: the epistemic term as the reference's code computes it — its reshape(p, (-1, 1)) - one_hot(label)
+// broadcasts to D_ij = p_i - onehot_j (Metrics.py:362-363) and (D D^T)_ik = Ce p_i p_k - p_i - p_k + 1, label-free
 __global__ void k_uncert_rows(const double* s1, const double* s2, const double* S2, double wsum, int64_t Nt, int C, int Ce,
-                              const int32_t* y, double* alea, double* epi) {
+                              const int32_t* y, int reference, double* alea, double* epi) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Nt * Ce * Ce) return;
   const int j = (int)(e % Ce), i = (int)((e / Ce) % Ce);
@@ -139,7 +142,7 @@ __global__ void k_uncert_rows(const double* s1, const double* s2, const double* 
   const int label = y[r];
   const double ei = (i == label) ? 1.0 : 0.0, ej = (j == label) ? 1.0 : 0.0;
   alea[e] = (i == j ? m1i : 0.0) - m2;
-  epi[e] = m2 - m1i * ej - ei * m1j + wsum * ei * ej;
+  epi[e] = reference ? (double)Ce * m2 - m1i - m1j + wsum : m2 - m1i * ej - ei * m1j + wsum * ei * ej;
 }
 template <int C>
 static void launch_uncert_s2(pyb_handle* h, const float* out, int64_t nb, int64_t Nt, const float* w, double* S2) {
@@ -319,7 +322,7 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
   count_launch(h);
   if (uq) {
     k_uncert_rows<<<(unsigned)((Nt * CC + 255) / 256), 256, 0, h->stream>>>(s1.p, s2.p, uS2.p, wsum, Nt, (int)C, Ce, uy.p,
-                                                                           ua.p, ue.p);
+                                                                           uq->cumulative ? 1 : 0, ua.p, ue.p);
     count_launch(h);
     if (uq->cumulative) {
       k_uncert_segsum<<<(unsigned)nseg, CC, 0, h->stream>>>(ua.p, Nt, CC, seg_a.p);

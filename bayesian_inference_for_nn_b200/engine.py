@@ -293,9 +293,12 @@ class Engine:
             raise ValueError("x has %d features per row, the model expects %d" % (int(np.prod(xa.shape[1:])), self.spec.in_dim))
         return (Wa, W, wptr), (xa, x, xptr)
 
-    def predict_uncertainty(self, W, x, y, weights=None, cumulative=True, divisor=None):
+    def predict_uncertainty(self, W, x, y, weights=None, semantics="reference", divisor=None):
         """Metrics.classification_uncertainty on the device (pyb_predict_uncertainty): -> (total, aleatoric, epistemic,
-        mean), the first three [Nt, Ce, Ce].  ``divisor`` defaults to the number of rows."""
+        mean), the first three [Nt, Ce, Ce].  ``semantics``: "reference" (what the reference's code computes: running
+        sums over the rows, broadcast epistemic term) or "canonical" (per-row matrices, (p - onehot)(p - onehot)^T).
+        ``divisor`` defaults to the number of rows."""
+        sem = {"reference": _lib.UQ_REFERENCE, "canonical": _lib.UQ_CANONICAL}[semantics]
         (Wa, _Wk, wptr), (xa, _xk, xptr) = self._predict_args(W, x)
         n, Nt, Cc = int(Wa.shape[0]), int(xa.shape[0]), self.spec.out_dim
         Ce = 2 if Cc == 1 else Cc
@@ -305,7 +308,7 @@ class Engine:
         w = None if weights is None else _f32(weights, (n,))
         tot, al, ep = (np.empty((Nt, Ce, Ce), np.float32) for _ in range(3))
         mean = np.empty((Nt, Cc), np.float32)
-        check(self.lib.pyb_predict_uncertainty(self.h, wptr, n, _ptr(w), xptr, Nt, _ptr(ya), int(bool(cumulative)),
+        check(self.lib.pyb_predict_uncertainty(self.h, wptr, n, _ptr(w), xptr, Nt, _ptr(ya), int(sem),
                                                float(Nt if divisor is None else divisor), _ptr(tot), _ptr(al), _ptr(ep),
                                                _ptr(mean)))
         return tot, al, ep, mean

@@ -159,16 +159,18 @@ class BayesianModel:
         self.last_variance = var
         return [allo[i] for i in dr.inverse], mean
 
-    def classification_uncertainty(self, x, y_true, nb_samples: int, divisor=None, cumulative=True,
+    def classification_uncertainty(self, x, y_true, nb_samples: int, divisor=None, semantics: str = "reference",
                                    mode: str = "reference", draws=None):
         """Metrics.classification_uncertainty (Metrics.py:344-375) evaluated on the device for nb_samples weight draws:
-        -> (epistemic + aleatoric, aleatoric, epistemic), each [N, C, C].  ``cumulative=True`` keeps the reference's
-        running sum over the rows, ``divisor`` is the n_samples argument it divides by (default: the number of rows)."""
+        -> (epistemic + aleatoric, aleatoric, epistemic), each [N, C, C].  ``semantics="reference"`` is what the
+        reference's code computes (running sums over the rows; its epistemic term broadcasts to a label-free matrix),
+        ``"canonical"`` the per-row decomposition with (p - onehot)(p - onehot)^T; ``divisor`` is the n_samples argument
+        the reference divides by (default: the number of rows)."""
         x = to_numpy(x, np.float32)
         x = x.reshape(x.shape[0], -1)
         dr = draws if draws is not None else self.draw(nb_samples, mode)
         tot, al, ep, _ = self._engine_for_predict().predict_uncertainty(
-            dr.W, x, to_numpy(y_true).reshape(-1), weights=dr.weights, cumulative=cumulative, divisor=divisor)
+            dr.W, x, to_numpy(y_true).reshape(-1), weights=dr.weights, semantics=semantics, divisor=divisor)
         if draws is None:
             dr.free()
         return tot, al, ep

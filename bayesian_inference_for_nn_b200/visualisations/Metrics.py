@@ -201,13 +201,14 @@ class Metrics:
         return res
 
     def classification_uncertainty(self, n_boundaries=30, n_samples=100, data_type="test", save_path=None,
-                                   cumulative=True):
+                                   semantics="reference"):
         """-> (epistemics + aleatorics, aleatorics, epistemics), each [rows, C, C] (Metrics.py:344-375).
-        ``cumulative=False`` returns the per-row matrices instead of the reference's running sums over the rows."""
+        ``semantics="canonical"`` returns the per-row decomposition with (p - onehot)(p - onehot)^T instead of what the
+        reference's code computes (running sums over the rows, label-free broadcast epistemic term)."""
         if self._dataset.likelihood_model != "Classification":
             raise Exception("only for classification")
         input, y_true = self._get_x_y(n_samples=n_samples, data_type=data_type)
         self._get_predictions(input, n_boundaries, y_true)          # fills / re-uses the cache and its weight draws
         return self._model.classification_uncertainty(self._cached_input, self._cached_true_values, n_boundaries,
-                                                      divisor=n_samples, cumulative=cumulative,
+                                                      divisor=n_samples, semantics=semantics,
                                                       draws=self._cached_draws)

@@ -52,6 +52,7 @@ typedef enum { PYB_SVGD_REFERENCE_LIVE = 0, PYB_SVGD_CANONICAL_MEDIAN = 1 } pyb_
 typedef enum { PYB_PATH_AUTO = 0, PYB_PATH_GENERIC = 1, PYB_PATH_FUSED_SMALL = 2, PYB_PATH_TENSOR = 3 } pyb_path;
 
 typedef enum { PYB_SG_SGLD = 0, PYB_SG_SWAG = 1 } pyb_sg_kind;
+typedef enum { PYB_UQ_CANONICAL = 0, PYB_UQ_REFERENCE = 1 } pyb_uq_semantics;
 
 typedef struct pyb_handle pyb_handle;
 
@@ -194,14 +195,17 @@ int pyb_predict(pyb_handle* h, const float* W, int64_t n, const float* weight, c
                 int64_t Nt, float* mean_out, float* var_out, float* all_out);
 
 /* Metrics.classification_uncertainty (Metrics.py:344-375): for the same n weight samples and inputs, with integer
- * labels y [Nt] (host), the per-row matrices  aleatoric = sum_k w_k (diag(p_k) - p_k p_k^T)  and
- * epistemic = sum_k w_k (p_k - onehot(y)) (p_k - onehot(y))^T, divided by `divisor` (the reference divides by its
- * n_samples ARGUMENT, :368-369).  cumulative_rows = 1 reproduces the reference, whose accumulators are never reset
- * between rows (row r holds the running sum over rows 0..r, :352-366); 0 gives the per-row matrices.  Outputs are host
- * float32 [Nt, Ce, Ce] with Ce = out_dim, or 2 for a one-unit output widened to [1-p, p] (:357-359);
+ * labels y [Nt] (host), per data row the matrices  aleatoric = sum_k w_k (diag(p_k) - p_k p_k^T)  and epistemic, divided
+ * by `divisor` (the reference divides by its n_samples ARGUMENT, :368-369).
+ *   PYB_UQ_REFERENCE: what the reference's code computes (pinned by goldens produced by the reference method itself,
+ *     tests/golden/reference_metrics.npz): its accumulators are never reset between rows, so row r holds the running sum
+ *     over rows 0..r (:352-366), and its epistemic term is D D^T with D = reshape(p, (-1,1)) - one_hot(label) BROADCAST
+ *     to D_ij = p_i - onehot_j (:362-363), i.e. C p p^T - p 1^T - 1 p^T + 1 1^T, independent of the label.
+ *   PYB_UQ_CANONICAL: per-row matrices with epistemic = sum_k w_k (p_k - onehot(y)) (p_k - onehot(y))^T.
+ * Outputs are host float32 [Nt, Ce, Ce] with Ce = out_dim, or 2 for a one-unit output widened to [1-p, p] (:357-359);
  * total = epistemic + aleatoric; mean_out [Nt, out_dim] may be NULL.  At most 32 classes. */
 int pyb_predict_uncertainty(pyb_handle* h, const float* W, int64_t n, const float* weight, const float* x, int64_t Nt,
-                            const int32_t* y, int32_t cumulative_rows, double divisor, float* total_out,
+                            const int32_t* y, int32_t semantics, double divisor, float* total_out,
                             float* aleatoric_out, float* epistemic_out, float* mean_out);
 
 /* ---- device-resident arrays owned by the caller (posterior samples kept in HBM between predict calls:

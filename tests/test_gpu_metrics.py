@@ -37,9 +37,9 @@ def test_uncertainty_matches_oracle(oracle, shape):
     Ce = 2 if units[-1] == 1 else units[-1]
     y = rng.integers(0, Ce, Nt)
     outs = per_draw_outputs(oracle, js, W, x)
-    for cumulative in (True, False):
-        want = oracle.classification_uncertainty(outs, y, n_samples_arg=100, cumulative=cumulative)
-        tot, al, ep, mean = eng.predict_uncertainty(W, x, y, cumulative=cumulative, divisor=100)
+    for semantics in ("reference", "canonical"):
+        want = oracle.classification_uncertainty(outs, y, n_samples_arg=100, semantics=semantics)
+        tot, al, ep, mean = eng.predict_uncertainty(W, x, y, semantics=semantics, divisor=100)
         for got, ref in zip((tot, al, ep), want):
             assert got.shape == (Nt, Ce, Ce)
             assert np.abs(got - ref).max() <= TOL * max(1.0, np.abs(ref).max())

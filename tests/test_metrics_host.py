@@ -1,5 +1,6 @@
 """CPU tests for the Metrics / Plotter adapters: the oracle's restatement of
-Metrics.classification_uncertainty against a literal transcription of the reference's loops (Metrics.py:344-375),
+Metrics.classification_uncertainty against a literal transcription of the reference's loops (Metrics.py:344-375; the
+oracle is additionally pinned to the output of the reference method itself in tests/test_reference_goldens.py),
 the calibration error against a hand-computed case, and the host logic of both classes (cache, error behaviour,
 reference quirks) with a stub model — no GPU calls."""
 import numpy as np
@@ -22,7 +23,7 @@ def literal_uncertainty(y_samples, y_true, n_samples):
         for prediction, label in zip(sample, y_true):
             col = prediction.reshape(-1, 1)
             aleatoric = aleatoric + (np.diag(prediction) - col @ col.T)
-            dev = col - np.eye(nb_classes)[label].reshape(-1, 1)
+            dev = col - np.eye(nb_classes)[label]       # [C,1] - [C] broadcasts to [C,C], as tf does at Metrics.py:362
             epistemic = epistemic + dev @ dev.T
             epistemics_tmp.append(epistemic)
             aleatorics_tmp.append(aleatoric)
@@ -48,12 +49,16 @@ def test_oracle_uncertainty_matches_the_literal_loops(oracle):
         got = oracle.classification_uncertainty(s, y, n_samples_arg=100)
         for a, b in zip(got, want):
             np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-14)
-    # per-row form = first differences of the running sums; weights = repeated draws
+    # the aleatoric part of the canonical form = first differences of the reference's running sums; weights = repeated draws
     s = probs(rng, 4, 9, 3)
     y = rng.integers(0, 3, 9)
     cum = oracle.classification_uncertainty(s, y, 9)[1]
-    row = oracle.classification_uncertainty(s, y, 9, cumulative=False)[1]
+    row = oracle.classification_uncertainty(s, y, 9, semantics="canonical")[1]
     np.testing.assert_allclose(np.diff(cum, axis=0, prepend=0 * cum[:1]), row, atol=1e-14)
+    # the reference's epistemic term does not depend on the labels at all (its broadcast sums over every class)
+    e1 = oracle.classification_uncertainty(s, y, 9)[2]
+    e2 = oracle.classification_uncertainty(s, (y + 1) % 3, 9)[2]
+    np.testing.assert_allclose(e1, e2, atol=1e-13)
     rep = np.concatenate([s, s[:1], s[:1]])
     a = oracle.classification_uncertainty(rep, y, 9)
     b = oracle.classification_uncertainty(s, y, 9, weights=[3, 1, 1, 1])
@@ -65,7 +70,7 @@ def test_uncertainty_identities(oracle):
     rng = np.random.default_rng(1)
     s = probs(rng, 6, 20, 5)
     y = rng.integers(0, 5, 20)
-    tot, al, ep = oracle.classification_uncertainty(s, y, 20, cumulative=False)
+    tot, al, ep = oracle.classification_uncertainty(s, y, 20, semantics="canonical")
     assert np.abs(al.sum(axis=-1)).max() < 1e-14
     assert min(np.linalg.eigvalsh(m).min() for m in al) > -1e-12
     assert min(np.linalg.eigvalsh(m).min() for m in ep) > -1e-12
