@@ -25,11 +25,17 @@ def _t(x):
         return x.t
     if isinstance(x, torch.Tensor):
         return x
-    return torch.as_tensor(np.asarray(x), dtype=torch.float32) if not isinstance(x, (int, float)) else torch.tensor(float(x))
+    if isinstance(x, (int, float)):
+        return torch.tensor(float(x))
+    a = np.asarray(x)
+    if a.dtype == np.float64:
+        return torch.as_tensor(a)                      # float64 stays float64 (SVGD keeps its particles in a float64 array)
+    return torch.as_tensor(a, dtype=torch.float32) if a.dtype.kind == "f" else torch.as_tensor(a)
 
 
 class TT:
     """immutable tensor"""
+    __array_ufunc__ = None          # numpy scalars (e.g. the SGLD learning rate) defer to the reflected operators below
 
     def __init__(self, t):
         self.t = t
@@ -89,12 +95,16 @@ class GradientTape:
     def __exit__(self, *a):
         return False
 
-    def watch(self, _):
-        pass
+    def watch(self, what):
+        for v in (what if isinstance(what, (list, tuple)) else [what]):
+            if not v.t.requires_grad:
+                v.t.requires_grad_(True)          # a watched plain tensor: gradients flow to it from here on
 
     def gradient(self, target, sources):
         single = not isinstance(sources, (list, tuple))
         srcs = [sources] if single else list(sources)
+        if not _t(target).requires_grad:              # nothing watched feeds the target
+            return None if single else [None] * len(srcs)
         grads = torch.autograd.grad(_t(target).sum(), [s.t for s in srcs], retain_graph=True, allow_unused=True)
         out = [None if g is None else TT(g) for g in grads]
         return out[0] if single else out
@@ -132,6 +142,23 @@ class Model:
     @property
     def trainable_variables(self):
         return [v for l in self.layers for v in l.trainable_variables]
+
+    def get_weights(self):
+        return [v.numpy().copy() for v in self.trainable_variables]
+
+    def set_weights(self, weights):
+        for v, w in zip(self.trainable_variables, weights):
+            v.assign(torch.as_tensor(np.asarray(w, dtype=np.float32)))
+
+    def clone(self):
+        m = Model.__new__(Model)
+        m.layers = []
+        for l in self.layers:
+            if isinstance(l, Dense):
+                m.layers.append(Dense(l.kernel.shape[0], l.units, l.activation_name, l.use_bias))
+            else:
+                m.layers.append(InputLike())
+        return m
 
     def __call__(self, x, training=False):
         a = _t(x).to(torch.float32)
@@ -271,6 +298,7 @@ def make_tf():
     tf.constant = lambda v, dtype=None: TT(_t(v).to(torch.float32))
     tf.convert_to_tensor = lambda v, dtype=None: TT(_t(v))
     tf.cast = lambda v, dtype=None: TT(_t(v).to(torch.float32 if dtype in ("float32", torch.float32, None) else dtype))
+    tf.float64 = torch.float64
     tf.identity = lambda v: TT(_t(v).detach().clone())
     tf.multiply = lambda a, b: TT(_t(a) * _t(b))
     tf.square = lambda a: TT(_t(a) ** 2)
@@ -286,9 +314,10 @@ def make_tf():
     tf.math = NS(reduce_sum=tf.reduce_sum, exp=tf.exp, square=tf.square,
                                     is_nan=lambda a: TT(torch.isnan(_t(a))))
     tf.where = lambda c, a, b: TT(torch.where(_t(c).bool(), _t(a), _t(b)))
+    tf.size = lambda a: TT(torch.tensor(int(np.prod(tuple(a.shape)))))
     tf.random = NS(normal=_random_normal)
     tf.keras = NS(
-        Model=Model, models=NS(Model=Model, model_from_json=model_from_json),
+        Model=Model, models=NS(Model=Model, model_from_json=model_from_json, clone_model=lambda m: m.clone()),
         losses=NS(SparseCategoricalCrossentropy=SparseCategoricalCrossentropy, MeanSquaredError=MeanSquaredError),
         optimizers=NS(legacy=NS(Adam=LegacyAdam)))
     tf.data = NS(Dataset=object)
@@ -316,6 +345,9 @@ class ArrayData:
 
     def batch(self, bs):
         return ArrayData(self.x, self.y, int(bs.numpy()) if hasattr(bs, "numpy") else int(bs))
+
+    def map(self, fn):
+        return [fn(a, b) for a, b in zip(self.x, self.y)]
 
     def __iter__(self):
         for i in range(0, len(self.x), self.bs):
