@@ -188,6 +188,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     dist = None
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's own prints (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
