@@ -188,8 +188,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     dist = None
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's own prints (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) go to stderr
+        # stdout carries ONE JSON line: NCCL's own prints go to stderr.  NCCL honours NCCL_DEBUG_FILE only above the
+        # VERSION level (at VERSION it prints "NCCL version ..." to stdout), and WARN prints the same version line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
