@@ -35,6 +35,16 @@ class SVGDResult(tuple):
         n = nb_samples if nb_samples is not None else len(self[0])
         return self.bayesian_model.predict(x, n, **kw)
 
+    def draw(self, nb_samples, mode="reference"):
+        return self.bayesian_model.draw(nb_samples, mode)
+
+    def classification_uncertainty(self, *a, **kw):
+        return self.bayesian_model.classification_uncertainty(*a, **kw)
+
+    @property
+    def last_variance(self):
+        return self.bayesian_model.last_variance
+
     def store(self, path):
         return self.bayesian_model.store(path)
 
