@@ -1,3 +1,8 @@
+#!/usr/bin/env python
+"""One pyb_predict_uncertainty call at the C5 shape (1000 weight samples x 10000x784 rows, 784-256-10) and three SWAG
+steps (784-128-10, minibatch 1024, 1024 chains) for ncu: launch list
+(`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv`) or one
+`--set full` capture (`-k regex:k_uncert_s2 -s 3 -c 1`, `-k regex:k_sg_update -s 1 -c 1`).  Run from the repo root."""
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, "tools")
 import numpy as np
