@@ -1,0 +1,159 @@
+#!/usr/bin/env python
+"""CPU study (NumPy emulation, no GPU): how accurate would cheaper operand splits be for the two big GEMMs of the C3
+gradient, against today's bf16x3 scheme and the 1e-4 parity budget?  Emulated per scheme: operand rounding only
+(products and sums in float64 — accumulation effects are the same for all schemes and are handled by split-K).
+
+  bf16x3            a_hi b_hi + a_lo b_hi + a_hi b_lo, hi/lo bf16                      (3 bf16-rate passes; today)
+  fp16x3            the same with fp16 parts                                           (3 passes)
+  fp16 + 2x mxfp8   a_h16 b_h16 + a_l8 b_h8 + a_h8 b_l8: hi part fp16 (11 bits), the two correction products with
+                    e4m3 operands block-scaled by powers of two over 32 K-elements (kind::mxf8f6f4, 2x the bf16 rate)
+                                                                                       (1 + 1/2 + 1/2 = 2 pass equivalents)
+  fp16x2 (one-sided) a_h16 (b_h16 + b_l16): only the B operand is split                (2 passes)
+  bf16 / fp16 x1    single pass                                                        (1 pass)
+
+Measured: norm-wise relative error of Z1 = X W1 (forward GEMM) and of dW1 = X^T dZ1 (the 60000-row reduction, here at
+N rows) for U[0,1) data, N(0, w_scale) weights and a softmax-CE dZ1; worst case over `chains` weight draws.
+Usage: python tools/study_split_precision.py [N=8192] [chains=3]
+"""
+import sys
+
+import numpy as np
+
+
+def round_bits(x, bits):
+    """round to `bits` significant binary digits (no exponent limits)"""
+    m, e = np.frexp(x)
+    return np.ldexp(np.round(m * (1 << bits)) / (1 << bits), e)
+
+
+def bf16(x):
+    return round_bits(x, 8)
+
+
+def fp16(x, scale=1.0):
+    """fp16 with its exponent range (normal >= 2^-14, subnormal step 2^-24); `scale` applied before and undone after"""
+    y = x * scale
+    q = round_bits(y, 11)
+    sub = np.abs(y) < 2.0 ** -14
+    q = np.where(sub, np.round(y * 2.0 ** 24) / 2.0 ** 24, q)
+    return q / scale
+
+
+def mxfp8(x, axis):
+    """e4m3 (4 significant bits, max 448, min normal 2^-6, subnormal step 2^-9) with one power-of-two scale per 32
+    consecutive elements along `axis` (the K dimension of the MMA)"""
+    x = np.moveaxis(x, axis, -1)
+    K = x.shape[-1]
+    pad = (-K) % 32
+    xp = np.pad(x, [(0, 0)] * (x.ndim - 1) + [(0, pad)])
+    blk = xp.reshape(xp.shape[:-1] + (-1, 32))
+    amax = np.abs(blk).max(axis=-1, keepdims=True)
+    e = np.where(amax > 0, np.ceil(np.log2(np.maximum(amax, 1e-300) / 448.0)), 0.0)
+    s = 2.0 ** e
+    y = blk / s
+    q = round_bits(y, 4)
+    sub = np.abs(y) < 2.0 ** -6
+    q = np.where(sub, np.round(y * 2.0 ** 9) / 2.0 ** 9, q)
+    out = (q * s).reshape(xp.shape)[..., :K]
+    return np.moveaxis(out, -1, axis)
+
+
+def schemes(A, B, k_axis_a, k_axis_b, scale_b=1.0):
+    """products A @ B under each scheme; k_axis_*: which axis of the operand is the contraction axis"""
+    out = {}
+    ah, bh = bf16(A), bf16(B)
+    al, bl = bf16(A - ah), bf16(B - bh)
+    out["bf16x3 (today)"] = ah @ bh + al @ bh + ah @ bl
+    out["bf16 x1"] = ah @ bh
+    a16, b16 = fp16(A), fp16(B, scale_b)
+    al16, bl16 = fp16(A - a16), fp16(B - b16, scale_b * 2.0 ** 11)
+    out["fp16x3"] = a16 @ b16 + al16 @ b16 + a16 @ bl16
+    out["fp16 x1"] = a16 @ b16
+    out["fp16x2 (B split only)"] = a16 @ b16 + a16 @ bl16
+    a_l8, b_l8 = mxfp8(A - a16, k_axis_a), mxfp8(B - b16, k_axis_b)
+    a_h8, b_h8 = mxfp8(A, k_axis_a), mxfp8(B, k_axis_b)
+    out["fp16 + 2x mxfp8 (2 pass-equivalents)"] = a16 @ b16 + a_l8 @ b_h8 + a_h8 @ b_l8
+    return out
+
+
+def product(A, B, name, k_axis_a, k_axis_b, scale_b=1.0):
+    return schemes(A, B, k_axis_a, k_axis_b, scale_b)[name]
+
+
+def full_gradient(X, y, W1, b1, W2, b2, name, mask=None):
+    """loss and flat gradient [dW1, db1, dW2, db2] of the mean sparse-CE loss with the three big GEMMs under `name`
+    (None: exact float64); layer 2 stays exact, as in the fused epilogue (fp32 there).  `mask`: relu'(z1) taken from the
+    exact forward pass — relu' is discontinuous, so ANY rounding of z1 (float32 itself included) flips the units that sit
+    within that rounding of zero and the flips, not the scheme, then dominate the comparison (the GPU parity tests move
+    the test points off the kinks for the same reason)"""
+    N, C = X.shape[0], W2.shape[1]
+    mm = (lambda A, B, ka, kb, sb=1.0: A @ B) if name is None else (lambda A, B, ka, kb, sb=1.0: product(A, B, name, ka, kb, sb))
+    Z1 = mm(X, W1, 1, 0) + b1
+    A1 = np.maximum(Z1, 0)
+    Z2 = A1 @ W2 + b2
+    m = Z2.max(1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(Z2 - m).sum(1))
+    loss = float((lse - Z2[np.arange(N), y]).mean())
+    P = np.exp(Z2 - lse[:, None])
+    dZ2 = (P - np.eye(C)[y]) / N
+    relu_mask = (Z1 > 0) if mask is None else mask
+    A1 = A1 * relu_mask if mask is not None else A1
+    dZ1 = (dZ2 @ W2.T) * relu_mask
+    sb = float(2 ** int(np.ceil(np.log2(N))))
+    dW1 = mm(X.T.copy(), dZ1, 1, 0, sb)
+    dW2 = mm(A1.T.copy(), dZ2, 1, 0, sb)
+    return loss, np.concatenate([dW1.ravel(), dZ1.sum(0), dW2.ravel(), dZ2.sum(0)]), relu_mask
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+    chains = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    D, H, C = 784, 256, 10
+    rng = np.random.default_rng(0)
+    X = rng.random((N, D))
+    y = rng.integers(0, C, N)
+    worst = {}
+    for w_scale in (0.05, 1.0):
+        for _ in range(chains):
+            W1, b1 = rng.normal(0, w_scale, (D, H)), rng.normal(0, w_scale, H)
+            W2, b2 = rng.normal(0, w_scale, (H, C)), rng.normal(0, w_scale, C)
+            Z1 = X @ W1
+            for name, z in schemes(X, W1, 1, 0).items():
+                worst[("Z1 = X W1", w_scale, name)] = max(worst.get(("Z1 = X W1", w_scale, name), 0), rel(z, Z1))
+            A1 = np.maximum(Z1 + b1, 0)
+            Z2 = A1 @ W2 + b2
+            P = np.exp(Z2 - Z2.max(1, keepdims=True))
+            P /= P.sum(1, keepdims=True)
+            dZ2 = (P - np.eye(C)[y]) / N
+            dZ1 = (dZ2 @ W2.T) * (Z1 + b1 > 0)
+            dW1 = X.T @ dZ1
+            # dZ1 carries the 1/N of the mean loss: the fp16 parts are taken of N * dZ1 (a power-of-two scale in practice)
+            for name, g in schemes(X.T.copy(), dZ1, 1, 0, scale_b=float(2 ** int(np.ceil(np.log2(N))))).items():
+                worst[("dW1 = X^T dZ1", w_scale, name)] = max(worst.get(("dW1 = X^T dZ1", w_scale, name), 0), rel(g, dW1))
+    # whole gradient with all three GEMMs under one scheme (forward error propagates into the deltas and relu masks)
+    names = ["bf16x3 (today)", "fp16x3", "fp16 + 2x mxfp8 (2 pass-equivalents)", "fp16x2 (B split only)", "fp16 x1", "bf16 x1"]
+    for w_scale in (0.05, 1.0):
+        for _ in range(chains):
+            W1, b1 = rng.normal(0, w_scale, (D, H)), rng.normal(0, w_scale, H)
+            W2, b2 = rng.normal(0, w_scale, (H, C)), rng.normal(0, w_scale, C)
+            l0, g0, mask0 = full_gradient(X, y, W1, b1, W2, b2, None)
+            for name in names:
+                l, g, mask = full_gradient(X, y, W1, b1, W2, b2, name)
+                key = ("gradient, relu flips", w_scale, name)        # fraction of hidden activations whose mask flipped
+                worst[key] = max(worst.get(key, 0), float((mask != mask0).mean()))
+                l, g, _ = full_gradient(X, y, W1, b1, W2, b2, name, mask0)
+                key = ("whole gradient", w_scale, name)
+                worst[key] = max(worst.get(key, 0), rel(g, g0))
+                key = ("loss", w_scale, name)
+                worst[key] = max(worst.get(key, 0), abs(l - l0) / abs(l0))
+    print("rows N = %d, %d weight draws per scale; norm-wise relative error (worst case); parity budget 1e-4" % (N, chains))
+    for (what, ws, name), v in sorted(worst.items(), key=lambda kv: (kv[0][0], kv[0][1], kv[1])):
+        print("  %-16s weights ~ N(0, %-4g)  %-40s %.2e" % (what, ws, name, v))
+
+
+if __name__ == "__main__":
+    main()
