@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from Pyesian.distributions import Mixture, MultivariateNormalDiagPlusLowRank, Normal, Sampled
+from Pyesian.distributions import Mixture, MultivariateNormalDiagPlusLowRank, Normal
 from Pyesian.nn import BayesianModel
 from bayesian_inference_for_nn_b200 import keras_json
 

@@ -6,7 +6,7 @@ steps (784-128-10, minibatch 1024, 1024 chains) for ncu: launch list
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, "tools")
 import numpy as np
-from bayesian_inference_for_nn_b200 import _lib, keras_json
+from bayesian_inference_for_nn_b200 import _lib
 from bayesian_inference_for_nn_b200.engine import Engine
 import bench_next
 rng = np.random.default_rng(0)
