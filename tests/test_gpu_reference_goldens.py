@@ -169,3 +169,36 @@ def test_classification_uncertainty_reproduces_the_reference_run():
             want = g["c%d_%s" % (i, key)]
             assert np.abs(got - want).max() <= 5e-5 * max(1.0, np.abs(want).max()), (i, key)
         eng.close()
+
+
+@pytest.mark.parametrize("name,sigma", [("shipped_neg", -1.0), ("pos", 1.0)])
+def test_hmc_on_make_moons_behaves_like_the_reference_run(name, sigma):
+    """BASELINE configs[0] (HMC_classification.py: make_moons, 2-50-2, epsilon 0.005, m 0.5, L 30): the reference's own
+    HMC.train / result / BayesianModel.predict were executed on the TensorFlow stand-in (reference_hmc_moons.npz: accept
+    rate 0.893 and 95.5 % test accuracy with sigma = +1; accept rate 0 and 96 % with the shipped sigma = -1, whose NaN
+    Hamiltonian rejects everything after the always-accept burn-in).  The device's chains (own Philox randomness, so only
+    statistics are comparable) must land in the same place."""
+    g = np.load(os.path.join(GOLDEN, "reference_hmc_moons.npz"))
+    eps, m, L, n_iter = float(g["hyper"][0]), float(g["hyper"][1]), int(g["hyper"][2]), int(g["hyper"][3])
+    S = 32
+    eng = make(2, [50, 2], ["relu", "softmax"], seed=3)
+    eng.set_dataset(g["x_train"], g["y_train"], _lib.LOSS_SPARSE_CE)
+    eng.set_prior([0.0], [sigma], _lib.PRIOR_SCALAR)
+    eng.hmc_init(S, eps, m, L, _lib.HMC_REFERENCE)
+    burn = eng.hmc_run(10, burning=True, sampling=False)          # HMC.train: 10 always-accept iterations first (:106-113)
+    assert burn["accept_rate"] == 1.0
+    d = eng.hmc_run(n_iter, burning=False, sampling=True)
+    ref_rate, ref_acc = float(g[name + "_accept_rate"]), float(g[name + "_accuracy"])
+    samples, freq, chain = eng.hmc_samples()
+    if sigma < 0:
+        assert ref_rate == 0.0 and d["n_accepted"] == 0 and d["n_nan"] == S * n_iter
+        assert samples.shape[0] == S and np.all(freq == n_iter + 1)                # the reference run: 1 sample, weight 151
+        assert int(g[name + "_n_samples"]) == 1 and int(g[name + "_frequencies"][0]) == n_iter + 1
+    else:
+        assert abs(d["accept_rate"] - ref_rate) < 0.08, (d["accept_rate"], ref_rate)
+        # mean returned loss over the last 30 iterations of the reference chain vs the device's chains
+        assert abs(d["mean_loss"] - float(np.mean(g[name + "_losses"][10:]))) < 0.03
+    mean, _, _ = eng.predict(samples, g["x_test"], weights=freq.astype(np.float32))
+    acc = float((mean.argmax(1) == g["y_test"]).mean())
+    assert acc > 0.9 and abs(acc - ref_acc) < 0.06, (acc, ref_acc)
+    eng.close()
