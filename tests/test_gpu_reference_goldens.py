@@ -202,3 +202,32 @@ def test_hmc_on_make_moons_behaves_like_the_reference_run(name, sigma):
     acc = float((mean.argmax(1) == g["y_test"]).mean())
     assert acc > 0.9 and abs(acc - ref_acc) < 0.06, (acc, ref_acc)
     eng.close()
+
+
+def test_svgd_on_make_moons_follows_the_reference_trajectory():
+    """BASELINE configs[1] as the reference ships it (2-64-2, M = 10, batch 64, lr 1e-3): 400 steps of the reference's own
+    SVGD.train executed on the TensorFlow stand-in (reference_svgd_moons.npz).  The device, started from the same
+    particles and fed the same minibatches, follows the run: returned losses, particles at the checkpoints, validation
+    loss and the ensemble's test accuracy."""
+    g = np.load(os.path.join(GOLDEN, "reference_svgd_moons.npz"))
+    steps, M, B, lr = int(g["hyper"][0]), int(g["hyper"][1]), int(g["hyper"][2]), float(g["hyper"][3])
+    X, y = g["x_train"], g["y_train"]
+    nb = -(-X.shape[0] // B)
+    eng = make(2, [64, 2], ["relu", "softmax"])
+    eng.set_dataset(X, y, _lib.LOSS_SPARSE_CE)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.svgd_init(M, lr, _lib.SVGD_REFERENCE_LIVE, particles0=g["particles0"])
+    eng.svgd_set_validation(g["x_valid"], g["y_valid"])
+    for s in range(steps):
+        b = s % nb
+        loss = eng.svgd_step(np.arange(b * B, min((b + 1) * B, X.shape[0]), dtype=np.int32))
+        assert abs(loss - g["ret"][s]) <= 5e-4 * max(1.0, abs(loss)), (s, loss, g["ret"][s])
+        key = "particles_%d" % (s + 1)
+        if key in g.files:
+            moved = np.abs(g[key] - g["particles0"]).max()
+            got = eng.svgd_particles()
+            assert np.abs(got - g[key]).max() <= 2e-2 * moved + 1e-6, (s + 1, np.abs(got - g[key]).max(), moved)
+    assert abs(eng.svgd_validation_loss() - g["valid_losses"][-1]) < 5e-3
+    mean, _, _ = eng.predict(eng.svgd_particles().astype(np.float32), g["x_test"])
+    assert abs(float((mean.argmax(1) == g["y_test"]).mean()) - float(g["accuracy"])) <= 0.01
+    eng.close()
