@@ -231,3 +231,40 @@ def test_svgd_on_make_moons_follows_the_reference_trajectory():
     mean, _, _ = eng.predict(eng.svgd_particles().astype(np.float32), g["x_test"])
     assert abs(float((mean.argmax(1) == g["y_test"]).mean()) - float(g["accuracy"])) <= 0.01
     eng.close()
+
+
+def test_tensor_path_reproduces_the_reference_at_the_headline_width():
+    """784-256-10: the reference's HMC.step (5 iterations, 2048 rows) and BayesianModel.predict (20 draws, 1024 rows)
+    executed on the TensorFlow stand-in (reference_wide.npz) against the device's TENSOR-CORE path (bf16x3 split GEMMs,
+    fused layer-2 epilogue), one continued chain with the carried evaluation."""
+    from test_reference_goldens import _wide_inputs
+    import bisect
+    g = np.load(os.path.join(GOLDEN, "reference_wide.npz"))
+    inp = _wide_inputs()
+    eps, m, L = float(g["hmc_hyper"][0]), float(g["hmc_hyper"][1]), int(g["hmc_hyper"][2])
+    eng = make(784, [256, 10], ["relu", "softmax"])
+    eng.set_dataset(inp["X"], inp["y"], _lib.LOSS_SPARSE_CE)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.hmc_init(1, eps, m, L, _lib.HMC_REFERENCE)                       # starts at the prior mean, like the reference
+    for it in range(5):
+        eng.hmc_inject(p=inp["p"][it][None], u=np.float32([g["hmc_u"][it]]))
+        burning = bool(g["hmc_burning"][it])
+        eng.hmc_run(1, burning=burning, sampling=not burning)
+        assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+        last = eng.hmc_last()
+        for k in ("K0", "U0", "K1", "U1"):
+            assert abs(last[k][0] - g["hmc_" + k][it]) <= 1e-4 * abs(g["hmc_" + k][it]), (it, k, last[k][0], g["hmc_" + k][it])
+        assert int(last["accept"][0]) == int(g["hmc_accepted"][it])
+        # the energies are ~2e5 and float32 on both sides (resolution 0.016): what decides is their difference
+        ref_la = (g["hmc_K0"][it] + g["hmc_U0"][it]) - g["hmc_K1"][it] - g["hmc_U1"][it]
+        assert abs(float(last["log_alpha"][0]) - ref_la) < 0.1, (it, float(last["log_alpha"][0]), ref_la)
+        q, _ = eng.hmc_state()
+        assert abs(np.linalg.norm(q.astype(np.float64)) - g["hmc_q_norms"][it]) <= 1e-4 * g["hmc_q_norms"][it]
+    assert np.linalg.norm(q[0] - g["hmc_q_final"]) <= 1e-3 * np.linalg.norm(g["hmc_q_final"])
+    acc = list(np.cumsum(inp["freq"]))
+    idx = [bisect.bisect_left(acc, int(t)) for t in g["pred_tickets"]]
+    mean, _, allo = eng.predict(inp["W"][idx], inp["x"], want_all=True)
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    np.testing.assert_allclose(allo, g["pred_samples"], rtol=2e-4, atol=5e-6)
+    np.testing.assert_allclose(mean, g["pred_mean"], rtol=2e-4, atol=5e-6)
+    eng.close()
