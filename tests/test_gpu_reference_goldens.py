@@ -268,3 +268,30 @@ def test_tensor_path_reproduces_the_reference_at_the_headline_width():
     np.testing.assert_allclose(allo, g["pred_samples"], rtol=2e-4, atol=5e-6)
     np.testing.assert_allclose(mean, g["pred_mean"], rtol=2e-4, atol=5e-6)
     eng.close()
+
+
+def test_tensor_path_reproduces_the_reference_svgd_steps_at_the_mnist_width():
+    """784-128-10 (SVGD_mnist's model), 5 close particles, minibatch 256, 3 live steps of the reference's own SVGD.step
+    (reference_wide_svgd.npz) against the device: minibatch gradients on the tensor-core path for 128 hidden units (dW1
+    with two particles per CTA pair and an odd particle count), float64 gamma = 1 kernel terms, legacy-Adam descent."""
+    from test_reference_goldens import _wide_svgd_inputs
+    g = np.load(os.path.join(GOLDEN, "reference_wide_svgd.npz"))
+    inp, ns = _wide_svgd_inputs()
+    B, M, lr = ns["B"], ns["M"], ns["LR"]
+    eng = make(784, [128, 10], ["relu", "softmax"])
+    eng.set_dataset(inp["X"], inp["y"], _lib.LOSS_SPARSE_CE)
+    eng.set_prior([0.0], [ns["SCALE"]], _lib.PRIOR_SCALAR)
+    eng.svgd_init(M, lr, _lib.SVGD_REFERENCE_LIVE, particles0=inp["particles0"])
+    for s in range(ns["STEPS"]):
+        loss = eng.svgd_step(np.arange(s * B, (s + 1) * B, dtype=np.int32))
+        assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+        assert abs(loss - g["ret"][s]) < 5e-6, (s, loss, g["ret"][s])
+        if s == 0:
+            step = eng.svgd_particles() - inp["particles0"]
+            agree = np.mean(np.sign(step) == g["step1_sign"])        # sign of -phi, element by element
+            assert agree > 0.999, agree
+            assert abs(np.abs(step).max() - float(g["step1_absmax"])) < 1e-5
+    got = eng.svgd_particles()
+    moved = np.abs(g["final"] - inp["particles0"]).max()
+    assert np.abs(got - g["final"]).max() <= 5e-2 * moved, (np.abs(got - g["final"]).max(), moved)
+    eng.close()
