@@ -63,3 +63,26 @@ def test_null_arguments_are_rejected(lib):
     assert L.pyb_param_count(None, None) == -1
     assert L.pyb_hmc_run(None, 1, 0, 1, None) == -1
     assert L.pyb_destroy(None) == 0
+
+
+def test_product_code_never_touches_the_oracle_or_the_test_stand_ins():
+    """the oracle, the goldens and the TensorFlow stand-in are test infrastructure: nothing under the package (or the
+    Pyesian alias, bench.py's b200 arm aside) may import them, and there is no CPU fallback module to route through"""
+    import ast
+    banned = {"pyesian_oracle", "tf_shim", "oracle", "tests", "conftest"}
+    for top in ("bayesian_inference_for_nn_b200", "Pyesian"):
+        for dp, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if not f.endswith(".py"):
+                    continue
+                tree = ast.parse(open(os.path.join(dp, f)).read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom) and node.level == 0:
+                        names = [node.module or ""]
+                    for n in names:
+                        assert n.split(".")[0] not in banned, (os.path.join(dp, f), n)
+    srcs = [f for f in os.listdir(os.path.join(ROOT, "bayesian_inference_for_nn_b200", "csrc")) if f.endswith((".cu", ".cuh"))]
+    assert len(srcs) >= 15 and not any("cpu" in f.lower() or "fallback" in f.lower() for f in srcs)
