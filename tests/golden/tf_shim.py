@@ -143,6 +143,9 @@ class Model:
     def trainable_variables(self):
         return [v for l in self.layers for v in l.trainable_variables]
 
+    def to_json(self):
+        return getattr(self, "_json", "{}")
+
     def get_weights(self):
         return [v.numpy().copy() for v in self.trainable_variables]
 
@@ -188,7 +191,9 @@ def model_from_json(text):
             specs.append((int(c["units"]), act if isinstance(act, str) else act["config"], bool(c.get("use_bias", True))))
         elif l["class_name"] in ("Flatten",) and not specs:
             leading += 1
-    return Model(in_dim, specs, leading)
+    m = Model(in_dim, specs, leading)
+    m._json = text                       # Keras round-trips the architecture JSON; the stand-in hands back what it was given
+    return m
 
 
 class SparseCategoricalCrossentropy:
