@@ -8,6 +8,11 @@ gradient, against today's bf16x3 scheme and the 1e-4 parity budget?  Emulated pe
   fp16 + 2x mxfp8   a_h16 b_h16 + a_l8 b_h8 + a_h8 b_l8: hi part fp16 (11 bits), the two correction products with
                     e4m3 operands block-scaled by powers of two over 32 K-elements (kind::mxf8f6f4, 2x the bf16 rate)
                                                                                        (1 + 1/2 + 1/2 = 2 pass equivalents)
+  fp16 + 2x e4m3 / e5m2, one scale per operand
+                    the same three products, the correction operands in plain FP8 (kind::f8f6f4, no block scales): each
+                    operand pre-scaled by ONE power of two by the kernel that writes it          (2 pass equivalents)
+  fp16 + 2x mxfp4   correction operands e2m1 with a power-of-two scale per 32 K-elements (kind::mxf4, 4x the bf16 rate)
+                                                                                       (1 + 1/4 + 1/4 = 1.5)
   fp16x2 (one-sided) a_h16 (b_h16 + b_l16): only the B operand is split                (2 passes)
   bf16 / fp16 x1    single pass                                                        (1 pass)
 
@@ -58,26 +63,70 @@ def mxfp8(x, axis):
     return np.moveaxis(out, -1, axis)
 
 
-def schemes(A, B, k_axis_a, k_axis_b, scale_b=1.0):
-    """products A @ B under each scheme; k_axis_*: which axis of the operand is the contraction axis"""
-    out = {}
-    ah, bh = bf16(A), bf16(B)
-    al, bl = bf16(A - ah), bf16(B - bh)
-    out["bf16x3 (today)"] = ah @ bh + al @ bh + ah @ bl
-    out["bf16 x1"] = ah @ bh
+def fp8_tensor(x, sig_bits=4, min_normal_exp=-6, sub_step_exp=-9, top=256.0):
+    """e4m3 (default; e5m2: sig_bits=3, min_normal_exp=-14, sub_step_exp=-16) with ONE power-of-two scale for the whole
+    operand, chosen so that its largest magnitude lands in (top/2, top] — what plain kind::f8f6f4 MMAs can use when the
+    producing kernel pre-scales the operand (no scale-factor tiles in TMEM); the product of the two operand scales is
+    then a constant that the main fp16 pass carries too and the epilogue divides out"""
+    amax = float(np.abs(x).max())
+    s = 2.0 ** np.floor(np.log2(top / amax)) if amax > 0 else 1.0
+    y = x * s
+    q = round_bits(y, sig_bits)
+    sub = np.abs(y) < 2.0 ** min_normal_exp
+    q = np.where(sub, np.round(y * 2.0 ** -sub_step_exp) / 2.0 ** -sub_step_exp, q)
+    return q / s
+
+
+def mxfp4(x, axis):
+    """e2m1 (2 significant bits, max 6, min normal 1, subnormal step 0.5) with one power-of-two scale per 32 consecutive
+    K-elements (kind::mxf4, 4x the bf16 rate)"""
+    x = np.moveaxis(x, axis, -1)
+    K = x.shape[-1]
+    pad = (-K) % 32
+    xp = np.pad(x, [(0, 0)] * (x.ndim - 1) + [(0, pad)])
+    blk = xp.reshape(xp.shape[:-1] + (-1, 32))
+    amax = np.abs(blk).max(axis=-1, keepdims=True)
+    e = np.where(amax > 0, np.ceil(np.log2(np.maximum(amax, 1e-300) / 6.0)), 0.0)
+    s = 2.0 ** e
+    y = blk / s
+    q = round_bits(y, 2)
+    q = np.where(np.abs(y) < 1.0, np.round(y * 2.0) / 2.0, q)
+    out = (q * s).reshape(xp.shape)[..., :K]
+    return np.moveaxis(out, -1, axis)
+
+
+def schemes(A, B, k_axis_a, k_axis_b, scale_b=1.0, only=None):
+    """products A @ B under each scheme (or just the scheme `only`); k_axis_*: which axis of the operand is the
+    contraction axis"""
     a16, b16 = fp16(A), fp16(B, scale_b)
-    al16, bl16 = fp16(A - a16), fp16(B - b16, scale_b * 2.0 ** 11)
-    out["fp16x3"] = a16 @ b16 + al16 @ b16 + a16 @ bl16
-    out["fp16 x1"] = a16 @ b16
-    out["fp16x2 (B split only)"] = a16 @ b16 + a16 @ bl16
-    a_l8, b_l8 = mxfp8(A - a16, k_axis_a), mxfp8(B - b16, k_axis_b)
-    a_h8, b_h8 = mxfp8(A, k_axis_a), mxfp8(B, k_axis_b)
-    out["fp16 + 2x mxfp8 (2 pass-equivalents)"] = a16 @ b16 + a_l8 @ b_h8 + a_h8 @ b_l8
-    return out
+    e5 = dict(sig_bits=3, min_normal_exp=-14, sub_step_exp=-16, top=32768.0)
+
+    def bf16x3():
+        ah, bh = bf16(A), bf16(B)
+        return ah @ bh + bf16(A - ah) @ bh + ah @ bf16(B - bh)
+
+    table = {
+        "bf16x3 (today)": bf16x3,
+        "bf16 x1": lambda: bf16(A) @ bf16(B),
+        "fp16x3": lambda: a16 @ b16 + fp16(A - a16) @ b16 + a16 @ fp16(B - b16, scale_b * 2.0 ** 11),
+        "fp16 x1": lambda: a16 @ b16,
+        "fp16x2 (B split only)": lambda: a16 @ b16 + a16 @ fp16(B - b16, scale_b * 2.0 ** 11),
+        "fp16 + 2x mxfp8 (2 pass-equivalents)": lambda: (a16 @ b16 + mxfp8(A - a16, k_axis_a) @ mxfp8(B, k_axis_b)
+                                                         + mxfp8(A, k_axis_a) @ mxfp8(B - b16, k_axis_b)),
+        "fp16 + 2x e4m3, one scale per operand (2)": lambda: (a16 @ b16 + fp8_tensor(A - a16) @ fp8_tensor(B)
+                                                              + fp8_tensor(A) @ fp8_tensor(B - b16)),
+        "fp16 + 2x e5m2, one scale per operand (2)": lambda: (a16 @ b16 + fp8_tensor(A - a16, **e5) @ fp8_tensor(B, **e5)
+                                                              + fp8_tensor(A, **e5) @ fp8_tensor(B - b16, **e5)),
+        "fp16 + 2x mxfp4 (1.5 pass-equivalents)": lambda: (a16 @ b16 + mxfp4(A - a16, k_axis_a) @ mxfp4(B, k_axis_b)
+                                                           + mxfp4(A, k_axis_a) @ mxfp4(B - b16, k_axis_b)),
+    }
+    if only is not None:
+        return {only: table[only]()}
+    return {k: f() for k, f in table.items()}
 
 
 def product(A, B, name, k_axis_a, k_axis_b, scale_b=1.0):
-    return schemes(A, B, k_axis_a, k_axis_b, scale_b)[name]
+    return schemes(A, B, k_axis_a, k_axis_b, scale_b, only=name)[name]
 
 
 def full_gradient(X, y, W1, b1, W2, b2, name, mask=None):
@@ -135,7 +184,9 @@ def main():
             for name, g in schemes(X.T.copy(), dZ1, 1, 0, scale_b=float(2 ** int(np.ceil(np.log2(N))))).items():
                 worst[("dW1 = X^T dZ1", w_scale, name)] = max(worst.get(("dW1 = X^T dZ1", w_scale, name), 0), rel(g, dW1))
     # whole gradient with all three GEMMs under one scheme (forward error propagates into the deltas and relu masks)
-    names = ["bf16x3 (today)", "fp16x3", "fp16 + 2x mxfp8 (2 pass-equivalents)", "fp16x2 (B split only)", "fp16 x1", "bf16 x1"]
+    names = ["bf16x3 (today)", "fp16x3", "fp16 + 2x mxfp8 (2 pass-equivalents)", "fp16 + 2x e4m3, one scale per operand (2)",
+             "fp16 + 2x e5m2, one scale per operand (2)", "fp16 + 2x mxfp4 (1.5 pass-equivalents)", "fp16x2 (B split only)",
+             "fp16 x1", "bf16 x1"]
     for w_scale in (0.05, 1.0):
         for _ in range(chains):
             W1, b1 = rng.normal(0, w_scale, (D, H)), rng.normal(0, w_scale, H)
@@ -152,7 +203,7 @@ def main():
                 worst[key] = max(worst.get(key, 0), abs(l - l0) / abs(l0))
     print("rows N = %d, %d weight draws per scale; norm-wise relative error (worst case); parity budget 1e-4" % (N, chains))
     for (what, ws, name), v in sorted(worst.items(), key=lambda kv: (kv[0][0], kv[0][1], kv[1])):
-        print("  %-16s weights ~ N(0, %-4g)  %-40s %.2e" % (what, ws, name, v))
+        print("  %-16s weights ~ N(0, %-4g)  %-44s %.2e" % (what, ws, name, v))
 
 
 if __name__ == "__main__":
