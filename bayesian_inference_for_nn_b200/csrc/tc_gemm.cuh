@@ -79,7 +79,13 @@ __device__ __forceinline__ float act_apply_t(float z) {
   return z;
 }
 
-template <int EPI, int ACT>
+// MIX = 1 (prototype of DESIGN 6b item 4, reached only through pyb_debug_tc_gemm_mixed): the "hi" operands are fp16,
+// the "lo" maps address an 8-bit tensor [rows, 2K] that holds, per 32 K-elements, 32 bytes e4m3(x * s_hi) followed by
+// 32 bytes e4m3((x - fp16(x)) * s_lo); one stage then takes 2 kind::f16 MMAs (K = 16 each) and 2 kind::f8f6f4 MMAs
+// (K = 32 each: a_lo b_hi and a_hi b_lo) into the SAME accumulator columns — 4 MMA slots instead of 6 for the same
+// stage bytes.  The caller picks the scales so that both correction products and the fp16 product carry one common
+// factor 2^k, which the epilogue removes (its reciprocal travels as the bit pattern of `act`).
+template <int EPI, int ACT, int MIX = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -138,14 +144,15 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           uint8_t* st = stage_base + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], bytes);
           const int k0 = kc * TC_BK;
+          const int k0_lo = MIX ? 2 * k0 : k0;                   // MIX: 64 bytes of the 8-bit tensor per 32 K-elements
           for (int mt = 0; mt < n_mt; ++mt) {
             const int arow = (p.a_blocked ? 0 : p.a_row0 + b * p.a_batch_rows) + (mt0 + mt) * 128;
             tma_load_operand(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], p.a_blocked, k0, arow, b, p.k_tiles);
-            tma_load_operand(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], p.a_blocked, k0, arow, b, p.k_tiles);
+            tma_load_operand(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], p.a_blocked, k0_lo, arow, b, p.k_tiles);
           }
           const int brow = p.b_blocked ? 0 : b * p.H;
           tma_load_operand(st + 4 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], p.b_blocked, k0, brow, b, p.k_tiles);
-          tma_load_operand(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &tmB_lo, &full_bar[stage], p.b_blocked, k0, brow, b,
+          tma_load_operand(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &tmB_lo, &full_bar[stage], p.b_blocked, k0_lo, brow, b,
                            p.k_tiles);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -155,7 +162,8 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===== MMA issuer =====
     if (lane == 0) {
       // instruction descriptor: D=F32, A=B=BF16, both K-major, N = H, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.H >> 3) << 17) | ((128u >> 4) << 24);
+      // (MIX: A = B = F16 for kind::f16 and A = B = E4M3 for kind::f8f6f4 are both format code 0)
+      const uint32_t idesc = (1u << 4) | (MIX ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(p.H >> 3) << 17) | ((128u >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       const int k_tail = p.K - (nk - 1) * TC_BK;                 // valid K elements of the last chunk
@@ -171,7 +179,17 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + stage * TC_STAGE_BYTES);
-          const int nks = (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
+          if (MIX) {
+            const uint32_t a8 = st + 2 * TC_A_TILE_BYTES, b16 = st + 4 * TC_A_TILE_BYTES, b8 = b16 + TC_B_TILE_BYTES;
+            for (int mt = 0; mt < n_mt; ++mt) {
+              const uint32_t d = tmem_base + (uint32_t)mt * 256;
+              tc_mma_bf16(d, make_smem_desc_sw64(st + mt * TC_A_TILE_BYTES), make_smem_desc_sw64(b16), idesc, kc != kc_begin);
+              tc_mma_bf16(d, make_smem_desc_sw64(st + mt * TC_A_TILE_BYTES + 32), make_smem_desc_sw64(b16 + 32), idesc, 1);
+              tc_mma_f8(d, make_smem_desc_sw64(a8 + mt * TC_A_TILE_BYTES + 32), make_smem_desc_sw64(b8), idesc, 1);       // a_lo b_hi
+              tc_mma_f8(d, make_smem_desc_sw64(a8 + mt * TC_A_TILE_BYTES), make_smem_desc_sw64(b8 + 32), idesc, 1);       // a_hi b_lo
+            }
+          }
+          const int nks = MIX ? 0 : (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
           for (int ks = 0; ks < nks; ++ks) {
             const uint32_t koff = ks * 32;                       // 16 bf16 = 32 bytes along K inside the atom
             const uint64_t bh = make_smem_desc_sw64(st + 4 * TC_A_TILE_BYTES + koff);
@@ -250,6 +268,11 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (valid) {
               float* o = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
               const int nvalid = p.n_cols_total > 0 ? min(p.N_valid, p.n_cols_total - b * p.H) : p.N_valid;
+              if (MIX) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= __int_as_float(p.act);   // 2^-k as a bit pattern (`act` is unused by EPI_STORE;
+                                                                               // a new field would move every kernel's parameters)
+              }
               if (p.vec_store && c0 + 32 <= nvalid) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)

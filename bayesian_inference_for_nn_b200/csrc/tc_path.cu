@@ -14,6 +14,8 @@
 //
 // This file is the host side: tensor maps, operand preparation, chain batching, kernel selection and launch.
 // The kernels live in tc_ptx.cuh (PTX helpers), tc_gemm.cuh, tc_layer2.cuh and tc_fused.cuh.
+#include <cstdlib>
+#include <cstring>
 #include "tc_fused.cuh"
 #include <algorithm>
 
@@ -534,6 +536,13 @@ void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t ld
   }
 }
 
+// the debug GEMM entries repeat their kernel launch PYB_DEBUG_GEMM_REPS times (default 1) so that tools/bench_mixed_proto.py
+// can read per-launch device times from the "profile" option's CUDA events
+static int debug_gemm_reps() {
+  const char* e = getenv("PYB_DEBUG_GEMM_REPS");
+  const int r = e ? atoi(e) : 1;
+  return r < 1 ? 1 : (r > 1000 ? 1000 : r);
+}
 // debug / unit-test entry: D[M,Nn] = A[M,K] B[Nn,K]^T through the tcgen05 kernel (host pointers)
 void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn, int K, float* Dout) {
   PYB_REQUIRE(Nn % 16 == 0 && Nn >= 16 && Nn <= 256 && K % 8 == 0, PYB_ERR_INVALID, "Nn%16, Nn<=256, K%8 required");
@@ -553,13 +562,77 @@ void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn,
   p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
   p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0; p.a_box_rows = 128;
   CUtensorMap mp_h = make_map(bh.p, K, Nn, K, std::max(Nn / 2, 8)), mp_l = make_map(bl.p, K, Nn, K, std::max(Nn / 2, 8));
-  launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K, &mp_h, &mp_l);
+  for (int r = 0; r < debug_gemm_reps(); ++r)
+    launch_gemm_tc(h, ma_h, ma_l, mb_h, mb_l, p, 2.0 * M * Nn * (double)K, &mp_h, &mp_l);
   PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
   PYB_CUDA(cudaStreamSynchronize(h->stream));
   PYB_CUDA(cudaGetLastError());
+  prof_resolve(h);
+}
+
+// debug / unit-test entry for the MIX prototype: D = out_scale * (A16 B16^T + A8lo B8hi^T + A8hi B8lo^T)
+// with A16/B16 fp16 bit patterns [rows, K] and A8/B8 e4m3 bytes [rows, 2K] (per 32 K-elements: 32 bytes hi, 32 bytes lo),
+// all prepared by the caller (host pointers); 1-CTA kernel, fp16 and FP8 MMAs accumulate into the same TMEM columns
+static CUtensorMap make_map_u8(const void* base, int64_t kbytes, int64_t rows, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kbytes};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PYB_REQUIRE(r == CUDA_SUCCESS, PYB_ERR_CUDA, "cuTensorMapEncodeTiled (8-bit) failed");
+  return m;
+}
+void tc_debug_gemm_mixed(pyb_handle* h, const uint16_t* A16, const uint8_t* A8, const uint16_t* B16, const uint8_t* B8,
+                         int M, int Nn, int K, float out_scale, float* Dout) {
+  PYB_REQUIRE(Nn % 16 == 0 && Nn >= 16 && Nn <= 256 && K % 32 == 0 && K > 0, PYB_ERR_INVALID, "Nn%16, Nn<=256, K%32 required");
+  DevBuf<uint16_t> a16, b16;
+  DevBuf<uint8_t> a8, b8;
+  DevBuf<float> dD;
+  a16.alloc((size_t)M * K); b16.alloc((size_t)Nn * K); a8.alloc((size_t)M * 2 * K); b8.alloc((size_t)Nn * 2 * K);
+  dD.alloc((size_t)M * Nn);
+  PYB_CUDA(cudaMemcpyAsync(a16.p, A16, (size_t)M * K * 2, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(b16.p, B16, (size_t)Nn * K * 2, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(a8.p, A8, (size_t)M * 2 * K, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(b8.p, B8, (size_t)Nn * 2 * K, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemsetAsync(dD.p, 0xff, (size_t)M * Nn * 4, h->stream));
+  CUtensorMap ma_h = make_map(a16.p, K, M, K, 128), mb_h = make_map(b16.p, K, Nn, K, Nn);   // 16-bit elements
+  CUtensorMap ma_l = make_map_u8(a8.p, 2 * (int64_t)K, M, 128), mb_l = make_map_u8(b8.p, 2 * (int64_t)K, Nn, Nn);
+  TcGemmParams p = {};
+  p.K = K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = 1; p.H = Nn;
+  p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
+  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0; p.a_box_rows = 128;
+  p.k_splits = 1; p.chunks_per_split = K / TC_BK; p.split_stride = 0; p.vec_store = 1; memcpy(&p.act, &out_scale, 4);   // see the MIX epilogue
+  const int grid = std::min(p.total_items, h->sm_count);
+  PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3<EPI_STORE, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  for (int r = 0; r < debug_gemm_reps(); ++r) {
+    prof_begin(h);
+    tc_gemm_bf16x3<EPI_STORE, 0, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(ma_h, ma_l, mb_h, mb_l, p);
+    prof_end(h, 2.0 * M * Nn * (double)K);
+    count_launch(h);
+  }
+  PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+  prof_resolve(h);
 }
 
 }  // namespace pyb
+
+extern "C" int pyb_debug_tc_gemm_mixed(pyb_handle* h, const uint16_t* A16, const uint8_t* A8, const uint16_t* B16,
+                                       const uint8_t* B8, int32_t M, int32_t Nn, int32_t K, float out_scale, float* D) {
+  try {
+    if (!h || !A16 || !A8 || !B16 || !B8 || !D) throw pyb::Error(PYB_ERR_INVALID, "NULL argument");
+    PYB_CUDA(cudaSetDevice(h->device));
+    pyb::tc_debug_gemm_mixed(h, A16, A8, B16, B8, M, Nn, K, out_scale, D);
+  } catch (const pyb::Error& e) {
+    pyb::set_last_error(e.what());
+    return e.code;
+  }
+  return PYB_OK;
+}
 
 extern "C" int pyb_debug_tc_gemm(pyb_handle* h, const float* A, const float* B, int32_t M, int32_t Nn, int32_t K,
                                  float* D) {

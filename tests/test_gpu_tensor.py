@@ -50,6 +50,62 @@ def test_split_bf16_gemm_matches_float64(M, Nn, K, pair):
     assert rel_err(D, want) < 2e-5
 
 
+def mixed_operands(X):
+    """fp16 hi part and the two e4m3 correction operands of DESIGN 6b item 4 for one [rows, K] operand (K % 32 == 0):
+    returns the scaled fp16 array, the e4m3 (hi, lo) arrays as float64 values, the interleaved byte tensor [rows, 2K]
+    the MIX kernel reads (per 32 K-elements: 32 bytes hi, 32 bytes lo) and the operand's power-of-two scale"""
+    import torch
+    X = X.astype(np.float64)
+    s = 2.0 ** np.floor(np.log2(256.0 / np.abs(X).max()))
+    Xs = X * s                                               # largest magnitude in (128, 256]
+    x16 = Xs.astype(np.float16)
+    lo = (Xs - x16.astype(np.float64)) * 2.0 ** 11           # |lo| <= 2^-11 |Xs| before the scale
+    q = lambda v: torch.from_numpy(v.astype(np.float32)).to(torch.float8_e4m3fn)
+    h8, l8 = q(Xs), q(lo)
+    R, K = X.shape
+    packed = np.stack([h8.view(torch.uint8).numpy().reshape(R, K // 32, 32),
+                       l8.view(torch.uint8).numpy().reshape(R, K // 32, 32)], axis=2).reshape(R, 2 * K)
+    return x16, h8.to(torch.float64).numpy(), l8.to(torch.float64).numpy(), np.ascontiguousarray(packed), s
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 64, 32), (300, 64, 96), (128, 256, 800), (1000, 128, 2048)])
+def test_mixed_fp16_e4m3_gemm_prototype(M, Nn, K):
+    """One fp16 pass + two plain-e4m3 correction passes (kind::f16 and kind::f8f6f4 MMAs accumulating into the same TMEM
+    columns, one power-of-two scale per operand): 4 MMA slots per 32 K-elements instead of the 6 of bf16x3.  Prototype
+    of DESIGN 6b item 4 on the 1-CTA kernel (`tc_gemm_bf16x3<EPI_STORE, 0, MIX=1>`); measured on B200: device vs the
+    float64 emulation of the quantised operands 1e-7 - 5e-6, vs the exact product 1.0e-5 - 1.2e-5
+    (profiles/r1_mixed_proto_test.log), 1.15x the bf16x3 kernel on a shape where both are fed at the L2 -> SM limit
+    (profiles/r1_mixed_proto_timing.json)."""
+    rng = np.random.default_rng(M + Nn + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((Nn, K)) * 0.3).astype(np.float32)
+    a16, a8h, a8l, a8, sa = mixed_operands(A)
+    b16, b8h, b8l, b8, sb = mixed_operands(B)
+    # fp16 operands carry 2^5 and 2^6 so that all three products share the factor 2^11 sa sb
+    a16s = (a16.astype(np.float64) * 32.0).astype(np.float16)
+    b16s = (b16.astype(np.float64) * 64.0).astype(np.float16)
+    assert np.isfinite(a16s).all() and np.isfinite(b16s).all()
+    out_scale = np.float32(2.0 ** -11 / (sa * sb))
+    eng = engine(64, 32, 4)
+    lib = _lib.load()
+    fn = lib.pyb_debug_tc_gemm_mixed
+    fn.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_float, C.c_void_p]
+    fn.restype = C.c_int
+    D = np.empty((M, Nn), np.float32)
+    a16b, b16b = np.ascontiguousarray(a16s.view(np.uint16)), np.ascontiguousarray(b16s.view(np.uint16))
+    _lib.check(fn(eng.h, a16b.ctypes.data, a8.ctypes.data, b16b.ctypes.data, b8.ctypes.data, M, Nn, K, out_scale,
+                  D.ctypes.data))
+    assert np.isfinite(D).all()
+    emul = float(out_scale) * (a16s.astype(np.float64) @ b16s.astype(np.float64).T + a8l @ b8h.T + a8h @ b8l.T)
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    single = float(out_scale) * (a16s.astype(np.float64) @ b16s.astype(np.float64).T)
+    print("mixed gemm %dx%dx%d: device vs emulation %.2e, device vs float64 %.2e (fp16 pass alone %.2e)"
+          % (M, Nn, K, rel_err(D, emul), rel_err(D, want), rel_err(single, want)))
+    assert rel_err(D, emul) < 2e-5          # the instruction does what the emulation says (fp32 accumulation apart)
+    assert rel_err(D, want) < 4e-5          # and the scheme is >= 5x better than the fp16 pass alone (~3e-4)
+    assert rel_err(single, want) > 1e-4
+
+
 def problem(oracle, D, H, Cc, N, S, seed, act="relu", loss="ce", q_scale=0.05):
     O = oracle
     rng = np.random.default_rng(seed)
