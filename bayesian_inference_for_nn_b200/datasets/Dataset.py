@@ -4,9 +4,10 @@ Kept: the shuffle + 80/10/10 ``take/skip`` split (:113-122), ``train_size/test_s
 ``training_dataset()`` (:143-150), the ``loss(reduction)`` factory (:152-159), ``input_shape()``,
 ``train_data/valid_data/test_data`` objects that still answer ``.batch(n)``, ``.cardinality()`` and
 iteration the way the scripts use them (e.g. ``next(iter(dataset.test_data.batch(n)))``,
-HMC_classification.py:64-65).  Out of scope (host I/O): tfds names, CSV, image
-folders, UCI ids — pass arrays, a DataFrame, or a ``tf.data.Dataset`` (materialised once, lazily
-importing TensorFlow only in that case).
+HMC_classification.py:64-65).  Out of scope (host I/O): tfds names, image folders,
+UCI ids — pass arrays, a DataFrame, the path of a CSV file (last ``target_dim`` columns are the
+labels, :124-133), or a ``tf.data.Dataset`` (materialised once, lazily importing TensorFlow only in
+that case).
 
 Differences that matter for the device path: the split is materialised ONCE into contiguous NumPy
 arrays (the reference re-shuffles on every iteration, SURVEY B-8), so the full training batch can be
@@ -106,6 +107,7 @@ class Dataset:
         self.likelihood_model = likelihoodModel
         self.target_dim = target_dim
         self._label_mean = self._label_std = None
+        self._load_images = load_images
         x, y = self._materialise(dataset)
         self._init_from_arrays(x, y, seed)
         if feature_normalisation:
@@ -119,6 +121,9 @@ class Dataset:
             return to_numpy(dataset[0]), to_numpy(dataset[1])
         if isinstance(dataset, ArrayDataset):
             return dataset.x, dataset.y
+        if isinstance(dataset, str) and not self._load_images and dataset.lower().endswith(".csv"):
+            import pandas as pd                      # _init_from_csv (:131-133): read_csv, then the DataFrame rule
+            dataset = pd.read_csv(dataset)
         mod = type(dataset).__module__ or ""
         if mod.startswith("pandas"):
             return (dataset.iloc[:, :-self.target_dim].values, dataset.iloc[:, -self.target_dim:].values)

@@ -206,3 +206,22 @@ def test_hyperparameters_parse_matches_the_reference_goldens():
         want = ("ok", c["params"]) if c["status"] == "ok" else ("err", c["error"])
         assert got == want, (c["text"], got, want)
     assert any(c["status"] == "err" for c in cases)            # a name without a number is an IndexError, kept
+
+
+def test_dataset_from_a_csv_file_and_a_dataframe(tmp_path):
+    """Dataset.py:124-133: the last `target_dim` columns are the labels; a CSV path goes through read_csv."""
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(0)
+    df = pd.DataFrame({"a": rng.random(50), "b": rng.random(50), "t": rng.random(50)})
+    path = tmp_path / "reg.csv"
+    df.to_csv(path, index=False)
+    from_df = Dataset(df, "MeanSquaredError", "Regression", seed=3)
+    from_csv = Dataset(str(path), "MeanSquaredError", "Regression", seed=3)
+    assert from_csv.size == 50 and from_csv.input_shape() == (2,)
+    np.testing.assert_allclose(from_csv.train_data.x, from_df.train_data.x, rtol=1e-12)
+    np.testing.assert_allclose(from_csv.train_data.y, from_df.train_data.y, rtol=1e-12)
+    assert from_csv.train_data.y.shape == (40, 1)
+    two = Dataset(df, "MeanSquaredError", "Regression", target_dim=2)
+    assert two.input_shape() == (1,) and two.train_data.y.shape == (40, 2)
+    with pytest.raises(ValueError):
+        Dataset("no_such_builder", "MeanSquaredError", "Regression")
