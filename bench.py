@@ -139,13 +139,40 @@ def cpu_reference_run(args, steps, warmup, rows):
     prob = O.Problem(spec, X, y, O.LOSS_SPARSE_CE, mu, sg)
     rng = np.random.default_rng(0)
     q = np.zeros((1, spec.n_params), np.float32)
-    for _ in range(warmup):
-        q, _, _ = O.reference_style_hmc_iteration(prob, q, rng, args.eps, 1.0, args.leapfrog)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        q, _, _ = O.reference_style_hmc_iteration(prob, q, rng, args.eps, 1.0, args.leapfrog)
-    dt = time.perf_counter() - t0
-    return args.leapfrog * steps / dt, dt
+    with host_blas_threads() as threads:
+        for _ in range(warmup):
+            q, _, _ = O.reference_style_hmc_iteration(prob, q, rng, args.eps, 1.0, args.leapfrog)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            q, _, _ = O.reference_style_hmc_iteration(prob, q, rng, args.eps, 1.0, args.leapfrog)
+        dt = time.perf_counter() - t0
+    return args.leapfrog * steps / dt, dt, threads[0]
+
+
+class host_blas_threads:
+    """Give NumPy's BLAS every core this process may run on for the CPU legs — torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which would time the reference arm on ONE thread at N > 1 — and report the thread count actually in use."""
+
+    def __enter__(self):
+        self.used = [1]
+        try:
+            want = len(os.sched_getaffinity(0))
+        except AttributeError:
+            want = os.cpu_count() or 1
+        try:
+            import threadpoolctl
+            self._ctl = threadpoolctl.threadpool_limits(limits=want, user_api="blas")
+            blas = [m for m in threadpoolctl.threadpool_info() if m.get("user_api") == "blas"]
+            self.used[0] = max([int(m.get("num_threads", 1)) for m in blas] or [1])
+        except Exception:            # no threadpoolctl: whatever the environment configured
+            self._ctl = None
+            self.used[0] = int(os.environ.get("OMP_NUM_THREADS", 0)) or want
+        return self.used
+
+    def __exit__(self, *exc):
+        if self._ctl is not None:
+            self._ctl.restore_original_limits()
+        return False
 
 
 def run_reference(args):
@@ -153,8 +180,7 @@ def run_reference(args):
     if rank != 0:
         return
     # bounded sample: each step is ONE reference-style iteration of ONE chain on the full dataset
-    val, dt = cpu_reference_run(args, args.steps, min(args.warmup, 1), args.rows)
-    cores = os.cpu_count() or 1
+    val, dt, cores = cpu_reference_run(args, args.steps, min(args.warmup, 1), args.rows)
     line = {
         "impl": "reference", "metric": "posterior_grad_evals_per_s", "value": val, "unit": "grad-evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
@@ -305,10 +331,10 @@ def main():
                         "pipe 95 % active, the fused layer-1 GEMM + layer-2 kernel is bound by the SM's 128 B/clk "
                         "shared-memory data path (MMA operand reads + TMA fills + epilogue stores), see DESIGN.md section 4"}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (the reference arm reports it at every N)
         # bounded sample (~10 s of CPU work): 1 chain, 3 timed iterations (+1 warm-up) on the full dataset
-        v, dt = cpu_reference_run(args, 3, 1, args.rows)
-        cpu = {"value": v, "unit": "grad-evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+        v, dt, cores = cpu_reference_run(args, 3, 1, args.rows)
+        cpu = {"value": v, "unit": "grad-evals/s", "cores": cores, "kind": "port",
                "sample": "1 chain x 3 iterations (L=%d, %d rows x 784, 784-256-10); numpy fp32 BLAS on all host cores, "
                          "reference loop shape (HMC.py:74-104: L+2 gradient + 2 potential evaluations per iteration); "
                          "%.1f s" % (L, args.rows, dt)}
