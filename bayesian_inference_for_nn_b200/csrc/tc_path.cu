@@ -619,7 +619,56 @@ void tc_debug_gemm_mixed(pyb_handle* h, const uint16_t* A16, const uint8_t* A8, 
   prof_resolve(h);
 }
 
+// debug / unit-test entry for the int8-slice prototype: D = Ah Bh^T + (Ah Bl^T + Al Bh^T) / 254 with
+// int8 slice tensors [rows, K] prepared by the caller (host pointers), K % 64 == 0; scales are applied by the caller
+void tc_debug_gemm_i8(pyb_handle* h, const int8_t* Ah, const int8_t* Al, const int8_t* Bh, const int8_t* Bl, int M, int Nn, int K,
+                      float* Dout) {
+  PYB_REQUIRE(Nn % 16 == 0 && Nn >= 16 && Nn <= 256 && K % 64 == 0 && K > 0, PYB_ERR_INVALID, "Nn%16, Nn<=256, K%64 required");
+  DevBuf<int8_t> ah, al, bh, bl;
+  DevBuf<float> dD;
+  ah.alloc((size_t)M * K); al.alloc((size_t)M * K); bh.alloc((size_t)Nn * K); bl.alloc((size_t)Nn * K);
+  dD.alloc((size_t)M * Nn);
+  PYB_CUDA(cudaMemcpyAsync(ah.p, Ah, (size_t)M * K, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(al.p, Al, (size_t)M * K, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(bh.p, Bh, (size_t)Nn * K, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(bl.p, Bl, (size_t)Nn * K, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemsetAsync(dD.p, 0xff, (size_t)M * Nn * 4, h->stream));
+  CUtensorMap ma_h = make_map_u8(ah.p, K, M, 128), ma_l = make_map_u8(al.p, K, M, 128);
+  CUtensorMap mb_h = make_map_u8(bh.p, K, Nn, Nn), mb_l = make_map_u8(bl.p, K, Nn, Nn);
+  TcGemmParams p = {};
+  p.K = K / 2;                                     // stages of 64 K-elements, counted in units of TC_BK = 32
+  p.n_mtiles = (M + 127) / 128; p.n_pairs = p.n_mtiles; p.n_batch = 1; p.H = Nn;   // one 128-row tile per item
+  p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
+  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0; p.a_box_rows = 128;
+  p.k_splits = 1; p.chunks_per_split = p.K / TC_BK; p.split_stride = 0; p.vec_store = 1;
+  const int grid = std::min(p.total_items, h->sm_count);
+  PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3<EPI_STORE, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  for (int r = 0; r < debug_gemm_reps(); ++r) {
+    prof_begin(h);
+    tc_gemm_bf16x3<EPI_STORE, 0, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(ma_h, ma_l, mb_h, mb_l, p);
+    prof_end(h, 2.0 * M * Nn * (double)K);
+    count_launch(h);
+  }
+  PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+  prof_resolve(h);
+}
+
 }  // namespace pyb
+
+extern "C" int pyb_debug_tc_gemm_i8(pyb_handle* h, const int8_t* Ah, const int8_t* Al, const int8_t* Bh, const int8_t* Bl,
+                                    int32_t M, int32_t Nn, int32_t K, float* D) {
+  try {
+    if (!h || !Ah || !Al || !Bh || !Bl || !D) throw pyb::Error(PYB_ERR_INVALID, "NULL argument");
+    PYB_CUDA(cudaSetDevice(h->device));
+    pyb::tc_debug_gemm_i8(h, Ah, Al, Bh, Bl, M, Nn, K, D);
+  } catch (const pyb::Error& e) {
+    pyb::set_last_error(e.what());
+    return e.code;
+  }
+  return PYB_OK;
+}
 
 extern "C" int pyb_debug_tc_gemm_mixed(pyb_handle* h, const uint16_t* A16, const uint8_t* A8, const uint16_t* B16,
                                        const uint8_t* B8, int32_t M, int32_t Nn, int32_t K, float out_scale, float* D) {

@@ -2,6 +2,7 @@
 NumPy, then log-prob/gradient/trajectory parity of the MNIST-width HMC path against the oracle and
 against the generic fp32 SIMT path on the same inputs."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -104,6 +105,46 @@ def test_mixed_fp16_e4m3_gemm_prototype(M, Nn, K):
     assert rel_err(D, emul) < 2e-5          # the instruction does what the emulation says (fp32 accumulation apart)
     assert rel_err(D, want) < 4e-5          # and the scheme is >= 5x better than the fp16 pass alone (~3e-4)
     assert rel_err(single, want) > 1e-4
+
+
+def int8_slices(X):
+    """two int8 fixed-point slices per row: X = s / 127 * (hi + lo / 254), one scale per row"""
+    X = X.astype(np.float64)
+    s = np.abs(X).max(axis=1, keepdims=True)
+    s = np.where(s > 0, s, 1.0)
+    r = X / s * 127.0
+    hi = np.clip(np.round(r), -127, 127)
+    lo = np.clip(np.round((r - hi) * 254.0), -127, 127)
+    return np.ascontiguousarray(hi.astype(np.int8)), np.ascontiguousarray(lo.astype(np.int8)), s
+
+
+@pytest.mark.skipif(os.environ.get("PYB_TEST_I8") != "1",
+                    reason="int8-slice prototype kernel (DESIGN 6b item 4b) has not run on a GPU yet: PYB_TEST_I8=1")
+@pytest.mark.parametrize("M,Nn,K", [(128, 64, 64), (300, 64, 128), (128, 256, 832), (1000, 128, 2048)])
+def test_int8_slice_gemm_prototype(M, Nn, K):
+    """hh + (hl + lh) / 254 with kind::i8 MMAs (exact int32 accumulation in two TMEM accumulators): 3 MMA slots per 32
+    K-elements and 2 bytes per operand element against 6 slots and 4 bytes for bf16x3."""
+    rng = np.random.default_rng(M + Nn + K)
+    A = rng.random((M, K)).astype(np.float32)                      # U[0,1) like the data operand
+    B = (rng.standard_normal((Nn, K)) * 0.3).astype(np.float32)
+    ah, al, sa = int8_slices(A)
+    bh, bl, sb = int8_slices(B)
+    eng = engine(64, 32, 4)
+    lib = _lib.load()
+    fn = lib.pyb_debug_tc_gemm_i8
+    fn.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_void_p]
+    fn.restype = C.c_int
+    D = np.empty((M, Nn), np.float32)
+    _lib.check(fn(eng.h, ah.ctypes.data, al.ctypes.data, bh.ctypes.data, bl.ctypes.data, M, Nn, K, D.ctypes.data))
+    i64 = lambda x: x.astype(np.int64)
+    exact = (i64(ah) @ i64(bh).T).astype(np.float64) + (i64(ah) @ i64(bl).T + i64(al) @ i64(bh).T).astype(np.float64) / 254.0
+    assert np.isfinite(D).all()
+    got = D.astype(np.float64) * sa * sb.T / 127.0 ** 2
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    print("int8 slice gemm %dx%dx%d: device vs exact integers %.2e, scaled vs float64 %.2e"
+          % (M, Nn, K, rel_err(D, exact), rel_err(got, want)))
+    assert rel_err(D, exact) < 5e-7          # integer accumulation is exact; only the fp32 conversions round
+    assert rel_err(got, want) < 1e-4
 
 
 def problem(oracle, D, H, Cc, N, S, seed, act="relu", loss="ce", q_scale=0.05):

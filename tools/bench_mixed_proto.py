@@ -2,7 +2,7 @@
 """Per-launch device time of the 1-CTA split GEMM kernel in its two operand schemes on the same shape (one item per SM,
 two 128-row tiles per item, N = 256, K = 3200): bf16x3 (6 MMA slots per 32 K-elements) against the prototype
 fp16 + 2x e4m3 (4 slots).  Both move the same stage bytes; times come from the CUDA events the
-library records around each launch ("profile" option).  Usage: python tools/bench_mixed_proto.py [reps=20]"""
+library records around each launch ("profile" option).  Usage: python tools/bench_mixed_proto.py [reps=20] [--i8]      (--i8 adds the int8 two-slice prototype, item 4b)"""
 import ctypes as C
 import json
 import os
@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+reps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20
 os.environ["PYB_DEBUG_GEMM_REPS"] = str(reps + 1)
 
 from bayesian_inference_for_nn_b200 import _lib, keras_json  # noqa: E402
@@ -66,4 +66,19 @@ ms, n = timed(lambda: _lib.check(fm(eng.h, a16s.ctypes.data, a8.ctypes.data, b16
                                     osc, D.ctypes.data)))
 out["fp16_2xe4m3"] = {"ms_per_launch": ms, "launches": n, "tflops_algorithmic": 2.0 * M * Nn * K / ms / 1e9, "rel_err": rel(D)}
 out["speedup"] = out["bf16x3"]["ms_per_launch"] / out["fp16_2xe4m3"]["ms_per_launch"]
+
+if "--i8" in sys.argv:      # int8 two-slice prototype (the kernel has not run on a GPU yet)
+    from test_gpu_tensor import int8_slices  # noqa: E402
+    ah, al, s_a = int8_slices(A0)
+    bh, bl, s_b = int8_slices(B)
+    ah, al = tile(ah), tile(al)
+    fi = lib.pyb_debug_tc_gemm_i8
+    fi.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_void_p]
+    fi.restype = C.c_int
+    ms, n = timed(lambda: _lib.check(fi(eng.h, ah.ctypes.data, al.ctypes.data, bh.ctypes.data, bl.ctypes.data, M, Nn, K,
+                                        D.ctypes.data)))
+    got = D[:base].astype(np.float64) * s_a * s_b.T / 127.0 ** 2
+    out["int8_2slices"] = {"ms_per_launch": ms, "launches": n, "tflops_algorithmic": 2.0 * M * Nn * K / ms / 1e9,
+                           "rel_err": float(np.linalg.norm(got - want) / np.linalg.norm(want))}
+    out["speedup_int8"] = out["bf16x3"]["ms_per_launch"] / ms
 print(json.dumps(out))
