@@ -85,7 +85,8 @@ __device__ __forceinline__ float act_apply_t(float z) {
 // (K = 32 each: a_lo b_hi and a_hi b_lo) into the SAME accumulator columns — 4 MMA slots instead of 6 for the same
 // stage bytes.  The caller picks the scales so that both correction products and the fp16 product carry one common
 // factor 2^k, which the epilogue removes (its reciprocal travels as the bit pattern of `act`).
-// MIX = 2 (prototype of DESIGN 6b item 4b, pyb_debug_tc_gemm_i8, NOT yet run on a GPU): all four maps address int8 slice
+// MIX = 2 (prototype of DESIGN 6b item 4b, pyb_debug_tc_gemm_i8; B200: 1.61x the bf16x3 kernel, result equal to the integer
+// emulation, profiles/r1_i8_proto_timing.json): all four maps address int8 slice
 // tensors [rows, K]; a stage covers 64 K-elements; one 128-row tile per item; kind::i8 MMAs accumulate hh into TMEM columns
 // [0, 256) and hl + lh into [256, 512) as exact int32, the epilogue stores hh + (hl + lh) / 254 as fp32 and the caller
 // applies the row and column scales.  The caller passes K / 2 as p.K (stages are counted in units of 32).

@@ -119,7 +119,8 @@ def int8_slices(X):
 
 
 @pytest.mark.skipif(os.environ.get("PYB_TEST_I8") != "1",
-                    reason="int8-slice prototype kernel (DESIGN 6b item 4b) has not run on a GPU yet: PYB_TEST_I8=1")
+                    reason="int8-slice prototype (DESIGN 6b item 4b): the entry ran on B200 through tools/bench_mixed_proto.py --i8 "
+                           "(profiles/r1_i8_proto_timing.json), these pytest shapes have not: PYB_TEST_I8=1")
 @pytest.mark.parametrize("M,Nn,K", [(128, 64, 64), (300, 64, 128), (128, 256, 832), (1000, 128, 2048)])
 def test_int8_slice_gemm_prototype(M, Nn, K):
     """hh + (hl + lh) / 254 with kind::i8 MMAs (exact int32 accumulation in two TMEM accumulators): 3 MMA slots per 32

@@ -67,7 +67,7 @@ ms, n = timed(lambda: _lib.check(fm(eng.h, a16s.ctypes.data, a8.ctypes.data, b16
 out["fp16_2xe4m3"] = {"ms_per_launch": ms, "launches": n, "tflops_algorithmic": 2.0 * M * Nn * K / ms / 1e9, "rel_err": rel(D)}
 out["speedup"] = out["bf16x3"]["ms_per_launch"] / out["fp16_2xe4m3"]["ms_per_launch"]
 
-if "--i8" in sys.argv:      # int8 two-slice prototype (the kernel has not run on a GPU yet)
+if "--i8" in sys.argv:      # int8 two-slice prototype
     from test_gpu_tensor import int8_slices  # noqa: E402
     ah, al, s_a = int8_slices(A0)
     bh, bl, s_b = int8_slices(B)
