@@ -619,6 +619,51 @@ void tc_debug_gemm_mixed(pyb_handle* h, const uint16_t* A16, const uint8_t* A8, 
   prof_resolve(h);
 }
 
+// operand producer of the int8-slice scheme (debug entry only so far): one warp per row finds the row's
+// largest magnitude s and writes x = s / 127 (hi + lo / 254) as two int8 slices [rows, Kpad] (Kpad % 4 == 0, zero padded)
+__global__ void k_slice_rows_i8(const float* __restrict__ src, int64_t rows, int K, int64_t ld, int8_t* __restrict__ hi,
+                                int8_t* __restrict__ lo, float* __restrict__ scale, int Kpad) {
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    const float* x = src + r * ld;
+    float m = 0.f;
+    for (int k = lane; k < K; k += 32) m = fmaxf(m, fabsf(x[k]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float s = m > 0.f ? m : 1.f;
+    if (lane == 0) scale[r] = s;
+    for (int k4 = lane * 4; k4 < Kpad; k4 += 128) {             // 4 consecutive elements per lane: one 32-bit store per slice
+      uint32_t hw = 0, lw = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = (k4 + j < K) ? __fdiv_rn(x[k4 + j], s) * 127.0f : 0.f;
+        const float q = fminf(fmaxf(rintf(v), -127.f), 127.f);
+        const float q2 = fminf(fmaxf(rintf((v - q) * 254.0f), -127.f), 127.f);
+        hw |= ((uint32_t)(int)q & 0xffu) << (8 * j);
+        lw |= ((uint32_t)(int)q2 & 0xffu) << (8 * j);
+      }
+      *reinterpret_cast<uint32_t*>(hi + r * Kpad + k4) = hw;
+      *reinterpret_cast<uint32_t*>(lo + r * Kpad + k4) = lw;
+    }
+  }
+}
+void tc_debug_slice_i8(pyb_handle* h, const float* X, int64_t rows, int K, int Kpad, int8_t* hi, int8_t* lo, float* scale) {
+  PYB_REQUIRE(rows > 0 && K > 0 && Kpad >= K && Kpad % 4 == 0, PYB_ERR_INVALID, "rows, K > 0 and Kpad >= K, Kpad % 4 == 0 required");
+  DevBuf<float> dX, dS;
+  DevBuf<int8_t> dH, dL;
+  dX.alloc((size_t)rows * K); dS.alloc((size_t)rows); dH.alloc((size_t)rows * Kpad); dL.alloc((size_t)rows * Kpad);
+  PYB_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)rows * K * 4, cudaMemcpyHostToDevice, h->stream));
+  const int wpb = 8;
+  const unsigned grid = (unsigned)std::min<int64_t>((rows + wpb - 1) / wpb, 8 * (int64_t)h->sm_count);
+  k_slice_rows_i8<<<grid, wpb * 32, 0, h->stream>>>(dX.p, rows, K, K, dH.p, dL.p, dS.p, Kpad);
+  count_launch(h);
+  PYB_CUDA(cudaMemcpyAsync(hi, dH.p, (size_t)rows * Kpad, cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(lo, dL.p, (size_t)rows * Kpad, cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(scale, dS.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  PYB_CUDA(cudaGetLastError());
+}
+
 // debug / unit-test entry for the int8-slice prototype: D = Ah Bh^T + (Ah Bl^T + Al Bh^T) / 254 with
 // int8 slice tensors [rows, K] prepared by the caller (host pointers), K % 64 == 0; scales are applied by the caller
 void tc_debug_gemm_i8(pyb_handle* h, const int8_t* Ah, const int8_t* Al, const int8_t* Bh, const int8_t* Bl, int M, int Nn, int K,
@@ -656,6 +701,19 @@ void tc_debug_gemm_i8(pyb_handle* h, const int8_t* Ah, const int8_t* Al, const i
 }
 
 }  // namespace pyb
+
+extern "C" int pyb_debug_slice_i8(pyb_handle* h, const float* X, int64_t rows, int32_t K, int32_t Kpad, int8_t* hi, int8_t* lo,
+                                  float* scale) {
+  try {
+    if (!h || !X || !hi || !lo || !scale) throw pyb::Error(PYB_ERR_INVALID, "NULL argument");
+    PYB_CUDA(cudaSetDevice(h->device));
+    pyb::tc_debug_slice_i8(h, X, rows, K, Kpad, hi, lo, scale);
+  } catch (const pyb::Error& e) {
+    pyb::set_last_error(e.what());
+    return e.code;
+  }
+  return PYB_OK;
+}
 
 extern "C" int pyb_debug_tc_gemm_i8(pyb_handle* h, const int8_t* Ah, const int8_t* Al, const int8_t* Bh, const int8_t* Bl,
                                     int32_t M, int32_t Nn, int32_t K, float* D) {

@@ -148,6 +148,31 @@ def test_int8_slice_gemm_prototype(M, Nn, K):
     assert rel_err(got, want) < 1e-4
 
 
+@pytest.mark.skipif(os.environ.get("PYB_TEST_I8") != "1", reason="int8-slice operand producer has not run on a GPU yet: PYB_TEST_I8=1")
+@pytest.mark.parametrize("rows,K", [(5, 64), (300, 784), (1000, 100)])
+def test_int8_slice_producer(rows, K):
+    """k_slice_rows_i8: per-row maximum as scale, x = s / 127 (hi + lo / 254) to 2^-16 of the row maximum, zero padding."""
+    rng = np.random.default_rng(rows + K)
+    X = rng.standard_normal((rows, K)).astype(np.float32)
+    X[0] = 0.0                                                   # an all-zero row keeps scale 1 and zero slices
+    Kpad = (K + 63) // 64 * 64
+    eng = engine(64, 32, 4)
+    fn = _lib.load().pyb_debug_slice_i8
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn.restype = C.c_int
+    hi, lo = np.empty((rows, Kpad), np.int8), np.empty((rows, Kpad), np.int8)
+    s = np.empty(rows, np.float32)
+    _lib.check(fn(eng.h, X.ctypes.data, rows, K, Kpad, hi.ctypes.data, lo.ctypes.data, s.ctypes.data))
+    want_s = np.abs(X).max(1)
+    want_s[want_s == 0] = 1.0
+    np.testing.assert_array_equal(s, want_s)
+    assert not hi[:, K:].any() and not lo[:, K:].any() and not hi[0].any() and not lo[0].any()
+    rec = s[:, None].astype(np.float64) / 127.0 * (hi[:, :K].astype(np.float64) + lo[:, :K].astype(np.float64) / 254.0)
+    assert (np.abs(rec - X).max(1) <= want_s * 2.0 ** -15.9).all()          # s / 127 * 0.5 / 254 = s * 2^-15.98
+    h_ref, l_ref, _ = int8_slices(X)
+    assert (np.abs(hi[:, :K].astype(np.int32) - h_ref) <= 1).all()           # fp32 against float64 division: ties may differ
+
+
 def problem(oracle, D, H, Cc, N, S, seed, act="relu", loss="ce", q_scale=0.05):
     O = oracle
     rng = np.random.default_rng(seed)
