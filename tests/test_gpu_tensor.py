@@ -168,7 +168,7 @@ def test_int8_slice_producer(rows, K):
     np.testing.assert_array_equal(s, want_s)
     assert not hi[:, K:].any() and not lo[:, K:].any() and not hi[0].any() and not lo[0].any()
     rec = s[:, None].astype(np.float64) / 127.0 * (hi[:, :K].astype(np.float64) + lo[:, :K].astype(np.float64) / 254.0)
-    assert (np.abs(rec - X).max(1) <= want_s * 2.0 ** -15.9).all()          # s / 127 * 0.5 / 254 = s * 2^-15.98
+    assert (np.abs(rec - X).max(1) <= want_s * 2.0 ** -15.8).all()          # s / 127 * 0.5 / 254 = s * 2^-15.98 (+ fp32 rounding of the quotient)
     h_ref, l_ref, _ = int8_slices(X)
     assert (np.abs(hi[:, :K].astype(np.int32) - h_ref) <= 1).all()           # fp32 against float64 division: ties may differ
 
