@@ -140,6 +140,8 @@ def schemes(A, B, k_axis_a, k_axis_b, scale_b=1.0, only=None):
                                                               + fp8_tensor(A, **e5) @ fp8_tensor(B - b16, **e5)),
         "int8 x 2 slices, hh + hl + lh (1.5, 2 B/element)": lambda: (lambda a, b: a[0] @ b[0] + a[0] @ b[1] + a[1] @ b[0])(
             int8_slices(A, k_axis_a), int8_slices(B, k_axis_b)),
+        "int8: A 2 slices, B 3 slices, 4 products (2, 2 + 3 B)": lambda: (lambda a, b: a[0] @ (b[0] + b[1] + b[2]) + a[1] @ b[0])(
+            int8_slices(A, k_axis_a), int8_slices(B, k_axis_b, 3)),
         "int8 x 2 slices, all four products (2)": lambda: (lambda a, b: (a[0] + a[1]) @ (b[0] + b[1]))(
             int8_slices(A, k_axis_a), int8_slices(B, k_axis_b)),
         "fp16 + 2x mxfp4 (1.5 pass-equivalents)": lambda: (a16 @ b16 + mxfp4(A - a16, k_axis_a) @ mxfp4(B, k_axis_b)
@@ -269,7 +271,7 @@ def main():
     # whole gradient with all three GEMMs under one scheme (forward error propagates into the deltas and relu masks)
     names = ["bf16x3 (today)", "fp16x3", "fp16 + 2x mxfp8 (2 pass-equivalents)", "fp16 + 2x e4m3, one scale per operand (2)",
              "fp16 + 2x e5m2, one scale per operand (2)", "fp16 + 2x mxfp4 (1.5 pass-equivalents)", "int8 x 2 slices, hh + hl + lh (1.5, 2 B/element)",
-             "int8 x 2 slices, all four products (2)", "fp16x2 (B split only)",
+             "int8 x 2 slices, all four products (2)", "int8: A 2 slices, B 3 slices, 4 products (2, 2 + 3 B)", "fp16x2 (B split only)",
              "fp16 x1", "bf16 x1"]
     for w_scale in (0.05, 1.0):
         for _ in range(chains):
@@ -287,7 +289,7 @@ def main():
                 worst[key] = max(worst.get(key, 0), abs(l - l0) / abs(l0))
     print("rows N = %d, %d weight draws per scale; norm-wise relative error (worst case); parity budget 1e-4" % (N, chains))
     for (what, ws, name), v in sorted(worst.items(), key=lambda kv: (kv[0][0], kv[0][1], kv[1])):
-        print("  %-16s weights ~ N(0, %-4g)  %-50s %.2e" % (what, ws, name, v))
+        print("  %-16s weights ~ N(0, %-4g)  %-54s %.2e" % (what, ws, name, v))
 
 
 if __name__ == "__main__":
