@@ -204,6 +204,9 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_predict_sharded = v != 0;
   } else if (!strcmp(key, "tc_fuse")) {
     h->opt_tc_fuse = v != 0;
+  } else if (!strcmp(key, "tc_i8")) {
+    PYB_REQUIRE(v == 0 || v == 1 || v == 2, PYB_ERR_INVALID, "tc_i8 must be 0 (bf16x3), 1 or 2 (int8 slices)");
+    h->opt_tc_i8 = (int)v;
   } else if (!strcmp(key, "profile")) {
     h->prof_enabled = v != 0;
     h->prof_ms = h->prof_flops = 0; h->prof_launches = 0; h->prof_used = 0;

@@ -279,6 +279,7 @@ struct pyb_handle {
   int opt_hmc_carry = 1;    // 1: loss and gradient at the current position are carried to the next HMC iteration
   int opt_predict_sharded = 0;   // 1: pyb_predict all-reduces its moment sums over the handle's communicator
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
+  int opt_tc_i8 = 0;     // operand split of the big GEMMs: 0 bf16x3, 1 int8 slices in the forward GEMM, 2 + in the dW1 GEMM (tc_i8.cuh)
   double opt_workspace_mb = 4096;
   int64_t opt_chain_batch = 0;
   int path_used = PYB_PATH_GENERIC;

@@ -29,7 +29,41 @@ template <int CP> struct TfCfg {
   static constexpr int ZX_BYTES = 2 * CP * 128 * 4;            // [2 halves][CP][128 rows] partial logits
   static constexpr int SMEM = STAGES * TP_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 2048 /*bias x2*/ +
                               128 /*b2 x2*/ + W2_BYTES + ZX_BYTES;
+  static constexpr int SMEM_I8 = SMEM + 4096;                  // + [2][256] W1 column scales, [2][256] dZ1 quantisation factors
 };
+// same 16x256b.x4 load, raw 32-bit words (the int32 accumulators of the int8-slice scheme)
+__device__ __forceinline__ void tc_ld_16x256b_x4_raw(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// two int8 slices of 4 values q[r] (already multiplied by 127 / scale): hi = rint(q), lo = rint((q - hi) * 254), one byte per
+// row, row 0 in the lowest byte
+__device__ __forceinline__ void slice4_i8(const float* q, uint32_t& hw, uint32_t& lw) {
+  hw = 0u; lw = 0u;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float h = fminf(fmaxf(rintf(q[r]), -127.f), 127.f);
+    const float l = fminf(fmaxf(rintf((q[r] - h) * 254.0f), -127.f), 127.f);
+    hw |= ((uint32_t)__float2int_rn(h) & 0xffu) << (8 * r);
+    lw |= ((uint32_t)__float2int_rn(l) & 0xffu) << (8 * r);
+  }
+}
 // 16 accumulator columns... 32 columns x rows {g, g+8} of the 16 TMEM lanes starting at the address's lane
 __device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -59,7 +93,14 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hw, uin
 
 // FWD = false: training step (everything above).  FWD = true: forward only (posterior predictive): phase A, the logit
 // reduction and the output activation; out[b][row][c] is the only thing written — no A1^T, no deltas, no loss.
-template <int CP, bool FWD>
+// I8 != 0: the int8-slice scheme (tc_i8.cuh).  The four tensor maps address int8 slice tensors (X rows centred by the
+// feature means and scaled per row, W1^T scaled per hidden unit), a stage covers 64 K-elements, kind::i8 MMAs accumulate
+// hi*hi into TMEM columns [0, 256) and hi*lo + lo*hi (weight 1/254) into [256, 512) as EXACT int32 — half the MMA slots
+// and half the operand bytes of bf16x3, no truncating accumulator.  Both accumulators fill TMEM, so the accumulator is
+// single-buffered: phase A of the epilogue is exposed, the rest of it still overlaps the next tile's main loop.
+// z1 = s_x[row] * (s_w[unit] / 127^2) * (hh + cross / 254) + b1'[unit], b1' = b1 + mu^T W1 (the data were centred).
+// I8 == 2: dZ1^T leaves as two int8 slices against the a-priori scale s_z[unit] >= max |dZ1[:, unit]| (softmax-CE only).
+template <int CP, bool FWD, int I8 = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1)
 tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -78,11 +119,14 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   float* b2_s = bias_s + 512;                                               // [2][16]
   float* W2_s = b2_s + 32;                                                  // [2][256*CP]
   float* zx_s = W2_s + 2 * 256 * CP;                                        // [2][CP][128]
+  float* cw_s = zx_s + 2 * CP * 128;                                        // [2][256]   (I8)
+  float* zq_s = cw_s + 512;                                                 // [2][256]   (I8 == 2)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  constexpr int KSTAGE = I8 ? 64 : TC_BK;         // K elements per stage (a stage row is 64 bytes either way)
+  const int nk = (p.K + KSTAGE - 1) / KSTAGE;
   const int H = p.H;
   const int half_rows = H >> 1;
   const uint32_t cta_bytes = 2 * TC_A_TILE_BYTES + 2 * (uint32_t)half_rows * TC_BK * 2;
@@ -128,7 +172,7 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * TP_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);
-          const int k0 = kc * TC_BK;
+          const int k0 = kc * KSTAGE;
           tma_load_2d_pair(st, &tmA_hi, &full_bar[stage], k0, arow);
           tma_load_2d_pair(st + TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], k0, arow);
           tma_load_2d_pair(st + 2 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], k0, brow);
@@ -140,11 +184,14 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   } else if (warp == 9) {
     // ===== MMA issuer (leader CTA only) =====
     if (rank == 0 && lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(H >> 3) << 17) | ((256u >> 4) << 24);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const int k_tail = p.K - (nk - 1) * TC_BK;
-      for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      // bf16: D = F32, A = B = BF16; int8 slices: D = S32, A = B = signed 8-bit; K-major, N = H, M = 256 across the pair
+      const uint32_t idesc = (I8 ? (2u << 4) : (1u << 4)) | (1u << 7) | (1u << 10) | ((uint32_t)(H >> 3) << 17) | ((256u >> 4) << 24);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      const int k_tail = p.K - (nk - 1) * KSTAGE;                // valid K elements of the last stage
+      for (int item = cluster_id; item < p.total_items; item += n_clusters, ++it) {
+        const int acc = I8 ? 0 : (it & 1);
+        const uint32_t acc_phase = I8 ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * 256;
@@ -152,22 +199,28 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + stage * TP_STAGE_BYTES);
-          const int nks = (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
+          const int nks = (kc == nk - 1 && k_tail <= KSTAGE / 2) ? 1 : 2;
           for (int ks = 0; ks < nks; ++ks) {
             const uint32_t koff = ks * 32;
             const uint64_t ah = make_smem_desc_sw64(st + koff);
             const uint64_t al = make_smem_desc_sw64(st + TC_A_TILE_BYTES + koff);
             const uint64_t bh = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + koff);
             const uint64_t bl = make_smem_desc_sw64(st + 2 * TC_A_TILE_BYTES + 8192 + koff);
-            tc_mma_bf16_pair(d, ah, bh, idesc, (kc != 0) || (ks != 0));
-            tc_mma_bf16_pair(d, al, bh, idesc, 1);
-            tc_mma_bf16_pair(d, ah, bl, idesc, 1);
+            const uint32_t accum = (kc != 0) || (ks != 0);
+            if (I8) {
+              tc_mma_i8_pair(d, ah, bh, idesc, accum);            // hi * hi           -> columns [0, 256)
+              tc_mma_i8_pair(d + 256, ah, bl, idesc, accum);      // hi * lo + lo * hi -> columns [256, 512)
+              tc_mma_i8_pair(d + 256, al, bh, idesc, 1);
+            } else {
+              tc_mma_bf16_pair(d, ah, bh, idesc, accum);
+              tc_mma_bf16_pair(d, al, bh, idesc, 1);
+              tc_mma_bf16_pair(d, ah, bl, idesc, 1);
+            }
           }
           tc_commit_pair(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit_pair(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
    }
@@ -212,17 +265,34 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       if (eall < C)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(b2_s + buf * 16 + eall)),
                      "l"(th + l2.b2_off + eall) : "memory");
+      if (I8 && eall < H) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(cw_s + buf * 256 + eall)),
+                     "l"(l2.cw + (int64_t)b * H + eall) : "memory");
+        if (I8 == 2 && !FWD)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zq_s + buf * 256 + eall)),
+                       "l"(l2.zq + (int64_t)b * H + eall) : "memory");
+      }
     };
     if (cluster_id < p.total_items) fetch_consts(cluster_id, 0);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+    int it = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters, ++it) {
       int b, mp, split;
       tc_decode(p, item, b, mp, split);
       const int mt = mp * 2 + (int)rank;
-      float* bs = bias_s + acc * 256;
-      float* b2b = b2_s + acc * 16;
-      float* W2b = W2_s + acc * 256 * CP;
+      const int cbuf = it & 1;                                    // buffer of the per-chain constants
+      const int acc = I8 ? 0 : cbuf;                              // TMEM accumulator (single-buffered with int8 slices)
+      const uint32_t acc_phase = I8 ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
+      float* bs = bias_s + cbuf * 256;
+      float* b2b = b2_s + cbuf * 16;
+      float* W2b = W2_s + cbuf * 256 * CP;
+      float sxr[4] = {0.f, 0.f, 0.f, 0.f};                        // row scales of this thread's 4 data rows (int8 slices)
+      if (I8) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int rg = mt * 128 + quad * 32 + g + 8 * r;
+          sxr[r] = rg < p.M_valid ? __ldg(l2.sx + rg) : 0.f;
+        }
+      }
       asm volatile("cp.async.wait_all;" ::: "memory");           // this thread's share of the constants has landed
       asm volatile("bar.sync 1, 256;" ::: "memory");             // constants visible; zx_s readers of the last item done
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -235,6 +305,14 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       uint2* pz_lo = reinterpret_cast<uint2*>(l2.zt_lo) + blk_w;
       const float4* w4b = reinterpret_cast<const float4*>(W2b) + (((half * Hh) >> 3) * 2 * (CP / 4)) * 4 + t;
       const float* bsb = bs + hbase;
+      const float* cwb = cw_s + cbuf * 256 + hbase;
+      const float* zqb = zq_s + cbuf * 256 + hbase;
+      uint32_t* pzi_hi = nullptr; uint32_t* pzi_lo = nullptr;      // dZ1^T int8 slices: 4 rows = one 32-bit word
+      if (I8 == 2 && !FWD) {
+        const int64_t blk_b = ((((int64_t)b * p.out_tiles + mt) * H) + hbase) * 128 + pos0;   // byte == element
+        pzi_hi = reinterpret_cast<uint32_t*>(l2.zi_hi + blk_b);
+        pzi_lo = reinterpret_cast<uint32_t*>(l2.zi_lo + blk_b);
+      }
       // ---- phase A  (rows >= M_valid need no masking: their X rows are TMA zero fill, so a1 = relu(b1) stays
       //      finite, and their dZ2 is zero, which zeroes dZ1 and every gradient contribution)
       float2 z[4][CP / 2];
@@ -248,19 +326,40 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         if (ch * 32 < Hh) {
           const uint32_t col = (uint32_t)(acc * 256 + half * Hh + ch * 32);
           float v[32];                                             // [rows g, g+8 | rows g+16, g+24][4 col blocks][2 rows][2 cols]
-          tc_ld_16x256b_x4(tmem_base + lane_addr + col, v);
-          tc_ld_16x256b_x4(tmem_base + lane_addr + (16u << 16) + col, v + 16);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (I8) {
+            // exact int32 sums: hh (|.| <= 127^2 K < 2^24 for K <= 1040: exact in fp32) + cross / 254
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t rh[16], rc[16];
+              tc_ld_16x256b_x4_raw(tmem_base + lane_addr + ((uint32_t)(16 * hf) << 16) + col, rh);
+              tc_ld_16x256b_x4_raw(tmem_base + lane_addr + ((uint32_t)(16 * hf) << 16) + 256u + col, rc);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                v[16 * hf + j] = fmaf((float)(int)rc[j], 1.0f / 254.0f, (float)(int)rh[j]);
+            }
+          } else {
+            tc_ld_16x256b_x4(tmem_base + lane_addr + col, v);
+            tc_ld_16x256b_x4(tmem_base + lane_addr + (16u << 16) + col, v + 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
           uint32_t m = 0u;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
             const float2 bb = *reinterpret_cast<const float2*>(bsb + ch * 32 + 8 * kb);
+            float2 cc = make_float2(0.f, 0.f);
+            if (I8) cc = *reinterpret_cast<const float2*>(cwb + ch * 32 + 8 * kb);
             float a[4][2];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const float* vv = v + (r >> 1) * 16 + kb * 4 + (r & 1) * 2;
-              a[r][0] = fmaxf(vv[0] + bb.x, 0.f);
-              a[r][1] = fmaxf(vv[1] + bb.y, 0.f);
+              if (I8) {
+                a[r][0] = fmaxf(fmaf(vv[0], sxr[r] * cc.x, bb.x), 0.f);
+                a[r][1] = fmaxf(fmaf(vv[1], sxr[r] * cc.y, bb.y), 0.f);
+              } else {
+                a[r][0] = fmaxf(vv[0] + bb.x, 0.f);
+                a[r][1] = fmaxf(vv[1] + bb.y, 0.f);
+              }
               if (!FWD) {
                 m |= (a[r][0] > 0.f ? 1u : 0u) << (kb * 8 + r * 2);
                 m |= (a[r][1] > 0.f ? 1u : 0u) << (kb * 8 + r * 2 + 1);
@@ -299,9 +398,9 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader_relaxed(&tmem_empty[acc]);
-      // next item's constants fly while this item's reductions and phase B run; buffer [acc ^ 1] was last read in
+      // next item's constants fly while this item's reductions and phase B run; buffer [cbuf ^ 1] was last read in
       // the previous item, which every epilogue thread has left (they all passed this item's bar.sync 1)
-      if (item + n_clusters < p.total_items) fetch_consts(item + n_clusters, acc ^ 1);
+      if (item + n_clusters < p.total_items) fetch_consts(item + n_clusters, cbuf ^ 1);
       // ---- partial logits: quad reduce-scatter (fixed order), lane t keeps row r_own
       float zo[CP];
       {
@@ -349,7 +448,6 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             for (int c = 0; c < CP; ++c) if (c < C) o[c] = act_apply(zf[c], l2.out_act);
           }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       float loss_r = 0.f;
@@ -412,17 +510,26 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               float d[4];
 #pragma unroll
               for (int r = 0; r < 4; ++r) d[r] = ((m >> (kb * 8 + r * 2 + i)) & 1u) ? s[r].x + s[r].y : 0.f;
-              uint32_t hw0, lw0, hw1, lw1;
-              split_pair(d[0], d[1], hw0, lw0);
-              split_pair(d[2], d[3], hw1, lw1);
               const int w_off = (ch * 32 + 8 * kb + i) * 32;
-              __stcs(pz_hi + w_off, make_uint2(hw0, hw1));
-              __stcs(pz_lo + w_off, make_uint2(lw0, lw1));
+              if (I8 == 2) {
+                const float zqv = zqb[ch * 32 + 8 * kb + i];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) d[r] *= zqv;
+                uint32_t hw, lw;
+                slice4_i8(d, hw, lw);
+                __stcs(pzi_hi + w_off, hw);                      // (unit, 4 adjacent rows): 32 words per 128-byte block row
+                __stcs(pzi_lo + w_off, lw);
+              } else {
+                uint32_t hw0, lw0, hw1, lw1;
+                split_pair(d[0], d[1], hw0, lw0);
+                split_pair(d[2], d[3], hw1, lw1);
+                __stcs(pz_hi + w_off, make_uint2(hw0, hw1));
+                __stcs(pz_lo + w_off, make_uint2(lw0, lw1));
+              }
             }
           }
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();

@@ -100,6 +100,11 @@ struct Layer2Params {
   float* b2_partial;           // [Bc][n_groups][16]
   int n_groups, n_tiles;
   float* fwd_out;              // fused forward-only mode: [Bc][N][C] outputs (softmax / output activation applied)
+  // int8-slice operands of the fused kernel (tc_fused.cuh, I8 != 0; tc_i8.cuh)
+  const float* sx;             // [N] per-row scale of the forward X slices (rows of the centred data)
+  const float* cw;             // [Bc][H] s_w / 127^2: column scale of the W1^T slices times the slice unit
+  const float* zq;             // [Bc][H] 127 / s_z: quantisation factor of the dZ1^T slices (I8 == 2)
+  int8_t* zi_hi; int8_t* zi_lo;   // dZ1^T int8 slices, blocked [chain][tile][H][128]
 };
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));

@@ -16,7 +16,7 @@
 // The kernels live in tc_ptx.cuh (PTX helpers), tc_gemm.cuh, tc_layer2.cuh and tc_fused.cuh.
 #include <cstdlib>
 #include <cstring>
-#include "tc_fused.cuh"
+#include "tc_i8.cuh"
 #include <algorithm>
 
 namespace pyb {
@@ -66,6 +66,33 @@ static CUtensorMap make_map(const void* base, int64_t k, int64_t rows, int64_t l
   return m;
 }
 
+// 8-bit tensors (int8 slices): 2-D [rows][kbytes] with box [64, box_rows]; row-tile-blocked 3-D [blocks][rows_per_block][128]
+static CUtensorMap make_map_u8p(const void* base, int64_t kbytes, int64_t rows, int64_t pitch, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  PYB_REQUIRE(pitch % 16 == 0, PYB_ERR_INVALID, "tensor map pitch must be a multiple of 16 bytes");
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PYB_REQUIRE(r == CUDA_SUCCESS, PYB_ERR_CUDA, "cuTensorMapEncodeTiled (8-bit) failed");
+  return m;
+}
+static CUtensorMap make_map_blocked_u8(const void* base, int64_t blocks, int rows_per_block, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {128, (cuuint64_t)rows_per_block, (cuuint64_t)blocks};
+  cuuint64_t strides[2] = {128, (cuuint64_t)rows_per_block * 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PYB_REQUIRE(r == CUDA_SUCCESS, PYB_ERR_CUDA, "cuTensorMapEncodeTiled (8-bit, blocked) failed");
+  return m;
+}
+
 struct TcData {   // split bf16 operands derived from one [N, D] fp32 matrix resident in HBM
   bool ready = false;
   int64_t N = 0, Npad = 0;
@@ -74,6 +101,13 @@ struct TcData {   // split bf16 operands derived from one [N, D] fp32 matrix res
   DevBuf<__nv_bfloat16> xtq_hi, xtq_lo;                 // [D+1][Npad] with the fused epilogue's row order (fused_row_pos)
   CUtensorMap mX_hi, mX_lo, mXT_hi, mXT_lo, mXTp_hi, mXTp_lo;   // mXTp: half-tile boxes for the hidden-major pair GEMM
   CUtensorMap mXTq_hi, mXTq_lo, mXTqp_hi, mXTqp_lo;     // the same two views of xtq
+  // int8 slices (tc_i8.cuh): centred rows [N][Dk] with per-row scales for the forward GEMM, [X^T;1] [D+1][Npad] in the
+  // fused row order with per-feature scales for the dW1 GEMM
+  int i8 = 0, Dk = 0;                                    // 0: none, 1: forward operand, 2: + backward operand
+  DevBuf<int8_t> xs_hi, xs_lo, xts_hi, xts_lo;
+  DevBuf<float> sx, col_mean, col_absmax, sf, stat_max;
+  DevBuf<double> stat_sum;
+  CUtensorMap mXs_hi, mXs_lo, mXTs_hi, mXTs_lo;
 };
 struct TcState {
   TcData train, aux;                                    // resident training set / minibatch or test inputs
@@ -87,6 +121,11 @@ struct TcState {
   DevBuf<float> kpart, gpart;                           // split-K partial sums (gradient GEMMs / exported GEMM)
   DevBuf<double> loss_partial;
   CUtensorMap mW_hi, mW_lo, mWp_hi, mWp_lo, mZ_hi, mZ_lo, mZa_hi, mZa_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
+  // int8 slices: W1^T [chains*H][Dk], dZ1^T blocked [block][H][128], per (chain, unit) factors (k_pack_w1_i8)
+  int64_t cap_chains_i8 = 0, cap_blocks_i8 = 0;
+  DevBuf<int8_t> ws_hi, ws_lo, zi_hi, zi_lo;
+  DevBuf<float> cw, b1c, zq, zd;
+  CUtensorMap mWs_hi, mWs_lo, mZi_hi, mZi_lo;
 };
 static TcState* tc_state(pyb_handle* h) {
   if (!h->tc) h->tc = new TcState();
@@ -179,9 +218,22 @@ static void launch_gemm_tc(pyb_handle* h, const CUtensorMap& a_hi, const CUtenso
 }
 
 
+template <int CP, bool FWD, int I8>
+static void launch_fused_i8(pyb_handle* h, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                            const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p, const Layer2Params& l2) {
+  PYB_CUDA(cudaFuncSetAttribute(tc_g1_layer2_fused<CP, FWD, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TfCfg<CP>::SMEM_I8));
+  tc_g1_layer2_fused<CP, FWD, I8><<<grid, TF_THREADS, TfCfg<CP>::SMEM_I8, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p, l2);
+}
 template <int CP>
 static void launch_fused_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
-                              const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p, const Layer2Params& l2) {
+                              const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p, const Layer2Params& l2,
+                              int i8 = 0) {
+  if (i8) {
+    if (l2.fwd_out) launch_fused_i8<CP, true, 1>(h, grid, a_hi, a_lo, b_hi, b_lo, p, l2);
+    else if (i8 >= 2) launch_fused_i8<CP, false, 2>(h, grid, a_hi, a_lo, b_hi, b_lo, p, l2);
+    else launch_fused_i8<CP, false, 1>(h, grid, a_hi, a_lo, b_hi, b_lo, p, l2);
+    return;
+  }
   if (l2.fwd_out) {
     PYB_CUDA(cudaFuncSetAttribute(tc_g1_layer2_fused<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TfCfg<CP>::SMEM));
     tc_g1_layer2_fused<CP, true><<<grid, TF_THREADS, TfCfg<CP>::SMEM, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p, l2);
@@ -193,6 +245,51 @@ static void launch_fused_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, 
 // fused G1 + layer 2 applies to: relu hidden layer of 128 or 256 units, CTA pairs enabled
 static bool fused_ok(const pyb_handle* h, int H, int act1) {
   return h->opt_tc_pair && h->opt_tc_fuse && act1 == PYB_ACT_RELU && (H == 128 || H == 256);
+}
+
+// int8-slice mode of an evaluation: 0 bf16x3, 1 forward GEMM on slices, 2 forward and dW1 GEMMs on slices.
+// The dW1 operand dZ1 needs an a-priori bound of its magnitude, which exists for the softmax cross-entropy only, and the
+// kernel takes one 256-unit chain per CTA pair.
+static int i8_mode(const pyb_handle* h, bool backward) {
+  const Model& m = h->model;
+  if (h->opt_tc_i8 <= 0 || !fused_ok(h, m.layer[0].fan_out, m.layer[0].act) || m.layer[1].fan_out > L2_CMAX) return 0;
+  if (m.layer[0].fan_in > 32768) return 0;                       // int32 range of the hi*lo + lo*hi accumulator
+  if (!backward) return 1;
+  const bool ce = h->loss_kind == PYB_LOSS_SPARSE_CE && m.layer[1].act == PYB_ACT_SOFTMAX;
+  return (h->opt_tc_i8 >= 2 && ce && m.layer[0].fan_out == 256) ? 2 : 1;
+}
+
+static void tc_prepare_data_i8(pyb_handle* h, TcData& d, const float* X, int64_t N, int mode) {
+  const int D = d.D;
+  const int64_t Npad = d.Npad;
+  d.Dk = (D + 15) / 16 * 16;
+  d.col_mean.alloc(D); d.col_absmax.alloc(D); d.sx.alloc(N); d.sf.alloc(D + 1);
+  d.xs_hi.alloc(N * d.Dk); d.xs_lo.alloc(N * d.Dk);
+  d.stat_sum.alloc((size_t)I8_STAT_CHUNKS * D); d.stat_max.alloc((size_t)I8_STAT_CHUNKS * D);
+  k_col_stats<<<dim3((D + 31) / 32, I8_STAT_CHUNKS), dim3(32, 32), 0, h->stream>>>(X, N, D, d.stat_sum.p, d.stat_max.p);
+  k_col_stats_final<<<(D + 255) / 256, 256, 0, h->stream>>>(d.stat_sum.p, d.stat_max.p, I8_STAT_CHUNKS, N, D, d.col_mean.p,
+                                                           d.col_absmax.p);
+  count_launch(h);
+  const int wpb = 8;
+  k_slice_x_rows_i8<<<(unsigned)std::min<int64_t>((N + wpb - 1) / wpb, 8 * (int64_t)h->sm_count), wpb * 32, 0, h->stream>>>(
+      X, N, D, d.col_mean.p, d.xs_hi.p, d.xs_lo.p, d.sx.p, d.Dk);
+  count_launch(h, 2);
+  d.mXs_hi = make_map_u8p(d.xs_hi.p, d.Dk, N, d.Dk, 128);
+  d.mXs_lo = make_map_u8p(d.xs_lo.p, d.Dk, N, d.Dk, 128);
+  if (mode >= 2) {
+    d.xts_hi.alloc((int64_t)(D + 1) * Npad); d.xts_lo.alloc((int64_t)(D + 1) * Npad);
+    PYB_CUDA(cudaMemsetAsync(d.xts_hi.p, 0, (size_t)(D + 1) * Npad, h->stream));
+    PYB_CUDA(cudaMemsetAsync(d.xts_lo.p, 0, (size_t)(D + 1) * Npad, h->stream));
+    dim3 g2((D + 31) / 32, (unsigned)((N + 31) / 32), 1), blk(32, 8);
+    k_slice_xt_i8<<<g2, blk, 0, h->stream>>>(X, N, D, d.col_absmax.p, d.xts_hi.p, d.xts_lo.p, Npad);
+    k_xt_i8_tail<<<(unsigned)((std::max<int64_t>(N, D + 1) + 255) / 256), 256, 0, h->stream>>>(
+        d.xts_hi.p + (int64_t)D * Npad, N, d.col_absmax.p, d.sf.p, D);
+    count_launch(h, 2);
+    const int n_t = (D + 1 + 255) / 256, Ht = (((D + 1 + n_t - 1) / n_t) + 15) / 16 * 16;
+    d.mXTs_hi = make_map_u8p(d.xts_hi.p, Npad, D + 1, Npad, Ht / 2);
+    d.mXTs_lo = make_map_u8p(d.xts_lo.p, Npad, D + 1, Npad, Ht / 2);
+  }
+  d.i8 = mode;
 }
 
 static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N, bool need_xt) {
@@ -232,6 +329,9 @@ static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N,
       d.mXTqp_lo = make_map(d.xtq_lo.p, Npad, D + 1, Npad, Ht / 2);
     }
   }
+  d.i8 = 0;
+  const int mode = i8_mode(h, need_xt);
+  if (mode) tc_prepare_data_i8(h, d, X, N, mode);
   d.ready = true;
 }
 
@@ -274,18 +374,43 @@ static int64_t tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S, int64_t Np
     st->mZ2_hi = make_map_blocked(st->z2_hi.p, cb, L2_CMAX, L2_CMAX);
     st->mZ2_lo = make_map_blocked(st->z2_lo.p, cb, L2_CMAX, L2_CMAX);
   }
+  const int mode = i8_mode(h, backward);
+  if (mode && (bc > st->cap_chains_i8 || (mode >= 2 && need_blocks > st->cap_blocks_i8))) {
+    PYB_CUDA(cudaStreamSynchronize(h->stream));
+    st->cap_chains_i8 = std::max(st->cap_chains_i8, bc);
+    const int64_t cc = st->cap_chains_i8, Dk = (D + 15) / 16 * 16;
+    st->ws_hi.alloc(cc * H * Dk); st->ws_lo.alloc(cc * H * Dk);
+    st->cw.alloc(cc * H); st->b1c.alloc(cc * H); st->zq.alloc(cc * H); st->zd.alloc(cc * H);
+    st->mWs_hi = make_map_u8p(st->ws_hi.p, Dk, cc * H, Dk, H / 2);
+    st->mWs_lo = make_map_u8p(st->ws_lo.p, Dk, cc * H, Dk, H / 2);
+    if (mode >= 2) {
+      st->cap_blocks_i8 = std::max(st->cap_blocks_i8, need_blocks);
+      const int64_t cb = st->cap_blocks_i8;
+      st->zi_hi.alloc(cb * H * 128); st->zi_lo.alloc(cb * H * 128);
+      st->mZi_hi = make_map_blocked_u8(st->zi_hi.p, cb, H, 128);
+      st->mZi_lo = make_map_blocked_u8(st->zi_lo.p, cb, H, 128);
+    }
+  }
   return bc;
 }
 
 static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* th, int nb,
-                           const Layer2Params* fused = nullptr) {
+                           const Layer2Params* fused = nullptr, int i8 = 0) {
   const Model& m = h->model;
   const LayerDesc& L1 = m.layer[0];
   const int D = st->D, H = st->H;
   const int64_t N = d.N, Npad = d.Npad, P = m.P;
+  if (i8) {
+    // W1 [D,H] per chain -> W1^T int8 slices [H, Dk] + the per (chain, unit) factors of the scheme
+    const float invN = fused->fwd_out ? 1.0f : fused->scale / (float)fused->N;
+    k_pack_w1_i8<<<dim3((H + 31) / 32, nb), dim3(32, 8), 0, h->stream>>>(
+        th, P, L1.w_off, L1.b_off, m.layer[1].w_off, D, H, m.layer[1].fan_out, d.col_mean.p, invN, st->ws_hi.p, st->ws_lo.p,
+        d.Dk, st->cw.p, st->b1c.p, st->zq.p, st->zd.p);
+  } else {
   // W1 [D,H] per chain -> W1^T hi/lo [H, D]
   dim3 g((H + 31) / 32, (D + 31) / 32, nb), blk(32, 8);
   k_split_transpose<<<g, blk, 0, h->stream>>>(th + L1.w_off, P, D, H, H, st->w_hi.p, st->w_lo.p, (int64_t)H * D, D);
+  }
   count_launch(h);
   // G1: A1^T = act(X W1 + b1)^T, split bf16 (all Npad/128 row tiles: rows >= N are written as zeros)
   TcGemmParams p = {};
@@ -299,11 +424,18 @@ static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* t
     // G1 with layer 2 (+ loss, dZ2, dZ1) in its epilogue
     const int grid = std::min(2 * p.total_items, (h->sm_count / 2) * 2);
     const int C = fused->C;
+    Layer2Params f2 = *fused;
+    const CUtensorMap &a_hi = i8 ? d.mXs_hi : d.mX_hi, &a_lo = i8 ? d.mXs_lo : d.mX_lo;
+    const CUtensorMap &b_hi = i8 ? st->mWs_hi : st->mWp_hi, &b_lo = i8 ? st->mWs_lo : st->mWp_lo;
+    if (i8) {
+      p.bias = st->b1c.p; p.bias_stride = H;                      // b1 + mu^T W1: the slices hold the centred data
+      f2.sx = d.sx.p; f2.cw = st->cw.p; f2.zq = st->zq.p; f2.zi_hi = st->zi_hi.p; f2.zi_lo = st->zi_lo.p;
+    }
     prof_begin(h);
-    if (C <= 4) launch_fused_inst<4>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
-    else if (C <= 8) launch_fused_inst<8>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
-    else if (C <= 12) launch_fused_inst<12>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
-    else launch_fused_inst<16>(h, grid, d.mX_hi, d.mX_lo, st->mWp_hi, st->mWp_lo, p, *fused);
+    if (C <= 4) launch_fused_inst<4>(h, grid, a_hi, a_lo, b_hi, b_lo, p, f2, i8);
+    else if (C <= 8) launch_fused_inst<8>(h, grid, a_hi, a_lo, b_hi, b_lo, p, f2, i8);
+    else if (C <= 12) launch_fused_inst<12>(h, grid, a_hi, a_lo, b_hi, b_lo, p, f2, i8);
+    else launch_fused_inst<16>(h, grid, a_hi, a_lo, b_hi, b_lo, p, f2, i8);
     prof_end(h, 2.0 * N * (D * (double)H + (fused->fwd_out ? 1.0 : 3.0) * H * C) * nb);
     count_launch(h);
     return;
@@ -321,6 +453,7 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
   const int64_t N = d.N, Npad = d.Npad, P = m.P;
   const int n_tiles = (int)(Npad / L2_ROWS);
   const bool fused = fused_ok(h, H, L1.act) && C <= L2_CMAX;
+  const int i8 = std::min(i8_mode(h, true), d.i8);
   // fused: one partial per (128-row tile, lane quadrant); unfused: one per k_layer2 block
   const int n_groups = fused ? (int)(Npad / 128) * 4
                              : std::min(n_tiles, std::max(1, (int)((8 * (int64_t)h->sm_count + Bc - 1) / Bc)));
@@ -341,7 +474,7 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
       p.loss_partial = st->loss_partial.p; p.b2_partial = st->b2_partial.p; p.n_groups = n_groups;
       p.n_tiles = n_tiles;
       if (fused) {
-        tc_pack_and_g1(h, st, d, th, nb, &p);
+        tc_pack_and_g1(h, st, d, th, nb, &p, i8);
       } else {
         tc_pack_and_g1(h, st, d, th, nb);
         dim3 g(n_groups, nb);
@@ -358,7 +491,7 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
     const int nk_rows = (int)(Npad / TC_BK);
     const int splits = (nk_rows + TC_SPLIT_CHUNKS - 1) / TC_SPLIT_CHUNKS;
     const int64_t cnt1 = (int64_t)(D + 1) * H, cnt2 = (int64_t)H * C;
-    if (splits > 1) st->kpart.alloc((size_t)splits * nb * std::max(cnt1, cnt2));
+    if (splits > 1 || i8 >= 2) st->kpart.alloc((size_t)(splits + 1) * nb * std::max(cnt1, cnt2));
     // G3: dW2[h][c] = sum_r a1[r][h] dZ2[r][c]   (A = A1^T per chain, B = dZ2^T per chain, N = 16)
     {
       TcGemmParams p = {};
@@ -383,7 +516,34 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
     // G2: [dW1; db1] = [X^T; 1] dZ1
     // two 128-unit chains per CTA pair: only the dual kernel knows that mode, and it needs at least two feature tiles
     const bool chain_pairs = H == 128 && h->opt_tc_dual && h->opt_tc_h128_pairs && (D + 1 + 255) / 256 > 1;
-    if ((H == 256 || chain_pairs) && h->opt_tc_pair) {
+    int splits_red = splits;                                      // partial sums the reduction below has to add up
+    if (i8 >= 2) {
+      // hidden-major on int8 slices: one feature tile per item, exact int32 accumulation (tc_i8.cuh)
+      const int n_t = (D + 1 + 255) / 256;
+      const int Ht = (((D + 1 + n_t - 1) / n_t) + 15) / 16 * 16;
+      const int nk64 = (int)(Npad / 64), cps = TC_SPLIT_CHUNKS / 2;   // 128 stages of 64 rows = the same 8192-row segments
+      const int sp = (nk64 + cps - 1) / cps;
+      splits_red = sp;
+      TcGemmParams p = {};
+      p.K = (int)Npad; p.n_mtiles = 2; p.n_pairs = 1; p.n_batch = nb; p.H = Ht; p.n_chains = nb;
+      p.a_blocked = 1; p.k_tiles = (int)(Npad / 128); p.a_box_rows = 128;
+      p.n_btiles = n_t; p.b_row0 = 0; p.transpose_out = 1; p.n_cols_total = D + 1;
+      p.epi = EPI_STORE; p.out_ld = H; p.M_valid = H; p.N_valid = Ht;
+      p.k_splits = sp; p.chunks_per_split = cps;
+      if (sp > 1) {
+        p.split_stride = nb * cnt1; p.out = st->kpart.p; p.out_stride = cnt1;
+      } else {
+        p.split_stride = 0; p.out = gr; p.out_stride = P;
+      }
+      p.total_items = nb * sp * n_t;
+      const int grid = std::min(2 * p.total_items, (h->sm_count / 2) * 2);
+      prof_begin(h);
+      PYB_CUDA(cudaFuncSetAttribute(tc_gemm_pair_dw1_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, TI_SMEM_BYTES));
+      tc_gemm_pair_dw1_i8<<<grid, TP_THREADS, TI_SMEM_BYTES, h->stream>>>(st->mZi_hi, st->mZi_lo, d.mXTs_hi, d.mXTs_lo, p,
+                                                                         st->zd.p, d.sf.p);
+      prof_end(h, 2.0 * N * (double)(D + 1) * H * nb);
+      count_launch(h);
+    } else if ((H == 256 || chain_pairs) && h->opt_tc_pair) {
       // hidden-major on the CTA-pair kernel: D[h, f] = sum_r dZ1^T[h, r] [X^T;1][f, r].  M = 256 hidden units is
       // exactly one CTA pair (no M padding), the D+1 feature rows are the N dimension in tiles of 256 plus one
       // narrow remainder tile, the accumulators are double-buffered so the partial-sum stores overlap the MMAs
@@ -421,9 +581,9 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
       launch_gemm_tc(h, fused ? d.mXTq_hi : d.mXT_hi, fused ? d.mXTq_lo : d.mXT_lo, st->mZ_hi, st->mZ_lo, p,
                      2.0 * N * (double)(D + 1) * H * nb);
     }
-    if (splits > 1) {
+    if (splits_red > 1) {
       dim3 rg((unsigned)std::min<int64_t>((cnt1 + 255) / 256, 256), nb);
-      k_reduce_ksplits<<<rg, 256, 0, h->stream>>>(st->kpart.p, splits, nb * cnt1, cnt1, cnt1, gr, P);
+      k_reduce_ksplits<<<rg, 256, 0, h->stream>>>(st->kpart.p, splits_red, nb * cnt1, cnt1, cnt1, gr, P);
       count_launch(h);
     }
   }
@@ -432,7 +592,7 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
 
 void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
   TcState* st = tc_state(h);
-  if (!st->train.ready) tc_prepare_data(h, st->train, h->X.p, h->N, true);
+  if (!st->train.ready || st->train.i8 != i8_mode(h, true)) tc_prepare_data(h, st->train, h->X.p, h->N, true);
   tc_eval_on(h, st, st->train, h->y_i.p, h->y_f.p, theta, S, scale, loss_out, grad_out);
 }
 
@@ -463,7 +623,7 @@ void tc_forward(pyb_handle* h, const float* theta, int64_t S, const float* x, in
       f.theta = th; f.P = P; f.w2_off = L2.w_off; f.b2_off = L2.b_off;
       f.H = st->H; f.C = st->C; f.N = (int)N; f.out_act = L2.act; f.scale = 1.0f;
       f.fwd_out = out + b0 * N * st->C;
-      tc_pack_and_g1(h, st, d, th, nb, &f);
+      tc_pack_and_g1(h, st, d, th, nb, &f, std::min(i8_mode(h, false), d.i8));
       continue;
     }
     tc_pack_and_g1(h, st, d, th, nb);

@@ -108,6 +108,8 @@ class BayesianModel:
         """One flat [P] weight vector assembled from every interval's distribution
         (``_sample_weights`` BayesianModel.py:63-77)."""
         w = np.zeros(self._spec.n_params, np.float32)
+        for sel in {id(s): s for s in (getattr(d, "selector", None) for d in self._distributions) if s is not None}.values():
+            sel.new_draw()                    # linked per-layer mixtures: one chain for the whole weight vector
         for (start, end), dist in zip(self._layers_dtbn_intervals, self._distributions):
             lo, hi = self._spec.layer_param_range(start, end)
             v = to_numpy(dist.sample(), np.float32).reshape(-1)

@@ -4,6 +4,7 @@ exhausted — SGLD.py:48-52, SWAG.py:46-50), the engine, and the per-layer poste
 import numpy as np
 
 from ..distributions import Mixture
+from ..distributions.Mixture import ChainSelector
 from ..engine import Engine
 from ..keras_json import parse_model_json
 from ..nn import BayesianModel
@@ -49,12 +50,16 @@ class StochasticGradientChains(Optimizer):
     def _layer_posteriors(self, make):
         """BayesianModel with one distribution per weight-carrying layer, applied on [idx, idx] like the reference
         (SGLD.py:147-165, SWAG.py:119-139).  ``make(lo, hi, chain)`` builds the distribution of one chain over the
-        flat range of one layer; several chains become an equal-weight Mixture."""
+        flat range of one layer; several chains become an equal-weight Mixture whose per-layer instances share ONE
+        chain selector, so that a drawn network takes every layer from the same chain (chains are not exchangeable
+        layer by layer)."""
         model = BayesianModel(self._model_config, device=int(self._hp("device", 0)))
+        selector = ChainSelector(self._n_chains) if self._n_chains > 1 else None
         for d in self._spec.dense:
             lo, hi = self._spec.layer_param_range(d.keras_index, d.keras_index)
             comps = [make(lo, hi, s) for s in range(self._n_chains)]
-            model.apply_distribution(comps[0] if len(comps) == 1 else Mixture(comps), d.keras_index, d.keras_index)
+            model.apply_distribution(comps[0] if len(comps) == 1 else Mixture(comps, selector=selector), d.keras_index,
+                                     d.keras_index)
         return model
 
     @property

@@ -1,0 +1,125 @@
+"""GPU tests of the int8-slice operand scheme (csrc/tc_i8.cuh; `tc_i8` option): the forward GEMM (mode 1) and the dW1 GEMM
+(mode 2) on `tcgen05.mma kind::i8` with exact int32 accumulation, against the float64 oracle at the 1e-4 parity budget
+and against the bf16x3 kernels on the same inputs."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from test_gpu_tensor import engine, problem
+
+pytestmark = pytest.mark.gpu
+
+from bayesian_inference_for_nn_b200 import _lib  # noqa: E402
+
+# (D, H, C, N, S, loss): relu hidden layer of 128 / 256 units (the fused kernel); mode 2 needs H = 256 and the
+# cross-entropy (else the dW1 GEMM stays on bf16x3, which the test then exercises together with the int8 forward GEMM)
+CASES = [(784, 256, 10, 512, 3, "ce"), (784, 256, 10, 128, 1, "ce"), (96, 256, 7, 1000, 2, "ce"), (784, 256, 12, 257, 1, "ce"),
+         (784, 128, 10, 300, 2, "ce"), (64, 128, 2, 129, 3, "ce"), (128, 256, 3, 385, 5, "mse"), (784, 256, 10, 9000, 2, "ce"),
+         (200, 256, 4, 640, 150, "ce")]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("D,H,Cc,N,S,loss", CASES)
+def test_int8_slices_logprob_and_gradient(oracle, D, H, Cc, N, S, loss, mode):
+    O = oracle
+    spec, prob, q, out_act, _ = problem(O, D, H, Cc, N, S, seed=D + H + N, act="relu", loss=loss)
+    U64, loss64, g64 = O.potential(prob, q, np.float64)
+    eng = engine(D, H, Cc, "relu", out_act)
+    eng.set_option("tc_i8", mode)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.set_option("path", _lib.PATH_TENSOR)
+    U, ls, g = eng.hmc_eval(q)
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    errs = [rel_err(g[s], g64[s]) for s in range(S)]
+    print("int8 slices mode %d, %d-%d-%d N=%d S=%d %s: gradient rel err max %.2e, loss rel err max %.2e"
+          % (mode, D, H, Cc, N, S, loss, max(errs), np.max(np.abs(ls - loss64) / np.abs(loss64))))
+    np.testing.assert_allclose(U, U64, rtol=1e-4)
+    np.testing.assert_allclose(ls, loss64, rtol=1e-4)
+    assert max(errs) < 1e-4, errs
+    # against bf16x3 on the same device
+    eng.set_option("tc_i8", 0)
+    U0, _, g0 = eng.hmc_eval(q)
+    np.testing.assert_allclose(U, U0, rtol=1e-4)
+    assert max(rel_err(g[s], g0[s]) for s in range(S)) < 1e-4
+    # repeatable bit for bit, and chain batching changes nothing
+    eng.set_option("tc_i8", mode)
+    eng.set_option("chain_batch", 1)
+    U1, _, g1 = eng.hmc_eval(q)
+    np.testing.assert_array_equal(U, U1)
+    np.testing.assert_array_equal(g, g1)
+
+
+def test_int8_slices_zero_weights_and_unnormalised_data(oracle):
+    """All chains of the reference start at W = 0 (HMC.py:69-72): every scale of the scheme degenerates there (zero W1
+    columns, constant W2 rows); and data with very different feature ranges, negative values and constant columns (the
+    forward operand is scaled per data row after centring, the backward operand per feature)."""
+    from test_gpu_tensor import move_off_relu_kinks
+    O = oracle
+    D, H, Cc, N, S = 784, 256, 10, 400, 3
+    spec, prob, q, out_act, rng = problem(O, D, H, Cc, N, S, seed=5)
+    X = ((prob.X - 0.3) * (10.0 ** rng.uniform(-2, 2, D))).astype(np.float32)
+    X[:, 7] = 0.0
+    X[:, 9] = 2.5
+    q = move_off_relu_kinks((q * 0.02).astype(np.float32), X, D, H)
+    q[0] = 0.0
+    prob = O.Problem(spec, X, prob.y, prob.loss_kind, prob.mu, prob.sigma)
+    U64, loss64, g64 = O.potential(prob, q, np.float64)
+    eng = engine(D, H, Cc, "relu", out_act)
+    eng.set_option("tc_i8", 2)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.set_option("path", _lib.PATH_TENSOR)
+    U, ls, g = eng.hmc_eval(q)
+    eng.set_option("tc_i8", 0)
+    _, _, g0 = eng.hmc_eval(q)
+    print("unnormalised data: int8 vs float64 %s, bf16x3 vs float64 %s" % (["%.1e" % rel_err(g[s], g64[s]) for s in range(S)],
+                                                                        ["%.1e" % rel_err(g0[s], g64[s]) for s in range(S)]))
+    np.testing.assert_allclose(ls, loss64, rtol=1e-4)
+    for s in range(S):
+        assert rel_err(g[s], g64[s]) < 1e-4
+
+
+def test_int8_slices_hmc_iteration_matches_oracle(oracle):
+    O = oracle
+    D, H, Cc, N, S, L, eps = 784, 256, 10, 640, 3, 4, 1e-3
+    spec, prob, q, out_act, rng = problem(O, D, H, Cc, N, S, seed=11)
+    p = rng.standard_normal((S, spec.n_params)).astype(np.float32)
+    u = np.float32([0.0, 0.999, 0.5])
+    want = O.hmc_iteration(prob, q, p, u, eps, 1.0, L, False, O.HMC_REFERENCE, np.float64)
+    eng = engine(D, H, Cc)
+    eng.set_option("tc_i8", 2)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.hmc_init(S, eps, 1.0, L, _lib.HMC_REFERENCE, q0=q)
+    eng.hmc_inject(p=p, u=u)
+    eng.hmc_run(1, burning=False, sampling=True)
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    last = eng.hmc_last()
+    for k in ("U0", "K0", "U1", "K1"):
+        np.testing.assert_allclose(last[k], want[k], rtol=1e-4, err_msg=k)
+    lu = np.log(np.maximum(u.astype(np.float64), 1e-300))
+    decisive = np.abs(want["log_alpha"] - lu) > 1e-5 * np.maximum(1.0, np.abs(want["U0"]))
+    np.testing.assert_array_equal(last["accept"][decisive], want["accept"][decisive])
+    qd, pd = eng.hmc_state()
+    for s in range(S):
+        if last["accept"][s] == want["accept"][s]:
+            assert rel_err(qd[s], want["q"][s]) < 1e-3
+            assert rel_err(pd[s], want["pL"][s]) < 1e-3
+
+
+def test_int8_slices_predictive(oracle):
+    O = oracle
+    D, H, Cc, Nt, n = 784, 256, 10, 300, 5
+    rng = np.random.default_rng(21)
+    spec = O.MLPSpec(D, [H, Cc], ["relu", "softmax"])
+    W = (rng.standard_normal((n, spec.n_params)) * 0.05).astype(np.float32)
+    x = rng.random((Nt, D)).astype(np.float32)
+    freq = np.float32([1, 2, 1, 3, 1])
+    mean64, var64 = O.predictive(spec, W, x, freq, np.float64)
+    eng = engine(D, H, Cc)
+    eng.set_option("tc_i8", 1)
+    mean, var, allo = eng.predict(W, x, weights=freq, want_all=True)
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    np.testing.assert_allclose(mean, mean64, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(allo, O.forward(spec, W, x, np.float64), rtol=1e-4, atol=1e-6)

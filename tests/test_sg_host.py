@@ -143,6 +143,40 @@ def test_bayesian_model_store_load_with_layer_distributions(tmp_path):
     np.testing.assert_array_equal(bm2._draw_flat(), w)
 
 
+def test_multi_chain_posterior_draws_one_chain_for_every_layer(tmp_path):
+    """n_chains > 1: the per-layer mixtures share one chain selector, so a drawn network equals ONE chain's layers
+    (independent chains are not exchangeable layer by layer) — also after store / load."""
+    from bayesian_inference_for_nn_b200.distributions.Mixture import ChainSelector
+    js = keras_json.make_sequential_json(2, [3, 2], ["relu", "softmax"])
+    spec = keras_json.parse_model_json(js)
+    n_chains = 5
+    chains = np.arange(n_chains, dtype=np.float32)[:, None] + np.zeros((n_chains, spec.n_params), np.float32)
+    bm = BayesianModel(js)
+    sel = ChainSelector(n_chains, rng=np.random.default_rng(0))
+    for d in spec.dense:
+        lo, hi = spec.layer_param_range(d.keras_index, d.keras_index)
+        bm.apply_distribution(Mixture([Normal(chains[c, lo:hi], 0.0) for c in range(n_chains)], selector=sel),
+                              d.keras_index, d.keras_index)
+    seen = set()
+    for _ in range(60):
+        w = bm._draw_flat()
+        assert np.all(w == w[0]), w                  # every layer from the same chain
+        seen.add(int(w[0]))
+    assert seen == set(range(n_chains))
+    bm.store(str(tmp_path / "bm"))
+    bm2 = BayesianModel.load(str(tmp_path / "bm"))
+    for _ in range(30):
+        w = bm2._draw_flat()
+        assert np.all(w == w[0])
+    # unlinked mixtures keep drawing per layer
+    bm3 = BayesianModel(js)
+    for d in spec.dense:
+        lo, hi = spec.layer_param_range(d.keras_index, d.keras_index)
+        bm3.apply_distribution(Mixture([Normal(chains[c, lo:hi], 0.0) for c in range(n_chains)],
+                                       rng=np.random.default_rng(d.keras_index)), d.keras_index, d.keras_index)
+    assert any(not np.all((w := bm3._draw_flat()) == w[0]) for _ in range(30))
+
+
 def test_swag_requires_a_starting_model():
     from Pyesian.datasets import Dataset
     from Pyesian.optimizers import SWAG
