@@ -81,6 +81,8 @@ SIGNATURES = {
     "pyb_buffer_create": [_P, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)],
     "pyb_buffer_destroy": [_P, C.c_void_p],
     "pyb_gather_rows": [_P, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p],
+    "pyb_debug_tc_gemm": [_P, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
+    "pyb_debug_relu_mask": [_P, C.c_int64, C.c_void_p],
 }
 
 _lib = None

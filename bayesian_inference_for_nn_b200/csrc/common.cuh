@@ -63,6 +63,10 @@ struct DevBuf {
     n = count;
   }
   size_t bytes() const { return n * sizeof(T); }
+  void swap(DevBuf& o) {
+    T* tp = p; p = o.p; o.p = tp;
+    size_t tn = n; n = o.n; o.n = tn;
+  }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -264,6 +268,9 @@ struct pyb_handle {
   pyb::DevBuf<float> X, y_f;
   pyb::DevBuf<int32_t> y_i;
   bool have_data = false;
+  pyb::DevBuf<float> X_stage, yf_stage;   // incoming copy of a re-submitted dataset: compared on the device with the resident one
+  pyb::DevBuf<int32_t> yi_stage, flag;
+  int64_t dataset_uploads = 0, dataset_kept = 0;   // pyb_set_dataset calls / calls whose data equalled the resident copy
   // prior (per element) + derived
   pyb::DevBuf<float> mu, sigma, inv_var;
   bool have_prior = false;
@@ -279,7 +286,7 @@ struct pyb_handle {
   int opt_hmc_carry = 1;    // 1: loss and gradient at the current position are carried to the next HMC iteration
   int opt_predict_sharded = 0;   // 1: pyb_predict all-reduces its moment sums over the handle's communicator
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
-  int opt_tc_i8 = 0;     // operand split of the big GEMMs: 0 bf16x3, 1 int8 slices in the forward GEMM, 2 + in the dW1 GEMM (tc_i8.cuh)
+  int opt_tc_i8 = -1;    // operand split of the big GEMMs: 0 bf16x3, 1 int8 slices in the forward GEMM, 2 + in the dW1 GEMM, -1 auto (tc_i8.cuh)
   double opt_workspace_mb = 4096;
   int64_t opt_chain_batch = 0;
   int path_used = PYB_PATH_GENERIC;

@@ -52,18 +52,27 @@ __device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// two int8 slices of 4 values q[r] (already multiplied by 127 / scale): hi = rint(q), lo = rint((q - hi) * 254), one byte per
-// row, row 0 in the lowest byte
-__device__ __forceinline__ void slice4_i8(const float* q, uint32_t& hw, uint32_t& lw) {
-  hw = 0u; lw = 0u;
+// two int8 slices of 4 values d[r] * zq (|d * zq| <= 127 by the caller's bound): hi = rint(q), lo = rint((q - hi) * 254),
+// one byte per row, row 0 in the lowest byte.  Round-to-nearest through the float32 magic number 1.5 * 2^23: the low
+// mantissa byte of q + M is rint(q) in two's complement — four full-rate FP instructions per value instead of two
+// FRND + two F2I (quarter rate) and the clamps; q - hi comes out of one fused multiply-add, so it is exact.
+__device__ __forceinline__ void slice4_i8(const float* d, float zq, uint32_t& hw, uint32_t& lw) {
+  constexpr float M = 12582912.0f;
+  uint32_t hb[4], lb[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const float h = fminf(fmaxf(rintf(q[r]), -127.f), 127.f);
-    const float l = fminf(fmaxf(rintf((q[r] - h) * 254.0f), -127.f), 127.f);
-    hw |= ((uint32_t)__float2int_rn(h) & 0xffu) << (8 * r);
-    lw |= ((uint32_t)__float2int_rn(l) & 0xffu) << (8 * r);
+    const float t = fmaf(d[r], zq, M);                // M + rint(q)
+    const float h = t - M;                            // rint(q)
+    const float e = fmaf(d[r], zq, -h);               // q - rint(q), exact
+    const float u = fmaf(e, 254.0f, M);               // M + rint((q - hi) * 254)
+    hb[r] = __float_as_uint(t);
+    lb[r] = __float_as_uint(u);
   }
+  // byte 0 of each word -> one packed word
+  hw = __byte_perm(__byte_perm(hb[0], hb[1], 0x0040), __byte_perm(hb[2], hb[3], 0x0040), 0x5410);
+  lw = __byte_perm(__byte_perm(lb[0], lb[1], 0x0040), __byte_perm(lb[2], lb[3], 0x0040), 0x5410);
 }
+
 // 16 accumulator columns... 32 columns x rows {g, g+8} of the 16 TMEM lanes starting at the address's lane
 __device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -169,7 +178,7 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const int arow = p.a_row0 + (mp * 2 + (int)rank) * 128;
         const int brow = b * H + (int)rank * half_rows;
         for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          (I8 ? mbar_wait_sleep(&empty_bar[stage], phase ^ 1) : mbar_wait(&empty_bar[stage], phase ^ 1));
           uint8_t* st = stage_base + stage * TP_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);
           const int k0 = kc * KSTAGE;
@@ -192,11 +201,11 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       for (int item = cluster_id; item < p.total_items; item += n_clusters, ++it) {
         const int acc = I8 ? 0 : (it & 1);
         const uint32_t acc_phase = I8 ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        (I8 ? mbar_wait_sleep(&tmem_empty[acc], acc_phase ^ 1) : mbar_wait(&tmem_empty[acc], acc_phase ^ 1));
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * 256;
         for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
+          (I8 ? mbar_wait_sleep(&full_bar[stage], phase) : mbar_wait(&full_bar[stage], phase));
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + stage * TP_STAGE_BYTES);
           const int nks = (kc == nk - 1 && k_tail <= KSTAGE / 2) ? 1 : 2;
@@ -295,7 +304,7 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       }
       asm volatile("cp.async.wait_all;" ::: "memory");           // this thread's share of the constants has landed
       asm volatile("bar.sync 1, 256;" ::: "memory");             // constants visible; zx_s readers of the last item done
-      mbar_wait(&tmem_full[acc], acc_phase);
+      (I8 ? mbar_wait_sleep(&tmem_full[acc], acc_phase) : mbar_wait(&tmem_full[acc], acc_phase));
       tc_fence_after();
       // (hidden unit hbase, this thread's 4 rows) inside this (chain, tile) block, in 8-byte units (4 bf16)
       const int64_t blk_w = (((((int64_t)b * p.out_tiles + mt) * H) + hbase) * 128 + pos0) >> 2;
@@ -512,11 +521,8 @@ tc_g1_layer2_fused(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               for (int r = 0; r < 4; ++r) d[r] = ((m >> (kb * 8 + r * 2 + i)) & 1u) ? s[r].x + s[r].y : 0.f;
               const int w_off = (ch * 32 + 8 * kb + i) * 32;
               if (I8 == 2) {
-                const float zqv = zqb[ch * 32 + 8 * kb + i];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) d[r] *= zqv;
                 uint32_t hw, lw;
-                slice4_i8(d, hw, lw);
+                slice4_i8(d, zqb[ch * 32 + 8 * kb + i], hw, lw);
                 __stcs(pzi_hi + w_off, hw);                      // (unit, 4 adjacent rows): 32 words per 128-byte block row
                 __stcs(pzi_lo + w_off, lw);
               } else {

@@ -79,18 +79,7 @@ __device__ __forceinline__ float act_apply_t(float z) {
   return z;
 }
 
-// MIX = 1 (prototype of DESIGN 6b item 4, reached only through pyb_debug_tc_gemm_mixed): the "hi" operands are fp16,
-// the "lo" maps address an 8-bit tensor [rows, 2K] that holds, per 32 K-elements, 32 bytes e4m3(x * s_hi) followed by
-// 32 bytes e4m3((x - fp16(x)) * s_lo); one stage then takes 2 kind::f16 MMAs (K = 16 each) and 2 kind::f8f6f4 MMAs
-// (K = 32 each: a_lo b_hi and a_hi b_lo) into the SAME accumulator columns — 4 MMA slots instead of 6 for the same
-// stage bytes.  The caller picks the scales so that both correction products and the fp16 product carry one common
-// factor 2^k, which the epilogue removes (its reciprocal travels as the bit pattern of `act`).
-// MIX = 2 (prototype of DESIGN 6b item 4b, pyb_debug_tc_gemm_i8; B200: 1.61x the bf16x3 kernel, result equal to the integer
-// emulation, profiles/r1_i8_proto_timing.json): all four maps address int8 slice
-// tensors [rows, K]; a stage covers 64 K-elements; one 128-row tile per item; kind::i8 MMAs accumulate hh into TMEM columns
-// [0, 256) and hl + lh into [256, 512) as exact int32, the epilogue stores hh + (hl + lh) / 254 as fp32 and the caller
-// applies the row and column scales.  The caller passes K / 2 as p.K (stages are counted in units of 32).
-template <int EPI, int ACT, int MIX = 0>
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -141,24 +130,22 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int b, mp, split;
         tc_decode(p, item, b, mp, split);
         const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
-        const int mt0 = MIX == 2 ? mp : mp * 2;
-        const int n_mt = MIX == 2 ? 1 : (mt0 + 1 < p.n_mtiles) ? 2 : 1;
+        const int mt0 = mp * 2;
+        const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
         const uint32_t bytes = (uint32_t)n_mt * 2 * (uint32_t)p.a_box_rows * TC_BK * 2 + 2 * b_bytes;
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * TC_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], bytes);
           const int k0 = kc * TC_BK;
-          const int k0_lo = MIX ? 2 * k0 : k0;                   // MIX: 64 bytes of the 8-bit tensor per 32 K-elements
-          const int k0_hi = MIX == 2 ? 2 * k0 : k0;              // MIX 2: all four operands are 8-bit, 64 K-elements a stage
           for (int mt = 0; mt < n_mt; ++mt) {
             const int arow = (p.a_blocked ? 0 : p.a_row0 + b * p.a_batch_rows) + (mt0 + mt) * 128;
-            tma_load_operand(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], p.a_blocked, k0_hi, arow, b, p.k_tiles);
-            tma_load_operand(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], p.a_blocked, k0_lo, arow, b, p.k_tiles);
+            tma_load_operand(st + mt * TC_A_TILE_BYTES, &tmA_hi, &full_bar[stage], p.a_blocked, k0, arow, b, p.k_tiles);
+            tma_load_operand(st + (2 + mt) * TC_A_TILE_BYTES, &tmA_lo, &full_bar[stage], p.a_blocked, k0, arow, b, p.k_tiles);
           }
           const int brow = p.b_blocked ? 0 : b * p.H;
-          tma_load_operand(st + 4 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], p.b_blocked, k0_hi, brow, b, p.k_tiles);
-          tma_load_operand(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &tmB_lo, &full_bar[stage], p.b_blocked, k0_lo, brow, b,
+          tma_load_operand(st + 4 * TC_A_TILE_BYTES, &tmB_hi, &full_bar[stage], p.b_blocked, k0, brow, b, p.k_tiles);
+          tma_load_operand(st + 4 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &tmB_lo, &full_bar[stage], p.b_blocked, k0, brow, b,
                            p.k_tiles);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -168,8 +155,7 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===== MMA issuer =====
     if (lane == 0) {
       // instruction descriptor: D=F32, A=B=BF16, both K-major, N = H, M = 128
-      // (MIX: A = B = F16 for kind::f16 and A = B = E4M3 for kind::f8f6f4 are both format code 0)
-      const uint32_t idesc = (1u << 4) | (MIX ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(p.H >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.H >> 3) << 17) | ((128u >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       const int k_tail = p.K - (nk - 1) * TC_BK;                 // valid K elements of the last chunk
@@ -177,35 +163,15 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int b, mp, split;
         tc_decode(p, item, b, mp, split);
         const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
-        const int mt0 = MIX == 2 ? mp : mp * 2;
-        const int n_mt = MIX == 2 ? 1 : (mt0 + 1 < p.n_mtiles) ? 2 : 1;
+        const int mt0 = mp * 2;
+        const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
         mbar_wait(tmem_empty, acc_phase ^ 1);                    // epilogue has drained the accumulators
         tc_fence_after();
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + stage * TC_STAGE_BYTES);
-          if (MIX == 2) {
-            // int8 slices: hh into columns [0, 256), hl + lh (weight 1/254) into [256, 512); D = S32, A = B = signed 8-bit
-            const uint32_t idesc_i8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.H >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t al = st + 2 * TC_A_TILE_BYTES, bh = st + 4 * TC_A_TILE_BYTES, bl = bh + TC_B_TILE_BYTES;
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t koff = ks * 32, first = (kc != kc_begin) || (ks != 0);
-              tc_mma_i8(tmem_base, make_smem_desc_sw64(st + koff), make_smem_desc_sw64(bh + koff), idesc_i8, first);
-              tc_mma_i8(tmem_base + 256, make_smem_desc_sw64(st + koff), make_smem_desc_sw64(bl + koff), idesc_i8, first);
-              tc_mma_i8(tmem_base + 256, make_smem_desc_sw64(al + koff), make_smem_desc_sw64(bh + koff), idesc_i8, 1);
-            }
-          } else if (MIX) {
-            const uint32_t a8 = st + 2 * TC_A_TILE_BYTES, b16 = st + 4 * TC_A_TILE_BYTES, b8 = b16 + TC_B_TILE_BYTES;
-            for (int mt = 0; mt < n_mt; ++mt) {
-              const uint32_t d = tmem_base + (uint32_t)mt * 256;
-              tc_mma_bf16(d, make_smem_desc_sw64(st + mt * TC_A_TILE_BYTES), make_smem_desc_sw64(b16), idesc, kc != kc_begin);
-              tc_mma_bf16(d, make_smem_desc_sw64(st + mt * TC_A_TILE_BYTES + 32), make_smem_desc_sw64(b16 + 32), idesc, 1);
-              tc_mma_f8(d, make_smem_desc_sw64(a8 + mt * TC_A_TILE_BYTES + 32), make_smem_desc_sw64(b8), idesc, 1);       // a_lo b_hi
-              tc_mma_f8(d, make_smem_desc_sw64(a8 + mt * TC_A_TILE_BYTES), make_smem_desc_sw64(b8 + 32), idesc, 1);       // a_hi b_lo
-            }
-          }
-          const int nks = MIX ? 0 : (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
+          const int nks = (kc == nk - 1 && k_tail <= 16) ? 1 : 2;
           for (int ks = 0; ks < nks; ++ks) {
             const uint32_t koff = ks * 32;                       // 16 bf16 = 32 bytes along K inside the atom
             const uint64_t bh = make_smem_desc_sw64(st + 4 * TC_A_TILE_BYTES + koff);
@@ -237,8 +203,8 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int b, mp, split;
       tc_decode(p, item, b, mp, split);
-      const int mt0 = MIX == 2 ? mp : mp * 2;
-      const int n_mt = MIX == 2 ? 1 : (mt0 + 1 < p.n_mtiles) ? 2 : 1;
+      const int mt0 = mp * 2;
+      const int n_mt = (mt0 + 1 < p.n_mtiles) ? 2 : 1;
       if (EPI == EPI_BIAS_ACT_T_SPLIT) {
         asm volatile("bar.sync 1, 512;" ::: "memory");           // previous item's readers are done
         for (int c = eall; c < p.H; c += 512) bias_s[c] = p.bias ? p.bias[(int64_t)b * p.bias_stride + c] : 0.f;
@@ -284,17 +250,6 @@ tc_gemm_bf16x3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (valid) {
               float* o = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + (int64_t)row * p.out_ld + c0;
               const int nvalid = p.n_cols_total > 0 ? min(p.N_valid, p.n_cols_total - b * p.H) : p.N_valid;
-              if (MIX == 2) {                                     // exact integers: hh + (hl + lh) / 254
-                float w[32];
-                tc_ld32(tmem_base + lane_base + (uint32_t)(256 + c0), w);
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  v[j] = (float)__float_as_int(v[j]) + (float)__float_as_int(w[j]) * (1.0f / 254.0f);
-              } else if (MIX) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= __int_as_float(p.act);   // 2^-k as a bit pattern (`act` is unused by EPI_STORE;
-                                                                               // a new field would move every kernel's parameters)
-              }
               if (p.vec_store && c0 + 32 <= nvalid) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)

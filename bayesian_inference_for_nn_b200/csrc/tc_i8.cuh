@@ -165,7 +165,8 @@ __global__ void k_pack_w1_i8(const float* __restrict__ theta, int64_t P, int64_t
       const float* w2 = th + w2_off + (int64_t)h * C;
       float lo2 = w2[0], hi2 = w2[0];
       for (int c = 1; c < C; ++c) { lo2 = fminf(lo2, w2[c]); hi2 = fmaxf(hi2, w2[c]); }
-      float sz = 1.001f * (hi2 - lo2) * invN;
+      // + the softmax probabilities sum to 1 only to float32 rounding: sum_c dZ2[c] = O(1e-6) / N multiplies the row's offset
+      float sz = (1.001f * (hi2 - lo2) + 8e-6f * fmaxf(fabsf(hi2), fabsf(lo2))) * invN;
       if (!(sz > 0.f) || !isfinite(sz)) sz = 1.f;               // W2 row constant (or not finite): dZ1 is 0 (or NaN anyway)
       zq[(int64_t)b * H + h] = 127.0f / sz;
       zd[(int64_t)b * H + h] = sz * (1.0f / 127.0f);
@@ -269,7 +270,7 @@ tc_gemm_pair_dw1_i8(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int arow = (int)rank * 128;
         const int brow = p.b_row0 + bt * p.H + (int)rank * half_rows;
         for (int kc = kc_begin; kc < kc_end; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_sleep(&empty_bar[stage], phase ^ 1);
           uint8_t* st = stage_base + stage * TP_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * cta_bytes);
           const int k0 = kc * 64;
@@ -292,10 +293,10 @@ tc_gemm_pair_dw1_i8(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         int b, mp, split, bt;
         tc_decode_pair(p, item, b, mp, split, bt);
         const int kc_begin = split * p.chunks_per_split, kc_end = min(nk, kc_begin + p.chunks_per_split);
-        mbar_wait(tmem_empty, acc_phase ^ 1);
+        mbar_wait_sleep(tmem_empty, acc_phase ^ 1);
         tc_fence_after();
         for (int kc = kc_begin; kc < kc_end; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_sleep(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + stage * TP_STAGE_BYTES);
           for (int ks = 0; ks < 2; ++ks) {
@@ -329,7 +330,7 @@ tc_gemm_pair_dw1_i8(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       tc_decode_pair(p, item, b, mp, split, bt);
       const int row = (int)rank * 128 + et;                         // hidden unit
       const float dq = row < p.M_valid ? zd[(int64_t)b * p.M_valid + row] : 0.f;
-      mbar_wait(tmem_full, acc_phase);
+      mbar_wait_sleep(tmem_full, acc_phase);
       tc_fence_after();
       const int colbase = p.b_row0 + bt * p.H;
       float* ob = p.out + (int64_t)split * p.split_stride + (int64_t)b * p.out_stride + row;

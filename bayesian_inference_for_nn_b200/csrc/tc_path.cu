@@ -135,6 +135,9 @@ void tc_release(pyb_handle* h) {
   if (h->tc) delete (TcState*)h->tc;
   h->tc = nullptr;
 }
+int tc_resident_split(const pyb_handle* h) {   // operand split the resident dataset was prepared for: 0 bf16x3, 1 / 2 int8 slices
+  return h->tc ? ((TcState*)h->tc)->train.i8 : 0;
+}
 void tc_invalidate_dataset(pyb_handle* h) {
   if (h->tc) ((TcState*)h->tc)->train.ready = false;
 }
@@ -250,13 +253,19 @@ static bool fused_ok(const pyb_handle* h, int H, int act1) {
 // int8-slice mode of an evaluation: 0 bf16x3, 1 forward GEMM on slices, 2 forward and dW1 GEMMs on slices.
 // The dW1 operand dZ1 needs an a-priori bound of its magnitude, which exists for the softmax cross-entropy only, and the
 // kernel takes one 256-unit chain per CTA pair.
-static int i8_mode(const pyb_handle* h, bool backward) {
+// Option tc_i8 = -1 (default): the slices are used where the 1e-4 parity budget is what the caller is held to — the
+// full-data log-posterior gradient of HMC on the RESIDENT dataset (`resident`); minibatch gradients (SVGD / SGLD / SWAG
+// feed them to Adam or a Langevin step, whose first steps are sign-like in the gradient) and the predictive stay on
+// bf16x3.  0 / 1 / 2 force a mode everywhere it applies.
+static int i8_mode(const pyb_handle* h, bool backward, bool resident) {
   const Model& m = h->model;
-  if (h->opt_tc_i8 <= 0 || !fused_ok(h, m.layer[0].fan_out, m.layer[0].act) || m.layer[1].fan_out > L2_CMAX) return 0;
+  int want = h->opt_tc_i8;
+  if (want < 0) want = (resident && backward) ? 2 : 0;
+  if (want <= 0 || !fused_ok(h, m.layer[0].fan_out, m.layer[0].act) || m.layer[1].fan_out > L2_CMAX) return 0;
   if (m.layer[0].fan_in > 32768) return 0;                       // int32 range of the hi*lo + lo*hi accumulator
   if (!backward) return 1;
   const bool ce = h->loss_kind == PYB_LOSS_SPARSE_CE && m.layer[1].act == PYB_ACT_SOFTMAX;
-  return (h->opt_tc_i8 >= 2 && ce && m.layer[0].fan_out == 256) ? 2 : 1;
+  return (want >= 2 && ce && m.layer[0].fan_out == 256) ? 2 : 1;
 }
 
 static void tc_prepare_data_i8(pyb_handle* h, TcData& d, const float* X, int64_t N, int mode) {
@@ -292,7 +301,7 @@ static void tc_prepare_data_i8(pyb_handle* h, TcData& d, const float* X, int64_t
   d.i8 = mode;
 }
 
-static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N, bool need_xt) {
+static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N, bool need_xt, bool resident = false) {
   const Model& m = h->model;
   const int D = m.layer[0].fan_in;
   d.N = N; d.D = D;
@@ -330,13 +339,13 @@ static void tc_prepare_data(pyb_handle* h, TcData& d, const float* X, int64_t N,
     }
   }
   d.i8 = 0;
-  const int mode = i8_mode(h, need_xt);
+  const int mode = i8_mode(h, need_xt, resident);
   if (mode) tc_prepare_data_i8(h, d, X, N, mode);
   d.ready = true;
 }
 
 // chain batch for S chains over Npad rows; grows the shared buffers (and their tensor maps) on demand
-static int64_t tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S, int64_t Npad, bool backward) {
+static int64_t tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S, int64_t Npad, bool backward, int mode) {
   const Model& m = h->model;
   st->D = m.layer[0].fan_in; st->H = m.layer[0].fan_out; st->C = m.layer[1].fan_out;
   const int H = st->H, D = st->D;
@@ -374,7 +383,6 @@ static int64_t tc_prepare_bufs(pyb_handle* h, TcState* st, int64_t S, int64_t Np
     st->mZ2_hi = make_map_blocked(st->z2_hi.p, cb, L2_CMAX, L2_CMAX);
     st->mZ2_lo = make_map_blocked(st->z2_lo.p, cb, L2_CMAX, L2_CMAX);
   }
-  const int mode = i8_mode(h, backward);
   if (mode && (bc > st->cap_chains_i8 || (mode >= 2 && need_blocks > st->cap_blocks_i8))) {
     PYB_CUDA(cudaStreamSynchronize(h->stream));
     st->cap_chains_i8 = std::max(st->cap_chains_i8, bc);
@@ -446,14 +454,14 @@ static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* t
 static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i, const float* y_f, const float* theta,
                        int64_t S, float scale, float* loss_out, float* grad_out) {
   const Model& m = h->model;
-  const int64_t Bc = tc_prepare_bufs(h, st, S, d.Npad, true);
+  const int64_t Bc = tc_prepare_bufs(h, st, S, d.Npad, true, d.i8);
   const LayerDesc& L1 = m.layer[0];
   const LayerDesc& L2 = m.layer[1];
   const int D = st->D, H = st->H, C = st->C;
   const int64_t N = d.N, Npad = d.Npad, P = m.P;
   const int n_tiles = (int)(Npad / L2_ROWS);
   const bool fused = fused_ok(h, H, L1.act) && C <= L2_CMAX;
-  const int i8 = std::min(i8_mode(h, true), d.i8);
+  const int i8 = d.i8;
   // fused: one partial per (128-row tile, lane quadrant); unfused: one per k_layer2 block
   const int n_groups = fused ? (int)(Npad / 128) * 4
                              : std::min(n_tiles, std::max(1, (int)((8 * (int64_t)h->sm_count + Bc - 1) / Bc)));
@@ -592,7 +600,7 @@ static void tc_eval_on(pyb_handle* h, TcState* st, TcData& d, const int32_t* y_i
 
 void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
   TcState* st = tc_state(h);
-  if (!st->train.ready || st->train.i8 != i8_mode(h, true)) tc_prepare_data(h, st->train, h->X.p, h->N, true);
+  if (!st->train.ready || st->train.i8 != i8_mode(h, true, true)) tc_prepare_data(h, st->train, h->X.p, h->N, true, true);
   tc_eval_on(h, st, st->train, h->y_i.p, h->y_f.p, theta, S, scale, loss_out, grad_out);
 }
 
@@ -610,7 +618,7 @@ void tc_forward(pyb_handle* h, const float* theta, int64_t S, const float* x, in
   const Model& m = h->model;
   tc_prepare_data(h, st->aux, x, N, false);
   TcData& d = st->aux;
-  const int64_t Bc = tc_prepare_bufs(h, st, S, d.Npad, false);
+  const int64_t Bc = tc_prepare_bufs(h, st, S, d.Npad, false, d.i8);
   const LayerDesc& L2 = m.layer[1];
   const int64_t P = m.P;
   const bool fused = fused_ok(h, st->H, m.layer[0].act) && st->C <= L2_CMAX;
@@ -623,7 +631,7 @@ void tc_forward(pyb_handle* h, const float* theta, int64_t S, const float* x, in
       f.theta = th; f.P = P; f.w2_off = L2.w_off; f.b2_off = L2.b_off;
       f.H = st->H; f.C = st->C; f.N = (int)N; f.out_act = L2.act; f.scale = 1.0f;
       f.fwd_out = out + b0 * N * st->C;
-      tc_pack_and_g1(h, st, d, th, nb, &f, std::min(i8_mode(h, false), d.i8));
+      tc_pack_and_g1(h, st, d, th, nb, &f, d.i8);
       continue;
     }
     tc_pack_and_g1(h, st, d, th, nb);
@@ -696,8 +704,8 @@ void tc_gemm_split(pyb_handle* h, const void* a_hi, const void* a_lo, int64_t ld
   }
 }
 
-// the debug GEMM entries repeat their kernel launch PYB_DEBUG_GEMM_REPS times (default 1) so that tools/bench_mixed_proto.py
-// can read per-launch device times from the "profile" option's CUDA events
+// the debug GEMM entry repeats its kernel launch PYB_DEBUG_GEMM_REPS times (default 1) so that a timing tool can read
+// per-launch device times from the "profile" option's CUDA events
 static int debug_gemm_reps() {
   const char* e = getenv("PYB_DEBUG_GEMM_REPS");
   const int r = e ? atoi(e) : 1;
@@ -730,170 +738,45 @@ void tc_debug_gemm(pyb_handle* h, const float* A, const float* B, int M, int Nn,
   prof_resolve(h);
 }
 
-// debug / unit-test entry for the MIX prototype: D = out_scale * (A16 B16^T + A8lo B8hi^T + A8hi B8lo^T)
-// with A16/B16 fp16 bit patterns [rows, K] and A8/B8 e4m3 bytes [rows, 2K] (per 32 K-elements: 32 bytes hi, 32 bytes lo),
-// all prepared by the caller (host pointers); 1-CTA kernel, fp16 and FP8 MMAs accumulate into the same TMEM columns
-static CUtensorMap make_map_u8(const void* base, int64_t kbytes, int64_t rows, int box_rows) {
-  CUtensorMap m;
-  cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)kbytes};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, es,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  PYB_REQUIRE(r == CUDA_SUCCESS, PYB_ERR_CUDA, "cuTensorMapEncodeTiled (8-bit) failed");
-  return m;
-}
-void tc_debug_gemm_mixed(pyb_handle* h, const uint16_t* A16, const uint8_t* A8, const uint16_t* B16, const uint8_t* B8,
-                         int M, int Nn, int K, float out_scale, float* Dout) {
-  PYB_REQUIRE(Nn % 16 == 0 && Nn >= 16 && Nn <= 256 && K % 32 == 0 && K > 0, PYB_ERR_INVALID, "Nn%16, Nn<=256, K%32 required");
-  DevBuf<uint16_t> a16, b16;
-  DevBuf<uint8_t> a8, b8;
-  DevBuf<float> dD;
-  a16.alloc((size_t)M * K); b16.alloc((size_t)Nn * K); a8.alloc((size_t)M * 2 * K); b8.alloc((size_t)Nn * 2 * K);
-  dD.alloc((size_t)M * Nn);
-  PYB_CUDA(cudaMemcpyAsync(a16.p, A16, (size_t)M * K * 2, cudaMemcpyHostToDevice, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(b16.p, B16, (size_t)Nn * K * 2, cudaMemcpyHostToDevice, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(a8.p, A8, (size_t)M * 2 * K, cudaMemcpyHostToDevice, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(b8.p, B8, (size_t)Nn * 2 * K, cudaMemcpyHostToDevice, h->stream));
-  PYB_CUDA(cudaMemsetAsync(dD.p, 0xff, (size_t)M * Nn * 4, h->stream));
-  CUtensorMap ma_h = make_map(a16.p, K, M, K, 128), mb_h = make_map(b16.p, K, Nn, K, Nn);   // 16-bit elements
-  CUtensorMap ma_l = make_map_u8(a8.p, 2 * (int64_t)K, M, 128), mb_l = make_map_u8(b8.p, 2 * (int64_t)K, Nn, Nn);
-  TcGemmParams p = {};
-  p.K = K; p.n_mtiles = (M + 127) / 128; p.n_pairs = (p.n_mtiles + 1) / 2; p.n_batch = 1; p.H = Nn;
-  p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
-  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0; p.a_box_rows = 128;
-  p.k_splits = 1; p.chunks_per_split = K / TC_BK; p.split_stride = 0; p.vec_store = 1; memcpy(&p.act, &out_scale, 4);   // see the MIX epilogue
-  const int grid = std::min(p.total_items, h->sm_count);
-  PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3<EPI_STORE, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  for (int r = 0; r < debug_gemm_reps(); ++r) {
-    prof_begin(h);
-    tc_gemm_bf16x3<EPI_STORE, 0, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(ma_h, ma_l, mb_h, mb_l, p);
-    prof_end(h, 2.0 * M * Nn * (double)K);
-    count_launch(h);
-  }
-  PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
-  PYB_CUDA(cudaStreamSynchronize(h->stream));
-  PYB_CUDA(cudaGetLastError());
-  prof_resolve(h);
-}
-
-// operand producer of the int8-slice scheme (debug entry only so far): one warp per row finds the row's
-// largest magnitude s and writes x = s / 127 (hi + lo / 254) as two int8 slices [rows, Kpad] (Kpad % 4 == 0, zero padded)
-__global__ void k_slice_rows_i8(const float* __restrict__ src, int64_t rows, int K, int64_t ld, int8_t* __restrict__ hi,
-                                int8_t* __restrict__ lo, float* __restrict__ scale, int Kpad) {
-  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
-    const float* x = src + r * ld;
-    float m = 0.f;
-    for (int k = lane; k < K; k += 32) m = fmaxf(m, fabsf(x[k]));
-#pragma unroll
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float s = m > 0.f ? m : 1.f;
-    if (lane == 0) scale[r] = s;
-    for (int k4 = lane * 4; k4 < Kpad; k4 += 128) {             // 4 consecutive elements per lane: one 32-bit store per slice
-      uint32_t hw = 0, lw = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v = (k4 + j < K) ? __fdiv_rn(x[k4 + j], s) * 127.0f : 0.f;
-        const float q = fminf(fmaxf(rintf(v), -127.f), 127.f);
-        const float q2 = fminf(fmaxf(rintf((v - q) * 254.0f), -127.f), 127.f);
-        hw |= ((uint32_t)(int)q & 0xffu) << (8 * j);
-        lw |= ((uint32_t)(int)q2 & 0xffu) << (8 * j);
-      }
-      *reinterpret_cast<uint32_t*>(hi + r * Kpad + k4) = hw;
-      *reinterpret_cast<uint32_t*>(lo + r * Kpad + k4) = lw;
-    }
+// relu'(z1) as the LAST tensor-path evaluation used it, for one chain of its (single) chain batch: read back from the
+// A1^T hi/lo blocks the fused kernel left in the workspace (a1 > 0 <=> one of its two bf16 parts is non-zero)
+__global__ void k_relu_mask_from_a1(const uint16_t* __restrict__ a_hi, const uint16_t* __restrict__ a_lo, int64_t chain,
+                                    int k_tiles, int H, int64_t N, int fused_order, uint8_t* __restrict__ out) {
+  const int64_t total = N * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / H;
+    const int hh = (int)(i - r * H);
+    const int pos = fused_order ? fused_row_pos((int)(r & 127)) : (int)(r & 127);
+    const int64_t o = (((chain * k_tiles + (r >> 7)) * H) + hh) * 128 + pos;
+    out[i] = ((a_hi[o] & 0x7fffu) | (a_lo[o] & 0x7fffu)) ? 1 : 0;
   }
 }
-void tc_debug_slice_i8(pyb_handle* h, const float* X, int64_t rows, int K, int Kpad, int8_t* hi, int8_t* lo, float* scale) {
-  PYB_REQUIRE(rows > 0 && K > 0 && Kpad >= K && Kpad % 4 == 0, PYB_ERR_INVALID, "rows, K > 0 and Kpad >= K, Kpad % 4 == 0 required");
-  DevBuf<float> dX, dS;
-  DevBuf<int8_t> dH, dL;
-  dX.alloc((size_t)rows * K); dS.alloc((size_t)rows); dH.alloc((size_t)rows * Kpad); dL.alloc((size_t)rows * Kpad);
-  PYB_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)rows * K * 4, cudaMemcpyHostToDevice, h->stream));
-  const int wpb = 8;
-  const unsigned grid = (unsigned)std::min<int64_t>((rows + wpb - 1) / wpb, 8 * (int64_t)h->sm_count);
-  k_slice_rows_i8<<<grid, wpb * 32, 0, h->stream>>>(dX.p, rows, K, K, dH.p, dL.p, dS.p, Kpad);
-  count_launch(h);
-  PYB_CUDA(cudaMemcpyAsync(hi, dH.p, (size_t)rows * Kpad, cudaMemcpyDeviceToHost, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(lo, dL.p, (size_t)rows * Kpad, cudaMemcpyDeviceToHost, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(scale, dS.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->stream));
+void tc_debug_relu_mask(pyb_handle* h, int64_t chain, uint8_t* out_host) {
+  PYB_REQUIRE(h->tc != nullptr, PYB_ERR_STATE, "no tensor-path evaluation has run on this handle");
+  TcState* st = (TcState*)h->tc;
+  const Model& m = h->model;
+  PYB_REQUIRE(st->train.ready && m.layer[0].act == PYB_ACT_RELU && st->cap_chains > 0, PYB_ERR_STATE,
+              "the relu mask is available after a tensor-path evaluation of a relu network on the resident dataset");
+  PYB_REQUIRE(chain >= 0 && chain < st->cap_chains, PYB_ERR_INVALID, "chain outside the last chain batch");
+  const int H = st->H;
+  const int64_t N = st->train.N;
+  DevBuf<uint8_t> out;
+  out.alloc((size_t)N * H);
+  const bool fused = fused_ok(h, H, m.layer[0].act) && st->C <= L2_CMAX;
+  k_relu_mask_from_a1<<<(unsigned)std::min<int64_t>((N * H + 255) / 256, 16 * (int64_t)h->sm_count), 256, 0, h->stream>>>(
+      (const uint16_t*)st->a_hi.p, (const uint16_t*)st->a_lo.p, chain, (int)(st->train.Npad / 128), H, N, fused ? 1 : 0, out.p);
+  PYB_CUDA(cudaMemcpyAsync(out_host, out.p, (size_t)N * H, cudaMemcpyDeviceToHost, h->stream));
   PYB_CUDA(cudaStreamSynchronize(h->stream));
   PYB_CUDA(cudaGetLastError());
-}
-
-// debug / unit-test entry for the int8-slice prototype: D = Ah Bh^T + (Ah Bl^T + Al Bh^T) / 254 with
-// int8 slice tensors [rows, K] prepared by the caller (host pointers), K % 64 == 0; scales are applied by the caller
-void tc_debug_gemm_i8(pyb_handle* h, const int8_t* Ah, const int8_t* Al, const int8_t* Bh, const int8_t* Bl, int M, int Nn, int K,
-                      float* Dout) {
-  PYB_REQUIRE(Nn % 16 == 0 && Nn >= 16 && Nn <= 256 && K % 64 == 0 && K > 0, PYB_ERR_INVALID, "Nn%16, Nn<=256, K%64 required");
-  DevBuf<int8_t> ah, al, bh, bl;
-  DevBuf<float> dD;
-  ah.alloc((size_t)M * K); al.alloc((size_t)M * K); bh.alloc((size_t)Nn * K); bl.alloc((size_t)Nn * K);
-  dD.alloc((size_t)M * Nn);
-  PYB_CUDA(cudaMemcpyAsync(ah.p, Ah, (size_t)M * K, cudaMemcpyHostToDevice, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(al.p, Al, (size_t)M * K, cudaMemcpyHostToDevice, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(bh.p, Bh, (size_t)Nn * K, cudaMemcpyHostToDevice, h->stream));
-  PYB_CUDA(cudaMemcpyAsync(bl.p, Bl, (size_t)Nn * K, cudaMemcpyHostToDevice, h->stream));
-  PYB_CUDA(cudaMemsetAsync(dD.p, 0xff, (size_t)M * Nn * 4, h->stream));
-  CUtensorMap ma_h = make_map_u8(ah.p, K, M, 128), ma_l = make_map_u8(al.p, K, M, 128);
-  CUtensorMap mb_h = make_map_u8(bh.p, K, Nn, Nn), mb_l = make_map_u8(bl.p, K, Nn, Nn);
-  TcGemmParams p = {};
-  p.K = K / 2;                                     // stages of 64 K-elements, counted in units of TC_BK = 32
-  p.n_mtiles = (M + 127) / 128; p.n_pairs = p.n_mtiles; p.n_batch = 1; p.H = Nn;   // one 128-row tile per item
-  p.order = 0; p.sub_batch = 1; p.total_items = p.n_pairs;
-  p.epi = EPI_STORE; p.out = dD.p; p.out_stride = 0; p.out_ld = Nn; p.M_valid = M; p.N_valid = Nn; p.a_batch_rows = 0; p.a_box_rows = 128;
-  p.k_splits = 1; p.chunks_per_split = p.K / TC_BK; p.split_stride = 0; p.vec_store = 1;
-  const int grid = std::min(p.total_items, h->sm_count);
-  PYB_CUDA(cudaFuncSetAttribute(tc_gemm_bf16x3<EPI_STORE, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  for (int r = 0; r < debug_gemm_reps(); ++r) {
-    prof_begin(h);
-    tc_gemm_bf16x3<EPI_STORE, 0, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, h->stream>>>(ma_h, ma_l, mb_h, mb_l, p);
-    prof_end(h, 2.0 * M * Nn * (double)K);
-    count_launch(h);
-  }
-  PYB_CUDA(cudaMemcpyAsync(Dout, dD.p, (size_t)M * Nn * 4, cudaMemcpyDeviceToHost, h->stream));
-  PYB_CUDA(cudaStreamSynchronize(h->stream));
-  PYB_CUDA(cudaGetLastError());
-  prof_resolve(h);
 }
 
 }  // namespace pyb
 
-extern "C" int pyb_debug_slice_i8(pyb_handle* h, const float* X, int64_t rows, int32_t K, int32_t Kpad, int8_t* hi, int8_t* lo,
-                                  float* scale) {
+extern "C" int pyb_debug_relu_mask(pyb_handle* h, int64_t chain, uint8_t* mask_out) {
   try {
-    if (!h || !X || !hi || !lo || !scale) throw pyb::Error(PYB_ERR_INVALID, "NULL argument");
+    if (!h || !mask_out) throw pyb::Error(PYB_ERR_INVALID, "NULL argument");
     PYB_CUDA(cudaSetDevice(h->device));
-    pyb::tc_debug_slice_i8(h, X, rows, K, Kpad, hi, lo, scale);
-  } catch (const pyb::Error& e) {
-    pyb::set_last_error(e.what());
-    return e.code;
-  }
-  return PYB_OK;
-}
-
-extern "C" int pyb_debug_tc_gemm_i8(pyb_handle* h, const int8_t* Ah, const int8_t* Al, const int8_t* Bh, const int8_t* Bl,
-                                    int32_t M, int32_t Nn, int32_t K, float* D) {
-  try {
-    if (!h || !Ah || !Al || !Bh || !Bl || !D) throw pyb::Error(PYB_ERR_INVALID, "NULL argument");
-    PYB_CUDA(cudaSetDevice(h->device));
-    pyb::tc_debug_gemm_i8(h, Ah, Al, Bh, Bl, M, Nn, K, D);
-  } catch (const pyb::Error& e) {
-    pyb::set_last_error(e.what());
-    return e.code;
-  }
-  return PYB_OK;
-}
-
-extern "C" int pyb_debug_tc_gemm_mixed(pyb_handle* h, const uint16_t* A16, const uint8_t* A8, const uint16_t* B16,
-                                       const uint8_t* B8, int32_t M, int32_t Nn, int32_t K, float out_scale, float* D) {
-  try {
-    if (!h || !A16 || !A8 || !B16 || !B8 || !D) throw pyb::Error(PYB_ERR_INVALID, "NULL argument");
-    PYB_CUDA(cudaSetDevice(h->device));
-    pyb::tc_debug_gemm_mixed(h, A16, A8, B16, B8, M, Nn, K, out_scale, D);
+    pyb::tc_debug_relu_mask(h, chain, mask_out);
   } catch (const pyb::Error& e) {
     pyb::set_last_error(e.what());
     return e.code;

@@ -74,12 +74,14 @@ def measured_peaks():
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
 
 
-def ncu_traffic():
-    """dram__bytes_read+write per tc_gemm launch (mean over the G1/G3/G2 launches of one chain batch) from the
-    committed `ncu --set full` capture (profiles/r1_traffic.json); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+def ncu_traffic(split):
+    """dram__bytes_read+write per tensor-core launch (mean over the fused forward, dW2 and dW1 launches of one 148-chain
+    batch) from the committed `ncu` captures (profiles/r2_traffic.json: int8 slices; r1_traffic.json: bf16x3); None when
+    no capture is committed."""
     try:
-        return json.load(open(p))["tc_gemm_bf16x3"]["dram_bytes_per_launch_mean"]
+        if split:
+            return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["int8_slices"]["dram_bytes_per_launch_mean"]
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["tc_gemm_bf16x3"]["dram_bytes_per_launch_mean"]
     except Exception:
         return None
 
@@ -316,20 +318,33 @@ def main():
     # roofline for the dominant kernel family (the fwd/bwd GEMMs): algorithmic flops they cover /
     # their summed CUDA-event time on the launching stream
     roof = None
+    split = int(eng.info("tc_split")) if path_used == 3 else 0
     if prof_ms > 0:
         achieved = prof_flops / (prof_ms / 1e3) / 1e12
+        # MMA passes per algorithmic product in bf16-rate equivalents: bf16x3 = 3 kind::f16 MMAs; int8 slices = 3 kind::i8
+        # MMAs at twice the kind::f16 rate = 1.5 (forward only on slices: the dW1 GEMM still pays 3)
+        passes = {0: 3.0, 1: 2.25, 2: 1.5}[split]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": ncu_traffic(),
-                "issued_mma_tflops": 3.0 * achieved, "issued_mma_frac": 3.0 * achieved / peaks["bf16_sustained"],
-                "peak_source": "%s bf16 dense sustained (cuBLAS)" % peaks["source"],
-                "kernel": {1: "k_sgemm (fp32 SIMT)", 2: "fused small", 3: "tc_gemm bf16x3 (tcgen05)"}.get(path_used, "?"),
+                "frac": achieved / peaks["bf16_sustained"], "traffic": ncu_traffic(split),
+                "issued_mma_tflops_bf16_equivalent": passes * achieved,
+                "issued_mma_frac": passes * achieved / peaks["bf16_sustained"],
+                "peak_source": "%s bf16 dense sustained (cuBLAS; MEASURED_PEAKS.json holds no int8 figure: kind::i8 issues at "
+                               "twice the kind::f16 rate, so against an int8 peak every fraction here halves)" % peaks["source"],
+                "kernel": {1: "k_sgemm (fp32 SIMT)", 2: "fused small",
+                           3: ("tc_g1_layer2_fused<.., I8> + tc_gemm_pair_dw1_i8 (tcgen05 kind::i8) + tc_gemm_bf16x3 (dW2)" if split
+                               else "tc_gemm bf16x3 (tcgen05 kind::f16)")}.get(path_used, "?"),
                 "launches": int(prof_n), "avg_launch_ms": prof_ms / max(1, prof_n),
                 "kernel_share_of_step": prof_ms / d["device_ms"],
                 "whole_step_algorithmic_tflops": value / max(1, world) * algo_flops_per_eval / 1e12,
-                "note": "fp32-grade products cost 3 bf16 MMA passes (hi*hi + lo*hi + hi*lo): algorithmic frac <= 1/3 of the "
-                        "bf16 peak, issued_mma_frac is the tensor-pipe view; ncu (profiles/): the dW1 GEMM runs the tensor "
-                        "pipe 95 % active, the fused layer-1 GEMM + layer-2 kernel is bound by the SM's 128 B/clk "
-                        "shared-memory data path (MMA operand reads + TMA fills + epilogue stores), see DESIGN.md section 4"}
+                "note": ("fp32-grade products on two int8 fixed-point slices per operand (hi*hi + hi*lo + lo*hi, exact int32 "
+                         "accumulation): 1.5 bf16-pass equivalents and 2 operand bytes per element instead of 3 and 4; ncu "
+                         "(profiles/r2_*): the dW1 GEMM runs the tensor pipe 89 % active, the fused forward kernel is bound by "
+                         "the instruction issue of its layer-2 epilogue (tensor pipe 34 %), the dW2 GEMM by HBM (84 %), see "
+                         "DESIGN.md section 4") if split else
+                        ("fp32-grade products cost 3 bf16 MMA passes (hi*hi + lo*hi + hi*lo): algorithmic frac <= 1/3 of the "
+                         "bf16 peak, issued_mma_frac is the tensor-pipe view; ncu (profiles/): the dW1 GEMM runs the tensor "
+                         "pipe 95 % active, the fused layer-1 GEMM + layer-2 kernel is bound by its epilogue, see DESIGN.md "
+                         "section 4")}
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (the reference arm reports it at every N)
         # bounded sample (~10 s of CPU work): 1 chain, 3 timed iterations (+1 warm-up) on the full dataset
@@ -341,8 +356,12 @@ def main():
     line = {
         "metric": "posterior_grad_evals_per_s", "value": value, "unit": "grad-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core products, fp32 accumulate)"
-        if path_used == 3 else "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": ("f32" if path_used != 3 else
+                  "f32 (bf16x3 split tensor-core products, fp32 accumulate)" if split == 0 else
+                  "f32 (tensor-core products on two int8 fixed-point slices per operand, kind::i8, exact int32 accumulate%s; "
+                  "f32 everywhere else)" % ("" if split == 2 else "; dW1 GEMM on bf16x3")),
+        "data": "synthetic",
         "config": workload_config(args, world, d["grad_evals"] / float(S * args.steps)),
         "wall_ms_per_step": 1e3 * wall_s / args.steps, "accept_rate": accept_rate, "path_used": path_used,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,

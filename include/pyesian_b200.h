@@ -218,6 +218,17 @@ int pyb_buffer_create(pyb_handle* h, const void* host_or_null, int64_t bytes, vo
 int pyb_buffer_destroy(pyb_handle* h, void* dev);
 int pyb_gather_rows(pyb_handle* h, const float* src, const int64_t* idx, int64_t n, int64_t row_len, float* dst);
 
+/* ---- diagnostic entry points (used by tests/, never by the host classes) ----
+ * pyb_debug_tc_gemm: D[M, Nn] = A[M, K] B[Nn, K]^T through the tcgen05 bf16x3 GEMM kernel (host pointers; Nn % 16 == 0,
+ *   Nn <= 256, K % 8 == 0): the unit test of the kernel every tensor-path GEMM is built from.
+ * pyb_debug_relu_mask: relu'(z1) exactly as the LAST tensor-path evaluation on the resident dataset used it, for one
+ *   chain of its chain batch: mask_out [N, H] uint8 on the host.  HMC._step_p (HMC.py:128-136) differentiates through
+ *   Keras' relu, whose derivative is discontinuous at 0; two correct float32 implementations disagree about the units
+ *   whose pre-activation lies within rounding of zero, so the full-size parity test evaluates the float64 oracle with
+ *   the device's own mask (tests/test_gpu_fullsize.py). */
+int pyb_debug_tc_gemm(pyb_handle* h, const float* A, const float* B, int32_t M, int32_t Nn, int32_t K, float* D);
+int pyb_debug_relu_mask(pyb_handle* h, int64_t chain, uint8_t* mask_out);
+
 #ifdef __cplusplus
 }
 #endif

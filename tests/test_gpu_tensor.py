@@ -21,10 +21,7 @@ def engine(D, H, Cc, act="relu", out_act="softmax", seed=0):
 
 
 def debug_gemm(eng, A, B):
-    lib = _lib.load()
-    fn = lib.pyb_debug_tc_gemm
-    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
-    fn.restype = C.c_int
+    fn = _lib.load().pyb_debug_tc_gemm
     A = np.ascontiguousarray(A, np.float32)
     B = np.ascontiguousarray(B, np.float32)
     D = np.empty((A.shape[0], B.shape[0]), np.float32)
@@ -49,128 +46,6 @@ def test_split_bf16_gemm_matches_float64(M, Nn, K, pair):
     assert np.isfinite(D).all()
     assert err.max() < 3e-5, err.max()        # ~2^-16 per product, error relative to |a||b|
     assert rel_err(D, want) < 2e-5
-
-
-def mixed_operands(X):
-    """fp16 hi part and the two e4m3 correction operands of DESIGN 6b item 4 for one [rows, K] operand (K % 32 == 0):
-    returns the scaled fp16 array, the e4m3 (hi, lo) arrays as float64 values, the interleaved byte tensor [rows, 2K]
-    the MIX kernel reads (per 32 K-elements: 32 bytes hi, 32 bytes lo) and the operand's power-of-two scale"""
-    import torch
-    X = X.astype(np.float64)
-    s = 2.0 ** np.floor(np.log2(256.0 / np.abs(X).max()))
-    Xs = X * s                                               # largest magnitude in (128, 256]
-    x16 = Xs.astype(np.float16)
-    lo = (Xs - x16.astype(np.float64)) * 2.0 ** 11           # |lo| <= 2^-11 |Xs| before the scale
-    q = lambda v: torch.from_numpy(v.astype(np.float32)).to(torch.float8_e4m3fn)
-    h8, l8 = q(Xs), q(lo)
-    R, K = X.shape
-    packed = np.stack([h8.view(torch.uint8).numpy().reshape(R, K // 32, 32),
-                       l8.view(torch.uint8).numpy().reshape(R, K // 32, 32)], axis=2).reshape(R, 2 * K)
-    return x16, h8.to(torch.float64).numpy(), l8.to(torch.float64).numpy(), np.ascontiguousarray(packed), s
-
-
-@pytest.mark.parametrize("M,Nn,K", [(128, 64, 32), (300, 64, 96), (128, 256, 800), (1000, 128, 2048)])
-def test_mixed_fp16_e4m3_gemm_prototype(M, Nn, K):
-    """One fp16 pass + two plain-e4m3 correction passes (kind::f16 and kind::f8f6f4 MMAs accumulating into the same TMEM
-    columns, one power-of-two scale per operand): 4 MMA slots per 32 K-elements instead of the 6 of bf16x3.  Prototype
-    of DESIGN 6b item 4 on the 1-CTA kernel (`tc_gemm_bf16x3<EPI_STORE, 0, MIX=1>`); measured on B200: device vs the
-    float64 emulation of the quantised operands 1e-7 - 5e-6, vs the exact product 1.0e-5 - 1.2e-5
-    (profiles/r1_mixed_proto_test.log), 1.15x the bf16x3 kernel on a shape where both are fed at the L2 -> SM limit
-    (profiles/r1_mixed_proto_timing.json)."""
-    rng = np.random.default_rng(M + Nn + K)
-    A = rng.standard_normal((M, K)).astype(np.float32)
-    B = (rng.standard_normal((Nn, K)) * 0.3).astype(np.float32)
-    a16, a8h, a8l, a8, sa = mixed_operands(A)
-    b16, b8h, b8l, b8, sb = mixed_operands(B)
-    # fp16 operands carry 2^5 and 2^6 so that all three products share the factor 2^11 sa sb
-    a16s = (a16.astype(np.float64) * 32.0).astype(np.float16)
-    b16s = (b16.astype(np.float64) * 64.0).astype(np.float16)
-    assert np.isfinite(a16s).all() and np.isfinite(b16s).all()
-    out_scale = np.float32(2.0 ** -11 / (sa * sb))
-    eng = engine(64, 32, 4)
-    lib = _lib.load()
-    fn = lib.pyb_debug_tc_gemm_mixed
-    fn.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_float, C.c_void_p]
-    fn.restype = C.c_int
-    D = np.empty((M, Nn), np.float32)
-    a16b, b16b = np.ascontiguousarray(a16s.view(np.uint16)), np.ascontiguousarray(b16s.view(np.uint16))
-    _lib.check(fn(eng.h, a16b.ctypes.data, a8.ctypes.data, b16b.ctypes.data, b8.ctypes.data, M, Nn, K, out_scale,
-                  D.ctypes.data))
-    assert np.isfinite(D).all()
-    emul = float(out_scale) * (a16s.astype(np.float64) @ b16s.astype(np.float64).T + a8l @ b8h.T + a8h @ b8l.T)
-    want = A.astype(np.float64) @ B.astype(np.float64).T
-    single = float(out_scale) * (a16s.astype(np.float64) @ b16s.astype(np.float64).T)
-    print("mixed gemm %dx%dx%d: device vs emulation %.2e, device vs float64 %.2e (fp16 pass alone %.2e)"
-          % (M, Nn, K, rel_err(D, emul), rel_err(D, want), rel_err(single, want)))
-    assert rel_err(D, emul) < 2e-5          # the instruction does what the emulation says (fp32 accumulation apart)
-    assert rel_err(D, want) < 4e-5          # and the scheme is >= 5x better than the fp16 pass alone (~3e-4)
-    assert rel_err(single, want) > 1e-4
-
-
-def int8_slices(X):
-    """two int8 fixed-point slices per row: X = s / 127 * (hi + lo / 254), one scale per row"""
-    X = X.astype(np.float64)
-    s = np.abs(X).max(axis=1, keepdims=True)
-    s = np.where(s > 0, s, 1.0)
-    r = X / s * 127.0
-    hi = np.clip(np.round(r), -127, 127)
-    lo = np.clip(np.round((r - hi) * 254.0), -127, 127)
-    return np.ascontiguousarray(hi.astype(np.int8)), np.ascontiguousarray(lo.astype(np.int8)), s
-
-
-@pytest.mark.skipif(os.environ.get("PYB_TEST_I8") != "1",
-                    reason="int8-slice prototype (DESIGN 6b item 4b): the entry ran on B200 through tools/bench_mixed_proto.py --i8 "
-                           "(profiles/r1_i8_proto_timing.json), these pytest shapes have not: PYB_TEST_I8=1")
-@pytest.mark.parametrize("M,Nn,K", [(128, 64, 64), (300, 64, 128), (128, 256, 832), (1000, 128, 2048)])
-def test_int8_slice_gemm_prototype(M, Nn, K):
-    """hh + (hl + lh) / 254 with kind::i8 MMAs (exact int32 accumulation in two TMEM accumulators): 3 MMA slots per 32
-    K-elements and 2 bytes per operand element against 6 slots and 4 bytes for bf16x3."""
-    rng = np.random.default_rng(M + Nn + K)
-    A = rng.random((M, K)).astype(np.float32)                      # U[0,1) like the data operand
-    B = (rng.standard_normal((Nn, K)) * 0.3).astype(np.float32)
-    ah, al, sa = int8_slices(A)
-    bh, bl, sb = int8_slices(B)
-    eng = engine(64, 32, 4)
-    lib = _lib.load()
-    fn = lib.pyb_debug_tc_gemm_i8
-    fn.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_void_p]
-    fn.restype = C.c_int
-    D = np.empty((M, Nn), np.float32)
-    _lib.check(fn(eng.h, ah.ctypes.data, al.ctypes.data, bh.ctypes.data, bl.ctypes.data, M, Nn, K, D.ctypes.data))
-    i64 = lambda x: x.astype(np.int64)
-    exact = (i64(ah) @ i64(bh).T).astype(np.float64) + (i64(ah) @ i64(bl).T + i64(al) @ i64(bh).T).astype(np.float64) / 254.0
-    assert np.isfinite(D).all()
-    got = D.astype(np.float64) * sa * sb.T / 127.0 ** 2
-    want = A.astype(np.float64) @ B.astype(np.float64).T
-    print("int8 slice gemm %dx%dx%d: device vs exact integers %.2e, scaled vs float64 %.2e"
-          % (M, Nn, K, rel_err(D, exact), rel_err(got, want)))
-    assert rel_err(D, exact) < 5e-7          # integer accumulation is exact; only the fp32 conversions round
-    assert rel_err(got, want) < 1e-4
-
-
-@pytest.mark.skipif(os.environ.get("PYB_TEST_I8") != "1", reason="int8-slice operand producer has not run on a GPU yet: PYB_TEST_I8=1")
-@pytest.mark.parametrize("rows,K", [(5, 64), (300, 784), (1000, 100)])
-def test_int8_slice_producer(rows, K):
-    """k_slice_rows_i8: per-row maximum as scale, x = s / 127 (hi + lo / 254) to 2^-16 of the row maximum, zero padding."""
-    rng = np.random.default_rng(rows + K)
-    X = rng.standard_normal((rows, K)).astype(np.float32)
-    X[0] = 0.0                                                   # an all-zero row keeps scale 1 and zero slices
-    Kpad = (K + 63) // 64 * 64
-    eng = engine(64, 32, 4)
-    fn = _lib.load().pyb_debug_slice_i8
-    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
-    fn.restype = C.c_int
-    hi, lo = np.empty((rows, Kpad), np.int8), np.empty((rows, Kpad), np.int8)
-    s = np.empty(rows, np.float32)
-    _lib.check(fn(eng.h, X.ctypes.data, rows, K, Kpad, hi.ctypes.data, lo.ctypes.data, s.ctypes.data))
-    want_s = np.abs(X).max(1)
-    want_s[want_s == 0] = 1.0
-    np.testing.assert_array_equal(s, want_s)
-    assert not hi[:, K:].any() and not lo[:, K:].any() and not hi[0].any() and not lo[0].any()
-    rec = s[:, None].astype(np.float64) / 127.0 * (hi[:, :K].astype(np.float64) + lo[:, :K].astype(np.float64) / 254.0)
-    assert (np.abs(rec - X).max(1) <= want_s * 2.0 ** -15.8).all()          # s / 127 * 0.5 / 254 = s * 2^-15.98 (+ fp32 rounding of the quotient)
-    h_ref, l_ref, _ = int8_slices(X)
-    assert (np.abs(hi[:, :K].astype(np.int32) - h_ref) <= 1).all()           # fp32 against float64 division: ties may differ
 
 
 def problem(oracle, D, H, Cc, N, S, seed, act="relu", loss="ce", q_scale=0.05):
@@ -264,6 +139,7 @@ def test_fused_epilogue_agrees_with_the_unfused_kernels(oracle, H, Cc, N, S):
     O = oracle
     spec, prob, q, out_act, _ = problem(O, 784, H, Cc, N, S, seed=H + N)
     eng = engine(784, H, Cc, "relu", out_act)
+    eng.set_option("tc_i8", 0)                       # this is an A/B of the bf16x3 kernels (the int8 slices: test_gpu_i8.py)
     eng.set_dataset(prob.X, prob.y, prob.loss_kind)
     eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
     eng.set_option("path", _lib.PATH_TENSOR)
