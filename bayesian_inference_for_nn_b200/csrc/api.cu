@@ -43,6 +43,7 @@ int resolve_path(pyb_handle* h, int64_t S, bool with_grad) {
 }
 
 void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, float* loss_out, float* grad_out) {
+  NvtxRange nv("pyb.eval.fwd_bwd");
   int path = resolve_path(h, S, grad_out != nullptr);
   if (path == PYB_PATH_TENSOR) {
     PYB_REQUIRE(tc_supported(h, S), PYB_ERR_UNSUPPORTED, "tensor path does not support this model/dataset shape");
@@ -60,6 +61,7 @@ void eval_loss_grad(pyb_handle* h, const float* theta, int64_t S, float scale, f
 void eval_on_batch(pyb_handle* h, const float* theta, int64_t S, const float* Xb, const int32_t* yb_i, const float* yb_f,
                    int64_t Nb, float scale, float* loss_out, float* grad_out) {
   if (Xb == h->X.p && Nb == h->N) { eval_loss_grad(h, theta, S, scale, loss_out, grad_out); return; }
+  NvtxRange nv("pyb.eval.fwd_bwd.minibatch");
   const bool tensor_ok = grad_out && tc_supported_rows(h, Nb) && (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_TENSOR);
   const bool small_ok = grad_out && Nb <= h->N && fused_small_supported(h) &&
                         (h->opt_path == PYB_PATH_AUTO || h->opt_path == PYB_PATH_FUSED_SMALL);
@@ -223,6 +225,9 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_predict_sharded = v != 0;
   } else if (!strcmp(key, "tc_fuse")) {
     h->opt_tc_fuse = v != 0;
+  } else if (!strcmp(key, "svgd_pshard")) {
+    h->opt_svgd_pshard = v != 0;
+    h->svgd.ps_ready = false;
   } else if (!strcmp(key, "tc_i8")) {
     PYB_REQUIRE(v == -1 || v == 0 || v == 1 || v == 2, PYB_ERR_INVALID, "tc_i8 must be -1 (auto), 0 (bf16x3), 1 or 2 (int8 slices)");
     h->opt_tc_i8 = (int)v;
@@ -246,6 +251,7 @@ int pyb_get_info(const pyb_handle* h, const char* key, double* out) {
   else if (!strcmp(key, "prof_flops")) *out = h->prof_flops;
   else if (!strcmp(key, "prof_launches")) *out = (double)h->prof_launches;
   else if (!strcmp(key, "n_train")) *out = (double)h->n_train;
+  else if (!strcmp(key, "svgd_h")) *out = h->svgd.last_h;
   else if (!strcmp(key, "tc_split")) *out = (double)tc_resident_split(h);
   else if (!strcmp(key, "dataset_uploads")) *out = (double)h->dataset_uploads;
   else if (!strcmp(key, "dataset_kept")) *out = (double)h->dataset_kept;

@@ -12,7 +12,18 @@
 #include <stdexcept>
 #include "../../include/pyesian_b200.h"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: the ranges cost one predictable branch unless a tool (nsys, ncu --nvtx) is attached
+
 namespace pyb {
+
+// RAII NVTX range on the calling host thread: marks the phases of the hot path in profiler timelines
+// (fwd/bwd evaluation, kick/drift, accept, Gram, exchange, ...)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ------------------------------------------------------------------------------------------
 // errors: C++ exceptions are used internally and converted to status codes at the ABI boundary
@@ -227,6 +238,14 @@ struct SvgdState {
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
   DevBuf<float> theta_all, g_all;
+  // parameter-sharded Stein phase (canonical mode, tensor path, world > 1): rank r owns columns [r Pw, (r+1) Pw) of ALL
+  // particles — theta slice, gathered gradient slice, Adam moments, phi — and the exchange is two all-to-alls of the
+  // LOCAL particles' rows (gradients out, updated particles back) plus one all-reduce of the St x St Gram matrix
+  double last_h = 0.0;          // bandwidth h of the last step (canonical: sqrt(0.5 median / log(St + 1)); live: gamma = 1)
+  bool ps_ready = false, ps_checked = false;
+  int64_t ps_Pw = 0;
+  DevBuf<float> ps_pack, ps_x, ps_g, ps_m, ps_v, ps_phi, ps_mu, ps_iv;
+  DevBuf<double> ps_norms;
   // the two all-gathers run on their own stream: particles while the local gradients are computed, gradients
   // while the Gram matrix is built (the exchange step is comm-bound at 8 GPUs unless overlapped)
   cudaStream_t comm_stream = nullptr;
@@ -286,6 +305,7 @@ struct pyb_handle {
   int opt_hmc_carry = 1;    // 1: loss and gradient at the current position are carried to the next HMC iteration
   int opt_predict_sharded = 0;   // 1: pyb_predict all-reduces its moment sums over the handle's communicator
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
+  int opt_svgd_pshard = 1;   // sharded canonical SVGD on the tensor path: shard the Stein phase over the parameters (all-to-all + Gram all-reduce)
   int opt_tc_i8 = -1;    // operand split of the big GEMMs: 0 bf16x3, 1 int8 slices in the forward GEMM, 2 + in the dW1 GEMM, -1 auto (tc_i8.cuh)
   double opt_workspace_mb = 4096;
   int64_t opt_chain_batch = 0;
@@ -319,6 +339,10 @@ inline void prof_begin(pyb_handle* h) {
   cudaEventRecord(h->prof_events[h->prof_used], h->stream);
 }
 inline void prof_end(pyb_handle* h, double flops) {
+  // a launch-configuration error ("too many resources requested for launch", a bad cluster shape) is returned by the launch
+  // itself and is LOST once a later runtime call succeeds (measured: the evaluation then continues on stale buffers), so
+  // every dominant-kernel launch is checked here, right behind it
+  PYB_CUDA(cudaGetLastError());
   if (!h->prof_enabled) return;
   cudaEventRecord(h->prof_events[h->prof_used + 1], h->stream);
   h->prof_used += 2;
@@ -395,6 +419,9 @@ void nccl_all_gather_f32(void* comm, const float* send, float* recv, size_t coun
 void nccl_all_reduce_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t s);
 void nccl_all_reduce_f64(void* comm, double* buf, size_t count, cudaStream_t s);
 void nccl_broadcast_f32(void* comm, float* buf, size_t count, int root, cudaStream_t s);
+void nccl_all_reduce_f32(void* comm, float* buf, size_t count, cudaStream_t s);
+void nccl_all_to_all_f32(void* comm, const float* send, float* recv, size_t count_per_peer, int world, cudaStream_t s);
+void nccl_check_async(void** comm);
 
 // predict.cu
 // optional classification-uncertainty request (Metrics.py:344-375): host labels [Nt], host outputs [Nt, Ce, Ce]

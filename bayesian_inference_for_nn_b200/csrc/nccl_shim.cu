@@ -1,5 +1,8 @@
 // nccl_shim.cu — NCCL is resolved at run time with dlopen/dlsym, so libpyesian_b200.so carries no link
-// dependency on it: only sharded SVGD (particle/gradient all-gather, histogram all-reduce) needs it.
+// dependency on it: only sharded SVGD (gradient / particle all-to-all, Gram and histogram all-reduce) and the sharded
+// predictive need it.  Every stream synchronisation behind a collective is followed by nccl_check_async(): an
+// asynchronous communicator error (a peer that died, a link fault) aborts the communicator and surfaces as PYB_ERR_CUDA
+// instead of a hang in the next collective.
 // The Python side preloads the libnccl.so.2 that ships with the CUDA stack (torch's bundled copy) so the
 // soname lookup below finds the already-mapped library.
 #include "common.cuh"
@@ -19,6 +22,12 @@ struct NcclApi {
   int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+  int (*CommGetAsyncError)(ncclComm_t, int*);
+  int (*CommAbort)(ncclComm_t);
   const char* (*GetErrorString)(int);
   bool ok = false;
 };
@@ -44,6 +53,12 @@ static NcclApi& api() {
   PYB_SYM(AllGather, "ncclAllGather")
   PYB_SYM(AllReduce, "ncclAllReduce")
   PYB_SYM(Broadcast, "ncclBroadcast")
+  PYB_SYM(Send, "ncclSend")
+  PYB_SYM(Recv, "ncclRecv")
+  PYB_SYM(GroupStart, "ncclGroupStart")
+  PYB_SYM(GroupEnd, "ncclGroupEnd")
+  PYB_SYM(CommGetAsyncError, "ncclCommGetAsyncError")
+  PYB_SYM(CommAbort, "ncclCommAbort")
   PYB_SYM(GetErrorString, "ncclGetErrorString")
 #undef PYB_SYM
   a.ok = true;
@@ -77,6 +92,30 @@ void nccl_all_reduce_u64(void* comm, unsigned long long* buf, size_t count, cuda
 }
 void nccl_all_reduce_f64(void* comm, double* buf, size_t count, cudaStream_t s) {
   nccl_check(api().AllReduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t)comm, s), "ncclAllReduce");
+}
+void nccl_all_reduce_f32(void* comm, float* buf, size_t count, cudaStream_t s) {
+  nccl_check(api().AllReduce(buf, buf, count, NCCL_FLOAT32, NCCL_SUM, (ncclComm_t)comm, s), "ncclAllReduce");
+}
+// personalised exchange: block q of `send` (count_per_peer floats) goes to rank q, block q of `recv` comes from rank q
+void nccl_all_to_all_f32(void* comm, const float* send, float* recv, size_t count_per_peer, int world, cudaStream_t s) {
+  nccl_check(api().GroupStart(), "ncclGroupStart");
+  for (int q = 0; q < world; ++q) {
+    nccl_check(api().Send(send + (size_t)q * count_per_peer, count_per_peer, NCCL_FLOAT32, q, (ncclComm_t)comm, s), "ncclSend");
+    nccl_check(api().Recv(recv + (size_t)q * count_per_peer, count_per_peer, NCCL_FLOAT32, q, (ncclComm_t)comm, s), "ncclRecv");
+  }
+  nccl_check(api().GroupEnd(), "ncclGroupEnd");
+}
+// after a stream synchronisation: has the communicator recorded an asynchronous error?  Abort it and fail cleanly.
+void nccl_check_async(void** comm) {
+  if (!comm || !*comm) return;
+  int err = 0;
+  nccl_check(api().CommGetAsyncError((ncclComm_t)*comm, &err), "ncclCommGetAsyncError");
+  if (err != 0) {
+    std::string msg = std::string("NCCL asynchronous error: ") + api().GetErrorString(err) + " (communicator aborted)";
+    api().CommAbort((ncclComm_t)*comm);
+    *comm = nullptr;
+    throw Error(PYB_ERR_CUDA, msg);
+  }
 }
 void nccl_broadcast_f32(void* comm, float* buf, size_t count, int root, cudaStream_t s) {
   nccl_check(api().Broadcast(buf, buf, count, NCCL_FLOAT32, root, (ncclComm_t)comm, s), "ncclBroadcast");

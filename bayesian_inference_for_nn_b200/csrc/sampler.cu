@@ -359,6 +359,7 @@ void hmc_flush_arena(pyb_handle* h) {
 
 static void launch_kick(pyb_handle* h, const float* g, float kick1, float kick2, float drift, bool snapshot, bool energy,
                         bool kinetic, float* Up_out, float* K_out) {
+  NvtxRange nv("pyb.hmc.kick_drift");
   HmcState& st = h->hmc;
   const int64_t P = h->model.P;
   int nblk = ew_blocks(P);
@@ -393,7 +394,9 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
   const int path = resolve_path(h, S, true);
   int64_t evals = 0;
   if (path == PYB_PATH_FUSED_SMALL) { st.have_cur = false; evals = (int64_t)n_iters * S * (st.L + 1); }
+  NvtxRange nv_run("pyb.hmc_run");
   for (int it = 0; it < n_iters; ++it) {
+    NvtxRange nv_it("pyb.hmc.iteration");
     bool first = sampling && !st.sampling_started;
     if (sampling) {
       int64_t need = S * (first ? 2 : 1);
@@ -408,11 +411,13 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
       h->path_used = path;
     } else {
     // momentum + K0  (HMC.py:78-79)
+    nvtxRangePushA("pyb.hmc.momentum");
     k_momentum<<<gridp, EW_THREADS, 0, h->stream>>>(st.p.p, st.have_inj_p ? st.inj_p.p : nullptr, P, stdv, h->seed,
                                                     (uint32_t)st.iter, st.chain_offset, st.partial_k.p, S);
     count_launch(h);
     k_finish<<<(unsigned)S, 128, 0, h->stream>>>(st.partial_k.p, nblk, 1.0 / (2.0 * st.m), st.K0.p);
     count_launch(h);
+    nvtxRangePop();
     // U0 and the first half kick share one evaluation at q0  (HMC.py:80-82).  The reference re-evaluates the
     // potential and its gradient at q0 in every iteration (HMC.py:80,82); q0 is where the previous iteration ended —
     // its end point q_L if that was accepted, its own q0 if not — and both were evaluated then, so with "hmc_carry"
@@ -436,6 +441,7 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
         launch_kick(h, st.g.p, half, 0.f, 0.f, false, true, true, st.Up1.p, st.K1.p);
       }
     }
+    NvtxRange nv_acc("pyb.hmc.accept");
     AcceptArgs a;
     a.Up0 = st.Up0.p; a.Up1 = st.Up1.p; a.loss0 = st.loss0.p; a.loss1 = st.loss.p; a.K0 = st.K0.p; a.K1 = st.K1.p;
     a.prior_const = (float)h->prior_const; a.n_train = n_train;

@@ -11,16 +11,18 @@ ignored (:106-126), chains start at the prior mean (:69-72).
 Underneath, every iteration is a handful of kernel launches on the handle's stream with no host
 sync (pyb_hmc_run); the reference's single chain becomes ``n_chains`` (optional hyper-parameter,
 default 1) independent chains whose accepted states are pooled into the returned ``Sampled``.
-Optional knobs (all absent => reference behaviour): ``n_chains``, ``seed``, ``semantics``
-("reference" | "canonical"), ``device``, ``path`` ("auto" | "generic" | "fused" | "tensor"),
-``chain_offset`` (global id of the first local chain when chains are sharded over ranks).
+Optional knobs (all absent => reference behaviour): ``n_chains``, ``seed`` (absent: a fresh 64-bit seed per
+optimizer, kept in ``self.seed``), ``semantics`` ("reference" | "canonical"), ``device``, ``path`` ("auto" | "generic" |
+"fused" | "tensor"), ``chain_offset`` (global id of the first local chain when chains are sharded over processes), and
+``devices=[0, 1, ...]`` / ``n_devices=k``: the chains are sharded over several GPUs of the box inside this process
+(multi.py) and ``result()`` pools them in global chain order — bit-identical to the one-device run.
 """
 import numpy as np
 
 from .. import _lib
 from ..distributions import Sampled
-from ..engine import Engine
 from ..keras_json import parse_model_json
+from ..multi import EngineGroup, devices_from
 from ..nn import BayesianModel
 from .Optimizer import Optimizer
 
@@ -51,12 +53,21 @@ class HMC(Optimizer):
         self._n_chains = int(self._hp("n_chains", 1))
         sem = self._hp("semantics", "reference")
         self._semantics = _lib.HMC_CANONICAL if sem in ("canonical", _lib.HMC_CANONICAL) else _lib.HMC_REFERENCE
-        self._engine = Engine(self._spec, device=int(self._hp("device", 0)), seed=int(self._hp("seed", 0)))
+        # the reference is stochastic by default (unseeded tf.random.normal / random.random, HMC.py:88,171): without an
+        # explicit seed every optimizer draws its own, so repeated runs are independent; self.seed reproduces a run
+        seed = self._hp("seed", None)
+        self.seed = int(np.random.SeedSequence().entropy & ((1 << 63) - 1)) if seed is None else int(seed)
+        self._devices = devices_from(self._hp)
+        self._engine = EngineGroup(self._spec, self._devices, seed=self.seed)
         path = self._hp("path", "auto")
-        self._engine.set_option("path", _PATHS.get(path, path) if isinstance(path, str) else path)
         x, y = self._dataset.training_arrays()          # ONE full-dataset batch, frozen for the run (HMC.py:63-65)
-        self._engine.set_dataset(x, y, self._dataset.loss_kind, n_train=self._dataset.train_size)
-        self._engine.set_prior(*prior.lower(self._spec))
+        lowered = prior.lower(self._spec)
+
+        def setup(i, e):
+            e.set_option("path", _PATHS.get(path, path) if isinstance(path, str) else path)
+            e.set_dataset(x, y, self._dataset.loss_kind, n_train=self._dataset.train_size)
+            e.set_prior(*lowered)
+        self._engine.each(setup)
         self._engine.hmc_init(self._n_chains, self._epsilon, self._m, int(self._L), self._semantics,
                               q0=kwargs.get("q0"), chain_offset=int(self._hp("chain_offset", 0)))
 
@@ -91,7 +102,7 @@ class HMC(Optimizer):
         self._accepted_runs = self._total_runs = 0
         self._phase(int(self._nb_burn_epoch), "HMC - Burning", sampling=False, burning=True)
         self._accepted_runs = self._total_runs = 0
-        self._engine.hmc_reset_samples()
+        self._engine.each(lambda i, e: e.hmc_reset_samples())
         self._phase(int(nb_iterations), "HMC - Sampling", sampling=True, burning=False)
 
     @property
@@ -103,6 +114,6 @@ class HMC(Optimizer):
         if samples.shape[0] == 0:
             q, _ = self._engine.hmc_state()          # no sampling iteration yet: current positions, weight 1
             samples, freq = q, np.ones(q.shape[0], np.int32)
-        posterior = BayesianModel(self._model_config, device=int(self._hp("device", 0)))
+        posterior = BayesianModel(self._model_config, device=self._devices[0])
         posterior.apply_distribution(Sampled(samples, freq.tolist()), 0, self._spec.n_keras_layers - 1)
         return posterior

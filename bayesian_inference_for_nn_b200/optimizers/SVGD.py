@@ -12,13 +12,18 @@ particle's gradient broadcast, legacy-Adam descent (:100-123).  ``semantics="can
 median-heuristic Stein update of ``baseline__kernel`` (:165-181) applied Jacobi-style with the prior
 gradient included.  Minibatches: one shuffled pass per epoch without replacement, last
 batch partial (Optimizer.py:35-41, SVGD.py:91-95).
+
+``devices=[0, 1, ...]`` / ``n_devices=k`` (optional hyper-parameters): the M particles are sharded over several GPUs of
+the box inside this process (multi.py; M must be a multiple of the device count); every device joins one NCCL
+communicator and the exchange step of the update runs inside the library (csrc/svgd.cu).  ``seed`` absent: a fresh seed
+per optimizer (``self.seed``), as the reference is unseeded.
 """
 import numpy as np
 
 from .. import _lib
 from ..distributions import Sampled
-from ..engine import Engine
 from ..keras_json import parse_model_json
+from ..multi import EngineGroup, devices_from
 from ..nn import BayesianModel, ParticleModel
 from .Optimizer import Optimizer
 
@@ -71,13 +76,29 @@ class SVGD(Optimizer):
         sem = self._hp("semantics", "reference")
         self._semantics = (_lib.SVGD_CANONICAL_MEDIAN if sem in ("canonical", _lib.SVGD_CANONICAL_MEDIAN)
                            else _lib.SVGD_REFERENCE_LIVE)
-        self._rng = np.random.default_rng(self._hp("seed", None))
-        self._engine = Engine(self._spec, device=int(self._hp("device", 0)), seed=int(self._hp("seed", 0)))
+        seed = self._hp("seed", None)
+        self.seed = int(np.random.SeedSequence().entropy & ((1 << 63) - 1)) if seed is None else int(seed)
+        self._rng = np.random.default_rng(self.seed)
+        self._devices = devices_from(self._hp)
+        R = len(self._devices)
+        if self._M % R:
+            raise ValueError("M = %d particles do not shard evenly over %d devices" % (self._M, R))
+        self._group = EngineGroup(self._spec, self._devices, seed=self.seed)
+        self._engine = self._group.engines[0]
         x, y = self._dataset.training_arrays()
         self._n_train = x.shape[0]
-        self._engine.set_dataset(x, y, self._dataset.loss_kind, n_train=self._n_train)
-        self._engine.set_prior(*self._prior.lower(self._spec))
-        self._engine.svgd_init(self._M, self._lr, self._semantics, particles0=kwargs.get("particles0"))
+        lowered = self._prior.lower(self._spec)
+        p0 = kwargs.get("particles0")
+        p0 = None if p0 is None else np.asarray(p0, np.float64)
+        Sl = self._M // R
+
+        def setup(i, e):
+            e.set_dataset(x, y, self._dataset.loss_kind, n_train=self._n_train)
+            e.set_prior(*lowered)
+        self._group.each(setup)
+        self._group.svgd_join()
+        self._group.each(lambda i, e: e.svgd_init(Sl, self._lr, self._semantics, offset=i * Sl,
+                                                  particles0=None if p0 is None else p0[i * Sl:(i + 1) * Sl]))
         self._num_particles = self._spec.n_params
         self._epoch_batches = iter(())
 
@@ -97,13 +118,14 @@ class SVGD(Optimizer):
             return 0.0
         if not self._valid_ready:
             xv, yv = self._dataset.split_arrays("valid")
-            self._engine.svgd_set_validation(xv, yv)
+            self._group.each(lambda i, e: e.svgd_set_validation(xv, yv))
             self._valid_ready = True
-        return float(self._engine.svgd_validation_loss())
+        return float(self._group.each(lambda i, e: e.svgd_validation_loss())[0])     # all-reduced: every rank holds it
 
     def step(self, save_document_path=None):
         self._step += 1
-        total_loss = self._engine.svgd_step(self._next_batch())
+        batch = self._next_batch()
+        total_loss = self._group.each(lambda i, e: e.svgd_step(batch))[0]            # all-reduced mean over all particles
         if self._step % 10 == 0:
             self.train_losses.append(total_loss)
             self.valid_losses.append(self._validation_loss())
@@ -111,11 +133,11 @@ class SVGD(Optimizer):
 
     @property
     def particles(self):
-        return self._engine.svgd_particles()
+        return np.concatenate(self._group.each(lambda i, e: e.svgd_particles()))
 
     def result(self):
-        parts = self._engine.svgd_particles().astype(np.float32)
-        bm = BayesianModel(self._model_config, device=int(self._hp("device", 0)))
+        parts = self.particles.astype(np.float32)
+        bm = BayesianModel(self._model_config, device=self._devices[0])
         bm.apply_distribution(Sampled(parts, [1] * parts.shape[0]), 0, self._spec.n_keras_layers - 1)
         models = [ParticleModel(bm, parts[i]) for i in range(parts.shape[0])]
         return SVGDResult(models, self.train_losses, self.valid_losses, bm)

@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--opt", action="append", default=[], help="development: library option key=value (e.g. tc_fuse=0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / C2 / C4 / C5 / strong-scaling sub-records")
     return ap.parse_args()
 
 
@@ -197,6 +198,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def named_default(args):
+    return bool(args.chains == 1024 and args.rows == 60000 and args.leapfrog == 20 and not args.opt)
+
+
 def workload_config(args, world, evals_per_step=None):
     return {"workload": "C3 HMC 784-256-10 MLP, %d chains/GPU, %d rows x 784 synthetic MNIST-shaped, L=%d, "
                         "reference leapfrog semantics, Gaussian prior N(0,1)" % (args.chains, args.rows, args.leapfrog),
@@ -204,7 +209,175 @@ def workload_config(args, world, evals_per_step=None):
             "epsilon": args.eps, "evals_executed_per_step_per_chain": evals_per_step if evals_per_step is not None else args.leapfrog + 1,
             "parallelism": "chains sharded x%d, no data-path collective" % world,
             "l2_policy": "inputs exceed L2 (X hi/lo 188 MB + per-chain operands >> 126 MB)",
-            "named_config": bool(args.chains == 1024 and args.rows == 60000 and args.leapfrog == 20 and not args.opt)}
+            "named_config": named_default(args)}
+
+
+FP32_SIMT_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: 148 SMs x 128 FMA lanes x 2 x 1.965 GHz (nominal)
+
+
+def moons(n, seed=0, noise=0.2):
+    rng = np.random.default_rng(seed)
+    n0 = n // 2
+    t0, t1 = rng.uniform(0, np.pi, n0), rng.uniform(0, np.pi, n - n0)
+    x = np.concatenate([np.stack([np.cos(t0), np.sin(t0)], 1), np.stack([1 - np.cos(t1), 0.5 - np.sin(t1)], 1)])
+    y = np.concatenate([np.zeros(n0, np.int32), np.ones(n - n0, np.int32)])
+    return (x + rng.normal(0, noise, x.shape)).astype(np.float32), y
+
+
+def run_extras(args, rank, local_rank, world, dist, X, y, peaks):
+    """The other named configurations of BASELINE.json (C1, C2, C4, C5) and the strong-scaling point of the headline, each
+    a few hundred milliseconds of device time after the timed HMC region: sub-records of the one JSON line (`extra`).
+    Every record is device-timed (max over ranks where the work is sharded); a failure is recorded, never raised."""
+    from bayesian_inference_for_nn_b200 import _lib, keras_json
+    from bayesian_inference_for_nn_b200.engine import Engine
+    out = {}
+
+    def maxr(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def mlp(D, H, C):
+        return keras_json.parse_model_json(keras_json.make_sequential_json(D, [H, C], ["relu", "softmax"]))
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:                                   # noqa: BLE001  (a sub-record must not cost the headline)
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if dist is not None:
+            dist.barrier()
+
+    # ---- C1: HMC on make_moons (1600 rows, 2-50-2, L = 30, eps = 0.005, m = 0.5), 16 384 chains per GPU (weak)
+    def c1():
+        Xm, ym = moons(1600)
+        S, L, iters = 16384, 30, 5
+        eng = Engine(mlp(2, 50, 2), device=local_rank, seed=1)
+        eng.set_dataset(Xm, ym, _lib.LOSS_SPARSE_CE)
+        eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+        eng.hmc_init(S, 0.005, 0.5, L, chain_offset=rank * S)
+        eng.hmc_run(3, burning=True, sampling=False)
+        d = eng.hmc_run(iters, burning=False, sampling=False)
+        ms = maxr(d["device_ms"])
+        eng.close()
+        rate = world * S * L * iters / (ms / 1e3)
+        tf = rate * 1.6e6 / 1e12
+        return {"workload": "C1 HMC make_moons 1600x2, 2-50-2, L=30, %d chains/GPU" % S, "value": rate, "unit": "grad-evals/s",
+                "ms": ms / iters, "scaling": "weak",
+                "roofline": {"bound": "fp32-simt", "achieved": tf, "peak": FP32_SIMT_PEAK_TFLOPS * world, "unit": "TFLOP/s",
+                             "frac": tf / (FP32_SIMT_PEAK_TFLOPS * world), "hbm_algorithmic_gbs": rate * 23232 / 1e9,
+                             "hbm_frac": rate * 23232 / 1e9 / (peaks["hbm"] * world)}}
+
+    # ---- C2: SVGD on make_moons, 64 particles, full batch (rank 0; 64 particles do not shard usefully)
+    def c2():
+        if rank != 0:
+            return None
+        Xm, ym = moons(1600)
+        res = {"workload": "C2 SVGD make_moons 1600x2, 2-50-2, 64 particles, full batch (one GPU)"}
+        for sem, name in ((_lib.SVGD_CANONICAL_MEDIAN, "canonical_median"), (_lib.SVGD_REFERENCE_LIVE, "reference_live")):
+            eng = Engine(mlp(2, 50, 2), device=local_rank, seed=1)
+            eng.set_dataset(Xm, ym, _lib.LOSS_SPARSE_CE)
+            eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+            eng.svgd_init(64, 1e-3, sem)
+            for _ in range(3):
+                eng.svgd_step(None)
+            ms = 0.0
+            for _ in range(20):
+                eng.svgd_step(None)
+                ms += eng.info("last_device_ms")
+            eng.close()
+            res[name] = {"value": 20 / (ms / 1e3), "unit": "steps/s", "ms": ms / 20,
+                         "particle_grad_evals_per_s": 64 * 20 / (ms / 1e3)}
+        gf = 0.107 * res["canonical_median"]["value"] / 1e3
+        res["roofline"] = {"bound": "latency / fp32-simt", "achieved": gf, "peak": FP32_SIMT_PEAK_TFLOPS, "unit": "TFLOP/s",
+                           "frac": gf / FP32_SIMT_PEAK_TFLOPS}
+        return res
+
+    # ---- C4: SVGD at the SVGD_mnist shape, 4096 particles in total sharded over the ranks (784-128-10, minibatch 1024)
+    def c4():
+        S_total, B, steps = 4096, 1024, 5
+        rng = np.random.default_rng(0)
+        idx = [rng.permutation(X.shape[0])[:B].astype(np.int32) for _ in range(steps + 2)]
+        eng = Engine(mlp(784, 128, 10), device=local_rank, seed=1)
+        eng.set_dataset(X, y, _lib.LOSS_SPARSE_CE)
+        eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+        Sl = S_total // world
+        if world > 1:
+            import torch
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(_lib.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            eng.svgd_set_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        eng.svgd_init(Sl, 0.01, _lib.SVGD_CANONICAL_MEDIAN, offset=rank * Sl)
+        ms, loss = [], None
+        for k, ix in enumerate(idx):
+            loss = eng.svgd_step(ix)
+            if k >= 2:
+                ms.append(eng.info("last_device_ms"))
+        t = maxr(float(np.mean(ms)))
+        eng.close()
+        P = 784 * 128 + 128 + 128 * 10 + 10
+        flops = S_total * 6.0 * B * (784 * 128 + 128 * 10) + 4.0 * S_total * S_total * P
+        tf = flops / (t / 1e3) / 1e12
+        return {"workload": "C4 SVGD 784-128-10, %d particles sharded x%d, minibatch 1024 of %d, median-heuristic RBF"
+                            % (S_total, world, X.shape[0]), "value": 1e3 / t, "unit": "steps/s", "ms": t, "scaling": "strong",
+                "particle_grad_evals_per_s": S_total * 1e3 / t, "mean_loss": float(loss),
+                "roofline": {"bound": "tensor (NVLink exchange at N > 1)", "achieved": tf, "peak": peaks["bf16_sustained"] * world,
+                             "unit": "TFLOP/s", "frac": tf / (peaks["bf16_sustained"] * world)}}
+
+    # ---- C5: posterior predictive, 1000 weight samples x 10000 x 784 test rows, 784-256-10 (rank 0)
+    def c5():
+        if rank != 0:
+            return None
+        import torch
+        n, Nt = 1000, 10000
+        g = torch.Generator(device="cuda").manual_seed(0)
+        Wd = torch.randn((n, 784 * 256 + 256 + 256 * 10 + 10), generator=g, device="cuda") * 0.05
+        xd = torch.rand((Nt, 784), generator=g, device="cuda")
+        torch.cuda.synchronize()
+        eng = Engine(mlp(784, 256, 10), device=local_rank)
+        eng.predict(Wd, xd)
+        eng.predict(Wd, xd)
+        ms = eng.info("last_device_ms")
+        eng.close()
+        flops = 2.0 * Nt * (784 * 256 + 256 * 10) * n
+        tf = flops / (ms / 1e3) / 1e12
+        return {"workload": "C5 predictive 1000 weight samples x 10000x784, 784-256-10, mean / variance on the device, samples "
+                            "and inputs resident in HBM (one GPU)", "value": n / (ms / 1e3), "unit": "samples/s", "ms": ms,
+                "rows_x_samples_per_s": n * Nt / (ms / 1e3),
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                             "frac": tf / peaks["bf16_sustained"]}}
+
+    # ---- the headline at FIXED total work: 1024 chains over all ranks (128 per GPU at 8: less than one 148-SM wave)
+    def strong():
+        S = max(1, 1024 // world)
+        eng = Engine(mlp(D_IN, HIDDEN, N_CLS), device=local_rank, seed=1234)
+        eng.set_dataset(X, y, _lib.LOSS_SPARSE_CE)
+        eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+        eng.hmc_init(S, args.eps, 1.0, args.leapfrog, _lib.HMC_REFERENCE, chain_offset=rank * S)
+        eng.hmc_run(2, burning=True, sampling=False)
+        eng.hmc_run(1, burning=False, sampling=True)
+        d = eng.hmc_run(1, burning=False, sampling=True)
+        ms = maxr(d["device_ms"])
+        eng.close()
+        rate = S * world * args.leapfrog / (ms / 1e3)
+        tf = rate * FLOPS_PER_GRADEVAL * args.rows / 1e12
+        return {"workload": "C3 HMC, 1024 chains in TOTAL over %d GPU(s) (%d per GPU)" % (world, S), "value": rate,
+                "unit": "grad-evals/s", "ms": ms, "scaling": "strong",
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_sustained"] * world, "unit": "TFLOP/s",
+                             "frac": tf / (peaks["bf16_sustained"] * world)}}
+
+    guarded("c1_hmc_moons", c1)
+    guarded("c2_svgd_moons", c2)
+    guarded("c4_svgd_mnist", c4)
+    guarded("c5_predictive", c5)
+    if world > 1:
+        guarded("strong_scaling_1024", strong)
+    return out
 
 
 def main():
@@ -308,17 +481,21 @@ def main():
         e2e = {"value": total_evals / e2e_s, "unit": "grad-evals/s", "h2d_bytes_per_step": int(Xp.nbytes + yp.nbytes),
                "d2h_bytes_per_step": int(d2h)}
 
+    split = int(eng.info("tc_split")) if path_used == 3 else 0
+    peaks = measured_peaks()
+    eng.close()                                            # the sub-records below bring their own engines
+    extra = None
+    if not args.no_extras and named_default(args):
+        extra = run_extras(args, rank, local_rank, world, dist, X, y, peaks)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    peaks = measured_peaks()
     algo_flops_per_eval = FLOPS_PER_GRADEVAL * args.rows
     # roofline for the dominant kernel family (the fwd/bwd GEMMs): algorithmic flops they cover /
     # their summed CUDA-event time on the launching stream
     roof = None
-    split = int(eng.info("tc_split")) if path_used == 3 else 0
     if prof_ms > 0:
         achieved = prof_flops / (prof_ms / 1e3) / 1e12
         # MMA passes per algorithmic product in bf16-rate equivalents: bf16x3 = 3 kind::f16 MMAs; int8 slices = 3 kind::i8
@@ -365,6 +542,7 @@ def main():
         "config": workload_config(args, world, d["grad_evals"] / float(S * args.steps)),
         "wall_ms_per_step": 1e3 * wall_s / args.steps, "accept_rate": accept_rate, "path_used": path_used,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

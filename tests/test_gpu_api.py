@@ -143,3 +143,63 @@ def test_svgd_validation_loss_on_device(oracle, shape):
     eng.svgd_validation_loss()
     np.testing.assert_array_equal(eng.svgd_particles(), before)
     eng.close()
+
+
+def _two_gpus():
+    from bayesian_inference_for_nn_b200 import _lib
+    return _lib.device_count() >= 2
+
+
+@pytest.mark.parametrize("shape", ["moons", "wide"])
+def test_hmc_multi_device_flow(shape):
+    """HyperParameters(devices=[0, 1]): the chains are sharded over two GPUs inside ONE optimizer (one engine and one host
+    thread per device, global chain ids in the Philox counters) and result() pools them in global chain order — the
+    samples, their frequencies and the accept rate are those of the one-device run, bit for bit."""
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    if shape == "moons":
+        x, y = moons(600, seed=3)
+        js, hp = MOONS_JSON, dict(epsilon=0.005, m=0.5, L=10, n_chains=7, seed=5)
+    else:
+        rng = np.random.default_rng(0)
+        x, y = rng.random((640, 784)), rng.integers(0, 10, 640)
+        js, hp = keras_json.make_sequential_json(784, [256, 10], ["relu", "softmax"]), dict(epsilon=1e-3, m=1.0, L=3, n_chains=5, seed=5)
+    runs = []
+    for devices in ([0], [0, 1]):
+        dataset = Dataset((x, y), "SparseCategoricalCrossentropy", "Classification", seed=0)
+        opt = HMC()
+        opt.compile(HyperParameters(devices=devices, **hp), js, dataset, verbose=False, prior=GaussianPrior(0.0, 1.0))
+        opt.train(6)
+        bm = opt.result()
+        d = bm._distributions[0]
+        runs.append((d.samples.copy(), list(d.frequencies), opt.accept_rate))
+    (s1, f1, a1), (s2, f2, a2) = runs
+    assert f1 == f2 and a1 == a2
+    np.testing.assert_array_equal(s1, s2)
+
+
+def test_svgd_multi_device_flow():
+    """SVGD with devices=[0, 1]: the particles are sharded over two GPUs behind the same optimizer object; losses and
+    particles follow the one-device run (same minibatches, same initial particles)."""
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    x, y = moons(800, seed=4)
+    rng = np.random.default_rng(1)
+    P = 2 * 50 + 50 + 50 * 2 + 2
+    p0 = rng.normal(0, 0.3, (8, P))
+    runs = []
+    for devices in ([0], [0, 1]):
+        dataset = Dataset((x, y), "SparseCategoricalCrossentropy", "Classification", seed=0)
+        opt = SVGD()
+        opt.compile(HyperParameters(lr=1e-2, batch_size=64, M=8, semantics="canonical", seed=2, devices=devices), MOONS_JSON,
+                    dataset, verbose=False, prior=GaussianPrior(0.0, 1.0), particles0=p0)
+        losses = [opt.step() for _ in range(12)]
+        runs.append((np.asarray(losses), opt.particles.copy()))
+        models, tl, vl = opt.result()
+        assert len(models) == 8 and len(tl) == 1 and len(vl) == 1
+    np.testing.assert_allclose(runs[1][0], runs[0][0], rtol=1e-4)
+    assert np.abs(runs[1][1] - runs[0][1]).max() < 2e-3 * 1e-2 * 12 + 1e-6
+    with pytest.raises(ValueError):
+        SVGD().compile(HyperParameters(lr=1e-2, batch_size=64, M=7, devices=[0, 1]), MOONS_JSON,
+                       Dataset((x, y), "SparseCategoricalCrossentropy", "Classification", seed=0), verbose=False,
+                       prior=GaussianPrior(0.0, 1.0))

@@ -104,3 +104,75 @@ def test_predictive_sharded_over_two_gpus_matches_one_gpu():
         np.testing.assert_allclose(r[1], mean, rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(r[2], var, rtol=1e-4, atol=1e-9)
         np.testing.assert_allclose(r[4], tot, rtol=1e-5, atol=1e-7)
+
+
+def _wide_setup():
+    rng = np.random.default_rng(11)
+    D, H, C, N, B, S, steps = 784, 128, 10, 2048, 512, 512, 3
+    X = rng.random((N, D)).astype(np.float32)
+    y = rng.integers(0, C, N).astype(np.int32)
+    P = D * H + H + H * C + C
+    parts = rng.normal(0, 0.05, (S, P))
+    idx = [rng.permutation(N)[:B].astype(np.int32) for _ in range(steps)]
+    return D, H, C, X, y, parts, idx
+
+
+def _wide_run(rank, world, uid, pshard):
+    from bayesian_inference_for_nn_b200 import _lib, keras_json
+    from bayesian_inference_for_nn_b200.engine import Engine
+    D, H, C, X, y, parts, idx = _wide_setup()
+    S = parts.shape[0]
+    Sl = S // world
+    eng = Engine(keras_json.parse_model_json(keras_json.make_sequential_json(D, [H, C], ["relu", "softmax"])), device=rank)
+    eng.set_dataset(X, y, _lib.LOSS_SPARSE_CE)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    if world > 1:
+        eng.svgd_set_comm(rank, world, uid)
+        eng.set_option("svgd_pshard", pshard)
+    eng.svgd_init(Sl, 1e-3, _lib.SVGD_CANONICAL_MEDIAN, particles0=parts[rank * Sl:(rank + 1) * Sl], offset=rank * Sl)
+    losses, hs = [], []
+    for ix in idx:
+        losses.append(eng.svgd_step(ix))
+        hs.append(eng.info("svgd_h"))
+    assert int(eng.info("path_used")) == _lib.PATH_TENSOR
+    res = (rank, eng.svgd_particles(), losses, hs)
+    eng.close()
+    return res
+
+
+def _wide_worker(rank, world, uid, pshard, out):
+    out.put(_wide_run(rank, world, uid, pshard))
+
+
+@pytest.mark.parametrize("pshard", [1, 0])
+def test_svgd_sharded_on_the_tensor_path_matches_one_gpu(pshard):
+    """C4's shape in small (784-128-10, 512 particles, minibatch 512, canonical median-heuristic update): the sharded step
+    on the tensor path — pshard = 1: Stein phase sharded over the parameters (gradient / particle all-to-all, all-reduced
+    Gram matrix and radix-select histograms); 0: row-sharded with particle and gradient all-gathers — against the SAME
+    step on one GPU: losses, bandwidth h and particles after three steps."""
+    from bayesian_inference_for_nn_b200 import _lib
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import multiprocessing as mp
+    _, one_parts, one_losses, one_h = _wide_run(0, 1, None, 0)
+    ctx = mp.get_context("spawn")
+    uid = _lib.nccl_unique_id()
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_wide_worker, args=(r, 2, uid, pshard, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    parts = np.concatenate([r[1] for r in res])
+    for r in res:
+        np.testing.assert_allclose(r[2], one_losses, rtol=1e-5)
+        np.testing.assert_allclose(r[3], one_h, rtol=1e-6)
+    lr, n = 1e-3, len(one_losses)
+    diff = np.abs(parts - one_parts)
+    # Adam's first steps are lr * phi / (|phi| + 1e-7): sign-like where |phi| ~ 1e-7, so bound the bulk tightly and the
+    # worst case by Adam's own bound (the same criterion as test_svgd_minibatch_gradients_on_tensor_path)
+    print("sharded (pshard=%d) vs one GPU: particle diff quantile(0.9995) %.2e, max %.2e" % (pshard, np.quantile(diff, 0.9995), diff.max()))
+    assert np.quantile(diff, 0.9995) < 2e-3 * lr * n + 1e-6
+    assert diff.max() <= 2.1 * lr * n

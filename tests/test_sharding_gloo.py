@@ -50,7 +50,8 @@ def _worker(rank, world, port, out):
     dist.all_gather_object(gathered, p_local)
     diag = {"n_accepted": 10 * (rank + 1), "n_total": 20, "n_nan": rank, "grad_evals": 100, "kernel_launches": 7,
             "mean_loss": 0.5 + rank, "accept_rate": 0.0, "device_ms": 3.0 + 2.0 * rank}
-    red = reduce_hmc_diag(diag, dist)
+    from dist_helpers import torch_all_reduce
+    red = reduce_hmc_diag(diag, torch_all_reduce(dist, "sum"), torch_all_reduce(dist, "max"))
     dist.barrier()
     if rank == 0:
         out.put((np.concatenate(gathered), red))
@@ -90,7 +91,8 @@ def _pred_worker(rank, world, port, out):
     x = rng.normal(size=(11, 3)).astype(np.float32)
     Wl, fl = shard_weight_samples(W, freq, rank, world)           # 4 + 3 samples
     mean_l, var_l = O.predictive(spec, Wl, x, weights=fl)         # what this rank's device call would return
-    mean, var, wsum = combine_predictive_moments(mean_l, var_l, float(fl.sum()), dist)
+    from dist_helpers import torch_all_reduce
+    mean, var, wsum = combine_predictive_moments(mean_l, var_l, float(fl.sum()), torch_all_reduce(dist, "sum"))
     dist.barrier()
     if rank == 1:                                        # any rank holds the full answer
         out.put((mean, var, wsum))

@@ -3,7 +3,7 @@
 #   tools/kernel_cycles.sh <tag> [extra bench args]   -> gpurun_out/cycles_<tag>.csv and a per-kernel summary on stdout
 tag=$1; shift
 ncu --metrics sm__cycles_elapsed.avg,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
-    --clock-control none -k regex:"tc_g|k_layer2<" -s 9 -c 12 --csv --log-file gpurun_out/cycles_$tag.csv \
+    --clock-control none -k regex:"tc_g|tc_fused|k_layer2<" -s 9 -c 12 --csv --log-file gpurun_out/cycles_$tag.csv \
     python bench.py --chains 148 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e "$@" > gpurun_out/cycles_$tag.log 2>&1
 python - <<PY
 import csv, collections
