@@ -228,6 +228,9 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
   } else if (!strcmp(key, "svgd_pshard")) {
     h->opt_svgd_pshard = v != 0;
     h->svgd.ps_ready = false;
+  } else if (!strcmp(key, "tc_i8_min_loss")) {
+    PYB_REQUIRE(v >= 0, PYB_ERR_INVALID, "tc_i8_min_loss must be >= 0");
+    h->opt_i8_min_loss = v;
   } else if (!strcmp(key, "tc_i8")) {
     PYB_REQUIRE(v == -1 || v == 0 || v == 1 || v == 2, PYB_ERR_INVALID, "tc_i8 must be -1 (auto), 0 (bf16x3), 1 or 2 (int8 slices)");
     h->opt_tc_i8 = (int)v;
@@ -251,7 +254,10 @@ int pyb_get_info(const pyb_handle* h, const char* key, double* out) {
   else if (!strcmp(key, "prof_flops")) *out = h->prof_flops;
   else if (!strcmp(key, "prof_launches")) *out = (double)h->prof_launches;
   else if (!strcmp(key, "n_train")) *out = (double)h->n_train;
+  else if (!strcmp(key, "i8_guard_ok")) *out = h->i8_guard_ok ? 1.0 : 0.0;
+  else if (!strcmp(key, "i8_guard_trips")) *out = (double)h->i8_guard_trips;
   else if (!strcmp(key, "svgd_h")) *out = h->svgd.last_h;
+  else if (!strncmp(key, "svgd_phase_ms_", 14) && key[14] >= '0' && key[14] <= '6' && !key[15]) *out = h->svgd.ps_ms[key[14] - '0'];
   else if (!strcmp(key, "tc_split")) *out = (double)tc_resident_split(h);
   else if (!strcmp(key, "dataset_uploads")) *out = (double)h->dataset_uploads;
   else if (!strcmp(key, "dataset_kept")) *out = (double)h->dataset_kept;
@@ -274,6 +280,7 @@ int pyb_set_dataset(pyb_handle* h, const float* X, int64_t N, const void* y, int
   else
     PYB_REQUIRE(last_act != PYB_ACT_SOFTMAX, PYB_ERR_UNSUPPORTED, "MeanSquaredError on a softmax output is not supported");
   use_device(h);
+  if (mem == PYB_MEM_DEVICE) PYB_CUDA(cudaDeviceSynchronize());   // the producer's stream is not ours (header: "device pointers")
   const bool ce = loss_kind == PYB_LOSS_SPARSE_CE;
   // labels are validated BEFORE any handle state changes (the loss kernels index the logits with them)
   if (ce && mem == PYB_MEM_HOST) {
@@ -683,6 +690,7 @@ int pyb_gather_rows(pyb_handle* h, const float* src, const int64_t* idx, int64_t
   PYB_TRY
   PYB_REQUIRE(h && src && idx && dst && n > 0 && row_len > 0, PYB_ERR_INVALID, "bad arguments");
   use_device(h);
+  PYB_CUDA(cudaDeviceSynchronize());      // src / dst are caller-owned device buffers (header: "device pointers")
   gather_rows_f32(h, src, idx, n, row_len, dst);
   PYB_CATCH
 }

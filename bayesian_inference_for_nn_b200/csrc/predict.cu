@@ -246,6 +246,9 @@ void predict(pyb_handle* h, const float* W, int64_t n, const float* weight, cons
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
   };
   const bool W_dev = on_device(W), x_dev = on_device(x);
+  // caller-owned device memory (DLPack tensors) was produced on the CALLER's stream; this library works on its own
+  // non-blocking stream, which is ordered against nothing else: wait for the device before reading (header: "device pointers")
+  if (W_dev || x_dev) PYB_CUDA(cudaDeviceSynchronize());
   const float* xd = x;
   if (!x_dev) {
     dx.alloc(Nt * m.in_dim);

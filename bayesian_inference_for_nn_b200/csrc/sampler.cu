@@ -281,6 +281,7 @@ void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double
   HmcState& st = h->hmc;
   const int64_t P = h->model.P;
   st.S = S; st.chain_offset = chain_offset; st.eps = eps; st.m = m; st.L = L; st.semantics = sem;
+  h->i8_guard_ok = (q0 == nullptr);   // the prior-mean start has loss log(C); supplied positions are unknown until evaluated
   st.iter = 0;
   st.q.alloc(S * P); st.p.alloc(S * P); st.g.alloc(S * P); st.q0.alloc(S * P);
   for (DevBuf<float>* b : {&st.loss, &st.loss0, &st.Up0, &st.Up1, &st.K0, &st.K1, &st.U0, &st.U1, &st.log_alpha,
@@ -294,18 +295,10 @@ void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double
   st.counters.alloc(4);
   st.loss_sum.alloc(1);
   st.arena_count.alloc(1);
-  // sample arena: at least 2S rows (the first sampling iteration records two states per chain);
-  // otherwise a quarter of the free HBM (<= 32 GiB) so that flushes to the host are rare
-  size_t free_b = 0, total_b = 0;
-  PYB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = std::min<size_t>(free_b / 4, (size_t)32 << 30);
-  budget = std::max<size_t>(budget, (size_t)1 << 28);
-  int64_t cap = (int64_t)(budget / (sizeof(float) * (size_t)P));
-  if (cap < 2 * S) cap = 2 * S;
-  if (cap > (1ll << 30)) cap = 1ll << 30;
-  st.arena_cap = cap;
-  st.arena.release();  // allocated lazily on the first sampling iteration
-  st.arena_freq.alloc(cap); st.arena_chain.alloc(cap);
+  // sample arena: sized and allocated at the first SAMPLING iteration (hmc_size_arena), when the evaluation workspaces
+  // already exist and the free memory is what it will be
+  st.arena_cap = 0;
+  st.arena.release(); st.arena_freq.release(); st.arena_chain.release();
   PYB_CUDA(cudaMemsetAsync(st.arena_count.p, 0, sizeof(int32_t), h->stream));
   PYB_CUDA(cudaMemsetAsync(st.pending_freq.p, 0, S * sizeof(int32_t), h->stream));
   PYB_CUDA(cudaMemsetAsync(st.last_idx.p, 0xff, S * sizeof(int32_t), h->stream));
@@ -326,6 +319,24 @@ void hmc_init(pyb_handle* h, int64_t S, int64_t chain_offset, double eps, double
   count_launch(h);
   PYB_CUDA(cudaStreamSynchronize(h->stream));
   st.inited = true;
+}
+
+// Sample arena [cap, P] on the device: 64 sampling iterations' worth of rows for every chain (a one-chain toy run keeps a
+// few KB, not gigabytes), never more than a quarter of the memory that is free NOW (the tensor-path workspaces are
+// allocated by then) nor 32 GiB, and at least the 2 S rows the first sampling iteration records; flushed to the host when full.
+static void hmc_size_arena(pyb_handle* h) {
+  HmcState& st = h->hmc;
+  const int64_t P = h->model.P, S = st.S;
+  size_t free_b = 0, total_b = 0;
+  PYB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = std::min<size_t>(free_b / 4, (size_t)32 << 30);
+  int64_t cap = (int64_t)(budget / (sizeof(float) * (size_t)P));
+  cap = std::min<int64_t>(cap, 64 * S);
+  cap = std::max<int64_t>(cap, 2 * S);
+  cap = std::min<int64_t>(cap, 1ll << 30);
+  st.arena_cap = cap;
+  st.arena.alloc((size_t)cap * P);
+  st.arena_freq.alloc(cap); st.arena_chain.alloc(cap);
 }
 
 void hmc_flush_arena(pyb_handle* h) {
@@ -377,6 +388,20 @@ static void launch_kick(pyb_handle* h, const float* g, float kick1, float kick2,
   }
 }
 
+// the int8-slice guard (common.cuh): smallest finite per-chain mean loss among `loss_dev[0..S)` against the threshold;
+// the stream has been synchronised.  Returns whether the slices may be used from here on.
+static bool update_i8_guard(pyb_handle* h, const float* loss_dev, int64_t S) {
+  std::vector<float> l((size_t)S);
+  PYB_CUDA(cudaMemcpy(l.data(), loss_dev, (size_t)S * sizeof(float), cudaMemcpyDeviceToHost));
+  float mn = INFINITY;
+  for (float v : l)
+    if (isfinite(v)) mn = fminf(mn, v);
+  const bool ok = !(mn < (float)h->opt_i8_min_loss);
+  if (!ok && h->i8_guard_ok) h->i8_guard_trips += 1;
+  h->i8_guard_ok = ok;
+  return ok;
+}
+
 void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_diag* out) {
   HmcState& st = h->hmc;
   PYB_REQUIRE(st.inited, PYB_ERR_STATE, "pyb_hmc_init must be called first");
@@ -400,8 +425,8 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
     bool first = sampling && !st.sampling_started;
     if (sampling) {
       int64_t need = S * (first ? 2 : 1);
+      if (!st.arena.p) hmc_size_arena(h);
       if (st.arena_used_upper + need > st.arena_cap) hmc_flush_arena(h);
-      if (!st.arena.p) st.arena.alloc((size_t)st.arena_cap * P);
       st.arena_used_upper += need;
     }
     dim3 gridp = chain_grid(nblk, S);
@@ -478,6 +503,8 @@ void hmc_run(pyb_handle* h, int n_iters, bool burning, bool sampling, pyb_hmc_di
   PYB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_device_ms = ms;
   prof_resolve(h);
+  if (n_iters > 0 && path == PYB_PATH_TENSOR && h->opt_tc_i8 < 0)
+    update_i8_guard(h, st.have_cur ? st.loss0.p : st.ret_loss.p, S);      // mean loss of every chain at its current position
   if (out) {
     unsigned long long c[4];
     double ls = 0.0;
@@ -506,6 +533,14 @@ void hmc_eval(pyb_handle* h, const float* q, int64_t S, float* U, float* loss, f
   part.alloc((size_t)S * nblk);
   PYB_CUDA(cudaMemcpyAsync(dq.p, q, S * P * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   eval_loss_grad(h, dq.p, S, (float)h->n_train, dloss.p, grad ? dg.p : nullptr);
+  if (h->path_used == PYB_PATH_TENSOR && h->opt_tc_i8 < 0 && grad) {
+    // automatic operand split: an answer computed on int8 slices for positions whose loss is below the guard's threshold
+    // is computed again on bf16x3 (and an answer on bf16x3 re-opens the guard when the losses allow)
+    const bool was_ok = h->i8_guard_ok;
+    PYB_CUDA(cudaStreamSynchronize(h->stream));
+    if (!update_i8_guard(h, dloss.p, S) && was_ok)
+      eval_loss_grad(h, dq.p, S, (float)h->n_train, dloss.p, dg.p);
+  }
   k_prior<<<chain_grid(nblk, S), EW_THREADS, 0, h->stream>>>(dq.p, grad ? dg.p : nullptr, h->mu.p, h->inv_var.p, P, part.p, S);
   k_finish<<<(unsigned)S, 128, 0, h->stream>>>(part.p, nblk, 1.0, dUp.p);
   k_potential<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(dUp.p, dloss.p, (float)h->prior_const,

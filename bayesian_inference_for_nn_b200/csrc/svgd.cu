@@ -652,13 +652,23 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     count_launch(h, 3);
     sv.ps_ready = true;
   }
+  const bool timed = h->prof_enabled;
+  auto mark = [&](int k) {
+    if (!timed) return;
+    if (!sv.ps_ev[k]) PYB_CUDA(cudaEventCreate(&sv.ps_ev[k]));
+    PYB_CUDA(cudaEventRecord(sv.ps_ev[k], h->stream));
+  };
+  sv.ps_timed = timed;
+  mark(0);
   // 1. local gradients, 2. gradient rows -> gradient slice of all particles
   eval_on_batch(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
+  mark(1);
   nvtxRangePushA("pyb.svgd.exchange.gradients(all-to-all)");
   k_pack_cols<<<eb, 256, 0, h->stream>>>(sv.g.p, S, P, Pw, R, sv.ps_pack.p);
   nccl_all_to_all_f32(sv.nccl_comm, sv.ps_pack.p, sv.ps_g.p, (size_t)S * Pw, R, h->stream);
   count_launch(h);
   nvtxRangePop();
+  mark(2);
   nvtxRangePushA("pyb.svgd.gram(+all-reduce)");
   // 3. partial Gram and squared norms over the slice, summed over the ranks
   sv.xh.alloc((size_t)St * Pw); sv.xl.alloc((size_t)St * Pw);
@@ -666,9 +676,11 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   tc_split_rows(h, sv.ps_x.p, St, (int)Pw, Pw, sv.xh.p, sv.xl.p, Pw);
   tc_gemm_split(h, sv.xh.p, sv.xl.p, Pw, St, 0, St, sv.xh.p, sv.xl.p, Pw, St, Pw, sv.gram.p, St);
   k_row_norms<<<St, 256, 0, h->stream>>>(sv.ps_x.p, Pw, sv.ps_norms.p);
+  mark(3);
   nccl_all_reduce_f32(sv.nccl_comm, sv.gram.p, (size_t)St * St, h->stream);
   nccl_all_reduce_f64(sv.nccl_comm, sv.ps_norms.p, St, h->stream);
   nvtxRangePop();
+  mark(4);
   nvtxRangePushA("pyb.svgd.median_kernel");
   // 4. distances, median bandwidth, kernel matrix (identical on every rank: the all-reduced inputs are)
   k_d2_from_gram<<<(unsigned)(((int64_t)St * St + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p);
@@ -677,6 +689,7 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   k_kernel_rowsum<<<St, 256, 0, h->stream>>>(sv.d2.p, St, sv.h2.p, sv.rowsum.p);
   count_launch(h);
   nvtxRangePop();
+  mark(5);
   nvtxRangePushA("pyb.svgd.stein_update(KY+Adam)");
   // 5. K Y and the Adam ascent step on the slice
   sv.kf.alloc((size_t)St * St); sv.kh.alloc((size_t)St * St); sv.kl.alloc((size_t)St * St);
@@ -691,11 +704,13 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
       sv.ps_phi.p, sv.ps_x.p, sv.ps_m.p, sv.ps_v.p, Pw, (int64_t)St * Pw, St, sv.h2.p, sv.rowsum.p, lr_t);
   count_launch(h, 3);
   nvtxRangePop();
+  mark(6);
   NvtxRange nv_back("pyb.svgd.exchange.particles(all-to-all)");
   // 6. the updated rows of every rank's own particles travel back (block q of the slice = rank q's particles)
   nccl_all_to_all_f32(sv.nccl_comm, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, R, h->stream);
   k_unpack_cols<<<eb, 256, 0, h->stream>>>(sv.ps_pack.p, S, P, Pw, R, sv.theta.p);
   count_launch(h);
+  mark(7);
 }
 
 void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
@@ -820,6 +835,8 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
   PYB_CUDA(cudaGetLastError());
   if (R > 1) nccl_check_async(&sv.nccl_comm);
   sv.last_h = sv.semantics != PYB_SVGD_REFERENCE_LIVE ? sqrt(h2v[0]) : 1.0;
+  if (pshard && sv.ps_timed)
+    for (int k = 0; k < 7; ++k) PYB_CUDA(cudaEventElapsedTime(&sv.ps_ms[k], sv.ps_ev[k], sv.ps_ev[k + 1]));
   float ms = 0.f;
   PYB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_device_ms = ms;

@@ -260,7 +260,7 @@ static bool fused_ok(const pyb_handle* h, int H, int act1) {
 static int i8_mode(const pyb_handle* h, bool backward, bool resident) {
   const Model& m = h->model;
   int want = h->opt_tc_i8;
-  if (want < 0) want = (resident && backward) ? 2 : 0;
+  if (want < 0) want = (resident && backward && h->i8_guard_ok) ? 2 : 0;
   if (want <= 0 || !fused_ok(h, m.layer[0].fan_out, m.layer[0].act) || m.layer[1].fan_out > L2_CMAX) return 0;
   if (m.layer[0].fan_in > 32768) return 0;                       // int32 range of the hi*lo + lo*hi accumulator
   if (!backward) return 1;

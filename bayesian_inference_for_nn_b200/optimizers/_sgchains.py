@@ -24,8 +24,12 @@ class StochasticGradientChains(Optimizer):
         self._n_chains = int(self._hp("n_chains", 1))
 
     def _setup_engine(self, k_dev=0, frequency=1, theta0=None):
-        self._rng = np.random.default_rng(self._hp("seed", None))
-        self._engine = Engine(self._spec, device=int(self._hp("device", 0)), seed=int(self._hp("seed", 0)))
+        # unseeded in the reference (tf.random / np.random without a library-level seed): a fresh seed per optimizer
+        # unless one is given; self.seed reproduces the run
+        seed = self._hp("seed", None)
+        self.seed = int(np.random.SeedSequence().entropy & ((1 << 63) - 1)) if seed is None else int(seed)
+        self._rng = np.random.default_rng(self.seed)
+        self._engine = Engine(self._spec, device=int(self._hp("device", 0)), seed=self.seed)
         x, y = self._dataset.training_arrays()
         self._n_train = x.shape[0]
         self._engine.set_dataset(x, y, self._dataset.loss_kind, n_train=self._n_train)

@@ -16,6 +16,13 @@
  *   - the library owns all device memory behind the handle; caller-owned buffers are only read
  *     or written for the duration of the call.  `mem` says whether a caller buffer is host or
  *     device memory (device pointers come from DLPack capsules on the Python side).
+ *   - device pointers: the library works on its own non-blocking stream, which is ordered against no other stream.  Every
+ *     entry point that READS caller-owned device memory (pyb_set_dataset with PYB_MEM_DEVICE, W / x of pyb_predict and
+ *     pyb_predict_uncertainty, src / dst of pyb_gather_rows) first waits for the whole device (cudaDeviceSynchronize), so a
+ *     tensor produced on any stream just before the call is complete when it is read; results the library WRITES to
+ *     caller-owned device memory are complete when the call returns (every call ends with a stream synchronisation).
+ *   - sharded runs (pyb_svgd_set_comm / pyb_set_comm): every rank must hold the same number of particles; the first
+ *     sharded step checks it (one all-reduce) and fails with PYB_ERR_INVALID instead of hanging in a collective.
  *   - one handle = one GPU; a handle is not thread-safe; there is NO CPU fallback: without a
  *     usable sm_100 device pyb_create fails with PYB_ERR_CUDA.
  *   - flat parameter order everywhere = model.layers order -> (kernel [in,out] C-order, bias)

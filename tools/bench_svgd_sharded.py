@@ -30,12 +30,14 @@ def worker(rank, world, uid, S_total, steps, out):
     if world > 1:
         eng.svgd_set_comm(rank, world, uid)
     eng.svgd_init(Sl, 0.01, _lib.SVGD_CANONICAL_MEDIAN, offset=rank * Sl)
-    ms, loss = [], []
+    ms, loss, phases = [], [], []
+    eng.set_option("profile", 1)
     for k, ix in enumerate(idx):
         loss.append(eng.svgd_step(ix))
         if k >= 2:
             ms.append(eng.info("last_device_ms"))
-    out.put((rank, float(np.mean(ms)), loss[-1]))
+            phases.append([eng.info("svgd_phase_ms_%d" % j) for j in range(7)] if world > 1 else [0.0] * 7)
+    out.put((rank, float(np.mean(ms)), loss[-1], np.mean(phases, axis=0).tolist()))
     eng.close()
 
 
@@ -64,7 +66,10 @@ def main():
         base = base or ms
         print(json.dumps({"case": "C4 SVGD canonical_median 784-128-10, minibatch 1024", "particles": a.particles,
                           "n_gpus": world, "device_ms_per_step": ms, "particle_grad_evals_per_s": a.particles * 1e3 / ms,
-                          "speedup_vs_1gpu": base / ms, "mean_loss_last": res[0][2]}), flush=True)
+                          "speedup_vs_1gpu": base / ms, "mean_loss_last": res[0][2],
+                          "phase_ms_max_over_ranks": dict(zip(["gradients", "gradient_all_to_all", "gram_partial", "gram_all_reduce",
+                                                               "median_kernel", "ky_adam", "particle_all_to_all"],
+                                                              np.max([r[3] for r in res], axis=0).round(3).tolist()))}), flush=True)
 
 
 if __name__ == "__main__":
