@@ -172,6 +172,7 @@ int pyb_destroy(pyb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   tc_release(h);
   if (h->svgd.comm_stream) cudaStreamSynchronize(h->svgd.comm_stream);
+  if (h->svgd.nccl_comm2) { nccl_comm_destroy(h->svgd.nccl_comm2); h->svgd.nccl_comm2 = nullptr; }
   if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }
   if (h->svgd.comm_stream) {
     cudaStreamDestroy(h->svgd.comm_stream); h->svgd.comm_stream = nullptr;
@@ -592,6 +593,7 @@ int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* id
   PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
   PYB_REQUIRE(world >= 1 && rank >= 0 && rank < world, PYB_ERR_INVALID, "bad rank/world");
   use_device(h);
+  if (h->svgd.nccl_comm2) { nccl_comm_destroy(h->svgd.nccl_comm2); h->svgd.nccl_comm2 = nullptr; }
   if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }
   if (world > 1) {
     PYB_REQUIRE(id != nullptr, PYB_ERR_INVALID, "nccl unique id is NULL");

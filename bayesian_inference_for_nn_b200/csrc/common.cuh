@@ -237,6 +237,7 @@ struct SvgdState {
   // comm
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
+  void* nccl_comm2 = nullptr;   // duplicate for the exchange that overlaps the Gram matrix (its own stream)
   DevBuf<float> theta_all, g_all;
   // parameter-sharded Stein phase (canonical mode, tensor path, world > 1): rank r owns columns [r Pw, (r+1) Pw) of ALL
   // particles — theta slice, gathered gradient slice, Adam moments, phi — and the exchange is two all-to-alls of the
@@ -437,6 +438,8 @@ void nccl_broadcast_f32(void* comm, float* buf, size_t count, int root, cudaStre
 void nccl_all_reduce_f32(void* comm, float* buf, size_t count, cudaStream_t s);
 void nccl_all_to_all_f32(void* comm, const float* send, float* recv, size_t count_per_peer, int world, cudaStream_t s);
 void nccl_check_async(void** comm);
+void nccl_all_reduce_min_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t s);
+void* nccl_comm_dup(void* comm, int rank);
 
 // predict.cu
 // optional classification-uncertainty request (Metrics.py:344-375): host labels [Nt], host outputs [Nt, Ce, Ce]

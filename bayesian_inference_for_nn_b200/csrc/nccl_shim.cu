@@ -13,7 +13,7 @@ namespace pyb {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { NCCL_UINT64 = 5, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };
-enum { NCCL_SUM = 0 };
+enum { NCCL_SUM = 0, NCCL_MIN = 3 };
 
 struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId*);
@@ -28,6 +28,7 @@ struct NcclApi {
   int (*GroupEnd)();
   int (*CommGetAsyncError)(ncclComm_t, int*);
   int (*CommAbort)(ncclComm_t);
+  int (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*);
   const char* (*GetErrorString)(int);
   bool ok = false;
 };
@@ -59,6 +60,7 @@ static NcclApi& api() {
   PYB_SYM(GroupEnd, "ncclGroupEnd")
   PYB_SYM(CommGetAsyncError, "ncclCommGetAsyncError")
   PYB_SYM(CommAbort, "ncclCommAbort")
+  PYB_SYM(CommSplit, "ncclCommSplit")
   PYB_SYM(GetErrorString, "ncclGetErrorString")
 #undef PYB_SYM
   a.ok = true;
@@ -89,6 +91,16 @@ void nccl_all_gather_f32(void* comm, const float* send, float* recv, size_t coun
 }
 void nccl_all_reduce_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t s) {
   nccl_check(api().AllReduce(buf, buf, count, NCCL_UINT64, NCCL_SUM, (ncclComm_t)comm, s), "ncclAllReduce");
+}
+void nccl_all_reduce_min_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t s) {
+  nccl_check(api().AllReduce(buf, buf, count, NCCL_UINT64, NCCL_MIN, (ncclComm_t)comm, s), "ncclAllReduce(min)");
+}
+// a second communicator over the same ranks (same rank order): collectives issued on ANOTHER stream run concurrently with
+// those of the first one without sharing its internal ordering
+void* nccl_comm_dup(void* comm, int rank) {
+  ncclComm_t c = nullptr;
+  nccl_check(api().CommSplit((ncclComm_t)comm, 0, rank, &c, nullptr), "ncclCommSplit");
+  return (void*)c;
 }
 void nccl_all_reduce_f64(void* comm, double* buf, size_t count, cudaStream_t s) {
   nccl_check(api().AllReduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t)comm, s), "ncclAllReduce");

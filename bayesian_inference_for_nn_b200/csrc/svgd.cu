@@ -209,20 +209,39 @@ __global__ void k_select_pick(SelectState* st, int shift, unsigned long long* hi
     }
     if (b > 255) b = 255;
     st->k = k - c;
+    if (shift == 0) st[1].k = hist[b];          // all 64 bits fixed: how many elements EQUAL the selected value
     st->prefix |= ((unsigned long long)b) << shift;
     st->mask |= 0xffull << shift;
   }
   __syncthreads();
   for (int t = threadIdx.x; t < 256; t += blockDim.x) hist[t] = 0;
 }
-// bandwidth from the two middle order statistics: h2 = 0.5*median/log(St+1)
-__global__ void k_bandwidth(const SelectState* a, const SelectState* b, int St, double* h2_out) {
-  double lo = __longlong_as_double((long long)a->prefix), hi = __longlong_as_double((long long)b->prefix);
+// smallest bit pattern strictly above the selected value (the next order statistic when the selected value is the last
+// of its group of equals); nxt is initialised to ~0
+__global__ void k_next_greater(const double* v, int64_t n, const SelectState* st, unsigned long long* nxt) {
+  const unsigned long long sel = st->prefix;
+  unsigned long long m = ~0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+    if (b > sel && b < m) m = b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t < m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(nxt, m);
+}
+// a: the select state of order statistic k0 = (n - 1) / 2 (prefix = its bits, k = its index inside its group of equals,
+// a[1].k = size of that group); the next order statistic is the same value unless k0 was the last of the group
+__global__ void k_bandwidth_next(const SelectState* a, const unsigned long long* nxt, int want_next, int St, double* h2_out) {
+  const double lo = __longlong_as_double((long long)a->prefix);
+  double hi = lo;
+  if (want_next && a->k + 1 >= a[1].k) hi = __longlong_as_double((long long)nxt[0]);
   double med = 0.5 * (lo + hi);
   h2_out[0] = 0.5 * med / log((double)St + 1.0);
   h2_out[1] = med;
 }
-
 // K = exp(-d2/(2 h2)) in place; rowsum per local row (one block per row)
 __global__ void k_kernel_rowsum(double* d2, int St, const double* h2, double* rowsum) {
   __shared__ double scratch[32];
@@ -455,22 +474,31 @@ static double adam_lr_t(double lr, int64_t t) {
 // histograms are all-reduced (2 KB per pass), so every rank picks the same bins
 static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t n_global, int St, double* h2_dev) {
   SvgdState& sc = h->svgd;
-  sc.sel.alloc(6);
+  sc.sel.alloc(8);
   sc.hist.alloc(256);
+  // ONE radix select for the lower middle order statistic (8 passes, each with a 2 KB histogram all-reduce when the
+  // rows are sharded); the upper middle one is the same value or the next greater element (one more pass, one all-reduce
+  // MIN) — half the latency-bound small collectives of two independent selects
   SelectState init[2];
   init[0].prefix = 0; init[0].mask = 0; init[0].k = (unsigned long long)((n_global - 1) / 2);
-  init[1].prefix = 0; init[1].mask = 0; init[1].k = (unsigned long long)(n_global / 2);
+  init[1].prefix = 0; init[1].mask = 0; init[1].k = 0;
+  const int want_next = (n_global / 2) != ((n_global - 1) / 2);
   PYB_CUDA(cudaMemcpyAsync(sc.sel.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   PYB_CUDA(cudaMemsetAsync(sc.hist.p, 0, 256 * sizeof(unsigned long long), h->stream));
+  PYB_CUDA(cudaMemsetAsync(sc.sel.p + 6, 0xff, sizeof(unsigned long long), h->stream));     // slot 6: the next-greater minimum
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)h->sm_count);
-  for (int w = 0; w < 2; ++w)
-    for (int shift = 56; shift >= 0; shift -= 8) {
-      k_select_hist<<<blocks, 256, 0, h->stream>>>(d2, n, reinterpret_cast<SelectState*>(sc.sel.p) + w, shift, sc.hist.p);
-      if (sc.world > 1) nccl_all_reduce_u64(sc.nccl_comm, sc.hist.p, 256, h->stream);
-      k_select_pick<<<1, 256, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p) + w, shift, sc.hist.p);
-      count_launch(h, 2);
-    }
-  k_bandwidth<<<1, 1, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p), reinterpret_cast<SelectState*>(sc.sel.p) + 1, St, h2_dev);
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    k_select_hist<<<blocks, 256, 0, h->stream>>>(d2, n, reinterpret_cast<SelectState*>(sc.sel.p), shift, sc.hist.p);
+    if (sc.world > 1) nccl_all_reduce_u64(sc.nccl_comm, sc.hist.p, 256, h->stream);
+    k_select_pick<<<1, 256, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p), shift, sc.hist.p);
+    count_launch(h, 2);
+  }
+  if (want_next) {
+    k_next_greater<<<blocks, 256, 0, h->stream>>>(d2, n, reinterpret_cast<SelectState*>(sc.sel.p), sc.sel.p + 6);
+    if (sc.world > 1) nccl_all_reduce_min_u64(sc.nccl_comm, sc.sel.p + 6, 1, h->stream);
+    count_launch(h);
+  }
+  k_bandwidth_next<<<1, 1, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p), sc.sel.p + 6, want_next, St, h2_dev);
   count_launch(h);
 }
 
@@ -594,22 +622,19 @@ void svgd_init(pyb_handle* h, int64_t S, int64_t offset, double lr, int sem, con
 // Per rank and step: 2 S P (R-1)/R floats sent + the 4 St^2-byte all-reduce: 0.36 GB + 67 MB at C4 on 8 GPUs.
 // ------------------------------------------------------------------------------------------
 // src [Sl, P] -> dst [R][Sl][Pw]: block q holds columns [q Pw, (q+1) Pw) (zero beyond P)
+// grid (ceil(Pw / 256), Sl, R)
 __global__ void k_pack_cols(const float* __restrict__ src, int64_t Sl, int64_t P, int64_t Pw, int R, float* __restrict__ dst) {
-  const int64_t total = (int64_t)R * Sl * Pw;
-  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = o % Pw, i = (o / Pw) % Sl, q = o / (Pw * Sl);
-    const int64_t col = q * Pw + c;
-    dst[o] = col < P ? src[i * P + col] : 0.f;
-  }
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, q = blockIdx.z;
+  if (c >= Pw) return;
+  const int64_t col = q * Pw + c;
+  dst[(q * Sl + i) * Pw + c] = col < P ? src[i * P + col] : 0.f;
 }
 // src [R][Sl][Pw] -> dst [Sl, P]
 __global__ void k_unpack_cols(const float* __restrict__ src, int64_t Sl, int64_t P, int64_t Pw, int R, float* __restrict__ dst) {
-  const int64_t total = Sl * P;
-  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t col = o % P, i = o / P;
-    const int64_t q = col / Pw, c = col - q * Pw;
-    dst[o] = src[(q * Sl + i) * Pw + c];
-  }
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, q = blockIdx.z;
+  const int64_t col = q * Pw + c;
+  if (c >= Pw || col >= P) return;
+  dst[i * P + col] = src[(q * Sl + i) * Pw + c];
 }
 __global__ void k_slice_vec(const float* __restrict__ v, int64_t P, int64_t c0, int64_t Pw, float* __restrict__ out) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -626,7 +651,7 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   const int eb = (int)std::min<int64_t>(((int64_t)St * Pw + 255) / 256, 16 * (int64_t)h->sm_count);
   if (!sv.ps_checked) {
     // every rank must hold the same number of particles (St = S * world, block q of an exchange = rank q's rows)
-    sv.sel.alloc(6);
+    sv.sel.alloc(8);
     unsigned long long v[2] = {(unsigned long long)S, (unsigned long long)(S * S)};
     PYB_CUDA(cudaMemcpyAsync(sv.sel.p, v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
     nccl_all_reduce_u64(sv.nccl_comm, sv.sel.p, 2, h->stream);
@@ -637,6 +662,13 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
                 "sharded SVGD needs the same number of particles on every rank");
     sv.ps_checked = true;
   }
+  if (!sv.comm_stream) {
+    PYB_CUDA(cudaStreamCreateWithFlags(&sv.comm_stream, cudaStreamNonBlocking));
+    PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_fork, cudaEventDisableTiming));
+    PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_theta, cudaEventDisableTiming));
+    PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_grad, cudaEventDisableTiming));
+  }
+  if (!sv.nccl_comm2) sv.nccl_comm2 = nccl_comm_dup(sv.nccl_comm, sv.rank);
   if (!sv.ps_ready || sv.ps_Pw != Pw) {
     sv.ps_Pw = Pw;
     sv.ps_pack.alloc((size_t)St * Pw); sv.ps_x.alloc((size_t)St * Pw); sv.ps_g.alloc((size_t)St * Pw);
@@ -647,7 +679,7 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     k_slice_vec<<<(unsigned)((Pw + 255) / 256), 256, 0, h->stream>>>(h->mu.p, P, c0, Pw, sv.ps_mu.p);
     k_slice_vec<<<(unsigned)((Pw + 255) / 256), 256, 0, h->stream>>>(h->inv_var.p, P, c0, Pw, sv.ps_iv.p);
     // the particle slice: one exchange at the start, afterwards the slice IS the master copy the update is applied to
-    k_pack_cols<<<eb, 256, 0, h->stream>>>(sv.theta.p, S, P, Pw, R, sv.ps_pack.p);
+    k_pack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)S, (unsigned)R), 256, 0, h->stream>>>(sv.theta.p, S, P, Pw, R, sv.ps_pack.p);
     nccl_all_to_all_f32(sv.nccl_comm, sv.ps_pack.p, sv.ps_x.p, (size_t)S * Pw, R, h->stream);
     count_launch(h, 3);
     sv.ps_ready = true;
@@ -663,9 +695,14 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   // 1. local gradients, 2. gradient rows -> gradient slice of all particles
   eval_on_batch(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
   mark(1);
-  nvtxRangePushA("pyb.svgd.exchange.gradients(all-to-all)");
-  k_pack_cols<<<eb, 256, 0, h->stream>>>(sv.g.p, S, P, Pw, R, sv.ps_pack.p);
-  nccl_all_to_all_f32(sv.nccl_comm, sv.ps_pack.p, sv.ps_g.p, (size_t)S * Pw, R, h->stream);
+  // the gradient exchange runs on its own stream and communicator WHILE the Gram matrix (which needs the particle slice
+  // only) is built and all-reduced on the main stream; the Stein right-hand side below waits for it
+  nvtxRangePushA("pyb.svgd.exchange.gradients(all-to-all, overlapped)");
+  PYB_CUDA(cudaEventRecord(sv.ev_fork, h->stream));
+  PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_fork, 0));
+  k_pack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)S, (unsigned)R), 256, 0, sv.comm_stream>>>(sv.g.p, S, P, Pw, R, sv.ps_pack.p);
+  nccl_all_to_all_f32(sv.nccl_comm2, sv.ps_pack.p, sv.ps_g.p, (size_t)S * Pw, R, sv.comm_stream);
+  PYB_CUDA(cudaEventRecord(sv.ev_grad, sv.comm_stream));
   count_launch(h);
   nvtxRangePop();
   mark(2);
@@ -697,6 +734,7 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   k_double_to_float<<<eb, 256, 0, h->stream>>>(sv.d2.p, sv.kf.p, (int64_t)St * St);
   tc_split_rows(h, sv.kf.p, St, St, St, sv.kh.p, sv.kl.p, St);
   dim3 gt((unsigned)((Pw + 31) / 32), (unsigned)((St + 63) / 64)), bt(32, 8);
+  PYB_CUDA(cudaStreamWaitEvent(h->stream, sv.ev_grad, 0));          // the gathered gradient slice is complete
   k_stein_rhs_split_t<<<gt, bt, 0, h->stream>>>(sv.ps_x.p, sv.ps_g.p, sv.h2.p, St, Pw, sv.yth.p, sv.ytl.p, St, sv.ps_mu.p,
                                                sv.ps_iv.p);
   tc_gemm_split(h, sv.kh.p, sv.kl.p, St, St, 0, St, sv.yth.p, sv.ytl.p, St, (int)Pw, St, sv.ps_phi.p, Pw);
@@ -708,7 +746,7 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   NvtxRange nv_back("pyb.svgd.exchange.particles(all-to-all)");
   // 6. the updated rows of every rank's own particles travel back (block q of the slice = rank q's particles)
   nccl_all_to_all_f32(sv.nccl_comm, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, R, h->stream);
-  k_unpack_cols<<<eb, 256, 0, h->stream>>>(sv.ps_pack.p, S, P, Pw, R, sv.theta.p);
+  k_unpack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)S, (unsigned)R), 256, 0, h->stream>>>(sv.ps_pack.p, S, P, Pw, R, sv.theta.p);
   count_launch(h);
   mark(7);
 }
