@@ -31,6 +31,7 @@ void tc_eval(pyb_handle* h, const float* theta, int64_t S, float scale, float* l
 void tc_release(pyb_handle* h);
 void tc_invalidate_dataset(pyb_handle* h);
 int tc_resident_split(const pyb_handle* h);
+void tc_read_timeline(pyb_handle* h, unsigned long long* out_8x160);
 
 int resolve_path(pyb_handle* h, int64_t S, bool with_grad) {
   int path = h->opt_path;
@@ -226,6 +227,10 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_predict_sharded = v != 0;
   } else if (!strcmp(key, "tc_fuse")) {
     h->opt_tc_fuse = v != 0;
+  } else if (!strcmp(key, "tc_timeline")) {
+    h->opt_tc_timeline = v != 0;
+  } else if (!strcmp(key, "tc_epi_mma")) {
+    h->opt_tc_epi_mma = v != 0;
   } else if (!strcmp(key, "svgd_pshard")) {
     h->opt_svgd_pshard = v != 0;
     h->svgd.ps_ready = false;
@@ -255,6 +260,18 @@ int pyb_get_info(const pyb_handle* h, const char* key, double* out) {
   else if (!strcmp(key, "prof_flops")) *out = h->prof_flops;
   else if (!strcmp(key, "prof_launches")) *out = (double)h->prof_launches;
   else if (!strcmp(key, "n_train")) *out = (double)h->n_train;
+  else if (!strncmp(key, "tc_timeline_", 12) && key[12] >= '0' && key[12] <= '7' && !key[13]) {
+    // mean over the CTAs (of cluster leaders for the issuer's entries) of the last fused launch's phase k, in cycles per item
+    std::vector<unsigned long long> t(8 * 160);
+    tc_read_timeline(const_cast<pyb_handle*>(h), t.data());
+    const int k = key[12] - '0';
+    double s = 0, n = 0;
+    for (int c = 0; c < 148; ++c) {
+      const unsigned long long items = t[(c & ~1) * 8 + 3];
+      if (items && (k >= 4 || !(c & 1))) { s += k == 3 ? (double)items : (double)t[c * 8 + k] / (double)items; n += 1; }
+    }
+    *out = n ? s / n : 0.0;
+  }
   else if (!strcmp(key, "i8_guard_ok")) *out = h->i8_guard_ok ? 1.0 : 0.0;
   else if (!strcmp(key, "i8_guard_trips")) *out = (double)h->i8_guard_trips;
   else if (!strcmp(key, "svgd_h")) *out = h->svgd.last_h;

@@ -311,6 +311,8 @@ struct pyb_handle {
   int opt_hmc_carry = 1;    // 1: loss and gradient at the current position are carried to the next HMC iteration
   int opt_predict_sharded = 0;   // 1: pyb_predict all-reduces its moment sums over the handle's communicator
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
+  int opt_tc_timeline = 0;   // diagnostics: the fused mma kernel records per-CTA cycle sums of its phases (info "tc_timeline_<k>")
+  int opt_tc_epi_mma = 1;    // int8 slices: the layer-2 products of the fused kernel's epilogue run on mma.sync (tc_fused_mma.cuh)
   int opt_svgd_pshard = 1;   // sharded canonical SVGD on the tensor path: shard the Stein phase over the parameters (all-to-all + Gram all-reduce)
   // Guard of the automatic choice (tc_i8 = -1).  16-bit FIXED-point slices carry an error relative to the LARGEST operand
   // magnitude; the float64 comparison of tests/test_gpu_i8.py fits err(gradient) ~ 1.3e-5 / rms_rows(1 - p_y) (+ 3e-5 from

@@ -16,7 +16,7 @@
 // The kernels live in tc_ptx.cuh (PTX helpers), tc_gemm.cuh, tc_layer2.cuh and tc_fused.cuh.
 #include <cstdlib>
 #include <cstring>
-#include "tc_i8.cuh"
+#include "tc_fused_mma.cuh"
 #include <algorithm>
 
 namespace pyb {
@@ -123,6 +123,7 @@ struct TcState {
   CUtensorMap mW_hi, mW_lo, mWp_hi, mWp_lo, mZ_hi, mZ_lo, mZa_hi, mZa_lo, mA_hi, mA_lo, mZ2_hi, mZ2_lo;
   // int8 slices: W1^T [chains*H][Dk], dZ1^T blocked [block][H][128], per (chain, unit) factors (k_pack_w1_i8)
   int64_t cap_chains_i8 = 0, cap_blocks_i8 = 0;
+  DevBuf<unsigned long long> dbg;                        // option "tc_timeline": per-CTA cycle sums of the fused kernel's phases
   DevBuf<int8_t> ws_hi, ws_lo, zi_hi, zi_lo;
   DevBuf<float> cw, b1c, zq, zd;
   CUtensorMap mWs_hi, mWs_lo, mZi_hi, mZi_lo;
@@ -134,6 +135,10 @@ static TcState* tc_state(pyb_handle* h) {
 void tc_release(pyb_handle* h) {
   if (h->tc) delete (TcState*)h->tc;
   h->tc = nullptr;
+}
+void tc_read_timeline(pyb_handle* h, unsigned long long* out_8x160) {
+  if (!h->tc || !((TcState*)h->tc)->dbg.p) { memset(out_8x160, 0, 8 * 160 * 8); return; }
+  PYB_CUDA(cudaMemcpy(out_8x160, ((TcState*)h->tc)->dbg.p, 8 * 160 * 8, cudaMemcpyDeviceToHost));
 }
 int tc_resident_split(const pyb_handle* h) {   // operand split the resident dataset was prepared for: 0 bf16x3, 1 / 2 int8 slices
   return h->tc ? ((TcState*)h->tc)->train.i8 : 0;
@@ -231,6 +236,17 @@ template <int CP>
 static void launch_fused_inst(pyb_handle* h, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                               const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcGemmParams& p, const Layer2Params& l2,
                               int i8 = 0) {
+  if (i8 && !l2.fwd_out && h->opt_tc_epi_mma) {
+    // layer-2 products of the epilogue on mma.sync (tc_fused_mma.cuh)
+    if (i8 >= 2) {
+      PYB_CUDA(cudaFuncSetAttribute(tc_fused_i8_mma<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TfmCfg::SMEM));
+      tc_fused_i8_mma<CP, true><<<grid, TFM_THREADS, TfmCfg::SMEM, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p, l2);
+    } else {
+      PYB_CUDA(cudaFuncSetAttribute(tc_fused_i8_mma<CP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TfmCfg::SMEM));
+      tc_fused_i8_mma<CP, false><<<grid, TFM_THREADS, TfmCfg::SMEM, h->stream>>>(a_hi, a_lo, b_hi, b_lo, p, l2);
+    }
+    return;
+  }
   if (i8) {
     if (l2.fwd_out) launch_fused_i8<CP, true, 1>(h, grid, a_hi, a_lo, b_hi, b_lo, p, l2);
     else if (i8 >= 2) launch_fused_i8<CP, false, 2>(h, grid, a_hi, a_lo, b_hi, b_lo, p, l2);
@@ -437,6 +453,8 @@ static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* t
     const CUtensorMap &b_hi = i8 ? st->mWs_hi : st->mWp_hi, &b_lo = i8 ? st->mWs_lo : st->mWp_lo;
     if (i8) {
       p.bias = st->b1c.p; p.bias_stride = H;                      // b1 + mu^T W1: the slices hold the centred data
+      f2.dbg = nullptr;
+      if (h->opt_tc_timeline) { st->dbg.alloc(8 * 160); f2.dbg = st->dbg.p; }
       f2.sx = d.sx.p; f2.cw = st->cw.p; f2.zq = st->zq.p; f2.zi_hi = st->zi_hi.p; f2.zi_lo = st->zi_lo.p;
     }
     prof_begin(h);

@@ -50,6 +50,34 @@ def test_int8_slices_logprob_and_gradient(oracle, D, H, Cc, N, S, loss, mode):
     np.testing.assert_array_equal(g, g1)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("D,H,Cc,N,S,loss", [(784, 256, 10, 1000, 5, "ce"), (96, 128, 16, 640, 3, "ce"), (128, 256, 3, 385, 150, "mse"),
+                                             (784, 256, 12, 257, 2, "ce")])
+def test_mma_epilogue_agrees_with_the_simt_epilogue(oracle, D, H, Cc, N, S, loss, mode):
+    """tc_epi_mma = 1 (default; tc_fused_mma.cuh: the two layer-2 products of the fused kernel's epilogue on mma.sync with
+    bf16 hi/lo fragments) against the FP32-SIMT epilogue of tc_g1_layer2_fused<.., I8>: the same layer-1 accumulators, the
+    layer-2 products in a different arithmetic (2^-16 per product), so the results agree far inside the parity budget —
+    and the relu masks, which depend on layer 1 only, are identical."""
+    spec, prob, q, out_act, _ = problem(oracle, D, H, Cc, N, S, seed=D + N, act="relu", loss=loss)
+    eng = engine(D, H, Cc, "relu", out_act)
+    eng.set_option("tc_i8", mode)
+    eng.set_dataset(prob.X, prob.y, prob.loss_kind)
+    eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
+    eng.set_option("path", _lib.PATH_TENSOR)
+    U2, l2, g2 = eng.hmc_eval(q)
+    m2 = np.empty((N, H), np.uint8)
+    _lib.check(_lib.load().pyb_debug_relu_mask(eng.h, 0, m2.ctypes.data))
+    eng.set_option("tc_epi_mma", 0)
+    U1, l1, g1 = eng.hmc_eval(q)
+    m1 = np.empty((N, H), np.uint8)
+    _lib.check(_lib.load().pyb_debug_relu_mask(eng.h, 0, m1.ctypes.data))
+    np.testing.assert_array_equal(m1, m2)
+    np.testing.assert_allclose(l2, l1, rtol=2e-6)
+    err = max(rel_err(g2[s], g1[s]) for s in range(S))
+    print("mma epilogue vs simt epilogue, mode %d %d-%d-%d: gradient %.2e" % (mode, D, H, Cc, err))
+    assert err < 3e-5
+
+
 def test_int8_slices_zero_weights_and_unnormalised_data(oracle):
     """All chains of the reference start at W = 0 (HMC.py:69-72): every scale of the scheme degenerates there (zero W1
     columns, constant W2 rows); and data with very different feature ranges, negative values and constant columns (the
