@@ -173,6 +173,13 @@ int pyb_destroy(pyb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   tc_release(h);
   if (h->svgd.comm_stream) cudaStreamSynchronize(h->svgd.comm_stream);
+  if (h->svgd.gram_stream) {
+    cudaStreamSynchronize(h->svgd.gram_stream);
+    cudaStreamDestroy(h->svgd.gram_stream); h->svgd.gram_stream = nullptr;
+    cudaEvent_t* evs[] = {&h->svgd.ev_kernel, &h->svgd.ev_gh[0], &h->svgd.ev_gh[1], &h->svgd.ev_p1, &h->svgd.ev_p2, &h->svgd.ev_back};
+    for (cudaEvent_t* e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+  }
+  if (h->svgd.nccl_comm3) { nccl_comm_destroy(h->svgd.nccl_comm3); h->svgd.nccl_comm3 = nullptr; }
   if (h->svgd.nccl_comm2) { nccl_comm_destroy(h->svgd.nccl_comm2); h->svgd.nccl_comm2 = nullptr; }
   if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }
   if (h->svgd.comm_stream) {
@@ -228,7 +235,7 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
   } else if (!strcmp(key, "tc_fuse")) {
     h->opt_tc_fuse = v != 0;
   } else if (!strcmp(key, "tc_timeline")) {
-    h->opt_tc_timeline = v != 0;
+    h->opt_tc_timeline = (int)v;
   } else if (!strcmp(key, "tc_epi_mma")) {
     h->opt_tc_epi_mma = v != 0;
   } else if (!strcmp(key, "svgd_pshard")) {
@@ -260,12 +267,20 @@ int pyb_get_info(const pyb_handle* h, const char* key, double* out) {
   else if (!strcmp(key, "prof_flops")) *out = h->prof_flops;
   else if (!strcmp(key, "prof_launches")) *out = (double)h->prof_launches;
   else if (!strcmp(key, "n_train")) *out = (double)h->n_train;
-  else if (!strncmp(key, "tc_timeline_", 12) && key[12] >= '0' && key[12] <= '7' && !key[13]) {
+  else if (!strncmp(key, "tc_timeline_", 12) && key[12] >= '0' && key[12] <= '9' && !key[13]) {
     // mean over the CTAs (of cluster leaders for the issuer's entries) of the last fused launch's phase k, in cycles per item
     std::vector<unsigned long long> t(8 * 160);
     tc_read_timeline(const_cast<pyb_handle*>(h), t.data());
-    const int k = key[12] - '0';
+    int k = key[12] - '0';
     double s = 0, n = 0;
+    if (k >= 8) {                                        // 8 / 9: the odd CTAs' epilogue entries kept in slots 0 / 1
+      for (int c = 1; c < 148; c += 2) {
+        const unsigned long long items = t[(c & ~1) * 8 + 3];
+        if (items) { s += (double)t[c * 8 + k - 8] / (double)items; n += 1; }
+      }
+      *out = n ? s / n : 0.0;
+      return PYB_OK;
+    }
     for (int c = 0; c < 148; ++c) {
       const unsigned long long items = t[(c & ~1) * 8 + 3];
       if (items && (k >= 4 || !(c & 1))) { s += k == 3 ? (double)items : (double)t[c * 8 + k] / (double)items; n += 1; }
@@ -610,6 +625,7 @@ int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* id
   PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
   PYB_REQUIRE(world >= 1 && rank >= 0 && rank < world, PYB_ERR_INVALID, "bad rank/world");
   use_device(h);
+  if (h->svgd.nccl_comm3) { nccl_comm_destroy(h->svgd.nccl_comm3); h->svgd.nccl_comm3 = nullptr; }
   if (h->svgd.nccl_comm2) { nccl_comm_destroy(h->svgd.nccl_comm2); h->svgd.nccl_comm2 = nullptr; }
   if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }
   if (world > 1) {

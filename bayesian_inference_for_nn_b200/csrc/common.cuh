@@ -237,7 +237,8 @@ struct SvgdState {
   // comm
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
-  void* nccl_comm2 = nullptr;   // duplicate for the exchange that overlaps the Gram matrix (its own stream)
+  void* nccl_comm2 = nullptr;   // duplicate for the gradient / particle exchanges (their own stream)
+  void* nccl_comm3 = nullptr;   // duplicate for the Gram all-reduce and the median's histograms (side stream)
   DevBuf<float> theta_all, g_all;
   // parameter-sharded Stein phase (canonical mode, tensor path, world > 1): rank r owns columns [r Pw, (r+1) Pw) of ALL
   // particles — theta slice, gathered gradient slice, Adam moments, phi — and the exchange is two all-to-alls of the
@@ -256,6 +257,8 @@ struct SvgdState {
   // while the Gram matrix is built (the exchange step is comm-bound at 8 GPUs unless overlapped)
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_theta = nullptr, ev_grad = nullptr;
+  cudaStream_t gram_stream = nullptr;     // parameter-sharded step: reduction / median / kernel-matrix chain beside the gradients
+  cudaEvent_t ev_kernel = nullptr, ev_gh[2] = {nullptr, nullptr}, ev_p1 = nullptr, ev_p2 = nullptr, ev_back = nullptr;
 };
 
 // S stochastic-gradient chains (sgmc.cu): SGLD / SWAG state per chain
@@ -312,7 +315,7 @@ struct pyb_handle {
   int opt_predict_sharded = 0;   // 1: pyb_predict all-reduces its moment sums over the handle's communicator
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
   int opt_tc_timeline = 0;   // diagnostics: the fused mma kernel records per-CTA cycle sums of its phases (info "tc_timeline_<k>")
-  int opt_tc_epi_mma = 1;    // int8 slices: the layer-2 products of the fused kernel's epilogue run on mma.sync (tc_fused_mma.cuh)
+  int opt_tc_epi_mma = 0;    // 1: fused int8 forward kernel with the layer-2 epilogue on mma.sync (tc_fused_mma.cuh): parity green, no faster
   int opt_svgd_pshard = 1;   // sharded canonical SVGD on the tensor path: shard the Stein phase over the parameters (all-to-all + Gram all-reduce)
   // Guard of the automatic choice (tc_i8 = -1).  16-bit FIXED-point slices carry an error relative to the LARGEST operand
   // magnitude; the float64 comparison of tests/test_gpu_i8.py fits err(gradient) ~ 1.3e-5 / rms_rows(1 - p_y) (+ 3e-5 from
@@ -442,6 +445,10 @@ void nccl_all_to_all_f32(void* comm, const float* send, float* recv, size_t coun
 void nccl_check_async(void** comm);
 void nccl_all_reduce_min_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t s);
 void* nccl_comm_dup(void* comm, int rank);
+void nccl_all_to_all_f32_strided(void* comm, const float* send, size_t send_stride, float* recv, size_t recv_stride,
+                                 size_t count, int world, cudaStream_t s);
+void nccl_exchange_f32(void* comm, const float* send, float* recv, size_t stride, size_t count, const int* send_to, int n_send,
+                       const int* recv_from, int n_recv, cudaStream_t s);
 
 // predict.cu
 // optional classification-uncertainty request (Metrics.py:344-375): host labels [Nt], host outputs [Nt, Ce, Ce]

@@ -117,6 +117,28 @@ void nccl_all_to_all_f32(void* comm, const float* send, float* recv, size_t coun
   }
   nccl_check(api().GroupEnd(), "ncclGroupEnd");
 }
+// block q of `send` (pitch send_stride) goes to rank q, rank q's block lands in block q of `recv` (pitch recv_stride)
+void nccl_all_to_all_f32_strided(void* comm, const float* send, size_t send_stride, float* recv, size_t recv_stride,
+                                 size_t count, int world, cudaStream_t s) {
+  nccl_check(api().GroupStart(), "ncclGroupStart");
+  for (int q = 0; q < world; ++q) {
+    nccl_check(api().Send(send + (size_t)q * send_stride, count, NCCL_FLOAT32, q, (ncclComm_t)comm, s), "ncclSend");
+    nccl_check(api().Recv(recv + (size_t)q * recv_stride, count, NCCL_FLOAT32, q, (ncclComm_t)comm, s), "ncclRecv");
+  }
+  nccl_check(api().GroupEnd(), "ncclGroupEnd");
+}
+// part of an all-to-all: block q of `send` to every rank q in send_to, block q of `recv` from every rank q in recv_from
+// (the lists of all ranks must pair up: q in send_to(r) <=> r in recv_from(q))
+void nccl_exchange_f32(void* comm, const float* send, float* recv, size_t stride, size_t count, const int* send_to, int n_send,
+                       const int* recv_from, int n_recv, cudaStream_t s) {
+  if (n_send == 0 && n_recv == 0) return;
+  nccl_check(api().GroupStart(), "ncclGroupStart");
+  for (int i = 0; i < n_send; ++i)
+    nccl_check(api().Send(send + (size_t)send_to[i] * stride, count, NCCL_FLOAT32, send_to[i], (ncclComm_t)comm, s), "ncclSend");
+  for (int i = 0; i < n_recv; ++i)
+    nccl_check(api().Recv(recv + (size_t)recv_from[i] * stride, count, NCCL_FLOAT32, recv_from[i], (ncclComm_t)comm, s), "ncclRecv");
+  nccl_check(api().GroupEnd(), "ncclGroupEnd");
+}
 // after a stream synchronisation: has the communicator recorded an asynchronous error?  Abort it and fail cleanly.
 void nccl_check_async(void** comm) {
   if (!comm || !*comm) return;

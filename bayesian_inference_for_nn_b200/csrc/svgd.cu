@@ -629,9 +629,9 @@ __global__ void k_pack_cols(const float* __restrict__ src, int64_t Sl, int64_t P
   const int64_t col = q * Pw + c;
   dst[(q * Sl + i) * Pw + c] = col < P ? src[i * P + col] : 0.f;
 }
-// src [R][Sl][Pw] -> dst [Sl, P]
-__global__ void k_unpack_cols(const float* __restrict__ src, int64_t Sl, int64_t P, int64_t Pw, int R, float* __restrict__ dst) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, q = blockIdx.z;
+// src [R][Sl][Pw] -> dst [Sl, P]: blocks q0 + blockIdx.z
+__global__ void k_unpack_cols(const float* __restrict__ src, int64_t Sl, int64_t P, int64_t Pw, int q0, float* __restrict__ dst) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, q = q0 + blockIdx.z;
   const int64_t col = q * Pw + c;
   if (c >= Pw || col >= P) return;
   dst[i * P + col] = src[(q * Sl + i) * Pw + c];
@@ -684,6 +684,12 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     count_launch(h, 3);
     sv.ps_ready = true;
   }
+  if (!sv.gram_stream) {
+    PYB_CUDA(cudaStreamCreateWithFlags(&sv.gram_stream, cudaStreamNonBlocking));
+    cudaEvent_t* evs[] = {&sv.ev_kernel, &sv.ev_gh[0], &sv.ev_gh[1], &sv.ev_p1, &sv.ev_p2, &sv.ev_back};
+    for (cudaEvent_t* e : evs) PYB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  if (!sv.nccl_comm3) sv.nccl_comm3 = nccl_comm_dup(sv.nccl_comm, sv.rank);
   const bool timed = h->prof_enabled;
   auto mark = [&](int k) {
     if (!timed) return;
@@ -691,63 +697,122 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     PYB_CUDA(cudaEventRecord(sv.ps_ev[k], h->stream));
   };
   sv.ps_timed = timed;
+  cudaStream_t main_stream = h->stream;
   mark(0);
-  // 1. local gradients, 2. gradient rows -> gradient slice of all particles
-  eval_on_batch(h, sv.theta.p, S, Xb, yb_i, yb_f, Nb, scale, sv.loss.p, sv.g.p);
-  mark(1);
-  // the gradient exchange runs on its own stream and communicator WHILE the Gram matrix (which needs the particle slice
-  // only) is built and all-reduced on the main stream; the Stein right-hand side below waits for it
-  nvtxRangePushA("pyb.svgd.exchange.gradients(all-to-all, overlapped)");
-  PYB_CUDA(cudaEventRecord(sv.ev_fork, h->stream));
-  PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_fork, 0));
-  k_pack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)S, (unsigned)R), 256, 0, sv.comm_stream>>>(sv.g.p, S, P, Pw, R, sv.ps_pack.p);
-  nccl_all_to_all_f32(sv.nccl_comm2, sv.ps_pack.p, sv.ps_g.p, (size_t)S * Pw, R, sv.comm_stream);
-  PYB_CUDA(cudaEventRecord(sv.ev_grad, sv.comm_stream));
-  count_launch(h);
-  nvtxRangePop();
-  mark(2);
-  nvtxRangePushA("pyb.svgd.gram(+all-reduce)");
-  // 3. partial Gram and squared norms over the slice, summed over the ranks
+  // ---- 1. partial Gram matrix and squared norms over the slice: they need the particle slice only, which is the master
+  //         copy since the last step, so they go first and their reduction hides behind the gradients
+  nvtxRangePushA("pyb.svgd.gram_partial");
   sv.xh.alloc((size_t)St * Pw); sv.xl.alloc((size_t)St * Pw);
   sv.gram.alloc((size_t)St * St); sv.d2.alloc((size_t)St * St); sv.rowsum.alloc(St); sv.h2.alloc(2);
+  sv.kf.alloc((size_t)St * St); sv.kh.alloc((size_t)St * St); sv.kl.alloc((size_t)St * St);
+  sv.yth.alloc((size_t)Pw * St); sv.ytl.alloc((size_t)Pw * St);
   tc_split_rows(h, sv.ps_x.p, St, (int)Pw, Pw, sv.xh.p, sv.xl.p, Pw);
   tc_gemm_split(h, sv.xh.p, sv.xl.p, Pw, St, 0, St, sv.xh.p, sv.xl.p, Pw, St, Pw, sv.gram.p, St);
   k_row_norms<<<St, 256, 0, h->stream>>>(sv.ps_x.p, Pw, sv.ps_norms.p);
-  mark(3);
-  nccl_all_reduce_f32(sv.nccl_comm, sv.gram.p, (size_t)St * St, h->stream);
-  nccl_all_reduce_f64(sv.nccl_comm, sv.ps_norms.p, St, h->stream);
-  nvtxRangePop();
-  mark(4);
-  nvtxRangePushA("pyb.svgd.median_kernel");
-  // 4. distances, median bandwidth, kernel matrix (identical on every rank: the all-reduced inputs are)
-  k_d2_from_gram<<<(unsigned)(((int64_t)St * St + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p);
-  count_launch(h, 2);
-  median_bandwidth(h, sv.d2.p + (int64_t)r0 * St, (int64_t)S * St, (int64_t)St * St, St, sv.h2.p);
-  k_kernel_rowsum<<<St, 256, 0, h->stream>>>(sv.d2.p, St, sv.h2.p, sv.rowsum.p);
   count_launch(h);
   nvtxRangePop();
-  mark(5);
-  nvtxRangePushA("pyb.svgd.stein_update(KY+Adam)");
-  // 5. K Y and the Adam ascent step on the slice
-  sv.kf.alloc((size_t)St * St); sv.kh.alloc((size_t)St * St); sv.kl.alloc((size_t)St * St);
-  sv.yth.alloc((size_t)Pw * St); sv.ytl.alloc((size_t)Pw * St);
-  k_double_to_float<<<eb, 256, 0, h->stream>>>(sv.d2.p, sv.kf.p, (int64_t)St * St);
-  tc_split_rows(h, sv.kf.p, St, St, St, sv.kh.p, sv.kl.p, St);
+  mark(1);
+  // ---- 2. side stream, third communicator: all-reduce of the Gram matrix, distances, median bandwidth, kernel matrix and
+  //         its bf16 hi / lo split (identical on every rank: the all-reduced inputs are) — while the gradients run
+  PYB_CUDA(cudaEventRecord(sv.ev_fork, main_stream));
+  PYB_CUDA(cudaStreamWaitEvent(sv.gram_stream, sv.ev_fork, 0));
+  {
+    nvtxRangePushA("pyb.svgd.gram_all_reduce+median_kernel(side stream)");
+    void* comm_main = sv.nccl_comm;
+    h->stream = sv.gram_stream; sv.nccl_comm = sv.nccl_comm3;       // the helpers below launch on h->stream / sv.nccl_comm
+    try {
+      nccl_all_reduce_f32(sv.nccl_comm, sv.gram.p, (size_t)St * St, h->stream);
+      nccl_all_reduce_f64(sv.nccl_comm, sv.ps_norms.p, St, h->stream);
+      k_d2_from_gram<<<(unsigned)(((int64_t)St * St + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p);
+      median_bandwidth(h, sv.d2.p + (int64_t)r0 * St, (int64_t)S * St, (int64_t)St * St, St, sv.h2.p);
+      k_kernel_rowsum<<<St, 256, 0, h->stream>>>(sv.d2.p, St, sv.h2.p, sv.rowsum.p);
+      k_double_to_float<<<eb, 256, 0, h->stream>>>(sv.d2.p, sv.kf.p, (int64_t)St * St);
+      tc_split_rows(h, sv.kf.p, St, St, St, sv.kh.p, sv.kl.p, St);
+      count_launch(h, 4);
+    } catch (...) {
+      h->stream = main_stream; sv.nccl_comm = comm_main;
+      throw;
+    }
+    h->stream = main_stream; sv.nccl_comm = comm_main;
+    PYB_CUDA(cudaEventRecord(sv.ev_kernel, sv.gram_stream));
+    nvtxRangePop();
+  }
+  // ---- 3. local gradients in (up to) two halves of the particles: a half's rows travel to the parameter slices of
+  //         every rank (all-to-all on the exchange stream, second communicator) while the next half is computed
+  nvtxRangePushA("pyb.svgd.gradients(+all-to-all)");
+  const int nh = (S >= 256 && S % 2 == 0) ? 2 : 1;
+  const int64_t Sh = S / nh;
+  for (int hf = 0; hf < nh; ++hf) {
+    eval_on_batch(h, sv.theta.p + hf * Sh * P, Sh, Xb, yb_i, yb_f, Nb, scale, sv.loss.p + hf * Sh, sv.g.p + hf * Sh * P);
+    PYB_CUDA(cudaEventRecord(sv.ev_gh[hf], main_stream));
+    PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_gh[hf], 0));
+    float* pk = sv.ps_pack.p + (int64_t)hf * R * Sh * Pw;
+    k_pack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)Sh, (unsigned)R), 256, 0, sv.comm_stream>>>(
+        sv.g.p + hf * Sh * P, Sh, P, Pw, R, pk);
+    nccl_all_to_all_f32_strided(sv.nccl_comm2, pk, (size_t)Sh * Pw, sv.ps_g.p + hf * Sh * Pw, (size_t)S * Pw, (size_t)Sh * Pw, R,
+                                sv.comm_stream);
+    count_launch(h);
+  }
+  PYB_CUDA(cudaEventRecord(sv.ev_grad, sv.comm_stream));
+  nvtxRangePop();
+  mark(2);
+  PYB_CUDA(cudaStreamWaitEvent(main_stream, sv.ev_kernel, 0));     // kernel matrix, bandwidth, row sums
+  mark(3);
+  PYB_CUDA(cudaStreamWaitEvent(main_stream, sv.ev_grad, 0));       // the gradient slice of all particles is complete
+  mark(4);
+  // ---- 4. K Y and the Adam ascent step on the slice, in two groups of particle blocks (block q = rank q's particles):
+  //         rank r takes the blocks in the order r+1, r+2, ..., r-1, r, so that the finished blocks of the first group
+  //         are on the wire (balanced: everybody sends to its next ranks and receives from its previous ones) while the
+  //         second group is multiplied
+  nvtxRangePushA("pyb.svgd.stein_update(KY+Adam, blocks leave as they finish)");
   dim3 gt((unsigned)((Pw + 31) / 32), (unsigned)((St + 63) / 64)), bt(32, 8);
-  PYB_CUDA(cudaStreamWaitEvent(h->stream, sv.ev_grad, 0));          // the gathered gradient slice is complete
   k_stein_rhs_split_t<<<gt, bt, 0, h->stream>>>(sv.ps_x.p, sv.ps_g.p, sv.h2.p, St, Pw, sv.yth.p, sv.ytl.p, St, sv.ps_mu.p,
                                                sv.ps_iv.p);
-  tc_gemm_split(h, sv.kh.p, sv.kl.p, St, St, 0, St, sv.yth.p, sv.ytl.p, St, (int)Pw, St, sv.ps_phi.p, Pw);
-  k_phi_finish_adam<<<(unsigned)(((int64_t)St * Pw + 1023) / 1024), 256, 0, h->stream>>>(
-      sv.ps_phi.p, sv.ps_x.p, sv.ps_m.p, sv.ps_v.p, Pw, (int64_t)St * Pw, St, sv.h2.p, sv.rowsum.p, lr_t);
-  count_launch(h, 3);
-  nvtxRangePop();
-  mark(6);
-  NvtxRange nv_back("pyb.svgd.exchange.particles(all-to-all)");
-  // 6. the updated rows of every rank's own particles travel back (block q of the slice = rank q's particles)
-  nccl_all_to_all_f32(sv.nccl_comm, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, R, h->stream);
-  k_unpack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)S, (unsigned)R), 256, 0, h->stream>>>(sv.ps_pack.p, S, P, Pw, R, sv.theta.p);
   count_launch(h);
+  const int n1 = R / 2;                                            // remote blocks in the first group
+  int send1[64], recv1[64], send2[64], recv2[64];
+  PYB_REQUIRE(R <= 64, PYB_ERR_INVALID, "at most 64 ranks");
+  for (int j = 1; j <= n1; ++j) { send1[j - 1] = (sv.rank + j) % R; recv1[j - 1] = (sv.rank - j + R) % R; }
+  for (int j = n1 + 1; j < R; ++j) { send2[j - n1 - 1] = (sv.rank + j) % R; recv2[j - n1 - 1] = (sv.rank - j + R) % R; }
+  auto update_blocks = [&](int j_lo, int j_hi) {                   // blocks (rank + j) % R for j in [j_lo, j_hi): <= 2 runs of rows
+    int j = j_lo;
+    while (j < j_hi) {
+      const int q0 = (sv.rank + j) % R;
+      int len = 1;
+      while (j + len < j_hi && q0 + len < R) ++len;                // a run ends where the block index wraps to 0
+      const int64_t m0 = (int64_t)q0 * S, mrows = (int64_t)len * S;
+      tc_gemm_split(h, sv.kh.p, sv.kl.p, St, St, (int)m0, (int)mrows, sv.yth.p, sv.ytl.p, St, (int)Pw, St, sv.ps_phi.p + m0 * Pw, Pw);
+      k_phi_finish_adam<<<(unsigned)((mrows * Pw + 1023) / 1024), 256, 0, h->stream>>>(
+          sv.ps_phi.p + m0 * Pw, sv.ps_x.p + m0 * Pw, sv.ps_m.p + m0 * Pw, sv.ps_v.p + m0 * Pw, Pw, mrows * Pw, St, sv.h2.p,
+          sv.rowsum.p + m0, lr_t);
+      count_launch(h);
+      j += len;
+    }
+  };
+  update_blocks(1, 1 + n1);
+  PYB_CUDA(cudaEventRecord(sv.ev_p1, main_stream));
+  PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_p1, 0));
+  auto unpack = [&](const float* src, int q, cudaStream_t st) {   // parameter slice q of this rank's rows -> theta
+    k_unpack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)S, 1), 256, 0, st>>>(src, S, P, Pw, q, sv.theta.p);
+    count_launch(h);
+  };
+  nccl_exchange_f32(sv.nccl_comm2, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, (size_t)S * Pw, send1, n1, recv1, n1, sv.comm_stream);
+  for (int i = 0; i < n1; ++i) unpack(sv.ps_pack.p, recv1[i], sv.comm_stream);
+  update_blocks(1 + n1, R + 1);                                    // ... r-1 and, last, this rank's own block
+  PYB_CUDA(cudaEventRecord(sv.ev_p2, main_stream));
+  PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_p2, 0));
+  nccl_exchange_f32(sv.nccl_comm2, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, (size_t)S * Pw, send2, R - 1 - n1, recv2, R - 1 - n1,
+                    sv.comm_stream);
+  for (int i = 0; i < R - 1 - n1; ++i) unpack(sv.ps_pack.p, recv2[i], sv.comm_stream);
+  PYB_CUDA(cudaEventRecord(sv.ev_back, sv.comm_stream));
+  nvtxRangePop();
+  mark(5);
+  // ---- 5. this rank's own rows: its own slice straight from the master copy; the other slices were unpacked on the
+  //         exchange stream as they arrived
+  NvtxRange nv_back("pyb.svgd.exchange.particles(own slice + wait)");
+  unpack(sv.ps_x.p, sv.rank, main_stream);
+  mark(6);
+  PYB_CUDA(cudaStreamWaitEvent(main_stream, sv.ev_back, 0));
   mark(7);
 }
 

@@ -231,14 +231,18 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                      "l"(th + l2.b2_off + eall) : "memory");
     };
     if (cluster_id < p.total_items) fetch_consts(cluster_id, 0);
-    int it = 0;
-    long long e_top = 0, e_wait = 0, e_A = 0, e_rest = 0;
+    int it = 0, b_prev = -1, cbuf = 1;
+    const bool ce = l2.loss_kind == PYB_LOSS_SPARSE_CE;
+    long long e_top = 0, e_wait = 0, e_A = 0, e_rest = 0, e_x = 0, e_sm = 0;
+    const int dfl = l2.dbg_flags;
     for (int item = cluster_id; item < p.total_items; item += n_clusters, ++it) {
       const long long s0 = clock64();
       int b, mp, split;
       tc_decode(p, item, b, mp, split);
       const int mt = mp * 2 + (int)rank;
-      const int cbuf = it & 1;
+      const bool new_chain = b != b_prev;                          // uniform over the CTA: constants and W2 fragments follow the chain
+      b_prev = b;
+      cbuf ^= new_chain ? 1 : 0;
       const float* bsb = bias_s + cbuf * 256 + hbase;
       const float* cwb = cw_s + cbuf * 256 + hbase;
       const float* zqb = zq_s + cbuf * 256 + hbase;
@@ -249,8 +253,11 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int rg = mt * 128 + quad * 32 + g + 8 * r;
         sxr[r] = rg < p.M_valid ? __ldg(l2.sx + rg) : 0.f;
       }
+      const int row_g = mt * 128 + row_own;
+      const int yi = (ce && row_g < p.M_valid) ? __ldg(l2.y_i + row_g) : 0;     // long before the softmax needs it
+      if (new_chain) {
       asm volatile("cp.async.wait_all;" ::: "memory");
-      asm volatile("bar.sync 1, 512;" ::: "memory");             // staging complete; every reader of the last item's fragments is done
+      asm volatile("bar.sync 1, 512;" ::: "memory");             // staging complete; every reader of the last chain's fragments is done
       if (eall < H) {
         // this chain's W2 row -> bf16 hi / lo (32-byte rows): what ldmatrix reads in both phases
         const float4* src = reinterpret_cast<const float4*>(w2st_s + eall * 16);
@@ -267,6 +274,7 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         dl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); dl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");             // fragments visible; the staging rows may be refilled
+      }
       const long long s1 = clock64();
       mbar_wait_sleep(tmem_full, (uint32_t)(it & 1));
       tc_fence_after();
@@ -319,6 +327,7 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               for (int i = 0; i < 2; ++i) {
                 const uint32_t sel = i ? 0x7632u : 0x5410u;
                 const int w_off = (ch * 32 + 8 * kb + i) * 32;
+                if (dfl & 4) continue;
                 __stcs(pa_hi + w_off, make_uint2(__byte_perm(ahw[0][kk], ahw[1][kk], sel), __byte_perm(ahw[2][kk], ahw[3][kk], sel)));
                 __stcs(pa_lo + w_off, make_uint2(__byte_perm(alw[0][kk], alw[1][kk], sel), __byte_perm(alw[2][kk], alw[3][kk], sel)));
               }
@@ -334,6 +343,7 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               const uint32_t Al[4] = {alw[2 * a][0], alw[2 * a + 1][0], alw[2 * a][1], alw[2 * a + 1][1]};
 #pragma unroll
               for (int n = 0; n < 2; ++n) {
+                if (dfl & 16) { acc[a][n][0] += __uint_as_float(Ah[n] ^ bh[n]); continue; }
                 mma_bf16_16816(acc[a][n], Ah, bh[2 * n], bh[2 * n + 1]);
                 mma_bf16_16816(acc[a][n], Al, bh[2 * n], bh[2 * n + 1]);
                 mma_bf16_16816(acc[a][n], Ah, bl[2 * n], bl[2 * n + 1]);
@@ -348,7 +358,11 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive_leader_relaxed(tmem_empty);
       const long long s3 = clock64();
-      if (item + n_clusters < p.total_items) fetch_consts(item + n_clusters, cbuf ^ 1);
+      if (item + n_clusters < p.total_items) {
+        int bn, mpn, sn;
+        tc_decode(p, item + n_clusters, bn, mpn, sn);
+        if (bn != b) fetch_consts(item + n_clusters, cbuf ^ 1);
+      }
       // ---- the partial logits of the two unit halves meet in shared memory (lane t holds classes 2t, 2t+1, 8+2t, 9+2t)
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -360,34 +374,60 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const int cls = 8 * n + 2 * t + (e & 1);
             zx_s[(half * 16 + cls) * 128 + row] = acc[a][n][e];
           }
-      asm volatile("bar.sync 2, 512;" ::: "memory");
+      // the four warps of a TMEM lane quadrant (one per quarter of the units) share these rows and nobody else does
+      asm volatile("bar.sync %0, 128;" ::"r"(4 + quad) : "memory");
+      const long long s4 = clock64();
       float zf[CP], dz[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c)
         zf[c] = ((b2b[c] + zx_s[c * 128 + row_own]) + zx_s[(16 + c) * 128 + row_own]) +
                 (zx_s[(32 + c) * 128 + row_own] + zx_s[(48 + c) * 128 + row_own]);
-      const int row_g = mt * 128 + row_own;
+      asm volatile("bar.sync %0, 128;" ::"r"(8 + quad) : "memory");   // all four have read: the next item's partial logits may land
       float loss_r = 0.f;
-      l2_loss_dz<CP>(l2, row_g, row_g < p.M_valid, zf, dz, loss_r, invN);
-      if (half == 0) {
-        const int64_t blk2 = (((int64_t)b * p.out_tiles + mt) * L2_CMAX) * 128 + pos0 + r_own;
+      if (dfl & 32) {
 #pragma unroll
-        for (int c = 0; c < CP; ++c) {
-          __nv_bfloat16 hb, lb;
-          split_bf16(dz[c], hb, lb);
-          z2_hi[blk2 + c * 128] = __bfloat16_as_ushort(hb);
-          z2_lo[blk2 + c * 128] = __bfloat16_as_ushort(lb);
+        for (int c = 0; c < CP; ++c) dz[c] = zf[c];
+      } else if (ce) {
+        // l2_loss_dz's sparse cross-entropy branch with the label already in a register and one exp per class
+#pragma unroll
+        for (int c = 0; c < CP; ++c) dz[c] = 0.f;
+        if (row_g < p.M_valid) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) if (c < C) mx = fmaxf(mx, zf[c]);
+          float se = 0.f, zy = 0.f;
+#pragma unroll
+          for (int c = 0; c < CP; ++c)
+            if (c < C) { dz[c] = expf(zf[c] - mx); se += dz[c]; zy = c == yi ? zf[c] : zy; }
+          loss_r = logf(se) - (zy - mx);
+          const float inv = 1.0f / se;
+#pragma unroll
+          for (int c = 0; c < CP; ++c)
+            if (c < C) dz[c] = (dz[c] * inv - (c == yi ? 1.f : 0.f)) * invN;
         }
+      } else
+      l2_loss_dz<CP>(l2, row_g, row_g < p.M_valid, zf, dz, loss_r, invN);
+      {
+        // every quarter holds the same dZ2 rows: quarter q stores / sums the classes c = q (mod 4), quarter 3 the loss
+        const int64_t blk2 = (((int64_t)b * p.out_tiles + mt) * L2_CMAX) * 128 + pos0 + r_own;
         const int64_t grp = (int64_t)b * l2.n_groups + mt * 4 + quad;
         float mine = 0.f;
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
-          const float sm = warp_sum(dz[c]);
-          if (lane == c) mine = sm;
+          if ((c & 3) == half) {
+            __nv_bfloat16 hb, lb;
+            split_bf16(dz[c], hb, lb);
+            z2_hi[blk2 + c * 128] = __bfloat16_as_ushort(hb);
+            z2_lo[blk2 + c * 128] = __bfloat16_as_ushort(lb);
+            const float sm = warp_sum(dz[c]);
+            if (lane == c) mine = sm;
+          }
         }
-        if (lane < CP) l2.b2_partial[grp * L2_CMAX + lane] = mine;
-        const float ls = warp_sum(loss_r);
-        if (lane == 0) l2.loss_partial[grp] = (double)ls;
+        if (lane < CP && (lane & 3) == half) l2.b2_partial[grp * L2_CMAX + lane] = mine;
+        if (half == 3) {
+          const float ls = warp_sum(loss_r);
+          if (lane == 0) l2.loss_partial[grp] = (double)ls;
+        }
       }
       // ---- dZ2 of the row this lane finished -> bf16 hi / lo A fragments for the whole quad, through shared memory:
       //      slot s of a row = {hi(2s, 2s+1), hi(2s+8, 2s+9), lo(2s, 2s+1), lo(2s+8, 2s+9)} (both halves write the same values)
@@ -412,6 +452,7 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         Dl[r >> 1][(r & 1)] = f.z; Dl[r >> 1][2 + (r & 1)] = f.w;
       }
       __syncwarp();                                                 // the rows are re-written by the next item
+      const long long s5 = clock64();
       uint2* pz_hi = reinterpret_cast<uint2*>(l2.zt_hi) + (blk_e >> 2);
       uint2* pz_lo = reinterpret_cast<uint2*>(l2.zt_lo) + (blk_e >> 2);
       uint32_t* pzi_hi = reinterpret_cast<uint32_t*>(l2.zi_hi + (ZI8 ? blk_e : 0));
@@ -435,6 +476,7 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               for (int a = 0; a < 2; ++a) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) d2[a][e] = 0.f;
+                if (dfl & 8) { d2[a][0] = __uint_as_float(Dh[a][0] ^ bh[kk]); d2[a][1] = __uint_as_float(Dl[a][1] ^ bl[kk]); continue; }
                 mma_bf16_16816(d2[a], Dh[a], bh[2 * kk], bh[2 * kk + 1]);
                 mma_bf16_16816(d2[a], Dl[a], bh[2 * kk], bh[2 * kk + 1]);
                 mma_bf16_16816(d2[a], Dh[a], bl[2 * kk], bl[2 * kk + 1]);
@@ -445,6 +487,7 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 #pragma unroll
                 for (int r = 0; r < 4; ++r) d[r] = ((m >> (kb * 8 + r * 2 + i)) & 1u) ? d[r] : 0.f;
                 const int w_off = (ch * 32 + 8 * kb + i) * 32;
+                if ((dfl & 2) && d[0] != 12345.f) continue;
                 if (ZI8) {
                   uint32_t hw, lw;
                   slice4_i8(d, zqb[ch * 32 + 8 * kb + i], hw, lw);
@@ -462,13 +505,17 @@ tc_fused_i8_mma(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           }
         }
       }
-      e_top += s1 - s0; e_wait += s2 - s1; e_A += s3 - s2; e_rest += clock64() - s3;
+      e_top += s1 - s0; e_wait += s2 - s1; e_A += s3 - s2; e_rest += clock64() - s5; e_x += s4 - s3; e_sm += s5 - s4;
+    }
+    if (l2.dbg && warp == 0 && lane == 0 && (blockIdx.x & 1)) {
+      l2.dbg[blockIdx.x * 8 + 0] = (unsigned long long)e_x;          // (odd CTAs' slots 0 / 1 are free) logits exchange incl. the barrier
+      l2.dbg[blockIdx.x * 8 + 1] = (unsigned long long)e_sm;         // softmax / loss / dZ2 fragments
     }
     if (l2.dbg && warp == 0 && lane == 0) {
       l2.dbg[blockIdx.x * 8 + 4] = (unsigned long long)e_top;        // epilogue warp 0: constants / barriers at the top of an item
       l2.dbg[blockIdx.x * 8 + 5] = (unsigned long long)e_wait;       // waiting for the accumulators
       l2.dbg[blockIdx.x * 8 + 6] = (unsigned long long)e_A;          // phase A (TMEM held)
-      l2.dbg[blockIdx.x * 8 + 7] = (unsigned long long)e_rest;       // logits exchange, loss, phase B
+      l2.dbg[blockIdx.x * 8 + 7] = (unsigned long long)e_rest;       // phase B
     }
   }
   tc_fence_before();

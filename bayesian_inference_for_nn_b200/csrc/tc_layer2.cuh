@@ -105,6 +105,7 @@ struct Layer2Params {
   const float* cw;             // [Bc][H] s_w / 127^2: column scale of the W1^T slices times the slice unit
   const float* zq;             // [Bc][H] 127 / s_z: quantisation factor of the dZ1^T slices (I8 == 2)
   int8_t* zi_hi; int8_t* zi_lo;   // dZ1^T int8 slices, blocked [chain][tile][H][128]
+  int dbg_flags;               // timing experiments only (results are wrong when set): 2 no phase-B stores, 4 no A1 stores, 8 no phase-B mma, 16 no phase-A mma, 32 no softmax
   unsigned long long* dbg;     // optional [grid][8] cycle sums of the kernel's phases (option "tc_timeline"), else null
 };
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {

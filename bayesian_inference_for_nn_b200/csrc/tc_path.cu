@@ -453,7 +453,7 @@ static void tc_pack_and_g1(pyb_handle* h, TcState* st, TcData& d, const float* t
     const CUtensorMap &b_hi = i8 ? st->mWs_hi : st->mWp_hi, &b_lo = i8 ? st->mWs_lo : st->mWp_lo;
     if (i8) {
       p.bias = st->b1c.p; p.bias_stride = H;                      // b1 + mu^T W1: the slices hold the centred data
-      f2.dbg = nullptr;
+      f2.dbg = nullptr; f2.dbg_flags = h->opt_tc_timeline & ~1;
       if (h->opt_tc_timeline) { st->dbg.alloc(8 * 160); f2.dbg = st->dbg.p; }
       f2.sx = d.sx.p; f2.cw = st->cw.p; f2.zq = st->zq.p; f2.zi_hi = st->zi_hi.p; f2.zi_lo = st->zi_lo.p;
     }

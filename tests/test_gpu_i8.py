@@ -54,7 +54,7 @@ def test_int8_slices_logprob_and_gradient(oracle, D, H, Cc, N, S, loss, mode):
 @pytest.mark.parametrize("D,H,Cc,N,S,loss", [(784, 256, 10, 1000, 5, "ce"), (96, 128, 16, 640, 3, "ce"), (128, 256, 3, 385, 150, "mse"),
                                              (784, 256, 12, 257, 2, "ce")])
 def test_mma_epilogue_agrees_with_the_simt_epilogue(oracle, D, H, Cc, N, S, loss, mode):
-    """tc_epi_mma = 1 (default; tc_fused_mma.cuh: the two layer-2 products of the fused kernel's epilogue on mma.sync with
+    """tc_epi_mma = 1 (option, default 0; tc_fused_mma.cuh: the two layer-2 products of the fused kernel's epilogue on mma.sync with
     bf16 hi/lo fragments) against the FP32-SIMT epilogue of tc_g1_layer2_fused<.., I8>: the same layer-1 accumulators, the
     layer-2 products in a different arithmetic (2^-16 per product), so the results agree far inside the parity budget —
     and the relu masks, which depend on layer 1 only, are identical."""

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """C4 (SVGD, 784-128-10, minibatch 1024 of a 60000-row pool) with the particles sharded over the GPUs of one box:
-one process per GPU, NCCL all-gather of the particle and gradient shards inside the library.
+one process per GPU; the Stein phase is sharded over the parameters (gradient / particle all-to-all, all-reduced Gram
+matrix).  The phase split is measured with CUDA events on the main stream: "wait_*" is what of an exchange or of
+the side-stream reduction / median chain is NOT hidden behind compute.
     python tools/bench_svgd_sharded.py [--particles 4096] [--world 1,2,4,8] [--steps 5]
 One JSON line per world size: device ms per step (max over ranks) and the speed-up over one GPU."""
 import argparse
@@ -67,8 +69,8 @@ def main():
         print(json.dumps({"case": "C4 SVGD canonical_median 784-128-10, minibatch 1024", "particles": a.particles,
                           "n_gpus": world, "device_ms_per_step": ms, "particle_grad_evals_per_s": a.particles * 1e3 / ms,
                           "speedup_vs_1gpu": base / ms, "mean_loss_last": res[0][2],
-                          "phase_ms_max_over_ranks": dict(zip(["gradients", "gradient_all_to_all", "gram_partial", "gram_all_reduce",
-                                                               "median_kernel", "ky_adam", "particle_all_to_all"],
+                          "phase_ms_max_over_ranks": dict(zip(["gram_partial", "gradients", "wait_reduced_kernel_matrix", "wait_gradient_all_to_all",
+                                                               "ky_adam", "unpack_own_slice", "wait_particle_exchange"],
                                                               np.max([r[3] for r in res], axis=0).round(3).tolist()))}), flush=True)
 
 

@@ -16,10 +16,12 @@ from bayesian_inference_for_nn_b200.engine import Engine
 S = int(os.environ.get("S", 1024))
 X, y = bench.synth(60000)
 spec = keras_json.parse_model_json(keras_json.make_sequential_json(784, [256, 10], ["relu", "softmax"]))
-for em in [int(v) for v in os.environ.get("EPI", "1").split(",")]:
+em = 1
+for flags in [int(v) for v in os.environ.get("FLAGS", "0").split(",")]:
     eng = Engine(spec, device=0, seed=1234)
     eng.set_option("tc_epi_mma", em)
-    eng.set_option("tc_timeline", 1)
+    eng.set_option("tc_i8", 2)
+    eng.set_option("tc_timeline", 1 | flags)
     for kv in sys.argv[1:]:
         k, v = kv.split("=")
         eng.set_option(k, float(v))
@@ -28,8 +30,8 @@ for em in [int(v) for v in os.environ.get("EPI", "1").split(",")]:
     eng.hmc_init(S, 2e-5, 1.0, 20, _lib.HMC_REFERENCE)
     eng.hmc_run(2, burning=True, sampling=False)
     d = eng.hmc_run(1, burning=False, sampling=True)
-    t = [eng.info("tc_timeline_%d" % k) for k in range(8)]
-    print("epi_mma=%d split=%d ms/iter %.0f | issuer: wait_tmem %.0f kloop %.0f (fill wait %.0f) items/cluster %.1f | "
-          "epilogue: top %.0f wait_acc %.0f phaseA %.0f rest %.0f  (cycles per item)" %
-          (em, int(eng.info("tc_split")), d["device_ms"], t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]), flush=True)
+    t = [eng.info("tc_timeline_%d" % k) for k in range(10)]
+    print("flags=%d split=%d ms/iter %.0f | issuer: wait_tmem %.0f kloop %.0f (fill wait %.0f) items/cluster %.1f | "
+          "epilogue: top %.0f wait_acc %.0f phaseA %.0f exchange %.0f softmax %.0f phaseB %.0f  (cycles per item)" %
+          (flags, int(eng.info("tc_split")), d["device_ms"], t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[8], t[9], t[7]), flush=True)
     eng.close()
