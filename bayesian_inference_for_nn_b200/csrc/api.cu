@@ -179,6 +179,7 @@ int pyb_destroy(pyb_handle* h) {
     cudaEvent_t* evs[] = {&h->svgd.ev_kernel, &h->svgd.ev_gh[0], &h->svgd.ev_gh[1], &h->svgd.ev_p1, &h->svgd.ev_p2, &h->svgd.ev_back};
     for (cudaEvent_t* e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
   }
+  svgd_p2p_release(h);
   if (h->svgd.nccl_comm3) { nccl_comm_destroy(h->svgd.nccl_comm3); h->svgd.nccl_comm3 = nullptr; }
   if (h->svgd.nccl_comm2) { nccl_comm_destroy(h->svgd.nccl_comm2); h->svgd.nccl_comm2 = nullptr; }
   if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }
@@ -240,6 +241,11 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_tc_epi_mma = v != 0;
   } else if (!strcmp(key, "svgd_pshard")) {
     h->opt_svgd_pshard = v != 0;
+  } else if (!strcmp(key, "svgd_halves")) {
+    h->opt_svgd_halves = v != 0;
+  } else if (!strcmp(key, "svgd_p2p")) {
+    h->opt_svgd_p2p = v != 0;
+    h->svgd.p2p_tried = false;
     h->svgd.ps_ready = false;
   } else if (!strcmp(key, "tc_i8_min_loss")) {
     PYB_REQUIRE(v >= 0, PYB_ERR_INVALID, "tc_i8_min_loss must be >= 0");
@@ -290,6 +296,7 @@ int pyb_get_info(const pyb_handle* h, const char* key, double* out) {
   else if (!strcmp(key, "i8_guard_ok")) *out = h->i8_guard_ok ? 1.0 : 0.0;
   else if (!strcmp(key, "i8_guard_trips")) *out = (double)h->i8_guard_trips;
   else if (!strcmp(key, "svgd_h")) *out = h->svgd.last_h;
+  else if (!strcmp(key, "svgd_p2p")) *out = h->svgd.p2p_ready ? 1.0 : 0.0;
   else if (!strncmp(key, "svgd_phase_ms_", 14) && key[14] >= '0' && key[14] <= '6' && !key[15]) *out = h->svgd.ps_ms[key[14] - '0'];
   else if (!strcmp(key, "tc_split")) *out = (double)tc_resident_split(h);
   else if (!strcmp(key, "dataset_uploads")) *out = (double)h->dataset_uploads;
@@ -625,6 +632,7 @@ int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* id
   PYB_REQUIRE(h, PYB_ERR_INVALID, "NULL handle");
   PYB_REQUIRE(world >= 1 && rank >= 0 && rank < world, PYB_ERR_INVALID, "bad rank/world");
   use_device(h);
+  svgd_p2p_release(h);
   if (h->svgd.nccl_comm3) { nccl_comm_destroy(h->svgd.nccl_comm3); h->svgd.nccl_comm3 = nullptr; }
   if (h->svgd.nccl_comm2) { nccl_comm_destroy(h->svgd.nccl_comm2); h->svgd.nccl_comm2 = nullptr; }
   if (h->svgd.nccl_comm) { nccl_comm_destroy(h->svgd.nccl_comm); h->svgd.nccl_comm = nullptr; }

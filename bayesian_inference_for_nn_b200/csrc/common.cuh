@@ -257,6 +257,15 @@ struct SvgdState {
   // while the Gram matrix is built (the exchange step is comm-bound at 8 GPUs unless overlapped)
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_theta = nullptr, ev_grad = nullptr;
+  // peer memory (NVLink): the gradient rows are written straight into every rank's gradient slice and the updated
+  // particle blocks straight into their owners' particle rows by this library's own kernels; NCCL only carries the
+  // one-float barrier after each of them.  Pointers: CUDA IPC between processes, plain peer access inside one process.
+  bool p2p_tried = false, p2p_ready = false;
+  const float* p2p_src_theta = nullptr; const float* p2p_src_g = nullptr;   // the allocations the tables were built for
+  std::vector<void*> p2p_opened;          // cudaIpcOpenMemHandle mappings to close
+  DevBuf<float*> p2p_theta, p2p_g;        // [world] device tables: rank q's particle rows / gradient slice
+  std::vector<float*> p2p_theta_host;
+  DevBuf<float> p2p_token;
   cudaStream_t gram_stream = nullptr;     // parameter-sharded step: reduction / median / kernel-matrix chain beside the gradients
   cudaEvent_t ev_kernel = nullptr, ev_gh[2] = {nullptr, nullptr}, ev_p1 = nullptr, ev_p2 = nullptr, ev_back = nullptr;
 };
@@ -316,6 +325,8 @@ struct pyb_handle {
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
   int opt_tc_timeline = 0;   // diagnostics: the fused mma kernel records per-CTA cycle sums of its phases (info "tc_timeline_<k>")
   int opt_tc_epi_mma = 0;    // 1: fused int8 forward kernel with the layer-2 epilogue on mma.sync (tc_fused_mma.cuh): parity green, no faster
+  int opt_svgd_halves = 0;   // parameter-sharded SVGD: gradients in two halves, the first half's exchange behind the second
+  int opt_svgd_p2p = 1;      // parameter-sharded SVGD: exchanges by peer-memory stores of our own kernels (0: NCCL send / recv)
   int opt_svgd_pshard = 1;   // sharded canonical SVGD on the tensor path: shard the Stein phase over the parameters (all-to-all + Gram all-reduce)
   // Guard of the automatic choice (tc_i8 = -1).  16-bit FIXED-point slices carry an error relative to the LARGEST operand
   // magnitude; the float64 comparison of tests/test_gpu_i8.py fits err(gradient) ~ 1.3e-5 / rms_rows(1 - p_y) (+ 3e-5 from
@@ -445,6 +456,7 @@ void nccl_all_to_all_f32(void* comm, const float* send, float* recv, size_t coun
 void nccl_check_async(void** comm);
 void nccl_all_reduce_min_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t s);
 void* nccl_comm_dup(void* comm, int rank);
+void svgd_p2p_release(pyb_handle* h);
 void nccl_all_to_all_f32_strided(void* comm, const float* send, size_t send_stride, float* recv, size_t recv_stride,
                                  size_t count, int world, cudaStream_t s);
 void nccl_exchange_f32(void* comm, const float* send, float* recv, size_t stride, size_t count, const int* send_to, int n_send,

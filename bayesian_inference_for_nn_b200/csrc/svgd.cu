@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <algorithm>
+#include <unistd.h>
 
 namespace pyb {
 
@@ -472,7 +473,10 @@ static double adam_lr_t(double lr, int64_t t) {
 // exact median bandwidth of d2 [n] (device, float64) -> h2 (device double[2] = {h2, median})
 // exact median over the GLOBAL set of St*St distances; each rank histograms its own rows and the 256-bin
 // histograms are all-reduced (2 KB per pass), so every rank picks the same bins
-static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t n_global, int St, double* h2_dev) {
+// reduce = false: d2 already IS the global set on every rank (bit-identical after the Gram all-reduce), so the select runs
+// without any collective and still picks the same value everywhere
+static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t n_global, int St, double* h2_dev,
+                             bool reduce = true) {
   SvgdState& sc = h->svgd;
   sc.sel.alloc(8);
   sc.hist.alloc(256);
@@ -489,13 +493,13 @@ static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)h->sm_count);
   for (int shift = 56; shift >= 0; shift -= 8) {
     k_select_hist<<<blocks, 256, 0, h->stream>>>(d2, n, reinterpret_cast<SelectState*>(sc.sel.p), shift, sc.hist.p);
-    if (sc.world > 1) nccl_all_reduce_u64(sc.nccl_comm, sc.hist.p, 256, h->stream);
+    if (sc.world > 1 && reduce) nccl_all_reduce_u64(sc.nccl_comm, sc.hist.p, 256, h->stream);
     k_select_pick<<<1, 256, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p), shift, sc.hist.p);
     count_launch(h, 2);
   }
   if (want_next) {
     k_next_greater<<<blocks, 256, 0, h->stream>>>(d2, n, reinterpret_cast<SelectState*>(sc.sel.p), sc.sel.p + 6);
-    if (sc.world > 1) nccl_all_reduce_min_u64(sc.nccl_comm, sc.sel.p + 6, 1, h->stream);
+    if (sc.world > 1 && reduce) nccl_all_reduce_min_u64(sc.nccl_comm, sc.sel.p + 6, 1, h->stream);
     count_launch(h);
   }
   k_bandwidth_next<<<1, 1, 0, h->stream>>>(reinterpret_cast<SelectState*>(sc.sel.p), sc.sel.p + 6, want_next, St, h2_dev);
@@ -641,6 +645,127 @@ __global__ void k_slice_vec(const float* __restrict__ v, int64_t P, int64_t c0, 
   if (c < Pw) out[c] = (c0 + c < P) ? v[c0 + c] : 0.f;
 }
 
+// ---- peer memory: the exchanges of the parameter-sharded step as stores of our own kernels over NVLink ----------------
+// rows of `rows` local particles -> the gradient slice of EVERY rank: peers[q][(row0 + i) * Pw + c] = src[i][q * Pw + c]
+// (four columns per thread: the source rows have an arbitrary pitch, the slices a pitch of 8 floats — one 16-byte store
+// per thread, 512 contiguous bytes per warp on the wire)
+__global__ void k_scatter_cols_p2p(const float* __restrict__ src, int64_t P, int64_t Pw, int64_t row0, float* const* __restrict__ peers) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4, i = blockIdx.y, q = blockIdx.z;
+  if (c >= Pw) return;
+  const int64_t col = q * Pw + c;
+  const float* s = src + i * P + col;
+  float4 v;
+  v.x = col < P ? s[0] : 0.f;
+  v.y = col + 1 < P ? s[1] : 0.f;
+  v.z = col + 2 < P ? s[2] : 0.f;
+  v.w = col + 3 < P ? s[3] : 0.f;
+  *reinterpret_cast<float4*>(peers[q] + (row0 + i) * Pw + c) = v;
+}
+// one block of the particle slice (the rows of one rank's particles, this rank's parameter columns) -> those particles'
+// rows on their owner: dst[i][col0 + c] = block[i][c]
+// (V = 2: two columns per thread as one 8-byte store — needs an even P, so that every row of the owner starts 8-byte aligned)
+template <int V>
+__global__ void k_scatter_block_p2p(const float* __restrict__ block, int64_t P, int64_t Pw, int64_t col0, float* __restrict__ dst) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V, i = blockIdx.y;
+  const int64_t col = col0 + c;
+  if (c >= Pw || col >= P) return;
+  if (V == 2) {
+    if (col + 1 < P) {
+      *reinterpret_cast<float2*>(dst + i * P + col) = *reinterpret_cast<const float2*>(block + i * Pw + c);
+      return;
+    }
+  }
+  dst[i * P + col] = block[i * Pw + c];
+}
+
+struct P2pCard {
+  long long pid, host;
+  int dev, pad;
+  unsigned long long theta, g;
+  cudaIpcMemHandle_t h_theta, h_g;
+};
+static_assert(sizeof(P2pCard) % sizeof(float) == 0, "card travels as floats");
+
+void svgd_p2p_release(pyb_handle* h) {
+  SvgdState& sv = h->svgd;
+  for (void* m : sv.p2p_opened) cudaIpcCloseMemHandle(m);
+  sv.p2p_opened.clear();
+  sv.p2p_ready = false;
+  sv.p2p_tried = false;
+}
+
+// collective over the communicator: every rank publishes where its particle rows and its gradient slice live; peers in
+// other processes map them through CUDA IPC, peers in this process (one engine per device, multi.py) through plain peer
+// access.  All ranks agree on the outcome (all-reduced flag); on any failure the NCCL send / recv exchange stays.
+static void svgd_p2p_setup(pyb_handle* h) {
+  SvgdState& sv = h->svgd;
+  const int R = sv.world;
+  svgd_p2p_release(h);
+  sv.p2p_tried = true;
+  sv.p2p_src_theta = sv.theta.p; sv.p2p_src_g = sv.ps_g.p;
+  P2pCard mine = {};
+  mine.pid = (long long)getpid();
+  char hn[256] = {0};
+  gethostname(hn, sizeof(hn) - 1);
+  unsigned long long hh = 1469598103934665603ull;
+  for (const char* c = hn; *c; ++c) hh = (hh ^ (unsigned char)*c) * 1099511628211ull;
+  mine.host = (long long)hh;
+  mine.dev = h->device;
+  mine.theta = (unsigned long long)(uintptr_t)sv.theta.p; mine.g = (unsigned long long)(uintptr_t)sv.ps_g.p;
+  unsigned long long ok = 1;
+  if (cudaIpcGetMemHandle(&mine.h_theta, sv.theta.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.h_g, sv.ps_g.p) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0;
+  }
+  const size_t nf = sizeof(P2pCard) / sizeof(float);
+  DevBuf<float> send, recv;
+  send.alloc(nf); recv.alloc(nf * R);
+  std::vector<P2pCard> cards(R);
+  PYB_CUDA(cudaMemcpyAsync(send.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  nccl_all_gather_f32(sv.nccl_comm, send.p, recv.p, nf, h->stream);
+  PYB_CUDA(cudaMemcpyAsync(cards.data(), recv.p, sizeof(P2pCard) * R, cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  std::vector<float*> pt(R, nullptr), pg(R, nullptr);
+  for (int q = 0; q < R && ok; ++q) {
+    const P2pCard& c = cards[q];
+    if (q == sv.rank) { pt[q] = sv.theta.p; pg[q] = sv.ps_g.p; continue; }
+    if (c.host != mine.host) { ok = 0; break; }
+    if (c.pid == mine.pid) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, h->device, c.dev) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(c.dev, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0; break; }
+      cudaGetLastError();
+      pt[q] = (float*)(uintptr_t)c.theta; pg[q] = (float*)(uintptr_t)c.g;
+    } else {
+      void *mt = nullptr, *mg = nullptr;
+      if (cudaIpcOpenMemHandle(&mt, c.h_theta, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      sv.p2p_opened.push_back(mt);
+      if (cudaIpcOpenMemHandle(&mg, c.h_g, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      sv.p2p_opened.push_back(mg);
+      pt[q] = (float*)mt; pg[q] = (float*)mg;
+    }
+  }
+  sv.sel.alloc(8);
+  PYB_CUDA(cudaMemcpyAsync(sv.sel.p, &ok, sizeof(ok), cudaMemcpyHostToDevice, h->stream));
+  nccl_all_reduce_min_u64(sv.nccl_comm, sv.sel.p, 1, h->stream);
+  PYB_CUDA(cudaMemcpyAsync(&ok, sv.sel.p, sizeof(ok), cudaMemcpyDeviceToHost, h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  nccl_check_async(&sv.nccl_comm);
+  if (!ok) {
+    for (void* m : sv.p2p_opened) cudaIpcCloseMemHandle(m);
+    sv.p2p_opened.clear();
+    return;
+  }
+  sv.p2p_theta.alloc(R); sv.p2p_g.alloc(R); sv.p2p_token.alloc(1);
+  sv.p2p_theta_host = pt;
+  PYB_CUDA(cudaMemcpyAsync(sv.p2p_theta.p, pt.data(), sizeof(float*) * R, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemcpyAsync(sv.p2p_g.p, pg.data(), sizeof(float*) * R, cudaMemcpyHostToDevice, h->stream));
+  PYB_CUDA(cudaMemsetAsync(sv.p2p_token.p, 0, sizeof(float), h->stream));
+  PYB_CUDA(cudaStreamSynchronize(h->stream));
+  sv.p2p_ready = true;
+}
+
 static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i, const float* yb_f, int64_t Nb, float lr_t,
                              float scale) {
   SvgdState& sv = h->svgd;
@@ -663,7 +788,9 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     sv.ps_checked = true;
   }
   if (!sv.comm_stream) {
-    PYB_CUDA(cudaStreamCreateWithFlags(&sv.comm_stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    PYB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PYB_CUDA(cudaStreamCreateWithPriority(&sv.comm_stream, cudaStreamNonBlocking, prio_hi));
     PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_fork, cudaEventDisableTiming));
     PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_theta, cudaEventDisableTiming));
     PYB_CUDA(cudaEventCreateWithFlags(&sv.ev_grad, cudaEventDisableTiming));
@@ -676,6 +803,7 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     sv.ps_mu.alloc(Pw); sv.ps_iv.alloc(Pw); sv.ps_norms.alloc(St);
     PYB_CUDA(cudaMemsetAsync(sv.ps_m.p, 0, (size_t)St * Pw * sizeof(float), h->stream));
     PYB_CUDA(cudaMemsetAsync(sv.ps_v.p, 0, (size_t)St * Pw * sizeof(float), h->stream));
+    PYB_CUDA(cudaMemsetAsync(sv.ps_g.p, 0, (size_t)St * Pw * sizeof(float), h->stream));
     k_slice_vec<<<(unsigned)((Pw + 255) / 256), 256, 0, h->stream>>>(h->mu.p, P, c0, Pw, sv.ps_mu.p);
     k_slice_vec<<<(unsigned)((Pw + 255) / 256), 256, 0, h->stream>>>(h->inv_var.p, P, c0, Pw, sv.ps_iv.p);
     // the particle slice: one exchange at the start, afterwards the slice IS the master copy the update is applied to
@@ -685,11 +813,17 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     sv.ps_ready = true;
   }
   if (!sv.gram_stream) {
-    PYB_CUDA(cudaStreamCreateWithFlags(&sv.gram_stream, cudaStreamNonBlocking));
+    // the side chain is a string of small dependent kernels beside persistent ones that fill the GPU: at every kernel
+    // boundary of the main stream the side kernel must win the SMs, or it waits for the next boundary
+    int prio_lo = 0, prio_hi = 0;
+    PYB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PYB_CUDA(cudaStreamCreateWithPriority(&sv.gram_stream, cudaStreamNonBlocking, prio_hi));
     cudaEvent_t* evs[] = {&sv.ev_kernel, &sv.ev_gh[0], &sv.ev_gh[1], &sv.ev_p1, &sv.ev_p2, &sv.ev_back};
     for (cudaEvent_t* e : evs) PYB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
   if (!sv.nccl_comm3) sv.nccl_comm3 = nccl_comm_dup(sv.nccl_comm, sv.rank);
+  if (h->opt_svgd_p2p && (!sv.p2p_tried || sv.p2p_src_theta != sv.theta.p || sv.p2p_src_g != sv.ps_g.p)) svgd_p2p_setup(h);
+  const bool p2p = h->opt_svgd_p2p && sv.p2p_ready;
   const bool timed = h->prof_enabled;
   auto mark = [&](int k) {
     if (!timed) return;
@@ -724,7 +858,13 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
       nccl_all_reduce_f32(sv.nccl_comm, sv.gram.p, (size_t)St * St, h->stream);
       nccl_all_reduce_f64(sv.nccl_comm, sv.ps_norms.p, St, h->stream);
       k_d2_from_gram<<<(unsigned)(((int64_t)St * St + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p);
-      median_bandwidth(h, sv.d2.p + (int64_t)r0 * St, (int64_t)S * St, (int64_t)St * St, St, sv.h2.p);
+      // every rank holds the whole (bit-identical) distance matrix: for a small one, nine passes over all of it beat nine
+      // passes over this rank's rows with a latency-bound 2 KB all-reduce after each; for a large one the passes are HBM
+      // time taken from the gradient kernels running beside this chain, and the rows of this rank are 1/world of it
+      if ((int64_t)St * St <= (4ll << 20))
+        median_bandwidth(h, sv.d2.p, (int64_t)St * St, (int64_t)St * St, St, sv.h2.p, false);
+      else
+        median_bandwidth(h, sv.d2.p + (int64_t)r0 * St, (int64_t)S * St, (int64_t)St * St, St, sv.h2.p);
       k_kernel_rowsum<<<St, 256, 0, h->stream>>>(sv.d2.p, St, sv.h2.p, sv.rowsum.p);
       k_double_to_float<<<eb, 256, 0, h->stream>>>(sv.d2.p, sv.kf.p, (int64_t)St * St);
       tc_split_rows(h, sv.kf.p, St, St, St, sv.kh.p, sv.kl.p, St);
@@ -740,19 +880,27 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   // ---- 3. local gradients in (up to) two halves of the particles: a half's rows travel to the parameter slices of
   //         every rank (all-to-all on the exchange stream, second communicator) while the next half is computed
   nvtxRangePushA("pyb.svgd.gradients(+all-to-all)");
-  const int nh = (S >= 256 && S % 2 == 0) ? 2 : 1;
+  const int nh = (h->opt_svgd_halves && S >= 256 && S % 2 == 0) ? 2 : 1;
   const int64_t Sh = S / nh;
   for (int hf = 0; hf < nh; ++hf) {
     eval_on_batch(h, sv.theta.p + hf * Sh * P, Sh, Xb, yb_i, yb_f, Nb, scale, sv.loss.p + hf * Sh, sv.g.p + hf * Sh * P);
     PYB_CUDA(cudaEventRecord(sv.ev_gh[hf], main_stream));
     PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_gh[hf], 0));
-    float* pk = sv.ps_pack.p + (int64_t)hf * R * Sh * Pw;
-    k_pack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)Sh, (unsigned)R), 256, 0, sv.comm_stream>>>(
-        sv.g.p + hf * Sh * P, Sh, P, Pw, R, pk);
-    nccl_all_to_all_f32_strided(sv.nccl_comm2, pk, (size_t)Sh * Pw, sv.ps_g.p + hf * Sh * Pw, (size_t)S * Pw, (size_t)Sh * Pw, R,
-                                sv.comm_stream);
+    if (p2p) {
+      // one kernel: every gradient row goes straight into the gradient slice of the rank that owns its columns
+      k_scatter_cols_p2p<<<dim3((unsigned)((Pw / 4 + 255) / 256), (unsigned)Sh, (unsigned)R), 256, 0, sv.comm_stream>>>(
+          sv.g.p + hf * Sh * P, P, Pw, (int64_t)r0 + hf * Sh, sv.p2p_g.p);
+    } else {
+      float* pk = sv.ps_pack.p + (int64_t)hf * R * Sh * Pw;
+      k_pack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)Sh, (unsigned)R), 256, 0, sv.comm_stream>>>(
+          sv.g.p + hf * Sh * P, Sh, P, Pw, R, pk);
+      nccl_all_to_all_f32_strided(sv.nccl_comm2, pk, (size_t)Sh * Pw, sv.ps_g.p + hf * Sh * Pw, (size_t)S * Pw, (size_t)Sh * Pw, R,
+                                  sv.comm_stream);
+    }
     count_launch(h);
   }
+  // peer stores are complete when their kernel is; the one-float all-reduce is the barrier that tells every rank so
+  if (p2p) nccl_all_reduce_f32(sv.nccl_comm2, sv.p2p_token.p, 1, sv.comm_stream);
   PYB_CUDA(cudaEventRecord(sv.ev_grad, sv.comm_stream));
   nvtxRangePop();
   mark(2);
@@ -769,7 +917,9 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   k_stein_rhs_split_t<<<gt, bt, 0, h->stream>>>(sv.ps_x.p, sv.ps_g.p, sv.h2.p, St, Pw, sv.yth.p, sv.ytl.p, St, sv.ps_mu.p,
                                                sv.ps_iv.p);
   count_launch(h);
-  const int n1 = R / 2;                                            // remote blocks in the first group
+  // remote blocks in the first group: what is left for the second (at most two remote blocks and the own one) is all
+  // that can stay exposed after the last multiplication
+  const int n1 = std::max(R / 2, R - 3);
   int send1[64], recv1[64], send2[64], recv2[64];
   PYB_REQUIRE(R <= 64, PYB_ERR_INVALID, "at most 64 ranks");
   for (int j = 1; j <= n1; ++j) { send1[j - 1] = (sv.rank + j) % R; recv1[j - 1] = (sv.rank - j + R) % R; }
@@ -796,14 +946,32 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     k_unpack_cols<<<dim3((unsigned)((Pw + 255) / 256), (unsigned)S, 1), 256, 0, st>>>(src, S, P, Pw, q, sv.theta.p);
     count_launch(h);
   };
-  nccl_exchange_f32(sv.nccl_comm2, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, (size_t)S * Pw, send1, n1, recv1, n1, sv.comm_stream);
-  for (int i = 0; i < n1; ++i) unpack(sv.ps_pack.p, recv1[i], sv.comm_stream);
+  auto scatter_block = [&](int q, cudaStream_t st) {            // rank q's updated rows, this rank's columns -> rank q
+    if (P % 2 == 0)
+      k_scatter_block_p2p<2><<<dim3((unsigned)((Pw / 2 + 255) / 256), (unsigned)S, 1), 256, 0, st>>>(
+          sv.ps_x.p + (int64_t)q * S * Pw, P, Pw, c0, sv.p2p_theta_host[q]);
+    else
+      k_scatter_block_p2p<1><<<dim3((unsigned)((Pw + 255) / 256), (unsigned)S, 1), 256, 0, st>>>(
+          sv.ps_x.p + (int64_t)q * S * Pw, P, Pw, c0, sv.p2p_theta_host[q]);
+    count_launch(h);
+  };
+  if (p2p) {
+    for (int i = 0; i < n1; ++i) scatter_block(send1[i], sv.comm_stream);
+  } else {
+    nccl_exchange_f32(sv.nccl_comm2, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, (size_t)S * Pw, send1, n1, recv1, n1, sv.comm_stream);
+    for (int i = 0; i < n1; ++i) unpack(sv.ps_pack.p, recv1[i], sv.comm_stream);
+  }
   update_blocks(1 + n1, R + 1);                                    // ... r-1 and, last, this rank's own block
   PYB_CUDA(cudaEventRecord(sv.ev_p2, main_stream));
   PYB_CUDA(cudaStreamWaitEvent(sv.comm_stream, sv.ev_p2, 0));
-  nccl_exchange_f32(sv.nccl_comm2, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, (size_t)S * Pw, send2, R - 1 - n1, recv2, R - 1 - n1,
-                    sv.comm_stream);
-  for (int i = 0; i < R - 1 - n1; ++i) unpack(sv.ps_pack.p, recv2[i], sv.comm_stream);
+  if (p2p) {
+    for (int i = 0; i < R - 1 - n1; ++i) scatter_block(send2[i], sv.comm_stream);
+    nccl_all_reduce_f32(sv.nccl_comm2, sv.p2p_token.p, 1, sv.comm_stream);      // barrier: every rank's stores have landed
+  } else {
+    nccl_exchange_f32(sv.nccl_comm2, sv.ps_x.p, sv.ps_pack.p, (size_t)S * Pw, (size_t)S * Pw, send2, R - 1 - n1, recv2, R - 1 - n1,
+                      sv.comm_stream);
+    for (int i = 0; i < R - 1 - n1; ++i) unpack(sv.ps_pack.p, recv2[i], sv.comm_stream);
+  }
   PYB_CUDA(cudaEventRecord(sv.ev_back, sv.comm_stream));
   nvtxRangePop();
   mark(5);

@@ -128,14 +128,15 @@ def _wide_run(rank, world, uid, pshard):
     eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
     if world > 1:
         eng.svgd_set_comm(rank, world, uid)
-        eng.set_option("svgd_pshard", pshard)
+        eng.set_option("svgd_pshard", 1 if pshard else 0)
+        eng.set_option("svgd_p2p", 1 if pshard == 1 else 0)
     eng.svgd_init(Sl, 1e-3, _lib.SVGD_CANONICAL_MEDIAN, particles0=parts[rank * Sl:(rank + 1) * Sl], offset=rank * Sl)
     losses, hs = [], []
     for ix in idx:
         losses.append(eng.svgd_step(ix))
         hs.append(eng.info("svgd_h"))
     assert int(eng.info("path_used")) == _lib.PATH_TENSOR
-    res = (rank, eng.svgd_particles(), losses, hs)
+    res = (rank, eng.svgd_particles(), losses, hs, int(eng.info("svgd_p2p")) if world > 1 else 0)
     eng.close()
     return res
 
@@ -144,17 +145,18 @@ def _wide_worker(rank, world, uid, pshard, out):
     out.put(_wide_run(rank, world, uid, pshard))
 
 
-@pytest.mark.parametrize("pshard", [1, 0])
+@pytest.mark.parametrize("pshard", [1, 2, 0])
 def test_svgd_sharded_on_the_tensor_path_matches_one_gpu(pshard):
     """C4's shape in small (784-128-10, 512 particles, minibatch 512, canonical median-heuristic update): the sharded step
-    on the tensor path — pshard = 1: Stein phase sharded over the parameters (gradient / particle all-to-all, all-reduced
-    Gram matrix and radix-select histograms); 0: row-sharded with particle and gradient all-gathers — against the SAME
-    step on one GPU: losses, bandwidth h and particles after three steps."""
+    on the tensor path — pshard = 1: Stein phase sharded over the parameters, the gradient rows and the updated particle
+    blocks exchanged by peer-memory stores of the library's own kernels (CUDA IPC between the rank processes), all-reduced
+    Gram matrix and radix-select histograms; 2: the same with NCCL send / recv exchanges; 0: row-sharded with particle and
+    gradient all-gathers — against the SAME step on one GPU: losses, bandwidth h and particles after three steps."""
     from bayesian_inference_for_nn_b200 import _lib
     if _lib.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import multiprocessing as mp
-    _, one_parts, one_losses, one_h = _wide_run(0, 1, None, 0)
+    _, one_parts, one_losses, one_h, _ = _wide_run(0, 1, None, 0)
     ctx = mp.get_context("spawn")
     uid = _lib.nccl_unique_id()
     q = ctx.Queue()
@@ -173,6 +175,9 @@ def test_svgd_sharded_on_the_tensor_path_matches_one_gpu(pshard):
     diff = np.abs(parts - one_parts)
     # Adam's first steps are lr * phi / (|phi| + 1e-7): sign-like where |phi| ~ 1e-7, so bound the bulk tightly and the
     # worst case by Adam's own bound (the same criterion as test_svgd_minibatch_gradients_on_tensor_path)
-    print("sharded (pshard=%d) vs one GPU: particle diff quantile(0.9995) %.2e, max %.2e" % (pshard, np.quantile(diff, 0.9995), diff.max()))
+    print("sharded (pshard=%d, peer-memory exchange %s) vs one GPU: particle diff quantile(0.9995) %.2e, max %.2e" %
+          (pshard, [r[4] for r in res], np.quantile(diff, 0.9995), diff.max()))
+    if pshard != 1:
+        assert [r[4] for r in res] == [0, 0]
     assert np.quantile(diff, 0.9995) < 2e-3 * lr * n + 1e-6
     assert diff.max() <= 2.1 * lr * n

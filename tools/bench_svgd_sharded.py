@@ -31,6 +31,8 @@ def worker(rank, world, uid, S_total, steps, out):
     Sl = S_total // world
     if world > 1:
         eng.svgd_set_comm(rank, world, uid)
+        eng.set_option("svgd_p2p", int(os.environ.get("PYB_SVGD_P2P", "1")))
+        eng.set_option("svgd_halves", int(os.environ.get("PYB_SVGD_HALVES", "1")))
     eng.svgd_init(Sl, 0.01, _lib.SVGD_CANONICAL_MEDIAN, offset=rank * Sl)
     ms, loss, phases = [], [], []
     eng.set_option("profile", 1)
@@ -39,7 +41,7 @@ def worker(rank, world, uid, S_total, steps, out):
         if k >= 2:
             ms.append(eng.info("last_device_ms"))
             phases.append([eng.info("svgd_phase_ms_%d" % j) for j in range(7)] if world > 1 else [0.0] * 7)
-    out.put((rank, float(np.mean(ms)), loss[-1], np.mean(phases, axis=0).tolist()))
+    out.put((rank, float(np.mean(ms)), loss[-1], np.mean(phases, axis=0).tolist(), int(eng.info("svgd_p2p")) if world > 1 else 0))
     eng.close()
 
 
@@ -69,6 +71,7 @@ def main():
         print(json.dumps({"case": "C4 SVGD canonical_median 784-128-10, minibatch 1024", "particles": a.particles,
                           "n_gpus": world, "device_ms_per_step": ms, "particle_grad_evals_per_s": a.particles * 1e3 / ms,
                           "speedup_vs_1gpu": base / ms, "mean_loss_last": res[0][2],
+                          "exchange": "peer-memory stores (own kernels)" if all(r[4] for r in res) else "nccl send/recv",
                           "phase_ms_max_over_ranks": dict(zip(["gram_partial", "gradients", "wait_reduced_kernel_matrix", "wait_gradient_all_to_all",
                                                                "ky_adam", "unpack_own_slice", "wait_particle_exchange"],
                                                               np.max([r[3] for r in res], axis=0).round(3).tolist()))}), flush=True)
