@@ -10,6 +10,9 @@
 //   phase 1  thread == data row:  z1, a1, z2 -> loss, dZ2 (kept in smem for all rows)
 //   phase 2  thread == (hidden unit, row slice): recompute a1 from the unit's own weights (registers),
 //            dZ1 = (dZ2 W2^T) act'(a1), accumulate dW1[:,h], db1[h], dW2[h,:] in registers
+//            — TWO data rows per step as packed FP32 pairs (fma.rn.f32x2: one issue slot, two FMAs per lane); the
+//            pair's inputs and deltas are (D + C) consecutive 8-byte words of the pair-interleaved array sm.xd: one
+//            address register, 16-byte shared loads.  Phase 1 runs its rows as packed pairs too.
 //   slices are combined in a fixed order (deterministic), db2 by one warp per class.
 //
 // Few chains (the reference runs ONE, HMC.py:74): a chain is then spread over a thread-block CLUSTER of up to 8
@@ -46,11 +49,10 @@ struct FsParams {
 };
 
 struct FsSmem {
-  float* xs;      // [N][D]
+  float* xd;      // [ceil(N / 2)][D + C][2]: rows 2j, 2j + 1 interleaved — inputs x[d], then the deltas dZ2[c] phase 1 leaves
   float* ys;      // labels as float bits (int) or targets [N][C]
-  float* dz2;     // [N][C]
   float* qs; float* ps; float* gs;   // [P]
-  float* pk;      // [H][PKW] packed per-unit parameters
+  float* pk;      // [H][FsPk::S] packed per-unit parameters, rows padded to 16 bytes
   float* part;    // [n_slices][H*(D+1+C)]
   float* gx;      // [2][GX] cluster exchange: partial gradient [P] + loss sum (double) of this CTA's rows
   double* red;    // [32]
@@ -69,6 +71,59 @@ __device__ __forceinline__ T fs_block_sum_all(T v, T* scratch) {
   return r;
 }
 
+// packed FP32 pairs (sm_100: FFMA2 / FADD2 — two lanes' worth of FMA per issue slot), carried in 64-bit registers
+typedef unsigned long long fs_f2;
+__device__ __forceinline__ fs_f2 fs_pack2(float x, float y) {
+  fs_f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void fs_unpack2(fs_f2 v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ fs_f2 fs_fma2(fs_f2 a, fs_f2 b, fs_f2 c) {
+  fs_f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ fs_f2 fs_add2(fs_f2 a, fs_f2 b) {
+  fs_f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t fs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// NW consecutive 8-byte words from one shared address: 16-byte loads when NW is even (a row pair is then a multiple of
+// 16 bytes, so every pair starts 16-byte aligned), 8-byte loads otherwise
+template <int NW>
+__device__ __forceinline__ void fs_lds_pairs(uint32_t a, fs_f2 (&v)[NW]) {
+  if (NW % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i + 1 < NW; i += 2)
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[i]), "=l"(v[i + 1]) : "r"(a + 8u * (uint32_t)i) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v[i]) : "r"(a + 8u * (uint32_t)i) : "memory");
+  }
+}
+// position of (row r, input d) / (row r, delta c) in the pair-interleaved array
+template <int D, int C>
+__device__ __forceinline__ int fs_xi(int r, int d) { return (r >> 1) * (2 * (D + C)) + 2 * d + (r & 1); }
+template <int D, int C>
+__device__ __forceinline__ int fs_dzi(int r, int c) { return (r >> 1) * (2 * (D + C)) + 2 * (D + c) + (r & 1); }
+// per-unit parameter rows {W1[0..D)[h], b1[h], W2[h][0..C)} padded to 16-byte multiples: 16-byte shared loads
+template <int D, int C>
+struct FsPk { static constexpr int W = D + 1 + C, S = (W + 3) & ~3; };
+template <int D, int C>
+__device__ __forceinline__ void fs_load_unit(const float* pk, int h, float (&wr)[FsPk<D, C>::S]) {
+  const float4* w4 = reinterpret_cast<const float4*>(pk + h * FsPk<D, C>::S);
+#pragma unroll
+  for (int i = 0; i < FsPk<D, C>::S / 4; ++i) {
+    const float4 v = w4[i];
+    wr[4 * i] = v.x; wr[4 * i + 1] = v.y; wr[4 * i + 2] = v.z; wr[4 * i + 3] = v.w;
+  }
+}
+
 // one pass of phase 1 over the rows r0 + t + k * 256 (k < RT, r < re): forward, loss, dZ2 -> sm.dz2; returns this
 // thread's loss sum.  Per row the arithmetic (and its order) is the same whatever RT is.
 template <int D, int C, int ACT, int RT>
@@ -77,28 +132,59 @@ __device__ __forceinline__ double fs_phase1_pass(const FsParams& p, const FsSmem
   constexpr int PKW = D + 1 + C;
   const int act1 = ACT >= 0 ? ACT : p.act1;
   const int t = threadIdx.x, H = p.H;
-  float x[RT][D], z2[RT][C];
+  float z2[RT][C];
+  if (RT == 1 && r0 + (t & ~31) >= re) return 0.0;      // partial last pass: warps without a row skip it (warp-uniform)
+  if (RT >= 2) {
+    // rows k = 2i, 2i + 1 in the two halves of packed registers; the unit's parameters are broadcast operands
+    constexpr int RP = RT / 2 > 0 ? RT / 2 : 1;
+    fs_f2 x[RP][D], zp[RP][C];
 #pragma unroll
-  for (int k = 0; k < RT; ++k) {
-    const int r = r0 + t + k * FS_THREADS;
+    for (int i = 0; i < RP; ++i) {
+      const int ra = r0 + t + 2 * i * FS_THREADS, rb2 = ra + FS_THREADS;
 #pragma unroll
-    for (int d = 0; d < D; ++d) x[k][d] = (r < re) ? sm.xs[r * D + d] : 0.f;
+      for (int d = 0; d < D; ++d)
+        x[i][d] = fs_pack2(ra < re ? sm.xd[fs_xi<D, C>(ra, d)] : 0.f, rb2 < re ? sm.xd[fs_xi<D, C>(rb2, d)] : 0.f);
 #pragma unroll
-    for (int c = 0; c < C; ++c) z2[k][c] = b2[c];
-  }
-  for (int h = 0; h < H; ++h) {
-    const float* w = sm.pk + h * PKW;
-    float wr[PKW];
+      for (int c = 0; c < C; ++c) zp[i][c] = fs_pack2(b2[c], b2[c]);
+    }
+    for (int h = 0; h < H; ++h) {
+      float wr[FsPk<D, C>::S];
+      fs_load_unit<D, C>(sm.pk, h, wr);
+      fs_f2 wb[PKW];
 #pragma unroll
-    for (int i = 0; i < PKW; ++i) wr[i] = w[i];
+      for (int i = 0; i < PKW; ++i) wb[i] = fs_pack2(wr[i], wr[i]);
 #pragma unroll
-    for (int k = 0; k < RT; ++k) {
+      for (int i = 0; i < RP; ++i) {
+        fs_f2 z = wb[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) z = fs_fma2(x[i][d], wb[d], z);
+        float z0, z1;
+        fs_unpack2(z, z0, z1);
+        const fs_f2 a = fs_pack2(act_apply(z0, act1), act_apply(z1, act1));
+#pragma unroll
+        for (int c = 0; c < C; ++c) zp[i][c] = fs_fma2(a, wb[D + 1 + c], zp[i][c]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RP; ++i)
+#pragma unroll
+      for (int c = 0; c < C; ++c) fs_unpack2(zp[i][c], z2[(2 * i) % RT][c], z2[(2 * i + 1) % RT][c]);
+  } else {
+    float x[D];
+    const int r = r0 + t;
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = (r < re) ? sm.xd[fs_xi<D, C>(r, d)] : 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) z2[0][c] = b2[c];
+    for (int h = 0; h < H; ++h) {
+      float wr[FsPk<D, C>::S];
+      fs_load_unit<D, C>(sm.pk, h, wr);
       float z = wr[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) z = fmaf(x[k][d], wr[d], z);
+      for (int d = 0; d < D; ++d) z = fmaf(x[d], wr[d], z);
       const float a = act_apply(z, act1);
 #pragma unroll
-      for (int c = 0; c < C; ++c) z2[k][c] = fmaf(a, wr[D + 1 + c], z2[k][c]);
+      for (int c = 0; c < C; ++c) z2[0][c] = fmaf(a, wr[D + 1 + c], z2[0][c]);
     }
   }
   double loss_acc = 0.0;
@@ -134,7 +220,7 @@ __device__ __forceinline__ double fs_phase1_pass(const FsParams& p, const FsSmem
       loss_acc += (double)(acc / (float)C);
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) sm.dz2[r * C + c] = dz[c];
+    for (int c = 0; c < C; ++c) sm.xd[fs_dzi<D, C>(r, c)] = dz[c];
   }
   return loss_acc;
 }
@@ -149,13 +235,14 @@ __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale,
   // switches in act_apply / act_grad_from_output fold away; ACT < 0: any activation, selected at run time
   const int act1 = ACT >= 0 ? ACT : p.act1;
   // pack per-unit parameters: {W1[0..D)[h], b1[h], W2[h][0..C)}
+  constexpr int PKS = FsPk<D, C>::S;
   for (int i = t; i < H * PKW; i += FS_THREADS) {
     int h = i / PKW, k = i - h * PKW;
     float v;
     if (k < D) v = sm.qs[p.w1_off + (int64_t)k * H + h];
     else if (k == D) v = sm.qs[p.b1_off + h];
     else v = sm.qs[p.w2_off + (int64_t)h * C + (k - D - 1)];
-    sm.pk[i] = v;
+    sm.pk[h * PKS + k] = v;
   }
   __syncthreads();
   float b2[C];
@@ -176,36 +263,66 @@ __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale,
   const int h = t % H, slice = t / H;
   const int NG = H * PKW;
   if (slice < n_slices && t < n_slices * H) {
-    const float* w = sm.pk + h * PKW;
-    float w1[D], w2[C], gw1[D], gw2[C], gb1 = 0.f;
-    const float b1 = w[D];
+    float w[PKS];
+    fs_load_unit<D, C>(sm.pk, h, w);
+    // two rows (2j, 2j + 1) per step in the two halves of packed registers; the weights sit in both halves
+    fs_f2 w1[D], w2[C], gw1[D], gw2[C], gb1 = 0ull;                  // (0.f, 0.f) is the all-zero bit pattern
+    const fs_f2 b1 = fs_pack2(w[D], w[D]);
 #pragma unroll
-    for (int d = 0; d < D; ++d) { w1[d] = w[d]; gw1[d] = 0.f; }
+    for (int d = 0; d < D; ++d) { w1[d] = fs_pack2(w[d], w[d]); gw1[d] = 0ull; }
 #pragma unroll
-    for (int c = 0; c < C; ++c) { w2[c] = w[D + 1 + c]; gw2[c] = 0.f; }
-    for (int r = rb + slice; r < re; r += n_slices) {
-      float z = b1;
-      float x[D];
+    for (int c = 0; c < C; ++c) { w2[c] = fs_pack2(w[D + 1 + c], w[D + 1 + c]); gw2[c] = 0ull; }
+    auto step = [&](const fs_f2 (&x)[D], const fs_f2 (&dzr)[C]) {
+      fs_f2 z = b1;
 #pragma unroll
-      for (int d = 0; d < D; ++d) { x[d] = sm.xs[r * D + d]; z = fmaf(x[d], w1[d], z); }
-      const float a = act_apply(z, act1);
-      float da = 0.f;
-      float dzr[C];
+      for (int d = 0; d < D; ++d) z = fs_fma2(x[d], w1[d], z);
+      float z0, z1;
+      fs_unpack2(z, z0, z1);
+      const float a0 = act_apply(z0, act1), a1 = act_apply(z1, act1);
+      fs_f2 da = 0ull;
 #pragma unroll
-      for (int c = 0; c < C; ++c) { dzr[c] = sm.dz2[r * C + c]; da = fmaf(dzr[c], w2[c], da); }
-      const float d1 = da * act_grad_from_output(a, act1);
+      for (int c = 0; c < C; ++c) da = fs_fma2(dzr[c], w2[c], da);
+      float da0, da1;
+      fs_unpack2(da, da0, da1);
+      const fs_f2 d1 = fs_pack2(da0 * act_grad_from_output(a0, act1), da1 * act_grad_from_output(a1, act1));
+      const fs_f2 a = fs_pack2(a0, a1);
 #pragma unroll
-      for (int d = 0; d < D; ++d) gw1[d] = fmaf(x[d], d1, gw1[d]);
-      gb1 += d1;
+      for (int d = 0; d < D; ++d) gw1[d] = fs_fma2(x[d], d1, gw1[d]);
+      gb1 = fs_add2(gb1, d1);
 #pragma unroll
-      for (int c = 0; c < C; ++c) gw2[c] = fmaf(a, dzr[c], gw2[c]);
+      for (int c = 0; c < C; ++c) gw2[c] = fs_fma2(a, dzr[c], gw2[c]);
+    };
+    // rb is even (fs_eval_cluster rounds the row ranges): pairs [rb / 2, re / 2) are whole, an odd re leaves one half pair
+    constexpr int PW2 = 2 * (D + C);
+    const int j0 = rb >> 1, j_full = re >> 1;
+    uint32_t pa = fs_smem_u32(sm.xd) + (uint32_t)((j0 + slice) * PW2 * 4);
+    const uint32_t pstep = (uint32_t)(n_slices * PW2 * 4);
+    int j = j0 + slice;
+    for (; j < j_full; j += n_slices, pa += pstep) {
+      fs_f2 v[D + C];
+      fs_lds_pairs<D + C>(pa, v);
+      fs_f2 x[D], dzr[C];
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[d] = v[d];
+#pragma unroll
+      for (int c = 0; c < C; ++c) dzr[c] = v[D + c];
+      step(x, dzr);
     }
+    if ((re & 1) && j == j_full) {                   // the odd tail row gets a zero partner: it adds nothing anywhere
+      fs_f2 x[D], dzr[C];
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[d] = fs_pack2(sm.xd[fs_xi<D, C>(re - 1, d)], 0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) dzr[c] = fs_pack2(sm.xd[fs_dzi<D, C>(re - 1, c)], 0.f);
+      step(x, dzr);
+    }
+    auto hsum = [](fs_f2 v) { float x, y; fs_unpack2(v, x, y); return x + y; };
     float* o = sm.part + slice * NG + h * PKW;
 #pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = gw1[d];
-    o[D] = gb1;
+    for (int d = 0; d < D; ++d) o[d] = hsum(gw1[d]);
+    o[D] = hsum(gb1);
 #pragma unroll
-    for (int c = 0; c < C; ++c) o[D + 1 + c] = gw2[c];
+    for (int c = 0; c < C; ++c) o[D + 1 + c] = hsum(gw2[c]);
   }
   __syncthreads();
   // combine slices in a fixed order and scatter into the flat gradient layout
@@ -221,7 +338,7 @@ __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale,
     const int wid = t >> 5, lane = t & 31;
     if (wid < C) {
       float s = 0.f;
-      for (int r = rb + lane; r < re; r += 32) s += sm.dz2[r * C + wid];
+      for (int r = rb + lane; r < re; r += 32) s += sm.xd[fs_dzi<D, C>(r, wid)];
       s = warp_sum(s);
       if (lane == 0) gout[p.b2_off + wid] = s;
     }
@@ -244,7 +361,9 @@ __device__ float fs_eval_cluster(const FsParams& p, const FsSmem& sm, float scal
   const int64_t P = p.P, GX = ((P + 1) & ~(int64_t)1) + 2;
   float* gx = sm.gx + (n_eval & 1) * GX;
   ++n_eval;
-  const int rb = (int)((int64_t)p.N * rank / n_ctas), re = (int)((int64_t)p.N * (rank + 1) / n_ctas);
+  // even boundaries: a row pair of the interleaved array belongs to one CTA
+  const int rb = (int)((int64_t)p.N * rank / n_ctas) & ~1;
+  const int re = rank + 1 == n_ctas ? p.N : ((int)((int64_t)p.N * (rank + 1) / n_ctas) & ~1);
   const double lsum = fs_eval_rows<D, C, ACT>(p, sm, scale, rb, re, gx);
   if (t == 0) *reinterpret_cast<double*>(gx + GX - 2) = lsum;
   cl.sync();
@@ -266,18 +385,21 @@ __device__ void fs_setup(const FsParams& p, FsSmem& sm, float* base) {
   constexpr int PKW = D + 1 + C;
   const int n_slices = FS_THREADS / p.H > 0 ? FS_THREADS / p.H : 1;
   float* cur = base;
+  const int np = (N + 1) & ~1;
   sm.red = (double*)cur; cur += 64;
-  sm.xs = cur; cur += (int64_t)N * D;
+  sm.xd = cur; cur += (int64_t)np * (D + C);
   sm.ys = cur; cur += (int64_t)N * (p.loss_kind == PYB_LOSS_SPARSE_CE ? 1 : C);
-  sm.dz2 = cur; cur += (int64_t)N * C;
   sm.qs = cur; cur += P;
   sm.ps = cur; cur += P;
   sm.gs = cur; cur += P;
-  sm.pk = cur; cur += p.H * PKW;
+  cur = (float*)(((uintptr_t)cur + 15) & ~(uintptr_t)15);
+  sm.pk = cur; cur += p.H * FsPk<D, C>::S;
   sm.part = cur; cur += n_slices * p.H * PKW;
   cur = (float*)(((uintptr_t)cur + 7) & ~(uintptr_t)7);
   sm.gx = cur; cur += 2 * (((P + 1) & ~(int64_t)1) + 2);
-  for (int i = threadIdx.x; i < N * D; i += FS_THREADS) sm.xs[i] = p.X[i];
+  for (int i = threadIdx.x; i < N * D; i += FS_THREADS) { const int r = i / D, d = i - r * D; sm.xd[fs_xi<D, C>(r, d)] = p.X[i]; }
+  if (np > N && threadIdx.x < D + C)                 // the pad row of an odd N: never read as data, kept finite
+    sm.xd[(N >> 1) * (2 * (D + C)) + 2 * threadIdx.x + 1] = 0.f;
   if (p.loss_kind == PYB_LOSS_SPARSE_CE) {
     for (int i = threadIdx.x; i < N; i += FS_THREADS) sm.ys[i] = __int_as_float(p.y_i[i]);
   } else {
@@ -287,7 +409,7 @@ __device__ void fs_setup(const FsParams& p, FsSmem& sm, float* base) {
 
 // eval-only: loss + scale * d(mean loss)/d theta  (parity hook, SVGD gradients)
 template <int D, int C, int ACT>
-__global__ void __launch_bounds__(FS_THREADS) k_fs_eval(FsParams p) {
+__global__ void __launch_bounds__(FS_THREADS, 4) k_fs_eval(FsParams p) {
   extern __shared__ __align__(16) float fs_smem[];
   FsSmem sm;
   fs_setup<D, C>(p, sm, fs_smem);
@@ -302,7 +424,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fs_eval(FsParams p) {
 
 // one full HMC iteration of one chain
 template <int D, int C, int ACT>
-__global__ void __launch_bounds__(FS_THREADS) k_fs_hmc(FsParams p) {
+__global__ void __launch_bounds__(FS_THREADS, 4) k_fs_hmc(FsParams p) {
   extern __shared__ __align__(16) float fs_smem[];
   FsSmem sm;
   fs_setup<D, C>(p, sm, fs_smem);
@@ -403,8 +525,9 @@ static size_t fs_smem_bytes(const pyb_handle* h) {
   const Model& m = h->model;
   const int D = m.layer[0].fan_in, H = m.layer[0].fan_out, C = m.layer[1].fan_out;
   const int n_slices = FS_THREADS / H > 0 ? FS_THREADS / H : 1;
-  size_t f = 64 + (size_t)h->N * D + (size_t)h->N * (h->loss_kind == PYB_LOSS_SPARSE_CE ? 1 : C) + (size_t)h->N * C +
-             3 * (size_t)m.P + (size_t)H * (D + 1 + C) * (1 + n_slices) + 2 * (((size_t)m.P + 1) / 2 * 2 + 2) + 2;
+  const size_t np = ((size_t)h->N + 1) & ~(size_t)1;
+  size_t f = 64 + np * D + (size_t)h->N * (h->loss_kind == PYB_LOSS_SPARSE_CE ? 1 : C) + np * C +
+             3 * (size_t)m.P + (size_t)H * (D + 1 + C) * n_slices + (size_t)H * (((D + 1 + C) + 3) / 4 * 4) + 4 + 2 * (((size_t)m.P + 1) / 2 * 2 + 2) + 2;
   return f * sizeof(float) + 16;
 }
 

@@ -319,6 +319,7 @@ def run_extras(args, rank, local_rank, world, dist, X, y, peaks):
             if k >= 2:
                 ms.append(eng.info("last_device_ms"))
         t = maxr(float(np.mean(ms)))
+        p2p = bool(world > 1 and int(eng.info("svgd_p2p")))
         eng.close()
         P = 784 * 128 + 128 + 128 * 10 + 10
         flops = S_total * 6.0 * B * (784 * 128 + 128 * 10) + 4.0 * S_total * S_total * P
@@ -326,6 +327,8 @@ def run_extras(args, rank, local_rank, world, dist, X, y, peaks):
         return {"workload": "C4 SVGD 784-128-10, %d particles sharded x%d, minibatch 1024 of %d, median-heuristic RBF"
                             % (S_total, world, X.shape[0]), "value": 1e3 / t, "unit": "steps/s", "ms": t, "scaling": "strong",
                 "particle_grad_evals_per_s": S_total * 1e3 / t, "mean_loss": float(loss),
+                "exchange": ("none (one GPU)" if world == 1 else "peer-memory stores of the library's kernels + NCCL barriers / Gram "
+                             "all-reduce" if p2p else "NCCL send/recv + Gram all-reduce"),
                 "roofline": {"bound": "tensor (NVLink exchange at N > 1)", "achieved": tf, "peak": peaks["bf16_sustained"] * world,
                              "unit": "TFLOP/s", "frac": tf / (peaks["bf16_sustained"] * world)}}
 
