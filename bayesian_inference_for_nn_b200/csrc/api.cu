@@ -226,6 +226,8 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_tc_gram_sym = v != 0;
   } else if (!strcmp(key, "fs_cluster")) {
     h->opt_fs_cluster = v != 0;
+  } else if (!strcmp(key, "live_cta")) {
+    h->opt_live_cta = v != 0;
   } else if (!strcmp(key, "live_fused")) {
     h->opt_live_fused = v != 0;
   } else if (!strcmp(key, "hmc_carry")) {
@@ -241,6 +243,8 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_tc_epi_mma = v != 0;
   } else if (!strcmp(key, "svgd_pshard")) {
     h->opt_svgd_pshard = v != 0;
+  } else if (!strcmp(key, "svgd_gram_sync")) {
+    h->opt_svgd_gram_sync = v != 0;
   } else if (!strcmp(key, "svgd_halves")) {
     h->opt_svgd_halves = v != 0;
   } else if (!strcmp(key, "svgd_p2p")) {

@@ -159,6 +159,57 @@ __global__ void __launch_bounds__(256) k_live_sweep(float* theta, const float* g
   }
 }
 
+// The same sweep in ONE CTA with the particles in shared memory, for the reference's own sizes (S = 10..64 particles of
+// P = 252 parameters: 64 KB): the 2 S grid barriers of k_live_sweep (a few microseconds each) become __syncthreads.
+// Kernel row: one warp per k, float64, lanes over the parameters; update: one thread per parameter, k in order — the
+// arithmetic of k_live_update (the row sums are reduced in a different order than block_sum's: float64, ~1e-16).
+__global__ void __launch_bounds__(1024) k_live_sweep_cta(float* theta, const float* __restrict__ g, float* am, float* av,
+                                                         float* phi_out, int P, int S, double gamma, float lr_t) {
+  extern __shared__ __align__(16) unsigned char live_raw[];
+  double* Ks = reinterpret_cast<double*>(live_raw);            // [S]
+  float* th = reinterpret_cast<float*>(Ks + S);                // [S][P]
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+  for (int idx = t; idx < S * P; idx += blockDim.x) th[idx] = theta[idx];
+  __syncthreads();
+  for (int i = 0; i < S; ++i) {
+    const float* xi_row = th + i * P;
+    // this particle's gradient and moments: in flight while the row and the sum over k are computed
+    float gq[1] = {0.f}, mq[1] = {0.f}, vq[1] = {0.f};
+    if (t < P) { gq[0] = g[i * P + t]; mq[0] = am[i * P + t]; vq[0] = av[i * P + t]; }
+    for (int k = w; k < S; k += nw) {
+      const float* xk = th + k * P;
+      double a = 0.0;
+      for (int e = lane; e < P; e += 32) {
+        const double d = (double)xi_row[e] - (double)xk[e];
+        a += d * d;
+      }
+      a = warp_sum(a);
+      if (lane == 0) Ks[k] = exp(-gamma * a);
+    }
+    __syncthreads();
+    for (int e = t; e < P; e += blockDim.x) {
+      const double xi = (double)th[i * P + e];
+      double acc = 0.0;
+      float wsum = 0.f;
+      for (int k = 0; k < S; ++k) {
+        const double kk = Ks[k];
+        acc += kk * (xi - (double)th[k * P + e]);
+        wsum += (float)kk;
+      }
+      const int o = i * P + e;
+      float gv = gq[0], m = mq[0], v = vq[0];
+      if (e != t) { gv = g[o]; m = am[o]; v = av[o]; }          // P > 1024: the later columns of this thread
+      const float gk = (float)(2.0 * gamma * acc);
+      const float phi = (wsum * gv + gk) / (float)S;
+      if (phi_out) phi_out[o] = phi;
+      th[o] = adam_update(th[o], phi, m, v, lr_t, 0.9f, 0.999f, 1e-7f);
+      am[o] = m; av[o] = v;
+    }
+    __syncthreads();
+  }
+  for (int idx = t; idx < S * P; idx += blockDim.x) theta[idx] = th[idx];
+}
+
 // ---- canonical (Jacobi) -------------------------------------------------------------------
 // d2[i][j] for local rows i in [r0, r0+Sl), all j in [0, St): direct difference form in float64
 // (what scipy pdist computes), 16x16 output tile per block, P streamed through shared memory.
@@ -848,6 +899,12 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
   mark(1);
   // ---- 2. side stream, third communicator: all-reduce of the Gram matrix, distances, median bandwidth, kernel matrix and
   //         its bf16 hi / lo split (identical on every rank: the all-reduced inputs are) — while the gradients run
+  // (option svgd_gram_sync: the 67 MB all-reduce stays on the main stream — a long collective kernel beside persistent
+  // kernels with a static tile schedule holds SMs those kernels' last CTAs then wait for)
+  if (h->opt_svgd_gram_sync) {
+    nccl_all_reduce_f32(sv.nccl_comm3, sv.gram.p, (size_t)St * St, main_stream);
+    nccl_all_reduce_f64(sv.nccl_comm3, sv.ps_norms.p, St, main_stream);
+  }
   PYB_CUDA(cudaEventRecord(sv.ev_fork, main_stream));
   PYB_CUDA(cudaStreamWaitEvent(sv.gram_stream, sv.ev_fork, 0));
   {
@@ -855,8 +912,10 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
     void* comm_main = sv.nccl_comm;
     h->stream = sv.gram_stream; sv.nccl_comm = sv.nccl_comm3;       // the helpers below launch on h->stream / sv.nccl_comm
     try {
-      nccl_all_reduce_f32(sv.nccl_comm, sv.gram.p, (size_t)St * St, h->stream);
-      nccl_all_reduce_f64(sv.nccl_comm, sv.ps_norms.p, St, h->stream);
+      if (!h->opt_svgd_gram_sync) {
+        nccl_all_reduce_f32(sv.nccl_comm, sv.gram.p, (size_t)St * St, h->stream);
+        nccl_all_reduce_f64(sv.nccl_comm, sv.ps_norms.p, St, h->stream);
+      }
       k_d2_from_gram<<<(unsigned)(((int64_t)St * St + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p);
       // every rank holds the whole (bit-identical) distance matrix: for a small one, nine passes over all of it beat nine
       // passes over this rank's rows with a latency-bound 2 KB all-reduce after each; for a large one the passes are HBM
@@ -1059,7 +1118,16 @@ void svgd_step(pyb_handle* h, const int32_t* idx, int64_t B, double* loss_out) {
     sc.Krow.alloc(St);
     float* th_all = (R > 1) ? sv.theta_all.p : sv.theta.p;
     bool swept = false;
-    if (R == 1 && h->opt_live_fused) {
+    const size_t cta_smem = (size_t)St * sizeof(double) + (size_t)St * P * sizeof(float);
+    if (R == 1 && h->opt_live_fused && cta_smem <= 200 * 1024 && h->opt_live_cta) {
+      // small enough for one CTA's shared memory: no grid barrier at all
+      PYB_CUDA(cudaFuncSetAttribute(k_live_sweep_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
+      k_live_sweep_cta<<<1, 1024, cta_smem, h->stream>>>(sv.theta.p, sv.g.p, sv.adam_m.p, sv.adam_v.p, sv.phi.p, (int)P, St, 1.0,
+                                                        lr_t);
+      count_launch(h);
+      swept = true;
+    }
+    if (R == 1 && h->opt_live_fused && !swept) {
       // one cooperative launch for the whole sweep (falls back to the per-particle launches if it cannot be co-resident)
       int per_sm = 0;
       PYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_live_sweep, 256, 0));

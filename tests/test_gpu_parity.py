@@ -270,6 +270,21 @@ def test_svgd_live_steps_match_oracle():
     assert np.abs(eng.svgd_particles() - g["live_particles"]).max() < 2e-3 * float(g["lr"]) * len(g["idx"]) + 1e-6
 
 
+@pytest.mark.parametrize("variant", ["one_cta", "cooperative", "per_particle_launches"])
+def test_svgd_live_sweep_variants_agree(variant):
+    """the sequential live sweep as ONE CTA with the particles in shared memory (default for the reference's sizes), as one
+    cooperative launch with grid barriers, and as 2 S launches: the same update up to the float64 reduction order of
+    the kernel rows, and all of them inside the oracle's budget"""
+    g = load_golden("svgd_mini")
+    eng = svgd_engine(g, _lib.SVGD_REFERENCE_LIVE)
+    eng.set_option("live_cta", 1 if variant == "one_cta" else 0)
+    eng.set_option("live_fused", 0 if variant == "per_particle_launches" else 1)
+    losses = [eng.svgd_step(ix) for ix in g["idx"]]
+    np.testing.assert_allclose(losses, g["live_losses"], rtol=TOL_LOGP)
+    assert np.abs(eng.svgd_particles() - g["live_particles"]).max() < 2e-3 * float(g["lr"]) * len(g["idx"]) + 1e-6
+    assert int(eng.info("kernel_launches")) > 0
+
+
 def test_svgd_canonical_steps_match_oracle():
     g = load_golden("svgd_mini")
     eng = svgd_engine(g, _lib.SVGD_CANONICAL_MEDIAN)

@@ -32,7 +32,8 @@ def worker(rank, world, uid, S_total, steps, out):
     if world > 1:
         eng.svgd_set_comm(rank, world, uid)
         eng.set_option("svgd_p2p", int(os.environ.get("PYB_SVGD_P2P", "1")))
-        eng.set_option("svgd_halves", int(os.environ.get("PYB_SVGD_HALVES", "1")))
+        eng.set_option("svgd_halves", int(os.environ.get("PYB_SVGD_HALVES", "0")))
+        eng.set_option("svgd_gram_sync", int(os.environ.get("PYB_SVGD_GRAM_SYNC", "0")))
     eng.svgd_init(Sl, 0.01, _lib.SVGD_CANONICAL_MEDIAN, offset=rank * Sl)
     ms, loss, phases = [], [], []
     eng.set_option("profile", 1)
