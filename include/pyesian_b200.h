@@ -164,7 +164,15 @@ int pyb_svgd_get_particles(pyb_handle* h, double* particles_out);
  * may be NULL) and returns their mean (all-reduced over the ranks of a sharded run). */
 int pyb_svgd_set_validation(pyb_handle* h, const float* X, const void* y, int64_t N);
 int pyb_svgd_validation_loss(pyb_handle* h, double* mean_loss_out, float* per_particle_out);
-/* NCCL plumbing for sharded particles: all ranks pass the same 128-byte ncclUniqueId. */
+/* NCCL plumbing for sharded particles: all ranks pass the same 128-byte ncclUniqueId.
+ * Options of the sharded canonical step on the tensor path (all ranks must set them alike): "svgd_pshard" (default 1:
+ * Stein phase sharded over the parameters; 0: row-sharded with all-gathers), "svgd_p2p" (default 1: the gradient rows and
+ * the updated particle blocks are exchanged by stores of the library's own kernels into peer memory - CUDA IPC between
+ * processes of one host, plain peer access inside one process - with one-float NCCL barriers; falls back to ncclSend /
+ * ncclRecv when a mapping is refused; 0: always NCCL; read-out "svgd_p2p" tells which one runs), "svgd_gram_sync" and
+ * "svgd_halves" (A/B switches of the pipeline, default 0), "live_cta" (default 1: the reference-live sweep of a particle
+ * set that fits one CTA's shared memory runs in one CTA); read-outs "svgd_phase_ms_0..6" (with "profile" on): CUDA-event
+ * split of the last sharded step. */
 int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id_128);
 /* The same communicator under its general name.  With option "predict_sharded" = 1, pyb_predict and
  * pyb_predict_uncertainty treat W as this rank's share of the weight samples (BayesianModel.predict's nb_samples
