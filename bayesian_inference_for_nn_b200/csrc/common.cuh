@@ -222,7 +222,7 @@ struct SvgdState {
   int64_t t = 0;
   DevBuf<float> theta, g, adam_m, adam_v, phi, loss;
   DevBuf<double> d2, K, rowsum;
-  DevBuf<unsigned long long> sel, hist;   // radix-select state (2 x {prefix,mask,k}) and 256-bin histogram
+  DevBuf<unsigned long long> sel, hist, cand;   // radix-select state (2 x {prefix,mask,k}, next-greater, candidate count), 256-bin histogram, compacted candidates
   DevBuf<double> h2, mean_loss, Krow;
   // tensor-core Gram / Stein contraction operands (bf16 hi/lo kept as raw 16-bit words)
   DevBuf<uint16_t> xh, xl, yth, ytl, kh, kl;
@@ -325,6 +325,7 @@ struct pyb_handle {
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
   int opt_tc_timeline = 0;   // diagnostics: the fused mma kernel records per-CTA cycle sums of its phases (info "tc_timeline_<k>")
   int opt_tc_epi_mma = 0;    // 1: fused int8 forward kernel with the layer-2 epilogue on mma.sync (tc_fused_mma.cuh): parity green, no faster
+  int opt_select_compact = 1;   // median radix select: compact the candidates after two passes (0: eight passes over the whole set)
   int opt_svgd_gram_sync = 0;   // parameter-sharded SVGD: 1 = the Gram all-reduce on the main stream (not beside the gradients)
   int opt_live_cta = 1;      // live SVGD sweep of a small problem (particles fit one CTA's shared memory) in one CTA, no grid barriers
   int opt_svgd_halves = 0;   // parameter-sharded SVGD: gradients in two halves, the first half's exchange behind the second

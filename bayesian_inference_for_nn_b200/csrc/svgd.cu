@@ -284,6 +284,67 @@ __global__ void k_next_greater(const double* v, int64_t n, const SelectState* st
   }
   if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(nxt, m);
 }
+// After the two leading passes the candidates (elements that share the 16 fixed top bits: sign, exponent and four mantissa
+// bits — a sixteenth of an octave) are a small fraction of the matrix: they are copied out once, the remaining six passes
+// and the next-greater search run over the copy.  Three passes over the matrix instead of ten.  The same scan finds the
+// smallest element ABOVE the candidates' bucket (the next order statistic when the selected value is the bucket's largest).
+__global__ void k_select_compact(const double* v, int64_t n, const SelectState* st, unsigned long long* cand,
+                                 unsigned long long* cnt, unsigned long long* nxt) {
+  const unsigned long long prefix = st->prefix, mask = st->mask, top = prefix | ~mask;
+  const int lane = threadIdx.x & 31;
+  unsigned long long m = ~0ull;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const bool valid = i < n;
+    const unsigned long long b = valid ? (unsigned long long)__double_as_longlong(v[i]) : 0ull;
+    const bool in = valid && (b & mask) == prefix;
+    const unsigned ballot = __ballot_sync(0xffffffffu, in);
+    if (ballot) {
+      unsigned long long off = 0;
+      if (lane == 0) off = atomicAdd(cnt, (unsigned long long)__popc(ballot));
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if (in) cand[off + __popc(ballot & ((1u << lane) - 1u))] = b;
+    }
+    if (valid && b > top && b < m) m = b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t < m ? t : m;
+  }
+  if (lane == 0 && m != ~0ull) atomicMin(nxt, m);
+}
+__global__ void k_select_hist_keys(const unsigned long long* keys, const unsigned long long* n_ptr, const SelectState* st, int shift,
+                                   unsigned long long* hist) {
+  __shared__ unsigned int h[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) h[t] = 0;
+  __syncthreads();
+  const unsigned long long prefix = st->prefix, mask = st->mask;
+  const int64_t n = (int64_t)n_ptr[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long b = keys[i];
+    if ((b & mask) == prefix) atomicAdd(&h[(b >> shift) & 0xff], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 256; t += blockDim.x)
+    if (h[t]) atomicAdd(&hist[t], (unsigned long long)h[t]);
+}
+__global__ void k_next_greater_keys(const unsigned long long* keys, const unsigned long long* n_ptr, const SelectState* st,
+                                    unsigned long long* nxt) {
+  const unsigned long long sel = st->prefix;
+  const int64_t n = (int64_t)n_ptr[0];
+  unsigned long long m = ~0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long b = keys[i];
+    if (b > sel && b < m) m = b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t < m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(nxt, m);
+}
 // a: the select state of order statistic k0 = (n - 1) / 2 (prefix = its bits, k = its index inside its group of equals,
 // a[1].k = size of that group); the next order statistic is the same value unless k0 was the last of the group
 __global__ void k_bandwidth_next(const SelectState* a, const unsigned long long* nxt, int want_next, int St, double* h2_out) {
@@ -542,6 +603,28 @@ static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t
   PYB_CUDA(cudaMemsetAsync(sc.hist.p, 0, 256 * sizeof(unsigned long long), h->stream));
   PYB_CUDA(cudaMemsetAsync(sc.sel.p + 6, 0xff, sizeof(unsigned long long), h->stream));     // slot 6: the next-greater minimum
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)h->sm_count);
+  if (!(sc.world > 1 && reduce) && n >= 4096 && h->opt_select_compact) {
+    // the whole set is here: two passes over it, one compaction, the rest over the candidates
+    SelectState* st = reinterpret_cast<SelectState*>(sc.sel.p);
+    unsigned long long* nxt = sc.sel.p + 6;
+    unsigned long long* cnt = sc.sel.p + 7;
+    sc.cand.alloc((size_t)n);
+    PYB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), h->stream));
+    for (int shift = 56; shift >= 48; shift -= 8) {
+      k_select_hist<<<blocks, 256, 0, h->stream>>>(d2, n, st, shift, sc.hist.p);
+      k_select_pick<<<1, 256, 0, h->stream>>>(st, shift, sc.hist.p);
+    }
+    k_select_compact<<<blocks, 256, 0, h->stream>>>(d2, n, st, sc.cand.p, cnt, nxt);
+    const int kb = 2 * h->sm_count;
+    for (int shift = 40; shift >= 0; shift -= 8) {
+      k_select_hist_keys<<<kb, 256, 0, h->stream>>>(sc.cand.p, cnt, st, shift, sc.hist.p);
+      k_select_pick<<<1, 256, 0, h->stream>>>(st, shift, sc.hist.p);
+    }
+    if (want_next) k_next_greater_keys<<<kb, 256, 0, h->stream>>>(sc.cand.p, cnt, st, nxt);
+    k_bandwidth_next<<<1, 1, 0, h->stream>>>(st, nxt, want_next, St, h2_dev);
+    count_launch(h, 19);
+    return;
+  }
   for (int shift = 56; shift >= 0; shift -= 8) {
     k_select_hist<<<blocks, 256, 0, h->stream>>>(d2, n, reinterpret_cast<SelectState*>(sc.sel.p), shift, sc.hist.p);
     if (sc.world > 1 && reduce) nccl_all_reduce_u64(sc.nccl_comm, sc.hist.p, 256, h->stream);
@@ -917,10 +1000,10 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
         nccl_all_reduce_f64(sv.nccl_comm, sv.ps_norms.p, St, h->stream);
       }
       k_d2_from_gram<<<(unsigned)(((int64_t)St * St + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p);
-      // every rank holds the whole (bit-identical) distance matrix: for a small one, nine passes over all of it beat nine
-      // passes over this rank's rows with a latency-bound 2 KB all-reduce after each; for a large one the passes are HBM
-      // time taken from the gradient kernels running beside this chain, and the rows of this rank are 1/world of it
-      if ((int64_t)St * St <= (4ll << 20))
+      // every rank holds the whole (bit-identical) distance matrix: the select runs over all of it without a collective
+      // (three passes over the matrix and six over the compacted candidates) instead of over this rank's rows with a
+      // latency-bound 2 KB all-reduce after each of nine passes
+      if ((int64_t)St * St <= (64ll << 20))
         median_bandwidth(h, sv.d2.p, (int64_t)St * St, (int64_t)St * St, St, sv.h2.p, false);
       else
         median_bandwidth(h, sv.d2.p + (int64_t)r0 * St, (int64_t)S * St, (int64_t)St * St, St, sv.h2.p);

@@ -301,12 +301,19 @@ def test_svgd_phi_hook_median_bandwidth_is_exact(oracle):
     assert rel_err(phi, g["phi_hook"]) < 1e-5
     # odd and even particle counts exercise both median branches
     rng = np.random.default_rng(5)
-    for S in (5, 8, 33):
+    # (from 64 particles on the select compacts its candidates after two passes: 80, 131 and the duplicated rows below —
+    # groups of EQUAL distances around the median — exercise that branch; select_compact = 0 is the plain eight-pass select)
+    for S in (5, 8, 33, 80, 131):
         X = rng.standard_normal((S, 252)) * 0.3
+        if S == 131:
+            X[40:80] = X[0:40]                      # exact ties: 40 duplicated particles
         G = rng.standard_normal((S, 252)).astype(np.float32)
-        phi, h = eng.svgd_phi(X.astype(np.float32).astype(np.float64), G, _lib.SVGD_CANONICAL_MEDIAN)
         want, h_ref, _ = oracle.svgd_phi_canonical(X.astype(np.float32).astype(np.float64), G)
-        assert abs(h - h_ref) < 1e-9 * h_ref and rel_err(phi, want) < 1e-5
+        for compact in (1, 0):
+            eng.set_option("select_compact", compact)
+            phi, h = eng.svgd_phi(X.astype(np.float32).astype(np.float64), G, _lib.SVGD_CANONICAL_MEDIAN)
+            assert abs(h - h_ref) < 1e-9 * h_ref and rel_err(phi, want) < 1e-5, (S, compact, h, h_ref)
+    eng.set_option("select_compact", 1)
 
 
 def test_svgd_live_formula_hook(oracle):
