@@ -86,6 +86,11 @@ __device__ __forceinline__ fs_f2 fs_fma2(fs_f2 a, fs_f2 b, fs_f2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
+__device__ __forceinline__ fs_f2 fs_mul2(fs_f2 a, fs_f2 b) {
+  fs_f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ fs_f2 fs_add2(fs_f2 a, fs_f2 b) {
   fs_f2 r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -282,9 +287,7 @@ __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale,
       fs_f2 da = 0ull;
 #pragma unroll
       for (int c = 0; c < C; ++c) da = fs_fma2(dzr[c], w2[c], da);
-      float da0, da1;
-      fs_unpack2(da, da0, da1);
-      const fs_f2 d1 = fs_pack2(da0 * act_grad_from_output(a0, act1), da1 * act_grad_from_output(a1, act1));
+      const fs_f2 d1 = fs_mul2(da, fs_pack2(act_grad_from_output(a0, act1), act_grad_from_output(a1, act1)));
       const fs_f2 a = fs_pack2(a0, a1);
 #pragma unroll
       for (int d = 0; d < D; ++d) gw1[d] = fs_fma2(x[d], d1, gw1[d]);
@@ -298,6 +301,7 @@ __device__ double fs_eval_rows(const FsParams& p, const FsSmem& sm, float scale,
     uint32_t pa = fs_smem_u32(sm.xd) + (uint32_t)((j0 + slice) * PW2 * 4);
     const uint32_t pstep = (uint32_t)(n_slices * PW2 * 4);
     int j = j0 + slice;
+#pragma unroll 2
     for (; j < j_full; j += n_slices, pa += pstep) {
       fs_f2 v[D + C];
       fs_lds_pairs<D + C>(pa, v);
