@@ -243,8 +243,10 @@ int pyb_set_option(pyb_handle* h, const char* key, double v) {
     h->opt_tc_epi_mma = v != 0;
   } else if (!strcmp(key, "svgd_pshard")) {
     h->opt_svgd_pshard = v != 0;
+  } else if (!strcmp(key, "svgd_chain_fused")) {
+    h->opt_svgd_chain_fused = v != 0;
   } else if (!strcmp(key, "select_compact")) {
-    h->opt_select_compact = v != 0;
+    h->opt_select_compact = (int)v;
   } else if (!strcmp(key, "svgd_gram_sync")) {
     h->opt_svgd_gram_sync = v != 0;
   } else if (!strcmp(key, "svgd_halves")) {

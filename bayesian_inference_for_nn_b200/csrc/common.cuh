@@ -325,7 +325,8 @@ struct pyb_handle {
   int opt_tc_fuse = 1;   // 1: layer 2 (+ loss, dZ2, dZ1) runs inside the layer-1 GEMM's epilogue where it applies
   int opt_tc_timeline = 0;   // diagnostics: the fused mma kernel records per-CTA cycle sums of its phases (info "tc_timeline_<k>")
   int opt_tc_epi_mma = 0;    // 1: fused int8 forward kernel with the layer-2 epilogue on mma.sync (tc_fused_mma.cuh): parity green, no faster
-  int opt_select_compact = 1;   // median radix select: compact the candidates after two passes (0: eight passes over the whole set)
+  int opt_select_compact = 0;   // median radix select of a local set: 0 eight passes, two kernels each; 1 candidates compacted after two passes (pays only for spread-out distances: in high dimension they concentrate and the candidates are the whole set); 2 eight passes, the digit picked inside the next pass (half the kernels)
+  int opt_svgd_chain_fused = 1; // parameter-sharded SVGD: the side chain with fused kernels (12 launches instead of 25)
   int opt_svgd_gram_sync = 0;   // parameter-sharded SVGD: 1 = the Gram all-reduce on the main stream (not beside the gradients)
   int opt_live_cta = 1;      // live SVGD sweep of a small problem (particles fit one CTA's shared memory) in one CTA, no grid barriers
   int opt_svgd_halves = 0;   // parameter-sharded SVGD: gradients in two halves, the first half's exchange behind the second

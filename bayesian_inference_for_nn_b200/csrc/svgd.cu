@@ -345,6 +345,101 @@ __global__ void k_next_greater_keys(const unsigned long long* keys, const unsign
   }
   if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(nxt, m);
 }
+// ---- the plain eight-pass select with HALF the kernels (in the sharded step it runs beside persistent kernels that own
+//      every SM: each of its kernels can only start at one of their boundaries, so the chain's length is its kernel
+//      count): every pass picks the previous digit itself, from the previous pass's own histogram ----
+// one radix digit of a select state from a 256-bin histogram in shared memory (the arithmetic of k_select_pick)
+__device__ __forceinline__ SelectState select_pick_local(SelectState s, const unsigned long long* hs, int shift,
+                                                         unsigned long long* group) {
+  unsigned long long c = 0;
+  int b = 0;
+  for (; b < 256; ++b) {
+    if (c + hs[b] > s.k) break;
+    c += hs[b];
+  }
+  if (b > 255) b = 255;
+  s.k -= c;
+  if (group) *group = hs[b];
+  s.prefix |= ((unsigned long long)b) << shift;
+  s.mask |= 0xffull << shift;
+  return s;
+}
+// every block picks digit `shift_prev` from hist_prev itself (identical everywhere), block 0 records the state
+__device__ __forceinline__ SelectState select_advance(const SelectState* st_in, const unsigned long long* hist_prev, int shift_prev,
+                                                      SelectState* st_out, unsigned long long* hs, SelectState* cur) {
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) hs[t] = hist_prev[t];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *cur = select_pick_local(*st_in, hs, shift_prev, nullptr);
+    if (blockIdx.x == 0) *st_out = *cur;
+  }
+  __syncthreads();
+  return *cur;
+}
+// pass `shift` over the whole set with the previous digit picked on the fly
+__global__ void k_select_hist_adv(const double* v, int64_t n, const SelectState* st_in, const unsigned long long* hist_prev,
+                                  int shift_prev, SelectState* st_out, int shift, unsigned long long* hist) {
+  __shared__ unsigned long long hs[256];
+  __shared__ SelectState cur;
+  __shared__ unsigned int h[256];
+  const SelectState s = select_advance(st_in, hist_prev, shift_prev, st_out, hs, &cur);
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) h[t] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+    if ((b & s.mask) == s.prefix) atomicAdd(&h[(b >> shift) & 0xff], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 256; t += blockDim.x)
+    if (h[t]) atomicAdd(&hist[t], (unsigned long long)h[t]);
+}
+// the LAST digit picked on the fly (block 0 records the final state and the size of the selected value's group of equals),
+// then the search for the smallest element above the selected value
+__global__ void k_next_greater_adv(const double* v, int64_t n, const SelectState* st_in, const unsigned long long* hist_prev,
+                                   SelectState* st_final, int want_next, unsigned long long* nxt) {
+  __shared__ unsigned long long hs[256];
+  __shared__ SelectState cur;
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) hs[t] = hist_prev[t];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long group = 0;
+    cur = select_pick_local(*st_in, hs, 0, &group);
+    if (blockIdx.x == 0) { st_final[0] = cur; st_final[1].k = group; }
+  }
+  __syncthreads();
+  if (!want_next) return;
+  const unsigned long long sel = cur.prefix;
+  unsigned long long m = ~0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+    if (b > sel && b < m) m = b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t < m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(nxt, m);
+}
+// K = exp(-d2 / (2 h2)) of one row per block: row sum (float64, block_sum's order) and the bf16 hi / lo split of (float)K in
+// one pass (k_kernel_rowsum + k_double_to_float + the row split); d2 is left untouched
+__global__ void k_kernel_rowsum_split(const double* d2, int St, const double* h2, double* rowsum, __nv_bfloat16* kh,
+                                      __nv_bfloat16* kl) {
+  __shared__ double scratch[32];
+  const int i = blockIdx.x;
+  const double inv = 1.0 / (2.0 * h2[0]);
+  double a = 0.0;
+  for (int j = threadIdx.x; j < St; j += blockDim.x) {
+    const double k = exp(-d2[(int64_t)i * St + j] * inv);
+    a += k;
+    const float kf = (float)k;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(kf);
+    kh[(int64_t)i * St + j] = hi;
+    kl[(int64_t)i * St + j] = __float2bfloat16_rn(kf - __bfloat162float(hi));
+  }
+  const double t = block_sum<double>(a, scratch);
+  if (threadIdx.x == 0) rowsum[i] = t;
+}
 // a: the select state of order statistic k0 = (n - 1) / 2 (prefix = its bits, k = its index inside its group of equals,
 // a[1].k = size of that group); the next order statistic is the same value unless k0 was the last of the group
 __global__ void k_bandwidth_next(const SelectState* a, const unsigned long long* nxt, int want_next, int St, double* h2_out) {
@@ -440,12 +535,27 @@ __global__ void k_row_norms(const float* X, int64_t P, double* norms) {
   if (threadIdx.x == 0) norms[blockIdx.x] = t;
 }
 // d2[i][j] = max(n_{r0+i} + n_j - 2 G[i][j], 0); exact zero on the diagonal (pdist has d(x,x) = 0)
-__global__ void k_d2_from_gram(const float* G, const double* norms, int r0, int Sl, int St, double* d2) {
+// hist56 != nullptr: also the 256-bin histogram of the results' top bytes — the first pass of the median's radix select
+__global__ void k_d2_from_gram(const float* G, const double* norms, int r0, int Sl, int St, double* d2,
+                               unsigned long long* hist56 = nullptr) {
+  __shared__ unsigned int hb[256];
+  if (hist56) {
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) hb[t] = 0;
+    __syncthreads();
+  }
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)Sl * St) return;
-  int i = (int)(idx / St), j = (int)(idx - (int64_t)i * St);
-  double v = norms[r0 + i] + norms[j] - 2.0 * (double)G[idx];
-  d2[idx] = (j == r0 + i || v < 0.0) ? 0.0 : v;
+  if (idx < (int64_t)Sl * St) {
+    int i = (int)(idx / St), j = (int)(idx - (int64_t)i * St);
+    double v = norms[r0 + i] + norms[j] - 2.0 * (double)G[idx];
+    v = (j == r0 + i || v < 0.0) ? 0.0 : v;
+    d2[idx] = v;
+    if (hist56) atomicAdd(&hb[((unsigned long long)__double_as_longlong(v)) >> 56], 1u);
+  }
+  if (hist56) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 256; t += blockDim.x)
+      if (hb[t]) atomicAdd(&hist56[t], (unsigned long long)hb[t]);
+  }
 }
 __global__ void k_double_to_float(const double* a, float* b, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -587,11 +697,49 @@ static double adam_lr_t(double lr, int64_t t) {
 // histograms are all-reduced (2 KB per pass), so every rank picks the same bins
 // reduce = false: d2 already IS the global set on every rank (bit-identical after the Gram all-reduce), so the select runs
 // without any collective and still picks the same value everywhere
+// The select of a LOCAL set with half the kernels: hist56_done = the caller's distance kernel has already filled histogram 0
+// with the top bytes (after median_prepare_fused zeroed the buffers).  Eight histograms, three state slots.
+static void median_prepare_fused(pyb_handle* h, int64_t n_global) {
+  SvgdState& sc = h->svgd;
+  sc.sel.alloc(16);
+  sc.hist.alloc(256 * 8);
+  SelectState init[2];
+  init[0].prefix = 0; init[0].mask = 0; init[0].k = (unsigned long long)((n_global - 1) / 2);
+  init[1].prefix = 0; init[1].mask = 0; init[1].k = 0;
+  PYB_CUDA(cudaMemsetAsync(sc.hist.p, 0, 256 * 8 * sizeof(unsigned long long), h->stream));
+  PYB_CUDA(cudaMemsetAsync(sc.sel.p + 6, 0xff, sizeof(unsigned long long), h->stream));   // slot 6: the next-greater minimum
+  PYB_CUDA(cudaMemcpyAsync(sc.sel.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+}
+static void median_bandwidth_fused(pyb_handle* h, const double* d2, int64_t n, int St, double* h2_dev, bool hist56_done) {
+  SvgdState& sc = h->svgd;
+  SelectState* st0 = reinterpret_cast<SelectState*>(sc.sel.p);            // initial and, at the end, final state (+ st0[1].k)
+  SelectState* alt[2] = {reinterpret_cast<SelectState*>(sc.sel.p + 8), reinterpret_cast<SelectState*>(sc.sel.p + 11)};
+  unsigned long long* nxt = sc.sel.p + 6;
+  unsigned long long* H = sc.hist.p;
+  const int want_next = (n / 2) != ((n - 1) / 2);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)h->sm_count);
+  if (!hist56_done) k_select_hist<<<blocks, 256, 0, h->stream>>>(d2, n, st0, 56, H);
+  const SelectState* in = st0;
+  for (int p = 1; p <= 7; ++p) {
+    SelectState* out = alt[p & 1];
+    k_select_hist_adv<<<blocks, 256, 0, h->stream>>>(d2, n, in, H + (p - 1) * 256, 64 - 8 * p, out, 56 - 8 * p, H + p * 256);
+    in = out;
+  }
+  k_next_greater_adv<<<blocks, 256, 0, h->stream>>>(d2, n, in, H + 7 * 256, st0, want_next, nxt);
+  k_bandwidth_next<<<1, 1, 0, h->stream>>>(st0, nxt, want_next, St, h2_dev);
+  count_launch(h, hist56_done ? 9 : 10);
+}
+
 static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t n_global, int St, double* h2_dev,
                              bool reduce = true) {
   SvgdState& sc = h->svgd;
-  sc.sel.alloc(8);
-  sc.hist.alloc(256);
+  if (!(sc.world > 1 && reduce) && h->opt_select_compact == 2) {
+    median_prepare_fused(h, n_global);
+    median_bandwidth_fused(h, d2, n, St, h2_dev, false);
+    return;
+  }
+  sc.sel.alloc(16);
+  sc.hist.alloc(256 * 8);
   // ONE radix select for the lower middle order statistic (8 passes, each with a 2 KB histogram all-reduce when the
   // rows are sharded); the upper middle one is the same value or the next greater element (one more pass, one all-reduce
   // MIN) — half the latency-bound small collectives of two independent selects
@@ -603,8 +751,8 @@ static void median_bandwidth(pyb_handle* h, const double* d2, int64_t n, int64_t
   PYB_CUDA(cudaMemsetAsync(sc.hist.p, 0, 256 * sizeof(unsigned long long), h->stream));
   PYB_CUDA(cudaMemsetAsync(sc.sel.p + 6, 0xff, sizeof(unsigned long long), h->stream));     // slot 6: the next-greater minimum
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)h->sm_count);
-  if (!(sc.world > 1 && reduce) && n >= 4096 && h->opt_select_compact) {
-    // the whole set is here: two passes over it, one compaction, the rest over the candidates
+  if (!(sc.world > 1 && reduce) && n >= 4096 && h->opt_select_compact == 1) {
+    // the whole set is here: two passes over it, one compaction, the rest over the candidates (one kernel per step)
     SelectState* st = reinterpret_cast<SelectState*>(sc.sel.p);
     unsigned long long* nxt = sc.sel.p + 6;
     unsigned long long* cnt = sc.sel.p + 7;
@@ -999,18 +1147,25 @@ static void svgd_step_pshard(pyb_handle* h, const float* Xb, const int32_t* yb_i
         nccl_all_reduce_f32(sv.nccl_comm, sv.gram.p, (size_t)St * St, h->stream);
         nccl_all_reduce_f64(sv.nccl_comm, sv.ps_norms.p, St, h->stream);
       }
-      k_d2_from_gram<<<(unsigned)(((int64_t)St * St + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p);
-      // every rank holds the whole (bit-identical) distance matrix: the select runs over all of it without a collective
-      // (three passes over the matrix and six over the compacted candidates) instead of over this rank's rows with a
-      // latency-bound 2 KB all-reduce after each of nine passes
-      if ((int64_t)St * St <= (64ll << 20))
-        median_bandwidth(h, sv.d2.p, (int64_t)St * St, (int64_t)St * St, St, sv.h2.p, false);
-      else
-        median_bandwidth(h, sv.d2.p + (int64_t)r0 * St, (int64_t)S * St, (int64_t)St * St, St, sv.h2.p);
-      k_kernel_rowsum<<<St, 256, 0, h->stream>>>(sv.d2.p, St, sv.h2.p, sv.rowsum.p);
-      k_double_to_float<<<eb, 256, 0, h->stream>>>(sv.d2.p, sv.kf.p, (int64_t)St * St);
-      tc_split_rows(h, sv.kf.p, St, St, St, sv.kh.p, sv.kl.p, St);
-      count_launch(h, 4);
+      // every rank holds the whole (bit-identical) distance matrix: the select runs over all of it without a collective,
+      // and the chain is kept to FEW kernels (each one waits for a kernel boundary of the main stream): distances + first
+      // histogram, seven passes that pick the previous digit themselves, last pick + next-greater, bandwidth, and one
+      // pass for the kernel matrix's row sums and bf16 split — 12 launches where the plain sequence has 25
+      const int64_t nn = (int64_t)St * St;
+      if (nn <= (64ll << 20) && h->opt_svgd_chain_fused) {
+        median_prepare_fused(h, nn);
+        k_d2_from_gram<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p, sv.hist.p);
+        median_bandwidth_fused(h, sv.d2.p, nn, St, sv.h2.p, true);
+      } else {
+        k_d2_from_gram<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(sv.gram.p, sv.ps_norms.p, 0, St, St, sv.d2.p);
+        if (nn <= (64ll << 20))
+          median_bandwidth(h, sv.d2.p, nn, nn, St, sv.h2.p, false);
+        else
+          median_bandwidth(h, sv.d2.p + (int64_t)r0 * St, (int64_t)S * St, nn, St, sv.h2.p);
+      }
+      k_kernel_rowsum_split<<<St, 256, 0, h->stream>>>(sv.d2.p, St, sv.h2.p, sv.rowsum.p, (__nv_bfloat16*)sv.kh.p,
+                                                       (__nv_bfloat16*)sv.kl.p);
+      count_launch(h, 3);
     } catch (...) {
       h->stream = main_stream; sv.nccl_comm = comm_main;
       throw;

@@ -302,18 +302,20 @@ def test_svgd_phi_hook_median_bandwidth_is_exact(oracle):
     # odd and even particle counts exercise both median branches
     rng = np.random.default_rng(5)
     # (from 64 particles on the select compacts its candidates after two passes: 80, 131 and the duplicated rows below —
-    # groups of EQUAL distances around the median — exercise that branch; select_compact = 0 is the plain eight-pass select)
+    # groups of EQUAL distances around the median — exercise that branch (select_compact = 1); 0 (default) is the plain
+    # eight-pass select, 2 the same passes with every digit picked inside the next pass (the kernels the sharded step's
+    # side chain uses))
     for S in (5, 8, 33, 80, 131):
         X = rng.standard_normal((S, 252)) * 0.3
         if S == 131:
             X[40:80] = X[0:40]                      # exact ties: 40 duplicated particles
         G = rng.standard_normal((S, 252)).astype(np.float32)
         want, h_ref, _ = oracle.svgd_phi_canonical(X.astype(np.float32).astype(np.float64), G)
-        for compact in (1, 0):
+        for compact in (2, 1, 0):
             eng.set_option("select_compact", compact)
             phi, h = eng.svgd_phi(X.astype(np.float32).astype(np.float64), G, _lib.SVGD_CANONICAL_MEDIAN)
             assert abs(h - h_ref) < 1e-9 * h_ref and rel_err(phi, want) < 1e-5, (S, compact, h, h_ref)
-    eng.set_option("select_compact", 1)
+    eng.set_option("select_compact", 0)
 
 
 def test_svgd_live_formula_hook(oracle):

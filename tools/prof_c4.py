@@ -19,6 +19,8 @@ eng = Engine(sp, seed=1)
 eng.set_dataset(X, y, _lib.LOSS_SPARSE_CE)
 eng.set_prior([0.0], [1.0], _lib.PRIOR_SCALAR)
 eng.svgd_init(S, 0.01, _lib.SVGD_CANONICAL_MEDIAN)
-for _ in range(2):
+if "PYB_SELECT_COMPACT" in os.environ:
+    eng.set_option("select_compact", int(os.environ["PYB_SELECT_COMPACT"]))
+for _ in range(int(os.environ.get("STEPS", 2))):
     eng.svgd_step(rng.permutation(60000)[:1024].astype(np.int32))
     print("step ms", eng.info("last_device_ms"))
