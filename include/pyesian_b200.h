@@ -170,7 +170,9 @@ int pyb_svgd_validation_loss(pyb_handle* h, double* mean_loss_out, float* per_pa
  * the updated particle blocks are exchanged by stores of the library's own kernels into peer memory - CUDA IPC between
  * processes of one host, plain peer access inside one process - with one-float NCCL barriers; falls back to ncclSend /
  * ncclRecv when a mapping is refused; 0: always NCCL; read-out "svgd_p2p" tells which one runs), "svgd_gram_sync" and
- * "svgd_halves" (A/B switches of the pipeline, default 0), "live_cta" (default 1: the reference-live sweep of a particle
+ * "svgd_halves" (A/B switches of the pipeline, default 0), "svgd_chain_fused" (default 1: the reduction / median /
+ * kernel-matrix chain in half the launches), "select_compact" (median radix select of a local set: 0 default, 1 with
+ * candidate compaction, 2 with every digit picked inside the next pass), "live_cta" (default 1: the reference-live sweep of a particle
  * set that fits one CTA's shared memory runs in one CTA); read-outs "svgd_phase_ms_0..6" (with "profile" on): CUDA-event
  * split of the last sharded step. */
 int pyb_svgd_set_comm(pyb_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id_128);
